@@ -1,0 +1,197 @@
+/*
+ * nsb.h -- C ABI of the B200-native NICE-SLAM ray-rendering hot path (libnsb.so).
+ *
+ * The reference (cjpurackal/nice-slam-cpp) has no plugin/FFI layer: its boundary is the C++ class API of
+ * include/Renderer.h, include/Mapper.h, include/Tracker.h and the free functions of
+ * include/torchlib/utils.h.  Every entry point below names the reference interface it replaces
+ * (file:line relative to the reference tree).  The same-named C++ wrapper classes that keep the
+ * reference's signatures live in include/nsb/ (Renderer, Mapper, Tracker, NICE) and call only this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch / STL types; every call returns 0 on success, non-zero on error,
+ *     nsb_last_error(ctx) gives the message (the reference throws c10::Error instead);
+ *   - "host" entry points take HOST buffers and include the host<->device copies (this is what the
+ *     reference's callers do: Mapper.cpp:430 uploads the rays inside the call expression);
+ *     "_dev" entry points take DEVICE pointers, enqueue on the context's stream and do not synchronise;
+ *   - one context per GPU, not thread-safe, no allocation after nsb_create on the hot path;
+ *   - there is NO CPU fallback: nsb_create fails if no sm_100 device is present.
+ *
+ * Layouts
+ *   - grids cross the ABI in the reference's layout (1, C, Z, Y, X) fp32 channel-first (main.cpp:39-43);
+ *     on the device they are stored channel-last [Z][Y][X][C] so that one voxel corner is one 128-byte line;
+ *   - decoders cross the ABI as ONE flat fp32 vector per decoder (PyTorch Linear layout, weight[out][in]):
+ *       MLP (middle/fine/color; MLP.cpp:14-46):
+ *         B[3][E] | for i<5: W_i[H][K_i], b_i[H] | for i<5: Fc_i[H][C], bc_i[H] | Wo[O][H], bo[O]
+ *         E=93, H=32, K={E,H,H,E+H,H} (skip input is cat(e,h)), C=c_dim (fine: 2*c_dim = cat(fine,middle)),
+ *         O=1 (middle, fine) or 4 (color)
+ *       MLP_no_xyz (coarse; MLP.cpp:104-138): for i<5: W_i[H][K_i], b_i[H] | Wo[1][H], bo[1],
+ *         K={C,H,H,C+H,H} (skip input is cat(c,h))
+ *   - a camera is either a row-major 4x4 c2w (16 floats) or the 7-vector (qw,qx,qy,qz,tx,ty,tz)
+ *     consumed by quad2rotation (utils.h:174-195).
+ */
+#ifndef NSB_H
+#define NSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_ABI_VERSION 1
+
+enum { NSB_COARSE = 0, NSB_MIDDLE = 1, NSB_FINE = 2, NSB_COLOR = 3 }; /* grid level / decoder / stage id */
+enum { NSB_PREC_3XTF32 = 0, NSB_PREC_TF32 = 1 };   /* decoder MMA precision: fp32-grade split / plain TF32 */
+enum { NSB_RAYDIR_REFERENCE = 0, NSB_RAYDIR_PINHOLE = 1 }; /* utils.h:44-47 as written / upstream pinhole */
+enum { NSB_DISTNORM_PER_RAY = 0, NSB_DISTNORM_REFERENCE = 1 }; /* upstream intent / utils.h:153 as written */
+
+typedef struct nsb_ctx nsb_ctx;
+
+/* All hyper-parameters the hot path consumes.  Key names follow config/nice_slam.yaml and
+ * config/cofusion.yaml; nsb_config_default() fills the reference's values. */
+typedef struct nsb_config {
+    /* cam.* (cofusion.yaml:23-29; Mapper.cpp:22-27, Tracker.cpp:25-30) */
+    int H, W;
+    float fx, fy, cx, cy;
+    /* scene bound, hard-coded in the reference (Renderer.cpp:15, Mapper.cpp:29, Tracker.cpp:23, main.cpp:33) */
+    float bound[3][2];
+    /* grid_len.* and model.* (main.cpp:22-30); grid_dim[level] = {Z,Y,X}; 0 = derive from bound/grid_len as main.cpp:34-78 */
+    float grid_len[4];
+    int coarse_bound_enlarge;
+    int grid_dim[4][3];
+    int c_dim;                       /* model.c_dim = 32 (only value this build supports) */
+    /* rendering.* -- the reference hard-codes them in Renderer::Renderer (Renderer.cpp:5-15) */
+    int n_samples, n_surface;        /* 32, 16 */
+    int occupancy;                   /* 0: density branch, what raw2outputs_nerf_color computes (utils.h:155); 1: sigmoid(10 raw) */
+    int dist_norm;                   /* NSB_DISTNORM_* */
+    int raydir;                      /* NSB_RAYDIR_* */
+    /* mapping.* (Mapper.cpp:11-19,28-33,351-368,502-503,521-522) */
+    int mapping_pixels, mapping_iters, mapping_iters_first, mapping_window_size, keyframe_every;
+    float middle_iter_ratio, fine_iter_ratio;
+    int second_stage;                /* stage used for middle_ratio < it <= fine_ratio: NSB_MIDDLE (Mapper.cpp:355-356 as written) or NSB_FINE (upstream) */
+    float lr_factor, lr_first_factor;
+    float stage_lr[4][5];            /* [stage][group: decoders, coarse, middle, fine, color] (nice_slam.yaml:102-126) */
+    float mapping_w_color_loss;      /* Mapper.cpp:33 reads tracking.w_color_loss */
+    int fix_fine, fix_color, frustum_feature_selection, BA;
+    float BA_cam_lr;
+    /* tracking.* (Tracker.cpp:14-21; lr / iters are hard-coded at Tracker.cpp:103,107 to 1e-2 / 10) */
+    float tracking_lr;
+    int tracking_iters, tracking_pixels, ignore_edge_W, ignore_edge_H, handle_dynamic, use_color_in_tracking;
+    float w_color_loss;
+    /* engine */
+    int precision;                   /* NSB_PREC_* */
+    int max_rays;                    /* capacity of the per-call ray batch */
+    int max_frames;                  /* resident frame slots (keyframes + current) */
+} nsb_config;
+
+/* ---- configuration ------------------------------------------------------------------------------ */
+/* Reference defaults: config/nice_slam.yaml + config/cofusion.yaml + the literals of Renderer.cpp:5-15. */
+void nsb_config_default(nsb_config* cfg);
+/* Replaces YAML::LoadFile + the .as<T>() lookups of Mapper.cpp:6-34, Tracker.cpp:5-34, main.cpp:7-30.
+ * Either path may be NULL.  Reads the YAML subset those files use (nested maps, scalars, comments). */
+int nsb_config_load_yaml(nsb_config* cfg, const char* nice_slam_yaml, const char* dataset_yaml, char* err, int err_len);
+/* main.cpp:34-78: grid dims from bound / grid_len with the reference's fp32 arithmetic + truncation. */
+void nsb_grid_dims(const nsb_config* cfg, int level, int* Z, int* Y, int* X);
+int64_t nsb_decoder_count(int which, int c_dim);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out);   /* fails without an sm_100 GPU */
+void nsb_destroy(nsb_ctx* ctx);
+const char* nsb_last_error(const nsb_ctx* ctx);
+int nsb_abi_version(void);
+const char* nsb_build_info(void);
+int nsb_synchronize(nsb_ctx* ctx);
+void* nsb_stream(nsb_ctx* ctx);                                       /* cudaStream_t the context enqueues on */
+
+/* ---- state: grids (main.cpp:33-78 c10::Dict "grid_*"), decoders (NICE.h:9-11), t-tables ------------ */
+int nsb_set_grid(nsb_ctx* ctx, int level, const float* host_ncdhw);
+int nsb_get_grid(nsb_ctx* ctx, int level, float* host_ncdhw);
+int nsb_get_grid_grad(nsb_ctx* ctx, int level, float* host_ncdhw);   /* gradient left by the last backward */
+int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host_flat, int64_t n);
+int nsb_get_decoder(nsb_ctx* ctx, int which, float* host_flat, int64_t n);
+int nsb_get_decoder_grad(nsb_ctx* ctx, int which, float* host_flat, int64_t n);
+/* torch::linspace(0,1,32) / (0,1,16) of Renderer.cpp:86,101 are ISA dependent in the last bit, so the
+ * tables are inputs; the default is the symmetric fp32 formula. */
+int nsb_set_ttables(nsb_ctx* ctx, const float* t_samples, const float* t_surface);
+/* Optional frustum voxel mask per level (Z*Y*X bytes, NULL clears): Adam touches masked voxels only
+ * (intent of Mapper.cpp:260-290,333-350,448-464). */
+int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host_mask_zyx);
+
+/* ---- frames (KeyFrame, Mapper.h:11-15) ------------------------------------------------------------ */
+/* Upload one RGB-D frame into resident slot `slot`: depth (H,W), colour (H,W,3), c2w row-major 4x4. */
+int nsb_set_frame(nsb_ctx* ctx, int slot, const float* host_depth, const float* host_color, const float* c2w16);
+int nsb_set_frame_pose(nsb_ctx* ctx, int slot, const float* c2w16);
+
+/* ---- camera utilities (utils.h:174-231) ------------------------------------------------------------- */
+void nsb_quad2rotation(const float* q4, float* R9);                    /* utils.h:174-195 */
+void nsb_get_camera_from_tensor(const float* cam7, float* RT12);      /* utils.h:198-210 */
+void nsb_get_tensor_from_camera(const float* c2w16, float* cam7);     /* utils.h:212-231, fixed: uses R, emits (w,x,y,z) */
+
+/* ---- ray sampling: get_samples / raySampler (utils.h:13-55,141-146) + inside filter (Mapper.cpp:416-427) ---- */
+/* Draws n pixels in the crop [H0,H1)x[W0,W1) of frame `slot`.  idx (host, n int64, flat index into the crop) may
+ * be NULL: then indices are std::mt19937(seed)() % crop, i.e. exactly what torch::randint draws on the CPU
+ * generator (utils.h:32), the stream continuing across calls until nsb_seed() reseeds it.
+ * c2w16 NULL = the slot's pose.  Outputs are host arrays and may be NULL. inside[i] = AABB exit t >= gt_depth. */
+int nsb_seed(nsb_ctx* ctx, uint64_t seed);
+int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H0, int H1, int W0, int W1, int n,
+                    const int64_t* idx, float* rays_o, float* rays_d, float* gt_depth, float* gt_color,
+                    uint8_t* inside, int64_t* idx_out);
+
+/* ---- rendering: Renderer::render_batch_ray (Renderer.h:13, Renderer.cpp:44-125) ---------------------- */
+/* stage in {NSB_COARSE..NSB_COLOR} replaces the std::string stage.  gt_depth NULL = the no-depth path
+ * (Renderer.cpp:54-58: N_surface = 0, near = 0.01).  weights is (n, n_samples + n_surface) or (n, n_samples). */
+int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o,
+                         const float* gt_depth, float* rgb, float* depth, float* var, float* weights);
+int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const float* d_rays_d, const float* d_rays_o,
+                             const float* d_gt_depth, float* d_rgb, float* d_depth, float* d_var, float* d_weights);
+/* Renderer::eval_points (Renderer.h:12, Renderer.cpp:19-42): raw (P,4) for P points. */
+int nsb_eval_points(nsb_ctx* ctx, int stage, int P, const float* pts, float* raw);
+/* z_vals of the last render (n, S) -- the "sample placement" intermediate of Renderer.cpp:61-119. */
+int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z_vals);
+
+/* Vector-Jacobian product of render_batch_ray: what loss.backward() (Mapper.cpp:444, Tracker.cpp:84) does
+ * for L = sum(g_rgb*rgb + g_depth*depth + g_var*var).  Leaves grid / decoder gradients in the context
+ * (nsb_get_grid_grad / nsb_get_decoder_grad) and returns the ray gradients (may be NULL).
+ * flags: bit0 grid grads, bit1 colour-decoder weight grads, bit2 ray (pose) grads. */
+int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o, const float* gt_depth,
+                   const float* g_rgb, const float* g_depth, const float* g_var, int flags,
+                   float* d_rays_d, float* d_rays_o);
+
+/* ---- mapping: Mapper::optimize_map inner loop (Mapper.cpp:330-465) ------------------------------------ */
+/* begin = the per-call setup of Mapper.cpp:198-330: chooses the frame slots to optimise (optimize_frame),
+ * resets Adam (a fresh torch::optim::Adam is built at :330).  lr_factor as Mapper::run passes it. */
+int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor);
+/* One joint iteration.  idx: host int64 [n_frames * (mapping_pixels / n_frames)] flat pixel indices, or NULL to
+ * draw them from the context's mt19937 stream.  loss (host, may be NULL; reading it synchronises). */
+int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss);
+/* Enqueue only (no host sync); the loss of iteration i is later read with nsb_mapping_losses. */
+int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx);
+int nsb_mapping_losses(nsb_ctx* ctx, int first_iter, int n, float* losses, int* n_inside);
+/* Optional: park the pixel indices of n_iters iterations ([n_iters][n] int64) in device memory; iterations called
+ * with idx = NULL then consume the rows in order (wrapping) instead of drawing/uploading (device-resident benchmarking). */
+int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n);
+/* Whole optimize_map: n_iters iterations, indices from the mt19937 stream; losses may be NULL. */
+int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, float* losses);
+
+/* ---- tracking: Tracker::run / optimize_cam_in_batch (Tracker.cpp:41-113) ------------------------------ */
+int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7);       /* Tracker.cpp:96-103 */
+int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, float* cam_grad7);   /* Tracker.cpp:41-89 */
+int nsb_tracking_get_camera(nsb_ctx* ctx, float* cam7);
+
+/* ---- multi-GPU: rays sharded over ranks, one fp32 SUM all-reduce of the gradient arena per iteration ---- */
+int nsb_comm_unique_id(char* id128);                                       /* ncclGetUniqueId */
+int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world);  /* ncclCommInitRank on the ctx device */
+int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world);
+
+/* ---- instrumentation ----------------------------------------------------------------------------------- */
+/* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */
+int64_t nsb_launch_count(nsb_ctx* ctx, int reset);
+/* Device time of the last instrumented kernels in ms (CUDA events on the ctx stream): [0] sample+zvals,
+ * [1] decode fwd, [2] composite/loss, [3] decode bwd, [4] wgrad, [5] adam, [6] allreduce. Enable with nsb_set_profiling. */
+int nsb_set_profiling(nsb_ctx* ctx, int on);
+int nsb_get_kernel_ms(nsb_ctx* ctx, float* ms7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB_H */

@@ -1,0 +1,1028 @@
+// Host side of libnsb.so: context, device arena, the C ABI of include/nsb.h.
+// Plain C++ + CUDA runtime; no libtorch, no CPU fallback (nsb_create fails without an sm_100 device).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/nsb.h"
+#include "misc_kernels.cuh"
+#include "params.h"
+#include "ray_kernels.cuh"
+
+namespace nsb {
+cudaError_t launch_decode_fwd(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_0(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_1(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_2(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_3(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_4(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+cudaError_t launch_decode_bwd_5(const DecodeParams& P, int precision, int grid, cudaStream_t st);
+// flags: bit0 grid gradients, bit1 colour-decoder weight-gradient stash, bit2 ray (pose) gradients
+inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int grid, cudaStream_t st) {
+    switch (P.flags & 7) {
+        case 1: return launch_decode_bwd_0(P, precision, grid, st);
+        case 3: return launch_decode_bwd_1(P, precision, grid, st);
+        case 4: return launch_decode_bwd_2(P, precision, grid, st);
+        case 5: return launch_decode_bwd_3(P, precision, grid, st);
+        case 7: return launch_decode_bwd_4(P, precision, grid, st);
+        case 2: return launch_decode_bwd_5(P, precision, grid, st);
+        default: return cudaErrorInvalidValue;   // 6 = RAY|WG is not instantiated
+    }
+}
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
+int decode_fwd_occupancy(int precision);
+}  // namespace nsb
+
+using namespace nsb;
+
+// ---- NCCL through dlopen: the library must not pull a second NCCL into a process that already has one ----------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // reuse the one already mapped (torch's)
+        if (!h) for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+static NcclApi g_nccl;
+enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+
+// ---- context ---------------------------------------------------------------------------------------------------
+enum { T_SAMPLE = 0, T_FWD, T_COMP, T_BWD, T_WGRAD, T_ADAM, T_COMM, T_N };
+constexpr int LOSS_RING = 4096;
+
+struct nsb_ctx {
+    nsb_config cfg;
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    Bound bnd;
+    // arena: [grid0 | dec0 | dec1 | grid1 | grid2 | grid3 | dec2 | dec3 | cams | tail]
+    size_t arena_n = 0;
+    float *param = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
+    size_t off_grid[4], off_dec[4], off_cam = 0, off_tail = 0, off_train = 0;
+    int gdim[4][3];
+    size_t nvox[4];
+    int64_t dec_n[4];
+    uint8_t* vmask[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *t_samples = nullptr, *t_surface = nullptr;
+    // frames
+    float *f_depth = nullptr, *f_color = nullptr, *f_pose = nullptr;
+    // per-ray buffers
+    int cap = 0;
+    float *rays_o = nullptr, *rays_d = nullptr, *gt_depth = nullptr, *gt_color = nullptr, *z = nullptr;
+    float *raw_rgb = nullptr, *occ[3] = {nullptr, nullptr, nullptr}, *g_raw = nullptr;
+    float *o_rgb = nullptr, *o_depth = nullptr, *o_var = nullptr, *o_w = nullptr;
+    float *g_rgb = nullptr, *g_depth = nullptr, *g_var = nullptr, *d_rays = nullptr, *absdiff = nullptr;
+    uint8_t* valid = nullptr;
+    int64_t* idx = nullptr;
+    int64_t* idx_pool = nullptr; int pool_iters = 0, pool_n = 0, pool_cursor = 0;   // optional device-resident pixel indices for many iterations
+    float* pts = nullptr;
+    float* stats = nullptr;       // [LOSS_RING][4]: max gt depth, n inside, sum 1/|d|, loss
+    float* median = nullptr; int* count = nullptr;
+    float* stash = nullptr; size_t stash_rows = 0;
+    float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
+    int last_n = 0, last_S = 0;
+    // host RNG (std::mt19937 == the CPU generator torch::randint uses, utils.h:32)
+    std::mt19937 rng{5489u};
+    std::vector<int64_t> h_idx;
+    // mapping state
+    int map_frames = 0, map_slots[MAX_OPT_FRAMES], map_iters = 0, map_step = 0; float map_lr_factor = 1.0f;
+    // tracking state
+    int trk_slot = 0, trk_step = 0;
+    // comm
+    ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    // instrumentation
+    int64_t launches = 0; bool profiling = false;
+    struct EvRec { int id; cudaEvent_t a, b; };
+    std::vector<EvRec> ev_pool; size_t ev_used = 0;   // profiling: one event pair per timed region since nsb_set_profiling(1)
+    int occ_blocks[2] = {0, 0};
+};
+
+static int fail(nsb_ctx* c, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return -1;
+}
+#define CK(call)                                                                                         \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+struct Timer {
+    nsb_ctx* c; int id; size_t slot;
+    Timer(nsb_ctx* c_, int id_) : c(c_), id(id_), slot(0) {
+        if (!c->profiling) return;
+        if (c->ev_used == c->ev_pool.size()) { nsb_ctx::EvRec r; r.id = id; cudaEventCreate(&r.a); cudaEventCreate(&r.b); c->ev_pool.push_back(r); }
+        slot = c->ev_used++;
+        c->ev_pool[slot].id = id;
+        cudaEventRecord(c->ev_pool[slot].a, c->stream);
+    }
+    ~Timer() { if (c->profiling) cudaEventRecord(c->ev_pool[slot].b, c->stream); }
+};
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static size_t pad32(size_t n) { return (n + 31) / 32 * 32; }
+
+// ---- configuration -----------------------------------------------------------------------------------------------
+extern "C" void nsb_config_default(nsb_config* c) {
+    memset(c, 0, sizeof *c);
+    c->H = 480; c->W = 640; c->fx = 360.f; c->fy = 360.f; c->cx = 320.f; c->cy = 240.f;        // cofusion.yaml:23-29
+    const float b[3][2] = {{-4.5f, 3.82f}, {-1.5f, 2.02f}, {-3.0f, 2.76f}};                     // Renderer.cpp:15
+    memcpy(c->bound, b, sizeof b);
+    c->grid_len[0] = 2.f; c->grid_len[1] = 0.32f; c->grid_len[2] = 0.16f; c->grid_len[3] = 0.16f;   // nice_slam.yaml:7-11
+    c->coarse_bound_enlarge = 2; c->c_dim = 32;
+    c->n_samples = 32; c->n_surface = 16; c->occupancy = 0;                                      // Renderer.cpp:9-10, utils.h:155
+    c->dist_norm = NSB_DISTNORM_PER_RAY; c->raydir = NSB_RAYDIR_REFERENCE;
+    c->mapping_pixels = 1000; c->mapping_iters = 60; c->mapping_iters_first = 1500;              // cofusion.yaml:20-22
+    c->mapping_window_size = 5; c->keyframe_every = 50;
+    c->middle_iter_ratio = 0.4f; c->fine_iter_ratio = 0.6f; c->second_stage = NSB_MIDDLE;        // Mapper.cpp:353-356
+    c->lr_factor = 1.f; c->lr_first_factor = 5.f;
+    const float lr[4][5] = {{0.f, 0.001f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.1f, 0.f, 0.f},
+                            {0.f, 0.f, 0.005f, 0.005f, 0.f}, {0.005f, 0.f, 0.005f, 0.005f, 0.005f}};   // nice_slam.yaml:102-126
+    memcpy(c->stage_lr, lr, sizeof lr);
+    c->mapping_w_color_loss = 0.5f;                                                              // Mapper.cpp:33
+    c->fix_fine = 1; c->fix_color = 0; c->frustum_feature_selection = 1; c->BA = 1; c->BA_cam_lr = 0.001f;
+    c->tracking_lr = 0.01f; c->tracking_iters = 10;                                              // Tracker.cpp:103,107
+    c->tracking_pixels = 200; c->ignore_edge_W = 20; c->ignore_edge_H = 20;
+    c->handle_dynamic = 1; c->use_color_in_tracking = 1; c->w_color_loss = 0.5f;
+    c->precision = NSB_PREC_3XTF32; c->max_rays = 8192; c->max_frames = 8;
+}
+
+// Minimal YAML subset: nested maps by indentation, "key: scalar", comments, quotes.  Flattened to "a.b.c" -> value.
+static bool yaml_flat(const char* path, std::map<std::string, std::string>& out, std::string& err) {
+    FILE* f = fopen(path, "r");
+    if (!f) { err = std::string("cannot open ") + path; return false; }
+    std::vector<std::pair<int, std::string>> stack;
+    char line[1024];
+    while (fgets(line, sizeof line, f)) {
+        std::string s(line);
+        bool inq = false; char qc = 0;
+        for (size_t i = 0; i < s.size(); ++i) {
+            if (inq) { if (s[i] == qc) inq = false; }
+            else if (s[i] == '\'' || s[i] == '"') { inq = true; qc = s[i]; }
+            else if (s[i] == '#') { s.erase(i); break; }
+        }
+        while (!s.empty() && (s.back() == '\n' || s.back() == '\r' || s.back() == ' ' || s.back() == '\t')) s.pop_back();
+        size_t ind = 0; while (ind < s.size() && s[ind] == ' ') ++ind;
+        if (ind >= s.size()) continue;
+        const size_t colon = s.find(':', ind);
+        if (colon == std::string::npos) continue;
+        std::string key = s.substr(ind, colon - ind), val = s.substr(colon + 1);
+        while (!val.empty() && val.front() == ' ') val.erase(0, 1);
+        if (val.size() >= 2 && (val.front() == '\'' || val.front() == '"')) val = val.substr(1, val.size() - 2);
+        while (!stack.empty() && stack.back().first >= (int)ind) stack.pop_back();
+        std::string full;
+        for (auto& p : stack) full += p.second + ".";
+        full += key;
+        if (val.empty()) stack.emplace_back((int)ind, key); else out[full] = val;
+    }
+    fclose(f);
+    return true;
+}
+static bool ybool(const std::string& v) { return v == "True" || v == "true" || v == "1" || v == "yes"; }
+
+extern "C" int nsb_config_load_yaml(nsb_config* c, const char* ns_yaml, const char* ds_yaml, char* errbuf, int errlen) {
+    std::string err;
+    std::map<std::string, std::string> ns, ds;
+    if (ns_yaml && !yaml_flat(ns_yaml, ns, err)) { if (errbuf) snprintf(errbuf, errlen, "%s", err.c_str()); return -1; }
+    if (ds_yaml && !yaml_flat(ds_yaml, ds, err)) { if (errbuf) snprintf(errbuf, errlen, "%s", err.c_str()); return -1; }
+    auto F = [](std::map<std::string, std::string>& m, const char* k, float& dst) { auto it = m.find(k); if (it != m.end()) dst = strtof(it->second.c_str(), nullptr); };
+    auto I = [](std::map<std::string, std::string>& m, const char* k, int& dst) { auto it = m.find(k); if (it != m.end()) dst = (int)strtol(it->second.c_str(), nullptr, 10); };
+    auto Bo = [](std::map<std::string, std::string>& m, const char* k, int& dst) { auto it = m.find(k); if (it != m.end()) dst = ybool(it->second) ? 1 : 0; };
+    // nice_slam.yaml first, the dataset file overrides it (upstream's config inheritance; the reference reads
+    // cam.* and mapping.pixels from cofusion.yaml: Mapper.cpp:22-28)
+    for (auto* m : {&ns, &ds}) {
+        I(*m, "cam.H", c->H); I(*m, "cam.W", c->W); F(*m, "cam.fx", c->fx); F(*m, "cam.fy", c->fy); F(*m, "cam.cx", c->cx); F(*m, "cam.cy", c->cy);
+        F(*m, "grid_len.coarse", c->grid_len[0]); F(*m, "grid_len.middle", c->grid_len[1]); F(*m, "grid_len.fine", c->grid_len[2]); F(*m, "grid_len.color", c->grid_len[3]);
+        I(*m, "model.c_dim", c->c_dim); I(*m, "model.coarse_bound_enlarge", c->coarse_bound_enlarge);
+        I(*m, "rendering.N_samples", c->n_samples); I(*m, "rendering.N_surface", c->n_surface);
+        I(*m, "mapping.pixels", c->mapping_pixels); I(*m, "mapping.iters", c->mapping_iters); I(*m, "mapping.iters_first", c->mapping_iters_first);
+        I(*m, "mapping.mapping_window_size", c->mapping_window_size); I(*m, "mapping.keyframe_every", c->keyframe_every);
+        F(*m, "mapping.middle_iter_ratio", c->middle_iter_ratio); F(*m, "mapping.fine_iter_ratio", c->fine_iter_ratio);
+        F(*m, "mapping.lr_factor", c->lr_factor); F(*m, "mapping.lr_first_factor", c->lr_first_factor);
+        Bo(*m, "mapping.fix_fine", c->fix_fine); Bo(*m, "mapping.fix_color", c->fix_color);
+        Bo(*m, "mapping.frustum_feature_selection", c->frustum_feature_selection); Bo(*m, "mapping.BA", c->BA);
+        F(*m, "mapping.BA_cam_lr", c->BA_cam_lr);
+        const char* st[4] = {"coarse", "middle", "fine", "color"};
+        const char* gr[5] = {"decoders_lr", "coarse_lr", "middle_lr", "fine_lr", "color_lr"};
+        for (int s = 0; s < 4; ++s) for (int g = 0; g < 5; ++g) {
+            const std::string k = std::string("mapping.stage.") + st[s] + "." + gr[g];
+            F(*m, k.c_str(), c->stage_lr[s][g]);
+        }
+        F(*m, "tracking.w_color_loss", c->w_color_loss); F(*m, "tracking.w_color_loss", c->mapping_w_color_loss);   // Mapper.cpp:33
+        F(*m, "tracking.lr", c->tracking_lr); I(*m, "tracking.iters", c->tracking_iters); I(*m, "tracking.pixels", c->tracking_pixels);
+        I(*m, "tracking.ignore_edge_W", c->ignore_edge_W); I(*m, "tracking.ignore_edge_H", c->ignore_edge_H);
+        Bo(*m, "tracking.handle_dynamic", c->handle_dynamic); Bo(*m, "tracking.use_color_in_tracking", c->use_color_in_tracking);
+    }
+    return 0;
+}
+
+extern "C" void nsb_grid_dims(const nsb_config* c, int level, int* Z, int* Y, int* X) {
+    if (c->grid_dim[level][0] > 0) { *Z = c->grid_dim[level][0]; *Y = c->grid_dim[level][1]; *X = c->grid_dim[level][2]; return; }
+    int d[3];
+    for (int a = 0; a < 3; ++a) {   // main.cpp:34,38,48,59,70: fp32 arithmetic, then .item<int>() truncation
+        const float len = c->bound[a][1] - c->bound[a][0];
+        float v = level == 0 ? len * (float)c->coarse_bound_enlarge / c->grid_len[0] : len / c->grid_len[level];
+        d[a] = (int)v;
+    }
+    *X = d[0]; *Y = d[1]; *Z = d[2];
+}
+
+extern "C" int64_t nsb_decoder_count(int which, int c_dim) {
+    const int E = EMB, H = HID;
+    if (which == 0) { const int K[5] = {c_dim, H, H, c_dim + H, H}; int64_t n = 0; for (int i = 0; i < 5; ++i) n += H * K[i] + H; return n + H + 1; }
+    const int C = which == 2 ? 2 * c_dim : c_dim, O = which == 3 ? 4 : 1;
+    const int K[5] = {E, H, H, E + H, H};
+    int64_t n = 3 * E;
+    for (int i = 0; i < 5; ++i) n += H * K[i] + H;
+    return n + 5 * (H * C + H) + O * H + O;
+}
+
+extern "C" int nsb_abi_version(void) { return NSB_ABI_VERSION; }
+extern "C" const char* nsb_build_info(void) {
+    return "libnsb sm_100a"
+#ifdef NSB_PRECISE_SIN
+           " precise-sin"
+#endif
+        ;
+}
+extern "C" const char* nsb_last_error(const nsb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" void* nsb_stream(nsb_ctx* c) { return c->stream; }
+extern "C" int nsb_synchronize(nsb_ctx* ctx) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+// ---- camera utilities (host) ------------------------------------------------------------------------------------
+extern "C" void nsb_quad2rotation(const float* q4, float* R9) { quad2rotation(q4, R9); }
+extern "C" void nsb_get_camera_from_tensor(const float* cam7, float* RT12) {
+    float R[9]; quad2rotation(cam7, R);
+    for (int r = 0; r < 3; ++r) { RT12[4 * r] = R[3 * r]; RT12[4 * r + 1] = R[3 * r + 1]; RT12[4 * r + 2] = R[3 * r + 2]; RT12[4 * r + 3] = cam7[4 + r]; }
+}
+extern "C" void nsb_get_tensor_from_camera(const float* c2w, float* cam7) {
+    const double m00 = c2w[0], m01 = c2w[1], m02 = c2w[2], m10 = c2w[4], m11 = c2w[5], m12 = c2w[6], m20 = c2w[8], m21 = c2w[9], m22 = c2w[10];
+    double w, x, y, z; const double tr = m00 + m11 + m22;
+    if (tr > 0) { double s = std::sqrt(tr + 1.0) * 2; w = s / 4; x = (m21 - m12) / s; y = (m02 - m20) / s; z = (m10 - m01) / s; }
+    else if (m00 > m11 && m00 > m22) { double s = std::sqrt(1.0 + m00 - m11 - m22) * 2; w = (m21 - m12) / s; x = s / 4; y = (m01 + m10) / s; z = (m02 + m20) / s; }
+    else if (m11 > m22) { double s = std::sqrt(1.0 + m11 - m00 - m22) * 2; w = (m02 - m20) / s; x = (m01 + m10) / s; y = s / 4; z = (m12 + m21) / s; }
+    else { double s = std::sqrt(1.0 + m22 - m00 - m11) * 2; w = (m10 - m01) / s; x = (m02 + m20) / s; y = (m12 + m21) / s; z = s / 4; }
+    cam7[0] = (float)w; cam7[1] = (float)x; cam7[2] = (float)y; cam7[3] = (float)z; cam7[4] = c2w[3]; cam7[5] = c2w[7]; cam7[6] = c2w[11];
+}
+
+// ---- create / destroy ------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
+    *out = nullptr;
+    nsb_ctx* ctx = new nsb_ctx();
+    *out = ctx;   // returned even on failure so that nsb_last_error works; caller destroys it
+    ctx->cfg = *cfg; ctx->device = device;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(ctx, "no CUDA device: libnsb has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ctx, "device %s is sm_%d%d; libnsb is built for sm_100a only", prop.name, prop.major, prop.minor);
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cfg->c_dim != CDIM) return fail(ctx, "c_dim %d unsupported (this build: 32)", cfg->c_dim);
+    if (cfg->n_samples != 32 || (cfg->n_surface != 16 && cfg->n_surface != 0)) return fail(ctx, "n_samples/n_surface %d/%d unsupported (32 / 16|0)", cfg->n_samples, cfg->n_surface);
+    if (cfg->max_frames < 1 || cfg->max_rays < 16) return fail(ctx, "max_frames / max_rays too small");
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; }
+    size_t off = 0;
+    auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
+    for (int l = 0; l < 4; ++l) {
+        nsb_grid_dims(cfg, l, &ctx->gdim[l][0], &ctx->gdim[l][1], &ctx->gdim[l][2]);
+        ctx->nvox[l] = (size_t)ctx->gdim[l][0] * ctx->gdim[l][1] * ctx->gdim[l][2];
+        if (ctx->nvox[l] == 0) return fail(ctx, "grid level %d has zero voxels", l);
+        ctx->dec_n[l] = nsb_decoder_count(l, cfg->c_dim);
+    }
+    ctx->off_grid[0] = seg(ctx->nvox[0] * CDIM);
+    ctx->off_dec[0] = seg(ctx->dec_n[0]); ctx->off_dec[1] = seg(ctx->dec_n[1]);
+    ctx->off_train = off;
+    for (int l = 1; l < 4; ++l) ctx->off_grid[l] = seg(ctx->nvox[l] * CDIM);
+    ctx->off_dec[2] = seg(ctx->dec_n[2]); ctx->off_dec[3] = seg(ctx->dec_n[3]);
+    ctx->off_cam = seg(8 * (size_t)cfg->max_frames);
+    ctx->off_tail = seg(32);
+    ctx->arena_n = off;
+    CK(dalloc(&ctx->param, off)); CK(dalloc(&ctx->grad, off)); CK(dalloc(&ctx->m, off)); CK(dalloc(&ctx->v, off));
+    CK(cudaMemsetAsync(ctx->param, 0, off * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->grad, 0, off * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->m, 0, off * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, off * 4, ctx->stream));
+    CK(dalloc(&ctx->t_samples, 32)); CK(dalloc(&ctx->t_surface, 16));
+    {
+        float t32[32], t16[16];   // torch::linspace symmetric formula
+        for (int n : {32, 16}) {
+            float* t = n == 32 ? t32 : t16; const float step = 1.0f / (float)(n - 1);
+            for (int i = 0; i < n; ++i) t[i] = i < n / 2 ? (float)i * step : 1.0f - (float)(n - 1 - i) * step;
+        }
+        CK(cudaMemcpyAsync(ctx->t_samples, t32, sizeof t32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->t_surface, t16, sizeof t16, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const size_t hw = (size_t)cfg->H * cfg->W;
+    CK(dalloc(&ctx->f_depth, hw * cfg->max_frames)); CK(dalloc(&ctx->f_color, 3 * hw * cfg->max_frames)); CK(dalloc(&ctx->f_pose, 12 * (size_t)cfg->max_frames));
+    const int cap = ctx->cap = (cfg->max_rays + 15) / 16 * 16;
+    const int S = cfg->n_samples + cfg->n_surface;
+    const size_t PS = (size_t)cap * S;
+    CK(dalloc(&ctx->rays_o, 3 * (size_t)cap)); CK(dalloc(&ctx->rays_d, 3 * (size_t)cap)); CK(dalloc(&ctx->gt_depth, cap)); CK(dalloc(&ctx->gt_color, 3 * (size_t)cap));
+    CK(dalloc(&ctx->z, PS)); CK(dalloc(&ctx->raw_rgb, 4 * PS)); CK(dalloc(&ctx->g_raw, 4 * PS));
+    for (int k = 0; k < 3; ++k) CK(dalloc(&ctx->occ[k], PS));
+    CK(dalloc(&ctx->o_rgb, 3 * (size_t)cap)); CK(dalloc(&ctx->o_depth, cap)); CK(dalloc(&ctx->o_var, cap)); CK(dalloc(&ctx->o_w, PS));
+    CK(dalloc(&ctx->g_rgb, 3 * (size_t)cap)); CK(dalloc(&ctx->g_depth, cap)); CK(dalloc(&ctx->g_var, cap)); CK(dalloc(&ctx->d_rays, 6 * (size_t)cap));
+    CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
+    CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
+    CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" void nsb_destroy(nsb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
+                    c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
+                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->scratch_ncdhw,
+                    c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- state ---------------------------------------------------------------------------------------------------------
+static int ensure_scratch(nsb_ctx* ctx, size_t n) {
+    if (ctx->scratch_n >= n) return 0;
+    if (ctx->scratch_ncdhw) cudaFree(ctx->scratch_ncdhw);
+    ctx->scratch_ncdhw = nullptr; ctx->scratch_n = 0;
+    CK(dalloc(&ctx->scratch_ncdhw, n));
+    ctx->scratch_n = n;
+    return 0;
+}
+
+extern "C" int nsb_set_grid(nsb_ctx* ctx, int level, const float* host) {
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    const size_t n = ctx->nvox[level] * CDIM;
+    if (ensure_scratch(ctx, n)) return -1;
+    CK(cudaMemcpyAsync(ctx->scratch_ncdhw, host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_ncdhw_to_cl<<<cdiv((int)n, 256), 256, 0, ctx->stream>>>(ctx->scratch_ncdhw, ctx->param + ctx->off_grid[level], CDIM, (int)ctx->nvox[level]);
+    ctx->launches++;
+    CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static int get_cl(nsb_ctx* ctx, const float* src, int level, float* host) {
+    const size_t n = ctx->nvox[level] * CDIM;
+    if (ensure_scratch(ctx, n)) return -1;
+    k_cl_to_ncdhw<<<cdiv((int)n, 256), 256, 0, ctx->stream>>>(src, ctx->scratch_ncdhw, CDIM, (int)ctx->nvox[level]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, ctx->scratch_ncdhw, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_get_grid(nsb_ctx* ctx, int level, float* host) {
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    return get_cl(ctx, ctx->param + ctx->off_grid[level], level, host);
+}
+extern "C" int nsb_get_grid_grad(nsb_ctx* ctx, int level, float* host) {
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    return get_cl(ctx, ctx->grad + ctx->off_grid[level], level, host);
+}
+extern "C" int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host, int64_t n) {
+    if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
+    CK(cudaMemcpyAsync(ctx->param + ctx->off_dec[which], host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static int get_dec(nsb_ctx* ctx, const float* base, int which, float* host, int64_t n) {
+    if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
+    CK(cudaMemcpyAsync(host, base + ctx->off_dec[which], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_get_decoder(nsb_ctx* ctx, int which, float* host, int64_t n) { return get_dec(ctx, ctx->param, which, host, n); }
+extern "C" int nsb_get_decoder_grad(nsb_ctx* ctx, int which, float* host, int64_t n) { return get_dec(ctx, ctx->grad, which, host, n); }
+extern "C" int nsb_set_ttables(nsb_ctx* ctx, const float* t32, const float* t16) {
+    CK(cudaMemcpyAsync(ctx->t_samples, t32, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->t_surface, t16, 16 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host) {
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    if (!host) { if (ctx->vmask[level]) { cudaFree(ctx->vmask[level]); ctx->vmask[level] = nullptr; } return 0; }
+    if (!ctx->vmask[level]) CK(dalloc(&ctx->vmask[level], ctx->nvox[level]));
+    CK(cudaMemcpyAsync(ctx->vmask[level], host, ctx->nvox[level], cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_set_frame_pose(nsb_ctx* ctx, int slot, const float* c2w16) {
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_set_frame(nsb_ctx* ctx, int slot, const float* depth, const float* color, const float* c2w16) {
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    const size_t hw = (size_t)ctx->cfg.H * ctx->cfg.W;
+    CK(cudaMemcpyAsync(ctx->f_depth + hw * slot, depth, hw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->f_color + 3 * hw * slot, color, 3 * hw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int nsb_seed(nsb_ctx* ctx, uint64_t seed) { ctx->rng.seed((uint32_t)seed); return 0; }
+
+// ---- shared pipeline pieces ---------------------------------------------------------------------------------------
+static void draw_indices(nsb_ctx* ctx, int n, int64_t range, int64_t* dst) {
+    for (int i = 0; i < n; ++i) dst[i] = (int64_t)((uint64_t)ctx->rng() % (uint64_t)range);   // torch::randint on the CPU generator
+}
+
+static GridView grid_view(nsb_ctx* ctx, int l) {
+    GridView g; g.data = ctx->param + ctx->off_grid[l]; g.grad = ctx->grad + ctx->off_grid[l];
+    g.Z = ctx->gdim[l][0]; g.Y = ctx->gdim[l][1]; g.X = ctx->gdim[l][2];
+    return g;
+}
+
+// Split `grid` CTAs between the decoders in proportion to their per-tile cost.
+static void partition(int grid, const float w[4], int cta_begin[5]) {
+    float tot = 0; int nact = 0;
+    for (int d = 0; d < 4; ++d) { tot += w[d]; nact += w[d] > 0; }
+    grid = std::max(grid, nact);
+    int n[4], used = 0;
+    for (int d = 0; d < 4; ++d) { n[d] = w[d] > 0 ? std::max(1, (int)std::floor(grid * w[d] / tot)) : 0; used += n[d]; }
+    for (int d = 0; used < grid; d = (d + 1) % 4) if (w[d] > 0) { n[d]++; used++; }
+    for (int d = 3; used > grid; d = (d + 3) % 4) if (n[d] > 1) { n[d]--; used--; }
+    cta_begin[0] = 0;
+    for (int d = 0; d < 4; ++d) cta_begin[d + 1] = cta_begin[d] + n[d];
+}
+
+static void env_weights(const char* name, float w[4]) {
+    const char* e = getenv(name);
+    if (!e) return;
+    float a, b, c, d;
+    if (sscanf(e, "%f,%f,%f,%f", &a, &b, &c, &d) == 4) { if (w[0] > 0) w[0] = a; if (w[1] > 0) w[1] = b; if (w[2] > 0) w[2] = c; if (w[3] > 0) w[3] = d; }
+}
+
+static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
+    memset(&P, 0, sizeof P);
+    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); }
+    P.bnd = ctx->bnd;
+    P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
+    P.S = S; P.P = n * S;
+    P.out_rgb = ctx->raw_rgb; P.out_occ[0] = ctx->occ[0]; P.out_occ[1] = ctx->occ[1]; P.out_occ[2] = ctx->occ[2];
+    P.g_raw = ctx->g_raw; P.d_rays = ctx->d_rays; P.stash = ctx->stash;
+}
+
+static int decode_grid_size(nsb_ctx* ctx, int P) {
+    const int occ = std::max(1, ctx->occ_blocks[ctx->cfg.precision ? 1 : 0]);
+    const int tiles = cdiv(P, TILE);
+    return std::max(1, std::min(ctx->n_sm * occ, cdiv(tiles, DECODE_WARPS)));
+}
+
+// Decoders a stage evaluates (NICE.cpp:16-51).
+static void stage_decoders(int stage, float w[4]) {
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (stage == NSB_COARSE) w[0] = 300;
+    else if (stage == NSB_MIDDLE) w[1] = 732;
+    else if (stage == NSB_FINE) { w[1] = 732; w[2] = 972; }
+    else { w[1] = 732; w[2] = 972; w[3] = 732; }
+}
+
+// rays (ctx->rays_*, ctx->gt_depth or null, ctx->valid or null) -> z, raw, composite outputs in ctx buffers.
+// `off`/`n` select the slice of the ray batch this rank renders (ranks share the batch-global statistics).
+static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, bool want_weights) {
+    const nsb_config& c = ctx->cfg;
+    const int S = have_depth ? c.n_samples + c.n_surface : c.n_samples;
+    ctx->last_n = n; ctx->last_S = S;
+    {
+        Timer t(ctx, T_SAMPLE);
+        ZParams Z; Z.rays_o = ctx->rays_o + 3 * off; Z.rays_d = ctx->rays_d + 3 * off; Z.gt_depth = have_depth ? ctx->gt_depth + off : nullptr;
+        Z.valid = valid ? valid + off : nullptr; Z.stats = stats; Z.t_samples = ctx->t_samples; Z.t_surface = ctx->t_surface; Z.bnd = ctx->bnd;
+        Z.n = n; Z.n_samples = c.n_samples; Z.n_surface = have_depth ? c.n_surface : 0; Z.z = ctx->z + (size_t)off * S;
+        k_zvals<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Z); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    {
+        Timer t(ctx, T_FWD);
+        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
+        P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
+        P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
+        float w[4]; stage_decoders(stage, w); env_weights("NSB_SPLIT_FWD", w);
+        const int grid = decode_grid_size(ctx, n * S);
+        partition(grid, w, P.cta_begin);
+        CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+    }
+    {
+        Timer t(ctx, T_COMP);
+        CompositeParams Q; memset(&Q, 0, sizeof Q);
+        Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
+        Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
+        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = want_weights ? ctx->o_w + (size_t)off * S : nullptr;
+        k_composite_fwd<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// cotangents in ctx->g_rgb / g_depth / g_var -> g_raw -> decoder backward (+ wgrad).  flags: F_GRID=1, F_WGRAD=2, F_RAY=4.
+static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, int flags, bool color_active) {
+    const nsb_config& c = ctx->cfg;
+    const int S = ctx->last_S;
+    {
+        Timer t(ctx, T_COMP);
+        CompositeParams Q; memset(&Q, 0, sizeof Q);
+        Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
+        Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
+        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.g_rgb = ctx->g_rgb + 3 * off; Q.g_depth = ctx->g_depth + off; Q.g_var = ctx->g_var + off; Q.g_raw = ctx->g_raw + 4 * (size_t)off * S;
+        if (flags & 4) { CK(cudaMemsetAsync(ctx->d_rays + 6 * (size_t)off, 0, 6 * (size_t)n * 4, ctx->stream)); Q.d_rays = ctx->d_rays + 6 * (size_t)off; }
+        k_composite_bwd<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    const bool wg = (flags & 2) && stage == NSB_COLOR && color_active;
+    if (wg) {
+        const size_t rows = (size_t)n * S;
+        if (ctx->stash_rows < rows) {
+            if (ctx->stash) cudaFree(ctx->stash);
+            ctx->stash = nullptr; ctx->stash_rows = 0;
+            CK(dalloc(&ctx->stash, rows * stash::W + 64));
+            ctx->stash_rows = rows;
+        }
+    }
+    {
+        Timer t(ctx, T_BWD);
+        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
+        P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S; P.g_raw += 4 * (size_t)off * S; P.d_rays += 6 * (size_t)off;
+        P.stash = ctx->stash;
+        P.flags = (flags & 1) | (wg ? 2 : 0) | (flags & 4);
+        if (P.flags == 0) return 0;
+        float w[4] = {0, 0, 0, 0};
+        const float ge = (flags & 4) ? 288.f : 0.f;
+        if (stage == NSB_MIDDLE) w[1] = 1164 + ge;
+        else if (stage == NSB_FINE) { w[1] = 1164 + ge; w[2] = 1404 + ge; }
+        else if (stage == NSB_COLOR) { w[1] = 1164 + ge; w[2] = 1404 + ge; if (color_active) w[3] = 1164 + (wg ? 288.f + 400.f : ge); }
+        else return fail(ctx, "backward through the coarse stage is not implemented");
+        env_weights("NSB_SPLIT_BWD", w);
+        const int grid = decode_grid_size(ctx, n * S);
+        partition(grid, w, P.cta_begin);
+        P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
+        CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+    }
+    if (wg) {
+        Timer t(ctx, T_WGRAD);
+        CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->grad + ctx->off_dec[3], c.precision, ctx->n_sm, ctx->stream)); ctx->launches++;
+    }
+    return 0;
+}
+
+static int zero_grads(nsb_ctx* ctx) {
+    CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
+    return 0;
+}
+
+// ---- sampling API ----------------------------------------------------------------------------------------------------
+static void fill_sample_params(nsb_ctx* ctx, SampleParams& P, int n, int H0, int H1, int W0, int W1, float* stats, int apply_filter) {
+    const nsb_config& c = ctx->cfg;
+    memset(&P, 0, sizeof P);
+    P.depth = ctx->f_depth; P.color = ctx->f_color; P.poses = ctx->f_pose; P.cam7 = nullptr; P.idx = ctx->idx;
+    P.H = c.H; P.W = c.W; P.H0 = H0; P.W0 = W0; P.Wc = W1 - W0;
+    P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.raydir = c.raydir; P.bnd = ctx->bnd; P.n = n;
+    P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.gt_depth = ctx->gt_depth; P.gt_color = ctx->gt_color; P.valid = ctx->valid;
+    P.stats = stats; P.apply_filter = apply_filter;
+}
+
+extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H0, int H1, int W0, int W1, int n, const int64_t* idx,
+                               float* rays_o, float* rays_d, float* gt_depth, float* gt_color, uint8_t* inside, int64_t* idx_out) {
+    if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    ctx->h_idx.resize(n);
+    if (idx) memcpy(ctx->h_idx.data(), idx, n * sizeof(int64_t)); else draw_indices(ctx, n, (int64_t)(H1 - H0) * (W1 - W0), ctx->h_idx.data());
+    if (idx_out) memcpy(idx_out, ctx->h_idx.data(), n * sizeof(int64_t));
+    CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
+    SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, ctx->stats, 1);
+    P.slots[0] = slot; P.n_frames = 1; P.pix_per_frame = n;
+    k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
+    CK(cudaGetLastError());
+    if (rays_o) CK(cudaMemcpyAsync(rays_o, ctx->rays_o, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rays_d) CK(cudaMemcpyAsync(rays_d, ctx->rays_d, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gt_depth) CK(cudaMemcpyAsync(gt_depth, ctx->gt_depth, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gt_color) CK(cudaMemcpyAsync(gt_color, ctx->gt_color, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inside) CK(cudaMemcpyAsync(inside, ctx->valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- render API -------------------------------------------------------------------------------------------------------
+static int render_prepare_stats(nsb_ctx* ctx, int n, bool have_depth) {
+    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
+    if (have_depth) { k_depth_max<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->gt_depth, n, ctx->stats); ctx->launches++; }
+    if (ctx->cfg.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, n, ctx->stats); ctx->launches++; }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const float* d_rays_d, const float* d_rays_o, const float* d_gt_depth,
+                                        float* d_rgb, float* d_depth, float* d_var, float* d_weights) {
+    if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    const bool hd = d_gt_depth != nullptr;
+    const int S = hd ? ctx->cfg.n_samples + ctx->cfg.n_surface : ctx->cfg.n_samples;
+    CK(cudaMemcpyAsync(ctx->rays_d, d_rays_d, 12 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rays_o, d_rays_o, 12 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (hd) CK(cudaMemcpyAsync(ctx->gt_depth, d_gt_depth, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (render_prepare_stats(ctx, n, hd)) return -1;
+    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, d_weights != nullptr)) return -1;
+    if (d_rgb) CK(cudaMemcpyAsync(d_rgb, ctx->o_rgb, 12 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_depth) CK(cudaMemcpyAsync(d_depth, ctx->o_depth, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_var) CK(cudaMemcpyAsync(d_var, ctx->o_var, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_weights) CK(cudaMemcpyAsync(d_weights, ctx->o_w, 4 * (size_t)n * S, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+static int upload_rays(nsb_ctx* ctx, int n, const float* rays_d, const float* rays_o, const float* gt_depth) {
+    CK(cudaMemcpyAsync(ctx->rays_d, rays_d, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rays_o, rays_o, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (gt_depth) CK(cudaMemcpyAsync(ctx->gt_depth, gt_depth, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o, const float* gt_depth,
+                                    float* rgb, float* depth, float* var, float* weights) {
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    if (n <= 0) return 0;
+    const bool hd = gt_depth != nullptr;
+    const int S = hd ? ctx->cfg.n_samples + ctx->cfg.n_surface : ctx->cfg.n_samples;
+    // the batch-global scalars of Renderer.cpp:76,93 (and utils.h:153 in reference mode) span the WHOLE call, so
+    // they are computed over all n rays before the batch is cut into max_rays chunks
+    float gmax = 0.f; double inv = 0.0;
+    if (hd) for (int i = 0; i < n; ++i) gmax = std::max(gmax, gt_depth[i]);
+    if (ctx->cfg.dist_norm == NSB_DISTNORM_REFERENCE) for (int i = 0; i < 3 * n; ++i) inv += 1.0 / std::fabs((double)rays_d[i]);
+    const float st[4] = {gmax, 0.f, (float)inv, 0.f};
+    for (int o = 0; o < n; o += ctx->cap) {
+        const int m = std::min(ctx->cap, n - o);
+        if (upload_rays(ctx, m, rays_d + 3 * (size_t)o, rays_o + 3 * (size_t)o, hd ? gt_depth + o : nullptr)) return -1;
+        CK(cudaMemcpyAsync(ctx->stats, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
+        if (run_forward(ctx, stage, 0, m, hd, nullptr, ctx->stats, weights != nullptr)) return -1;
+        if (rgb) CK(cudaMemcpyAsync(rgb + 3 * (size_t)o, ctx->o_rgb, 12 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (depth) CK(cudaMemcpyAsync(depth + o, ctx->o_depth, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (var) CK(cudaMemcpyAsync(var + o, ctx->o_var, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (weights) CK(cudaMemcpyAsync(weights + (size_t)o * S, ctx->o_w, 4 * (size_t)m * S, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z) {
+    if (n != ctx->last_n || S != ctx->last_S) return fail(ctx, "last render was %d x %d, asked %d x %d", ctx->last_n, ctx->last_S, n, S);
+    CK(cudaMemcpyAsync(z, ctx->z, 4 * (size_t)n * S, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts, float* raw) {
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    const nsb_config& c = ctx->cfg;
+    const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
+    std::vector<float> h_rgb, h_occ[3];
+    for (size_t o = 0; o < (size_t)Pn; o += cap_pts) {
+        const int m = (int)std::min(cap_pts, (size_t)Pn - o);
+        CK(cudaMemcpyAsync(ctx->pts, pts + 3 * o, 12 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr);
+        P.pts = ctx->pts; P.P = m;
+        float w[4]; stage_decoders(stage, w);
+        partition(decode_grid_size(ctx, m), w, P.cta_begin);
+        CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        h_rgb.resize(4 * (size_t)m); for (int k = 0; k < 3; ++k) h_occ[k].resize(m);
+        CK(cudaMemcpyAsync(h_rgb.data(), ctx->raw_rgb, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(h_occ[k].data(), ctx->occ[k], 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < m; ++i) {   // NICE.cpp:16-51 assembly + the bound mask of Renderer.cpp:26-36
+            const float* p = pts + 3 * (o + i);
+            float* r = raw + 4 * (o + i);
+            r[0] = r[1] = r[2] = 0.f;
+            if (stage == NSB_COLOR) { r[0] = h_rgb[4 * i]; r[1] = h_rgb[4 * i + 1]; r[2] = h_rgb[4 * i + 2]; }
+            float occ = stage == NSB_COARSE ? h_occ[0][i] : stage == NSB_MIDDLE ? h_occ[1][i] : h_occ[2][i] + h_occ[1][i];
+            bool in = true;
+            for (int a = 0; a < 3; ++a) in = in && p[a] < c.bound[a][1] && p[a] > c.bound[a][0];
+            r[3] = in ? occ : 100.f;
+        }
+    }
+    return 0;
+}
+
+extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o, const float* gt_depth,
+                              const float* g_rgb, const float* g_depth, const float* g_var, int flags, float* d_rays_d, float* d_rays_o) {
+    if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
+    if (stage < 1 || stage > 3) return fail(ctx, "vjp supports stages middle/fine/color");
+    const bool hd = gt_depth != nullptr;
+    if (upload_rays(ctx, n, rays_d, rays_o, gt_depth)) return -1;
+    if (render_prepare_stats(ctx, n, hd)) return -1;
+    if (zero_grads(ctx)) return -1;
+    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, false)) return -1;
+    CK(cudaMemcpyAsync(ctx->g_rgb, g_rgb, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->g_depth, g_depth, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->g_var, g_var, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (run_backward(ctx, stage, 0, n, nullptr, ctx->stats, flags, true)) return -1;
+    if (flags & 4) {
+        std::vector<float> h(6 * (size_t)n);
+        CK(cudaMemcpyAsync(h.data(), ctx->d_rays, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {
+            if (d_rays_o) d_rays_o[3 * i + a] = h[6 * (size_t)i + a];
+            if (d_rays_d) d_rays_d[3 * i + a] = h[6 * (size_t)i + 3 + a];
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- Adam -----------------------------------------------------------------------------------------------------------
+static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats) {
+    Timer t(ctx, T_ADAM);
+    AdamParams A; memset(&A, 0, sizeof A);
+    A.param = ctx->param; A.grad = ctx->grad; A.m = ctx->m; A.v = ctx->v;
+    const double b1 = 0.9, b2 = 0.999;
+    const double bc1 = 1.0 - std::pow(b1, (double)step), bc2 = 1.0 - std::pow(b2, (double)step);
+    A.beta1 = (float)b1; A.beta2 = (float)b2; A.om_beta1 = (float)(1.0 - b1); A.om_beta2 = (float)(1.0 - b2); A.eps = 1e-8f;
+    A.bc2_sqrt = (float)std::sqrt(bc2); A.grad_scale = 1.0f;
+    int k = 0;
+    auto add = [&](size_t begin, size_t n, float lr, const uint8_t* mask, int active) {
+        AdamSegment& s = A.seg[k++]; s.begin = (int)begin; s.end = (int)(begin + pad32(n)); s.step = (float)((double)lr / bc1); s.mask = mask; s.active = active;
+    };
+    for (int l = 1; l < 4; ++l) add(ctx->off_grid[l], ctx->nvox[l] * CDIM, lr_group[1 + l], ctx->vmask[l], 1);   // groups 2,3,4 = middle, fine, color
+    add(ctx->off_dec[2], ctx->dec_n[2], lr_group[0], nullptr, dec_fine ? 1 : 0);
+    add(ctx->off_dec[3], ctx->dec_n[3], lr_group[0], nullptr, dec_color ? 1 : 0);
+    if (n_cam_floats > 0) add(ctx->off_cam, n_cam_floats, lr_group[5], nullptr, 1);
+    add(ctx->off_tail, 32, 0.f, nullptr, 0);
+    A.n_seg = k;
+    k_adam<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(A); ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- mapping ----------------------------------------------------------------------------------------------------------
+static int stage_of_iter(const nsb_config& c, int it, int n_iters) {   // Mapper.cpp:351-358
+    if (it <= (int)((float)n_iters * c.middle_iter_ratio)) return NSB_MIDDLE;
+    if (it <= (int)((float)n_iters * c.fine_iter_ratio)) return c.second_stage;
+    return NSB_COLOR;
+}
+
+extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor) {
+    if (n_frames < 1 || n_frames > MAX_OPT_FRAMES) return fail(ctx, "n_frames %d out of range", n_frames);
+    const int pix = ctx->cfg.mapping_pixels / n_frames;   // Mapper.cpp:223
+    if (pix * n_frames > ctx->cap) return fail(ctx, "mapping_pixels %d exceeds max_rays %d", ctx->cfg.mapping_pixels, ctx->cap);
+    for (int f = 0; f < n_frames; ++f) { if (slots[f] < 0 || slots[f] >= ctx->cfg.max_frames) return fail(ctx, "bad slot %d", slots[f]); ctx->map_slots[f] = slots[f]; }
+    ctx->map_frames = n_frames; ctx->map_iters = n_iters; ctx->map_step = 0; ctx->map_lr_factor = lr_factor;
+    // a fresh torch::optim::Adam is constructed per optimize_map (Mapper.cpp:330): state starts at zero
+    CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    if (!ctx->cfg.fix_color) {   // make sure the stash exists before the hot loop
+        const size_t rows = (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64;
+        if (ctx->stash_rows < rows) {
+            if (ctx->stash) cudaFree(ctx->stash);
+            ctx->stash = nullptr; ctx->stash_rows = 0;
+            CK(dalloc(&ctx->stash, rows * stash::W + 64));
+            ctx->stash_rows = rows;
+        }
+    }
+    return 0;
+}
+
+extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
+    const nsb_config& c = ctx->cfg;
+    if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
+    const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
+    const int stage = stage_of_iter(c, iter, ctx->map_iters);
+    float* stats = ctx->stats + 4 * (iter % LOSS_RING);
+    {
+        Timer t(ctx, T_SAMPLE);
+        const int64_t* d_idx = ctx->idx;
+        if (idx) CK(cudaMemcpyAsync(ctx->idx, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        else if (ctx->idx_pool && ctx->pool_n == n) d_idx = ctx->idx_pool + (size_t)(ctx->pool_cursor++ % ctx->pool_iters) * n;   // already resident
+        else {
+            ctx->h_idx.resize(n);
+            for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
+            CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
+        SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
+        P.idx = d_idx;
+        for (int f = 0; f < ctx->map_frames; ++f) P.slots[f] = ctx->map_slots[f];
+        P.n_frames = ctx->map_frames; P.pix_per_frame = pix;
+        k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
+        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
+        CK(cudaGetLastError());
+    }
+    // this rank's slice of the (already filtered, batch-global) ray list
+    const int per = cdiv(cdiv(n, ctx->world), 1), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
+    const bool use_color = stage == NSB_COLOR;
+    if (nl > 0) {
+        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false)) return -1;   // render is always called with "color" (Mapper.cpp:430)
+        {
+            Timer t(ctx, T_COMP);
+            LossParams L; memset(&L, 0, sizeof L);
+            L.gt_depth = ctx->gt_depth + off; L.gt_color = ctx->gt_color + 3 * off; L.valid = ctx->valid + off;
+            L.rgb = ctx->o_rgb + 3 * off; L.depth = ctx->o_depth + off; L.var = ctx->o_var + off; L.n = nl; L.use_color = use_color; L.w_color = c.mapping_w_color_loss;
+            L.g_rgb = ctx->g_rgb + 3 * off; L.g_depth = ctx->g_depth + off; L.g_var = ctx->g_var + off;
+            L.loss = ctx->grad + ctx->off_tail;   // rides in the gradient arena so that the all-reduce sums it too
+            k_loss_mapping<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(L); ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        const int flags = 1 | (c.fix_color ? 0 : 2);
+        if (run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color)) return -1;
+    }
+    if (ctx->world > 1) {
+        Timer t(ctx, T_COMM);
+        const size_t cnt = ctx->arena_n - ctx->off_train;
+        const int rc = g_nccl.AllReduce(ctx->grad + ctx->off_train, ctx->grad + ctx->off_train, cnt, NCCL_FLOAT32, NCCL_SUM, ctx->comm, ctx->stream);
+        if (rc != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    CK(cudaMemcpyAsync(stats + 3, ctx->grad + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->map_step++;
+    float lr[6];
+    for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
+    lr[5] = 0.f;
+    // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups
+    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, 0)) return -1;
+    return 0;
+}
+
+// Pre-load pixel indices for n_iters iterations ([n_iters][n] int64, host) so that nsb_mapping_iter(idx = NULL) runs
+// with every input already resident in HBM; rows are consumed in order, wrapping around.  NULL clears the pool.
+extern "C" int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n) {
+    if (ctx->idx_pool) { cudaFree(ctx->idx_pool); ctx->idx_pool = nullptr; ctx->pool_iters = ctx->pool_n = 0; }
+    if (!host_idx) return 0;
+    CK(dalloc(&ctx->idx_pool, (size_t)n_iters * n));
+    CK(cudaMemcpyAsync(ctx->idx_pool, host_idx, (size_t)n_iters * n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pool_iters = n_iters; ctx->pool_n = n; ctx->pool_cursor = 0;
+    return 0;
+}
+
+extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses, int* n_inside) {
+    std::vector<float> h(4 * (size_t)n);
+    for (int i = 0; i < n; ++i)
+        CK(cudaMemcpyAsync(h.data() + 4 * i, ctx->stats + 4 * ((first + i) % LOSS_RING), 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        if (losses) losses[i] = h[4 * i + 3];
+        if (n_inside) { int v; memcpy(&v, &h[4 * i + 1], 4); n_inside[i] = v; }
+    }
+    return 0;
+}
+
+extern "C" int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss) {
+    if (nsb_mapping_iter_async(ctx, iter, idx)) return -1;
+    if (loss) return nsb_mapping_losses(ctx, iter, 1, loss, nullptr);
+    return 0;
+}
+
+extern "C" int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, float* losses) {
+    if (nsb_mapping_begin(ctx, n_frames, slots, n_iters, lr_factor)) return -1;
+    for (int it = 0; it < n_iters; ++it) if (nsb_mapping_iter_async(ctx, it, nullptr)) return -1;
+    if (losses) { for (int o = 0; o < n_iters; o += LOSS_RING) if (nsb_mapping_losses(ctx, o, std::min(LOSS_RING, n_iters - o), losses + o, nullptr)) return -1; }
+    else CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- tracking -----------------------------------------------------------------------------------------------------------
+extern "C" int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7) {
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    if (ctx->cfg.tracking_pixels > ctx->cap) return fail(ctx, "tracking_pixels %d exceeds max_rays %d", ctx->cfg.tracking_pixels, ctx->cap);
+    ctx->trk_slot = slot; ctx->trk_step = 0;
+    CK(cudaMemcpyAsync(ctx->param + ctx->off_cam, cam7, 28, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->m + ctx->off_cam, 0, 32, ctx->stream)); CK(cudaMemsetAsync(ctx->v + ctx->off_cam, 0, 32, ctx->stream));   // fresh Adam (Tracker.cpp:103)
+    CK(cudaMemsetAsync(ctx->grad + ctx->off_cam, 0, 32, ctx->stream));
+    return 0;
+}
+
+extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, float* cam_grad7) {
+    const nsb_config& c = ctx->cfg;
+    const int n = c.tracking_pixels;
+    const int H0 = c.ignore_edge_H, H1 = c.H - c.ignore_edge_H, W0 = c.ignore_edge_W, W1 = c.W - c.ignore_edge_W;   // Tracker.cpp:46
+    float* stats = ctx->stats;
+    float* cam = ctx->param + ctx->off_cam;
+    {
+        Timer t(ctx, T_SAMPLE);
+        if (idx) CK(cudaMemcpyAsync(ctx->idx, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        else {
+            ctx->h_idx.resize(n);
+            draw_indices(ctx, n, (int64_t)(H1 - H0) * (W1 - W0), ctx->h_idx.data());
+            CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
+        CK(cudaMemsetAsync(ctx->count, 0, 16, ctx->stream));
+        SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, stats, 1);
+        P.slots[0] = ctx->trk_slot; P.n_frames = 1; P.pix_per_frame = n; P.cam7 = cam;
+        k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
+        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
+        CK(cudaGetLastError());
+    }
+    if (run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false)) return -1;   // Tracker.cpp:61
+    {
+        Timer t(ctx, T_COMP);
+        LossParams L; memset(&L, 0, sizeof L);
+        L.gt_depth = ctx->gt_depth; L.gt_color = ctx->gt_color; L.valid = ctx->valid; L.rgb = ctx->o_rgb; L.depth = ctx->o_depth; L.var = ctx->o_var;
+        L.n = n; L.use_color = c.use_color_in_tracking; L.w_color = c.w_color_loss;
+        L.g_rgb = ctx->g_rgb; L.g_depth = ctx->g_depth; L.g_var = ctx->g_var; L.loss = stats + 3; L.median = ctx->median; L.absdiff = ctx->absdiff;
+        if (c.handle_dynamic) {
+            k_track_absdiff<<<cdiv(n, 256), 256, 0, ctx->stream>>>(L, ctx->count);
+            k_median<<<1, 1024, 0, ctx->stream>>>(ctx->absdiff, ctx->count, ctx->median);
+            ctx->launches += 2;
+        }
+        k_loss_tracking<<<cdiv(n, 256), 256, 0, ctx->stream>>>(L, c.handle_dynamic); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (run_backward(ctx, NSB_COLOR, 0, n, ctx->valid, stats, 4, true)) return -1;
+    {
+        Timer t(ctx, T_COMP);
+        PoseGradParams G; memset(&G, 0, sizeof G);
+        G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.valid = ctx->valid; G.cam7 = cam; G.n = n; G.H0 = H0; G.W0 = W0; G.Wc = W1 - W0; G.raydir = c.raydir;
+        G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy; G.g_cam7 = ctx->grad + ctx->off_cam;
+        k_pose_grad<<<1, 1024, 0, ctx->stream>>>(G); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (cam_grad7) CK(cudaMemcpyAsync(cam_grad7, ctx->grad + ctx->off_cam, 28, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->trk_step++;
+    {
+        Timer t(ctx, T_ADAM);
+        AdamParams A; memset(&A, 0, sizeof A);
+        A.param = ctx->param; A.grad = ctx->grad; A.m = ctx->m; A.v = ctx->v;
+        const double b1 = 0.9, b2 = 0.999, bc1 = 1.0 - std::pow(b1, (double)ctx->trk_step), bc2 = 1.0 - std::pow(b2, (double)ctx->trk_step);
+        A.beta1 = (float)b1; A.beta2 = (float)b2; A.om_beta1 = (float)(1.0 - b1); A.om_beta2 = (float)(1.0 - b2); A.eps = 1e-8f; A.bc2_sqrt = (float)std::sqrt(bc2); A.grad_scale = 1.f;
+        A.seg[0].begin = (int)ctx->off_cam; A.seg[0].end = (int)ctx->off_cam + 8; A.seg[0].step = (float)((double)c.tracking_lr / bc1); A.seg[0].mask = nullptr; A.seg[0].active = 1;
+        A.n_seg = 1;
+        k_adam<<<1, 32, 0, ctx->stream>>>(A); ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (loss) CK(cudaMemcpyAsync(loss, stats + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (loss || cam_grad7) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int nsb_tracking_get_camera(nsb_ctx* ctx, float* cam7) {
+    CK(cudaMemcpyAsync(cam7, ctx->param + ctx->off_cam, 28, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------------------------------
+extern "C" int nsb_comm_unique_id(char* id128) {
+    if (!g_nccl.load()) return -1;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return -1;
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world) {
+    if (!g_nccl.load()) return fail(ctx, "libnccl.so.2 not found");
+    ncclUniqueId id; memcpy(id.internal, id128, 128);
+    CK(cudaSetDevice(ctx->device));
+    const int rc = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (rc != 0) return fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    ctx->rank = rank; ctx->world = world;
+    return 0;
+}
+extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }
+
+// ---- instrumentation ----------------------------------------------------------------------------------------------------
+extern "C" int64_t nsb_launch_count(nsb_ctx* ctx, int reset) { const int64_t v = ctx->launches; if (reset) ctx->launches = 0; return v; }
+extern "C" int nsb_set_profiling(nsb_ctx* ctx, int on) { ctx->profiling = on != 0; ctx->ev_used = 0; return 0; }
+// Sum of the device times of every region timed since nsb_set_profiling(1), per category.
+extern "C" int nsb_get_kernel_ms(nsb_ctx* ctx, float* ms) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < T_N; ++i) ms[i] = 0.f;
+    for (size_t k = 0; k < ctx->ev_used; ++k) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ctx->ev_pool[k].a, ctx->ev_pool[k].b));
+        ms[ctx->ev_pool[k].id] += t;
+    }
+    return 0;
+}

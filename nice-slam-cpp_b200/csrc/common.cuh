@@ -1,0 +1,189 @@
+// Shared device helpers for the sm_100a kernels of libnsb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nsb {
+
+constexpr int EMB = 93;       // Fourier embedding width (MLP.cpp:21)
+constexpr int EMBP = 96;      // padded to a multiple of the MMA k-step
+constexpr int HID = 32;       // hidden width (main.cpp:29)
+constexpr int CDIM = 32;      // grid channels (nice_slam.yaml model.c_dim)
+constexpr int TILE = 16;      // samples per warp tile (MMA m16)
+
+// Scene bound and derived constants, all in fp32 exactly as the reference computes them.
+struct Bound {
+    float lo[3], hi[3], len[3];   // len = hi - lo in fp32 (utils.h:135-137)
+};
+
+// One feature grid, channel-last [Z][Y][X][32] fp32: a voxel corner is one 128-byte line.
+struct GridView {
+    const float* data;
+    float* grad;       // same layout, may be null
+    int Z, Y, X;
+};
+
+// ---- tensor-core helpers: mma.sync m16n8k8 tf32, optional 3xTF32 split (fp32-grade accuracy) ------------
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// A operand of one k-step (8 features) for the 16 rows of the tile, pre-split.
+template <bool P3>
+struct AFrag {
+    uint32_t hi[4], lo[4];
+    __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
+        if (P3) {
+            split_tf32(a0, hi[0], lo[0]); split_tf32(a1, hi[1], lo[1]);
+            split_tf32(a2, hi[2], lo[2]); split_tf32(a3, hi[3], lo[3]);
+        } else {
+            hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
+        }
+    }
+};
+
+template <bool P3>
+__device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float w0, float w1) {
+    if (P3) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(w0, bh0, bl0); split_tf32(w1, bh1, bl1);
+        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], bh0, bh1);   // small terms first
+        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bl0, bl1);
+        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bh0, bh1);
+    } else {
+        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], f2tf32(w0), f2tf32(w1));
+    }
+}
+
+// Weight matrices W[out][in] live in shared memory with row stride ld (a multiple of 32 floats) and the
+// column index XOR-swizzled by the row:  col' = col ^ swz(row),  swz(row) = ((row ^ (row>>1)) & 3) << 3.
+// That makes BOTH access patterns bank-conflict free:
+//   forward  B fragment  W[8j+g][8kk+2t .. +1]   (one 64-bit load, rows vary with g)
+//   backward B fragment  W[8kk+2t+r][8j+g]       (32-bit loads, rows vary with t)
+__host__ __device__ __forceinline__ int swz(int row) { return ((row ^ (row >> 1)) & 3) << 3; }
+
+// acc[j] += A(kk) * W[8j+g][8kk+2t..]^T for the NJ output tiles (forward: out = x W^T).
+template <bool P3, int NJ>
+__device__ __forceinline__ void kstep_fwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
+                                          int ld, int kk, int g, int t) {
+    const int col = (8 * kk + 2 * t) ^ swz(g);   // swz(8j+g) == swz(g)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float2 w = *reinterpret_cast<const float2*>(W + (8 * j + g) * ld + col);
+        mma_acc<P3>(acc[j], a, w.x, w.y);
+    }
+}
+
+// acc[j] += A(kk) * W[8kk+2t..][8(j0+j)+g] (backward data gradient: g_in = g_out W).
+template <bool P3, int NJ>
+__device__ __forceinline__ void kstep_bwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
+                                          int ld, int kk, int j0, int g, int t) {
+    const int r0 = 8 * kk + 2 * t, r1 = r0 + 1;
+    const float* w0p = W + r0 * ld;
+    const float* w1p = W + r1 * ld;
+    const int s0 = swz(r0), s1 = swz(r1);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int c = 8 * (j0 + j) + g;
+        mma_acc<P3>(acc[j], a, w0p[c ^ s0], w1p[c ^ s1]);
+    }
+}
+
+// C-fragment (rows g, g+8; cols 2t, 2t+1 of tile kk) reused as the A operand of k-step kk: the k index of
+// the MMA is permuted (k=t <-> feature 2t, k=t+4 <-> feature 2t+1), which the B fragments above match.
+template <bool P3>
+__device__ __forceinline__ void afrag_from_c(AFrag<P3>& a, const float (&c)[4]) { a.set(c[0], c[2], c[1], c[3]); }
+
+// ---- trilinear sampling, identical arithmetic to ATen grid_sampler_3d (bilinear, border, align_corners) ----
+struct Tri {
+    int i0[3], i1[3];     // x,y,z corner indices (i1 clamped)
+    float w0[3], w1[3];   // weights of i0 / i1 per axis
+    float gm[3];          // d(index)/d(p) per axis, 0 where the border clamp is active
+};
+
+__device__ __forceinline__ void tri_setup(const GridView& G, const Bound& B, const float (&p)[3], Tri& s) {
+    const int dim[3] = {G.X, G.Y, G.Z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // utils.h:135-137: ((p - lo) / (hi - lo)) * 2 - 1, each op rounded separately
+        float pn = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p[a], B.lo[a]), B.len[a]), 2.0f), 1.0f);
+        // grid_sampler_unnormalize(align_corners): ((x + 1) / 2) * (size - 1)
+        const float sm1 = (float)(dim[a] - 1);
+        float ix = __fmul_rn(__fdiv_rn(__fadd_rn(pn, 1.0f), 2.0f), sm1);
+        const bool clipped = !(ix > 0.0f && ix < sm1);
+        ix = fminf(sm1, fmaxf(ix, 0.0f));
+        const float f = floorf(ix);
+        const int i = (int)f;
+        s.i0[a] = i;
+        s.i1[a] = min(i + 1, dim[a] - 1);
+        s.w1[a] = __fsub_rn(ix, f);
+        s.w0[a] = __fsub_rn(__fadd_rn(f, 1.0f), ix);
+        s.gm[a] = clipped ? 0.0f : __fdiv_rn(sm1, B.len[a]);
+    }
+}
+
+// weight and voxel offset (in floats, channel-last) of corner k in ATen's order tnw,tne,tsw,tse,bnw,bne,bsw,bse
+__device__ __forceinline__ float tri_corner(const GridView& G, const Tri& s, int k, int& off) {
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+    const int x = dx ? s.i1[0] : s.i0[0], y = dy ? s.i1[1] : s.i0[1], z = dz ? s.i1[2] : s.i0[2];
+    off = ((z * G.Y + y) * G.X + x) * CDIM;
+    const float wx = dx ? s.w1[0] : s.w0[0], wy = dy ? s.w1[1] : s.w0[1], wz = dz ? s.w1[2] : s.w0[2];
+    return __fmul_rn(__fmul_rn(wx, wy), wz);
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Fourier feature sin(x) for |x| up to a few thousand: exact two-term Cody-Waite reduction to [-pi, pi]
+// (k < 2^10 so k*2PI_HI is exact in the fma), then the SFU.  Absolute error ~5e-7, far below the
+// ~3e-5 rad the fp32 argument p.B itself carries at |x| ~ 300.
+__device__ __forceinline__ float reduce_2pi(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    return fmaf(-k, -1.7484555314695172e-07f, r);
+}
+__device__ __forceinline__ float ff_sin(float x) {
+#ifdef NSB_PRECISE_SIN
+    return sinf(x);
+#else
+    return __sinf(reduce_2pi(x));
+#endif
+}
+__device__ __forceinline__ void ff_sincos(float x, float& s, float& c) {
+#ifdef NSB_PRECISE_SIN
+    sincosf(x, &s, &c);
+#else
+    const float r = reduce_2pi(x);
+    s = __sinf(r);
+    c = __cosf(r);
+#endif
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+}  // namespace nsb

@@ -1,0 +1,270 @@
+// Backward decoder kernel: recomputes the decoder forward for each 16-sample tile (only relu bit masks are
+// kept), then back-propagates the raw cotangent through the MLP on tensor cores, scatters the grid-feature
+// gradient with 128-bit vector reductions into the channel-last gradient grids, accumulates the ray (pose)
+// gradient, and -- for the colour decoder when its weights are being optimised -- stashes the per-layer
+// activations / gradients for the split-K weight-gradient kernel (wgrad.cu).
+// This is the autograd backward of NICE::forward (NICE.cpp:43-50) that loss.backward() runs at
+// Mapper.cpp:444 / Tracker.cpp:84.
+#pragma once
+#include "decode.cuh"
+#include "params.h"
+
+namespace nsb {
+
+enum { F_GRID = 1, F_WGRAD = 2, F_RAY = 4 };
+
+__device__ __forceinline__ void zero_tile(float (&a)[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[j][q] = 0.0f;
+}
+__device__ __forceinline__ void apply_mask(float (&gu)[4][4], const float (&gh)[4][4], uint32_t m) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gu[j][q] = ((m >> (4 * j + q)) & 1u) ? gh[j][q] : 0.0f;
+}
+
+// Scatter the feature gradient of the thread's two samples into grid G (channels 8t..8t+7), and/or
+// accumulate d c / d p (coordinate derivative of the trilinear sample) into gp.  gc[r][8].
+template <bool DO_GRID, bool DO_RAY>
+__device__ __forceinline__ void grid_backward(const GridView& G, const Bound& bnd, const float (&p)[2][3],
+                                              const float (&gc)[2][8], int t, float (&gp)[2][3]) {
+    Tri s[2];
+    tri_setup(G, bnd, p[0], s[0]);
+    tri_setup(G, bnd, p[1], s[1]);
+    if (DO_RAY) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int off;
+                tri_corner(G, s[r], k, off);
+                const float4 v0 = ldg4(G.data + off + 8 * t), v1 = ldg4(G.data + off + 8 * t + 4);
+                const float dot = gc[r][0] * v0.x + gc[r][1] * v0.y + gc[r][2] * v0.z + gc[r][3] * v0.w +
+                                  gc[r][4] * v1.x + gc[r][5] * v1.y + gc[r][6] * v1.z + gc[r][7] * v1.w;
+                const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+                const float wx = dx ? s[r].w1[0] : s[r].w0[0], wy = dy ? s[r].w1[1] : s[r].w0[1], wz = dz ? s[r].w1[2] : s[r].w0[2];
+                gx += (dx ? dot : -dot) * wy * wz;
+                gy += (dy ? dot : -dot) * wx * wz;
+                gz += (dz ? dot : -dot) * wx * wy;
+            }
+            gp[r][0] += gx * s[r].gm[0]; gp[r][1] += gy * s[r].gm[1]; gp[r][2] += gz * s[r].gm[2];   // partial over the quad's channels
+        }
+    }
+    if (DO_GRID) {
+        // the thread's two samples are neighbours on the ray: when they fall in the same cell one reduction serves both
+        const bool same = s[0].i0[0] == s[1].i0[0] && s[0].i0[1] == s[1].i0[1] && s[0].i0[2] == s[1].i0[2];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int off0, off1;
+            const float w0 = tri_corner(G, s[0], k, off0);
+            const float w1 = tri_corner(G, s[1], k, off1);
+            float* a0 = G.grad + off0 + 8 * t;
+            if (same) {
+                red_add_v4(a0, w0 * gc[0][0] + w1 * gc[1][0], w0 * gc[0][1] + w1 * gc[1][1], w0 * gc[0][2] + w1 * gc[1][2], w0 * gc[0][3] + w1 * gc[1][3]);
+                red_add_v4(a0 + 4, w0 * gc[0][4] + w1 * gc[1][4], w0 * gc[0][5] + w1 * gc[1][5], w0 * gc[0][6] + w1 * gc[1][6], w0 * gc[0][7] + w1 * gc[1][7]);
+            } else {
+                float* a1 = G.grad + off1 + 8 * t;
+                red_add_v4(a0, w0 * gc[0][0], w0 * gc[0][1], w0 * gc[0][2], w0 * gc[0][3]);
+                red_add_v4(a0 + 4, w0 * gc[0][4], w0 * gc[0][5], w0 * gc[0][6], w0 * gc[0][7]);
+                red_add_v4(a1, w1 * gc[1][0], w1 * gc[1][1], w1 * gc[1][2], w1 * gc[1][3]);
+                red_add_v4(a1 + 4, w1 * gc[1][4], w1 * gc[1][5], w1 * gc[1][6], w1 * gc[1][7]);
+            }
+        }
+    }
+}
+
+// Backward of one decoder for one tile.  gout[r][o] = cotangent of the decoder outputs of the thread's two rows.
+// On return: gcf[r][8] = d L / d c for the thread's 8 grid channels (first 32 channels only: the middle half of
+// the fine decoder's input is stop-gradient, MLP.cpp:79-84); gp[r][3] = partial d L / d p from the Fourier path.
+template <int C, int O, bool P3, bool NEED_C, bool NEED_E, bool STASH>
+__device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, const float (&p)[2][3], int g, int t,
+                                                 const float (&gout)[2][4], const uint32_t (&masks)[5],
+                                                 float (&gcf)[2][8], float (&gp)[2][3], float* st0, float* st1) {
+    using L = DecSmem<C>;
+    constexpr int NO = O == 4 ? 3 : 1;
+    float gh[4][4], gu[4][4], gc[4][4], gu0[4][4], gu3[4][4];
+    // output layer: g_h5 = g_out Wo
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            const float2 w = *reinterpret_cast<const float2*>(sm + L::WO + o * HID + 8 * j + 2 * t);
+            gh[j][0] = fmaf(gout[0][o], w.x, gh[j][0]); gh[j][1] = fmaf(gout[0][o], w.y, gh[j][1]);
+            gh[j][2] = fmaf(gout[1][o], w.x, gh[j][2]); gh[j][3] = fmaf(gout[1][o], w.y, gh[j][3]);
+        }
+    }
+    if (NEED_C) zero_tile(gc);
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        if (STASH) stash_tile(st0, st1, stash::GH + HID * i, gh, t);
+        if (NEED_C) {   // g_c += g_h Fc_i  (only the first 32 input columns carry gradient)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                AFrag<P3> a;
+                afrag_from_c<P3>(a, gh[kk]);
+                kstep_bwd<P3, 4>(gc, a, sm + L::FC + i * HID * C, C, kk, 0, g, t);
+            }
+        }
+        apply_mask(gu, gh, masks[i]);
+        if (STASH) stash_tile(st0, st1, stash::GU + HID * i, gu, t);
+        if (NEED_E && i == 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gu3[j][q] = gu[j][q];
+        }
+        if (i == 0) {
+            if (NEED_E) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gu0[j][q] = gu[j][q];
+            }
+        } else {   // g_h_i = g_u W_i
+            zero_tile(gh);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                AFrag<P3> a;
+                afrag_from_c<P3>(a, gu[kk]);
+                kstep_bwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, 0, g, t);
+            }
+        }
+    }
+    if (NEED_C) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gcf[0][2 * j] = gc[j][0]; gcf[0][2 * j + 1] = gc[j][1];
+            gcf[1][2 * j] = gc[j][2]; gcf[1][2 * j + 1] = gc[j][3];
+        }
+    }
+    if (NEED_E) {
+        // g_e = g_u0 W0 + g_u3 W3e, one 8-feature tile at a time; chain through e = sin(p B)
+        AFrag<P3> a0[4], a3[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { afrag_from_c<P3>(a0[kk], gu0[kk]); afrag_from_c<P3>(a3[kk], gu3[kk]); }
+#pragma unroll 2
+        for (int je = 0; je < EMBP / 8; ++je) {
+            float ge[1][4] = {{0.0f, 0.0f, 0.0f, 0.0f}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                kstep_bwd<P3, 1>(ge, a0[kk], sm + L::W0, EMBP, kk, je, g, t);
+                kstep_bwd<P3, 1>(ge, a3[kk], sm + L::W3E, EMBP, kk, je, g, t);
+            }
+            const int f0 = 8 * je + 2 * t;
+            const float2 B0 = *reinterpret_cast<const float2*>(sm + L::B + f0);
+            const float2 B1 = *reinterpret_cast<const float2*>(sm + L::B + EMBP + f0);
+            const float2 B2 = *reinterpret_cast<const float2*>(sm + L::B + 2 * EMBP + f0);
+            float sn, c00, c01, c10, c11;
+            ff_sincos(fmaf(p[0][2], B2.x, fmaf(p[0][1], B1.x, p[0][0] * B0.x)), sn, c00);
+            ff_sincos(fmaf(p[0][2], B2.y, fmaf(p[0][1], B1.y, p[0][0] * B0.y)), sn, c01);
+            ff_sincos(fmaf(p[1][2], B2.x, fmaf(p[1][1], B1.x, p[1][0] * B0.x)), sn, c10);
+            ff_sincos(fmaf(p[1][2], B2.y, fmaf(p[1][1], B1.y, p[1][0] * B0.y)), sn, c11);
+            const float q00 = ge[0][0] * c00, q01 = ge[0][1] * c01, q10 = ge[0][2] * c10, q11 = ge[0][3] * c11;
+            if (STASH) {
+                *reinterpret_cast<float2*>(st0 + stash::GE + f0) = make_float2(q00, q01);
+                *reinterpret_cast<float2*>(st1 + stash::GE + f0) = make_float2(q10, q11);
+            }
+            gp[0][0] += q00 * B0.x + q01 * B0.y; gp[0][1] += q00 * B1.x + q01 * B1.y; gp[0][2] += q00 * B2.x + q01 * B2.y;
+            gp[1][0] += q10 * B0.x + q11 * B0.y; gp[1][1] += q10 * B1.x + q11 * B1.y; gp[1][2] += q10 * B2.x + q11 * B2.y;
+        }
+    }
+}
+
+template <int C, int O, bool P3, bool GRID, bool RAY, bool WG>
+__device__ __forceinline__ void backward_tile(const DecodeParams& P, const float* __restrict__ sm, int dec, int base,
+                                              int g, int t, int lane) {
+    float p[2][3]; int sidx[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) sidx[r] = base + 2 * g + r;
+    const int ray = base / P.S;
+    if (P.valid && !P.valid[ray]) return;
+    const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
+    const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
+    float zz[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        zz[r] = P.z[sidx[r]];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], zz[r]));
+    }
+    float gout[2][4];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float4 gr = *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[r]);
+        if (O == 4) { gout[r][0] = gr.x; gout[r][1] = gr.y; gout[r][2] = gr.z; gout[r][3] = 0.0f; any = any || gr.x != 0.0f || gr.y != 0.0f || gr.z != 0.0f; }
+        else { gout[r][0] = gr.w; gout[r][1] = gout[r][2] = gout[r][3] = 0.0f; any = any || gr.w != 0.0f; }
+    }
+    if (!WG && !__any_sync(0xffffffffu, any)) return;   // nothing flows into this tile
+
+    float c[2][C / 4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        gather8(P.grid[dec], P.bnd, p[r], t, c[r]);
+        if (C == 64) gather8(P.grid[1], P.bnd, p[r], t, c[r] + 8);
+    }
+    float* st0 = nullptr; float* st1 = nullptr;
+    if (WG) {
+        st0 = P.stash + (size_t)sidx[0] * stash::W; st1 = P.stash + (size_t)sidx[1] * stash::W;
+        *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t) = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+        *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t + 4) = make_float4(c[0][4], c[0][5], c[0][6], c[0][7]);
+        *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t) = make_float4(c[1][0], c[1][1], c[1][2], c[1][3]);
+        *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t + 4) = make_float4(c[1][4], c[1][5], c[1][6], c[1][7]);
+        if (t == 0) {
+            *reinterpret_cast<float4*>(st0 + stash::GO) = make_float4(gout[0][0], gout[0][1], gout[0][2], 0.0f);
+            *reinterpret_cast<float4*>(st1 + stash::GO) = make_float4(gout[1][0], gout[1][1], gout[1][2], 0.0f);
+            *reinterpret_cast<float4*>(st0 + stash::Pp) = make_float4(p[0][0], p[0][1], p[0][2], 1.0f);
+            *reinterpret_cast<float4*>(st1 + stash::Pp) = make_float4(p[1][0], p[1][1], p[1][2], 1.0f);
+        }
+    }
+    float out[2][4], h[4][4]; uint32_t masks[5];
+    decoder_forward<C, O, P3, WG>(sm, p, c, g, t, out, masks, h, st0, st1);
+
+    float gcf[2][8], gp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    decoder_backward<C, O, P3, GRID || RAY, RAY || WG, WG>(sm, p, g, t, gout, masks, gcf, gp, st0, st1);
+    if (GRID || RAY) grid_backward<GRID, RAY>(P.grid[dec], P.bnd, p, gcf, t, gp);
+    if (RAY) {
+        // gp holds per-thread partials (over the quad's channels / features): finish the quad sum, then the
+        // 16 rows of the tile belong to one ray: d L/d o = sum g_p, d L/d d = sum z g_p
+        float acc[6];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float g0 = quad_sum(gp[0][a]), g1 = quad_sum(gp[1][a]);
+            acc[a] = g0 + g1;
+            acc[3 + a] = zz[0] * g0 + zz[1] * g1;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            float v = acc[a];
+            v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane == 0) atomicAdd(P.d_rays + 6 * (size_t)ray + a, v);
+        }
+    }
+}
+
+template <bool P3, bool GRID, bool RAY, bool WG>
+__global__ void __launch_bounds__(DECODE_THREADS) k_decode_bwd(const DecodeParams P) {
+    extern __shared__ __align__(128) float sm[];
+    int dec = 1;
+#pragma unroll
+    for (int d = 2; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
+    const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
+    if (dec == 1) stage_decoder<32, 1>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
+    else if (dec == 2) stage_decoder<64, 1>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
+    else stage_decoder<32, 4>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int ntiles = P.P / TILE;
+    for (int tile = cta * DECODE_WARPS + warp; tile < ntiles; tile += ncta * DECODE_WARPS) {
+        if (dec == 1) backward_tile<32, 1, P3, GRID, RAY, false>(P, sm, 1, tile * TILE, g, t, lane);
+        else if (dec == 2) backward_tile<64, 1, P3, GRID, RAY, false>(P, sm, 2, tile * TILE, g, t, lane);
+        else backward_tile<32, 4, P3, GRID, RAY, WG>(P, sm, 3, tile * TILE, g, t, lane);
+    }
+}
+
+}  // namespace nsb

@@ -1,0 +1,48 @@
+// Kernel parameter blocks shared between the host API (api.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace nsb {
+
+constexpr int DECODE_WARPS = 8;
+constexpr int DECODE_THREADS = DECODE_WARPS * 32;
+
+// Which decoders a launch evaluates and how the grid is split between them.
+struct DecodeParams {
+    const float* dec_flat[4];      // coarse, middle, fine, color flat parameter vectors (device)
+    GridView grid[4];
+    Bound bnd;
+    // sample source: ray mode (rays + z) or points mode (pts != nullptr)
+    const float* rays_o;           // [N][3]
+    const float* rays_d;           // [N][3]
+    const float* z;                // [N][S]
+    const uint8_t* valid;          // [N] or nullptr: rays dropped by the inside filter are skipped
+    const float* pts;              // [P][3] or nullptr
+    int S;                         // samples per ray (multiple of 16)
+    int P;                         // total samples
+    // outputs (forward): raw colour (P,4: r,g,b,-) and the three occupancy terms
+    float* out_rgb;
+    float* out_occ[3];             // coarse, middle, fine
+    // grid partition: decoder d runs on CTAs [cta_begin[d], cta_begin[d+1])
+    int cta_begin[5];
+    // ---- backward only ----
+    const float* g_raw;            // [P][4] cotangent of raw (r,g,b,occ); occ already zero where out of bound
+    int flags;                     // bit0 grid grads, bit1 colour-decoder weight grads (stash), bit2 ray grads
+    float* d_rays;                 // [N][6]: d L / d rays_o, d L / d rays_d (atomically accumulated)
+    float* stash;                  // [P][STASH_W] colour-decoder activations / gradients for the wgrad kernel
+};
+
+// Row layout of the colour-decoder weight-gradient stash (floats per sample).
+namespace stash {
+constexpr int E = 0;          // embedding e            96
+constexpr int H = 96;         // h_1..h_5               5 x 32  (inputs of layers 1..4 and of the output layer)
+constexpr int Cc = 256;       // grid feature c         32 (channel order)
+constexpr int GU = 288;       // g_u_0..g_u_4           5 x 32  (gradient at the relu output, masked)
+constexpr int GH = 448;       // g_h_1..g_h_5           5 x 32  (gradient at the block output)
+constexpr int GE = 608;       // g_e * cos(pB)          96
+constexpr int GO = 704;       // g_out                  4
+constexpr int Pp = 708;       // p                      4
+constexpr int W = 712;
+}  // namespace stash
+
+}  // namespace nsb

@@ -1,0 +1,491 @@
+// Per-ray kernels: pixel -> ray generation + inside filter, depth-guided sample placement, alpha compositing
+// (forward and backward), losses, lower-median select, pose-gradient reduction.
+// Replaces raySampler/get_samples (utils.h:13-55,141-146), the filter of Mapper.cpp:416-427 / Tracker.cpp:48-58,
+// Renderer.cpp:46-119 (z values), raw2outputs_nerf_color (utils.h:148-172), the losses of Mapper.cpp:435-442 and
+// Tracker.cpp:67-82 and the autograd backward of all of them.
+#pragma once
+#include "common.cuh"
+
+namespace nsb {
+
+constexpr int MAX_OPT_FRAMES = 16;
+
+// ---- utils.h:174-195 -------------------------------------------------------------------------------------
+__host__ __device__ inline void quad2rotation(const float* q, float* R) {
+    const float qr = q[0], qi = q[1], qj = q[2], qk = q[3];
+    const float two_s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);
+    R[0] = 1 - two_s * (qj * qj + qk * qk); R[1] = two_s * (qi * qj - qk * qr); R[2] = two_s * (qi * qk + qj * qr);
+    R[3] = two_s * (qi * qj + qk * qr); R[4] = 1 - two_s * (qi * qi + qk * qk); R[5] = two_s * (qj * qk - qi * qr);
+    R[6] = two_s * (qi * qk - qj * qr); R[7] = two_s * (qj * qk + qi * qr); R[8] = 1 - two_s * (qi * qi + qj * qj);
+}
+
+// d L / d q given G = d L / d R (row-major 3x3): R = I + two_s * A(q), two_s = 2 / |q|^2.
+__host__ __device__ inline void quad2rotation_vjp(const float* q, const float* G, float* gq) {
+    const float qr = q[0], qi = q[1], qj = q[2], qk = q[3];
+    const float n = qr * qr + qi * qi + qj * qj + qk * qk, two_s = 2.0f / n;
+    const float A[9] = {-(qj * qj + qk * qk), qi * qj - qk * qr, qi * qk + qj * qr,
+                        qi * qj + qk * qr, -(qi * qi + qk * qk), qj * qk - qi * qr,
+                        qi * qk - qj * qr, qj * qk + qi * qr, -(qi * qi + qj * qj)};
+    float GA = 0.0f;
+    for (int i = 0; i < 9; ++i) GA += G[i] * A[i];
+    // dA/dq_m contracted with G
+    const float dqr = G[1] * (-qk) + G[2] * qj + G[3] * qk + G[5] * (-qi) + G[6] * (-qj) + G[7] * qi;
+    const float dqi = G[1] * qj + G[2] * qk + G[3] * qj + G[4] * (-2 * qi) + G[5] * (-qr) + G[6] * qk + G[7] * qr + G[8] * (-2 * qi);
+    const float dqj = G[0] * (-2 * qj) + G[1] * qi + G[2] * qr + G[3] * qi + G[5] * qk + G[6] * (-qr) + G[7] * qk + G[8] * (-2 * qj);
+    const float dqk = G[0] * (-2 * qk) + G[1] * (-qr) + G[2] * qi + G[3] * qr + G[4] * (-2 * qk) + G[5] * qj + G[6] * qi + G[7] * qj;
+    const float k = two_s * two_s * GA;   // d two_s / d q_m = -two_s^2 q_m
+    gq[0] = two_s * dqr - k * qr; gq[1] = two_s * dqi - k * qi; gq[2] = two_s * dqj - k * qj; gq[3] = two_s * dqk - k * qk;
+}
+
+struct SampleParams {
+    const float* depth;      // [max_frames][H*W]
+    const float* color;      // [max_frames][H*W*3]
+    const float* poses;      // [max_frames][12]  row-major [R|t]
+    const float* cam7;       // non-null: every ray uses this 7-vector pose (tracking), R via quad2rotation
+    const int64_t* idx;      // [n] flat index into the crop
+    int slots[MAX_OPT_FRAMES];
+    int n_frames, pix_per_frame;
+    int H, W, H0, W0, Wc;
+    float fx, fy, cx, cy;
+    int raydir;
+    Bound bnd;
+    int n;
+    float* rays_o; float* rays_d; float* gt_depth; float* gt_color; uint8_t* valid;
+    float* stats;            // [0] max gt_depth over valid rays (as int bits), [1] count of valid rays (int)
+    int apply_filter;        // 0: valid = 1 for every ray (render API)
+};
+
+__device__ __forceinline__ float aabb_exit(const Bound& b, const float* o, const float* d) {
+    float t = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t0 = __fdiv_rn(__fsub_rn(b.lo[a], o[a]), d[a]);
+        const float t1 = __fdiv_rn(__fsub_rn(b.hi[a], o[a]), d[a]);
+        t = fminf(t, fmaxf(t0, t1));
+    }
+    return t;
+}
+
+__global__ void k_sample(SampleParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float gd = 0.0f; bool ok = false;
+    if (i < P.n) {
+        const int f = min(i / P.pix_per_frame, P.n_frames - 1);
+        const int slot = P.slots[f];
+        const int64_t id = P.idx[i];
+        const int x = P.W0 + (int)(id % P.Wc), y = P.H0 + (int)(id / P.Wc);
+        const size_t pix = (size_t)slot * P.H * P.W + (size_t)y * P.W + x;
+        gd = P.depth[pix];
+        const float* c = P.color + pix * 3;
+        P.gt_color[3 * i + 0] = c[0]; P.gt_color[3 * i + 1] = c[1]; P.gt_color[3 * i + 2] = c[2];
+        P.gt_depth[i] = gd;
+        float R[9], tr[3];
+        if (P.cam7) {
+            quad2rotation(P.cam7, R);
+            tr[0] = P.cam7[4]; tr[1] = P.cam7[5]; tr[2] = P.cam7[6];
+        } else {
+            const float* m = P.poses + slot * 12;
+            for (int r = 0; r < 3; ++r) { R[3 * r] = m[4 * r]; R[3 * r + 1] = m[4 * r + 1]; R[3 * r + 2] = m[4 * r + 2]; tr[r] = m[4 * r + 3]; }
+        }
+        // utils.h:44-47 (reference: j_t uses i and is not negated) or upstream pinhole
+        const float xf = (float)x, yf = (float)y;
+        const float d0 = __fdiv_rn(__fsub_rn(xf, P.cx), P.fx);
+        const float d1 = P.raydir == 0 ? __fdiv_rn(__fsub_rn(xf, P.cy), P.fy) : -__fdiv_rn(__fsub_rn(yf, P.cy), P.fy);
+        const float d2 = -1.0f;
+        float o[3], d[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {   // utils.h:51: sum(dirs * c2w[:3,:3], -1)
+            d[r] = __fadd_rn(__fadd_rn(__fmul_rn(d0, R[3 * r]), __fmul_rn(d1, R[3 * r + 1])), __fmul_rn(d2, R[3 * r + 2]));
+            o[r] = tr[r];
+            P.rays_d[3 * i + r] = d[r]; P.rays_o[3 * i + r] = o[r];
+        }
+        ok = P.apply_filter ? (aabb_exit(P.bnd, o, d) >= gd) : true;   // Mapper.cpp:420-423
+        P.valid[i] = ok ? 1 : 0;
+    }
+    // batch-global scalars of Renderer.cpp:76,93 are taken over the rays that pass the filter
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    float m = ok ? gd : 0.0f;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && bal) {
+        atomicMax(reinterpret_cast<int*>(P.stats), __float_as_int(m));
+        atomicAdd(reinterpret_cast<int*>(P.stats) + 1, __popc(bal));
+    }
+}
+
+// max gt_depth for the direct render API (rays supplied by the caller)
+__global__ void k_depth_max(const float* __restrict__ gt_depth, int n, float* stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = i < n ? fmaxf(gt_depth[i], 0.0f) : 0.0f;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats), __float_as_int(m));
+}
+
+// utils.h:153 as written: torch::norm(x, -1) = (sum |x|^-1)^-1 over the whole batch.  stats[2] accumulates sum 1/|d_ij|.
+__global__ void k_dirnorm_ref(const float* __restrict__ rays_d, const uint8_t* __restrict__ valid, int n, float* stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.0f;
+    if (i < n && (!valid || valid[i])) s = 1.0f / fabsf(rays_d[3 * i]) + 1.0f / fabsf(rays_d[3 * i + 1]) + 1.0f / fabsf(rays_d[3 * i + 2]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(stats + 2, s);
+}
+
+struct ZParams {
+    const float* rays_o; const float* rays_d; const float* gt_depth;   // gt_depth null: no-depth path
+    const uint8_t* valid;
+    const float* stats;      // [0] max gt_depth
+    const float* t_samples;  // [32]
+    const float* t_surface;  // [16]
+    Bound bnd;
+    int n, n_samples, n_surface;
+    float* z;                // [n][S]
+};
+
+// Renderer.cpp:46-119: one warp per ray.  32 stratified + 16 near-surface values, then an exact rank sort.
+__global__ void k_zvals(ZParams P) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) return;
+    const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
+    const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
+    const float far_bb = __fadd_rn(aabb_exit(P.bnd, o, d), 0.01f);                 // :69-73
+    const float t = P.t_samples[l], u = __fsub_rn(1.0f, t);
+    if (!P.gt_depth) {                                                               // :54-58,78,106
+        P.z[ray * P.n_samples + l] = __fadd_rn(__fmul_rn(0.01f, u), __fmul_rn(far_bb, t));
+        return;
+    }
+    const float gd = P.gt_depth[ray], gmax = P.stats[0];
+    const float near = __fmul_rn(gd, 0.01f);                                         // :63
+    const float far = fminf(fmaxf(far_bb, 0.0f), __fmul_rn(gmax, 1.2f));            // :76
+    const float v0 = __fadd_rn(__fmul_rn(near, u), __fmul_rn(far, t));              // :106
+    float v1 = 0.0f;
+    const int S = P.n_samples + P.n_surface;
+    if (l < P.n_surface) {
+        const float ts = P.t_surface[l], us = __fsub_rn(1.0f, ts);
+        if (gd > 0.0f) v1 = __fadd_rn(__fmul_rn(__fmul_rn(0.95f, gd), us), __fmul_rn(__fmul_rn(1.05f, gd), ts));   // :88
+        else v1 = __fadd_rn(__fmul_rn(0.001f, us), __fmul_rn(gmax, ts));             // :94
+    }
+    if (P.n_surface == 0) { P.z[ray * S + l] = v0; return; }
+    int r0 = 0, r1 = 0;                                                              // :119 sort == rank placement
+    for (int k = 0; k < S; ++k) {
+        const float uk = k < 32 ? __shfl_sync(0xffffffffu, v0, k) : __shfl_sync(0xffffffffu, v1, k - 32);
+        r0 += (uk < v0) || (uk == v0 && k < l);
+        r1 += (uk < v1) || (uk == v1 && k < 32 + l);
+    }
+    P.z[ray * S + r0] = v0;
+    if (l < P.n_surface) P.z[ray * S + r1] = v1;
+}
+
+// ---- compositing -------------------------------------------------------------------------------------
+struct CompositeParams {
+    const float* rays_o; const float* rays_d; const float* z; const uint8_t* valid;
+    const float* raw_rgb;     // [P][4]
+    const float* occ[3];      // coarse, middle, fine
+    const float* stats;       // [2] sum 1/|d| for the reference dist norm
+    Bound bnd;
+    int n, S, stage, occupancy, dist_norm;
+    // forward outputs
+    float* rgb; float* depth; float* var; float* weights;
+    // backward
+    const float* g_rgb; const float* g_depth; const float* g_var;   // per-ray cotangents
+    float* g_raw;             // [P][4]
+    float* d_rays;            // [n][6] or null: receives d L / d rays_d through dists * |rays_d| (utils.h:153)
+};
+
+struct RaySamples {   // lane l owns samples l and l+32
+    float z[2], sig[2], col[2][3], delta[2], alpha[2], T[2], w[2];
+    bool in[2], has[2];
+};
+
+__device__ __forceinline__ float warp_scan_mul(float v, int l) {   // inclusive prefix product
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, v, o);
+        if (l >= o) v *= n;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add_rev(float v, int l) {   // inclusive suffix sum
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_down_sync(0xffffffffu, v, o);
+        if (l + o < 32) v += n;
+    }
+    return v;
+}
+
+// Loads the ray's samples and runs the forward composite (utils.h:150-171).  Returns rgb/depth/var in all lanes.
+__device__ __forceinline__ void composite_forward(const CompositeParams& P, int ray, int l, RaySamples& s,
+                                                  float (&rgb)[3], float& depth, float& var) {
+    const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
+    const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
+    float norm;
+    if (P.dist_norm == 0) norm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    else norm = 1.0f / P.stats[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = l + 32 * h;
+        s.has[h] = k < P.S;
+        s.z[h] = 0.0f; s.sig[h] = 0.0f; s.in[h] = false; s.delta[h] = 0.0f;
+        s.col[h][0] = s.col[h][1] = s.col[h][2] = 0.0f;
+        if (s.has[h]) {
+            const int q = ray * P.S + k;
+            const float z = P.z[q];
+            s.z[h] = z;
+            const float zn = k + 1 < P.S ? P.z[q + 1] : 0.0f;
+            s.delta[h] = __fmul_rn(k + 1 < P.S ? __fsub_rn(zn, z) : 1e10f, norm);
+            float sig;
+            if (P.stage == 0) sig = P.occ[0][q];
+            else if (P.stage == 1) sig = P.occ[1][q];
+            else sig = __fadd_rn(P.occ[2][q], P.occ[1][q]);                        // NICE.cpp:40,49
+            if (P.stage == 3) { const float4 c = *reinterpret_cast<const float4*>(P.raw_rgb + 4 * (size_t)q); s.col[h][0] = c.x; s.col[h][1] = c.y; s.col[h][2] = c.z; }
+            bool in = true;                                                         // Renderer.cpp:26-29
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float p = __fadd_rn(o[a], __fmul_rn(d[a], z));               // Renderer.cpp:121
+                in = in && (p < P.bnd.hi[a]) && (p > P.bnd.lo[a]);
+            }
+            s.in[h] = in;
+            s.sig[h] = in ? sig : 100.0f;                                           // Renderer.cpp:36
+        }
+        if (P.occupancy) s.alpha[h] = s.has[h] ? 1.0f / (1.0f + expf(-10.0f * s.sig[h])) : 0.0f;
+        else s.alpha[h] = s.has[h] ? 1.0f - expf(-(fmaxf(s.sig[h], 0.0f) * s.delta[h])) : 0.0f;
+    }
+    // transmittance: exclusive prefix product of (1 - alpha + 1e-10)  (utils.h:159-164)
+    const float q0 = __fadd_rn(__fsub_rn(1.0f, s.alpha[0]), 1e-10f);
+    const float q1 = s.has[1] ? __fadd_rn(__fsub_rn(1.0f, s.alpha[1]), 1e-10f) : 1.0f;
+    const float inc0 = warp_scan_mul(q0, l);
+    float ex0 = __shfl_up_sync(0xffffffffu, inc0, 1); if (l == 0) ex0 = 1.0f;
+    const float tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    const float inc1 = warp_scan_mul(q1, l);
+    float ex1 = __shfl_up_sync(0xffffffffu, inc1, 1); if (l == 0) ex1 = 1.0f;
+    s.T[0] = ex0; s.T[1] = tot0 * ex1;
+    s.w[0] = s.alpha[0] * s.T[0];
+    s.w[1] = s.has[1] ? s.alpha[1] * s.T[1] : 0.0f;
+    rgb[0] = warp_sum(s.w[0] * s.col[0][0] + s.w[1] * s.col[1][0]);
+    rgb[1] = warp_sum(s.w[0] * s.col[0][1] + s.w[1] * s.col[1][1]);
+    rgb[2] = warp_sum(s.w[0] * s.col[0][2] + s.w[1] * s.col[1][2]);
+    depth = warp_sum(s.w[0] * s.z[0] + s.w[1] * s.z[1]);
+    const float t0 = s.z[0] - depth, t1 = s.z[1] - depth;
+    var = warp_sum(s.w[0] * t0 * t0 + s.w[1] * t1 * t1);
+}
+
+__global__ void k_composite_fwd(CompositeParams P) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) {
+        if (l == 0) { P.rgb[3 * ray] = P.rgb[3 * ray + 1] = P.rgb[3 * ray + 2] = 0.0f; P.depth[ray] = 0.0f; P.var[ray] = 0.0f; }
+        if (P.weights) for (int k = l; k < P.S; k += 32) P.weights[ray * P.S + k] = 0.0f;
+        return;
+    }
+    RaySamples s; float rgb[3], depth, var;
+    composite_forward(P, ray, l, s, rgb, depth, var);
+    if (l == 0) { P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var; }
+    if (P.weights) {
+        P.weights[ray * P.S + l] = s.w[0];
+        if (s.has[1]) P.weights[ray * P.S + 32 + l] = s.w[1];
+    }
+}
+
+// Backward of the composite for per-ray cotangents (g_rgb, g_depth, g_var) -> g_raw (r,g,b,occ) per sample.
+__global__ void k_composite_bwd(CompositeParams P) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) return;   // tiles of dropped rays are skipped by the decoder kernels too
+    RaySamples s; float rgb[3], depth, var;
+    composite_forward(P, ray, l, s, rgb, depth, var);
+    const float gC[3] = {P.g_rgb[3 * ray], P.g_rgb[3 * ray + 1], P.g_rgb[3 * ray + 2]};
+    const float gV = P.g_var[ray];
+    // var = sum w (z - D)^2  =>  dvar/dD = -2 sum w (z - D)
+    const float sw = warp_sum(s.w[0] * (s.z[0] - depth) + s.w[1] * (s.z[1] - depth));
+    const float gD = P.g_depth[ray] - 2.0f * gV * sw;
+    float gw[2], gwsum[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float dz = s.z[h] - depth;
+        gw[h] = s.has[h] ? gC[0] * s.col[h][0] + gC[1] * s.col[h][1] + gC[2] * s.col[h][2] + gD * s.z[h] + gV * dz * dz : 0.0f;
+    }
+    // suffix sums of gw_k * w_k over k > j  (cumprod backward: d T_k / d q_j = T_k / q_j)
+    const float a0 = gw[0] * s.w[0], a1 = gw[1] * s.w[1];
+    const float suf1 = warp_scan_add_rev(a1, l), tot1 = __shfl_sync(0xffffffffu, suf1, 0);
+    const float suf0 = warp_scan_add_rev(a0, l);
+    gwsum[0] = (suf0 - a0) + tot1;
+    gwsum[1] = suf1 - a1;
+    float g_norm = 0.0f;   // d L / d |rays_d| through delta = dz * |rays_d|
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (!s.has[h]) continue;
+        const int q = ray * P.S + l + 32 * h;
+        const float qq = __fadd_rn(__fsub_rn(1.0f, s.alpha[h]), 1e-10f);
+        const float g_alpha = gw[h] * s.T[h] - gwsum[h] / qq;
+        if (!P.occupancy && s.sig[h] > 0.0f) {
+            const float e = expf(-(s.sig[h] * s.delta[h]));
+            if (e > 0.0f) g_norm += g_alpha * s.sig[h] * e * s.delta[h];   // times 1/|d| below (delta = dz |d|)
+        }
+        float g_sig;
+        if (P.occupancy) g_sig = g_alpha * 10.0f * s.alpha[h] * (1.0f - s.alpha[h]);
+        else g_sig = s.sig[h] > 0.0f ? g_alpha * s.delta[h] * expf(-(s.sig[h] * s.delta[h])) : 0.0f;
+        if (!s.in[h]) g_sig = 0.0f;   // occupancy overwritten with 100 (Renderer.cpp:36): no gradient to the decoders
+        float4 o;
+        o.x = s.w[h] * gC[0]; o.y = s.w[h] * gC[1]; o.z = s.w[h] * gC[2]; o.w = g_sig;
+        if (P.stage != 3) { o.x = o.y = o.z = 0.0f; }
+        *reinterpret_cast<float4*>(P.g_raw + 4 * (size_t)q) = o;
+    }
+    if (P.d_rays && P.dist_norm == 0) {
+        g_norm = warp_sum(g_norm);
+        if (l < 3) {
+            const float dx = P.rays_d[3 * ray], dy = P.rays_d[3 * ray + 1], dz = P.rays_d[3 * ray + 2];
+            const float n2 = dx * dx + dy * dy + dz * dz;   // d|d|/d d = d/|d|, and delta/|d| = dz
+            atomicAdd(P.d_rays + 6 * (size_t)ray + 3 + l, g_norm * P.rays_d[3 * ray + l] / n2);
+        }
+    }
+}
+
+// ---- losses ------------------------------------------------------------------------------------------
+struct LossParams {
+    const float* gt_depth; const float* gt_color; const uint8_t* valid;
+    const float* rgb; const float* depth; const float* var;
+    int n, use_color; float w_color;
+    float* g_rgb; float* g_depth; float* g_var;
+    float* loss;              // scalar accumulator
+    const float* median;      // tracking: [0] = median |gt - depth| (handle_dynamic), null otherwise
+    float* absdiff;           // tracking pass 1 output
+};
+
+__device__ __forceinline__ float sgn(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// Mapper.cpp:435-442: sum_{gt>0} |gt - depth| + w * sum |gt_color - color|
+__global__ void k_loss_mapping(LossParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.0f;
+    if (i < P.n) {
+        float gd = 0.0f, gc[3] = {0.0f, 0.0f, 0.0f};
+        if (!P.valid || P.valid[i]) {
+            const float g = P.gt_depth[i];
+            if (g > 0.0f) { const float df = g - P.depth[i]; loss += fabsf(df); gd = -sgn(df); }
+            if (P.use_color) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { const float df = P.gt_color[3 * i + c] - P.rgb[3 * i + c]; loss += P.w_color * fabsf(df); gc[c] = -P.w_color * sgn(df); }
+            }
+        }
+        P.g_depth[i] = gd; P.g_var[i] = 0.0f;
+        P.g_rgb[3 * i] = gc[0]; P.g_rgb[3 * i + 1] = gc[1]; P.g_rgb[3 * i + 2] = gc[2];
+    }
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0 && loss != 0.0f) atomicAdd(P.loss, loss);
+}
+
+// Tracker.cpp:69: |gt - depth| of the rays that passed the filter (compacted for the median)
+__global__ void k_track_absdiff(LossParams P, int* count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n && (!P.valid || P.valid[i])) {
+        const int slot = atomicAdd(count, 1);
+        P.absdiff[slot] = fabsf(P.gt_depth[i] - P.depth[i]);
+    }
+}
+
+// torch.median (lower median) of n non-negative floats by 4-pass radix select on the bit pattern; one block.
+__global__ void k_median(const float* __restrict__ v, const int* __restrict__ count, float* out) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned prefix_s, want_s;
+    const int n = *count;
+    if (n <= 0) { if (threadIdx.x == 0) out[0] = 0.0f; return; }
+    if (threadIdx.x == 0) { prefix_s = 0; want_s = (unsigned)((n - 1) / 2); }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        const unsigned prefix = prefix_s;
+        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned u = __float_as_uint(v[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned want = want_s, b = 0;
+            while (b < 255 && hist[b] <= want) { want -= hist[b]; ++b; }
+            want_s = want; prefix_s = prefix | (b << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = __uint_as_float(prefix_s);
+}
+
+// Tracker.cpp:67-82: mask = (|gt-depth| < 10 median) & (gt > 0); loss = sum_mask |gt-depth|/sqrt(var+1e-10) + w sum_mask |dc|
+__global__ void k_loss_tracking(LossParams P, int handle_dynamic) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.0f;
+    if (i < P.n) {
+        float gd = 0.0f, gv = 0.0f, gc[3] = {0.0f, 0.0f, 0.0f};
+        if (!P.valid || P.valid[i]) {
+            const float g = P.gt_depth[i], df = g - P.depth[i];
+            bool m = g > 0.0f;
+            if (handle_dynamic) m = m && (fabsf(df) < 10.0f * P.median[0]);
+            if (m) {
+                const float vv = P.var[i] + 1e-10f, r = 1.0f / sqrtf(vv);
+                loss += fabsf(df) * r;
+                gd = -sgn(df) * r;
+                gv = -0.5f * fabsf(df) * r / vv;
+                if (P.use_color) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { const float dc = P.gt_color[3 * i + c] - P.rgb[3 * i + c]; loss += P.w_color * fabsf(dc); gc[c] = -P.w_color * sgn(dc); }
+                }
+            }
+        }
+        P.g_depth[i] = gd; P.g_var[i] = gv;
+        P.g_rgb[3 * i] = gc[0]; P.g_rgb[3 * i + 1] = gc[1]; P.g_rgb[3 * i + 2] = gc[2];
+    }
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0 && loss != 0.0f) atomicAdd(P.loss, loss);
+}
+
+// ---- pose gradient: d L / d (q, t) from the per-ray gradients (block reduction, one block) -------------
+struct PoseGradParams {
+    const float* d_rays;     // [n][6]: d_o, d_d
+    const int64_t* idx; const uint8_t* valid;
+    const float* cam7;
+    int n, H0, W0, Wc, raydir;
+    float fx, fy, cx, cy;
+    float* g_cam7;           // [7]
+};
+
+__global__ void k_pose_grad(PoseGradParams P) {
+    __shared__ float red[12][32];
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+        if (P.valid && !P.valid[i]) continue;
+        const int64_t id = P.idx[i];
+        const float xf = (float)(P.W0 + (int)(id % P.Wc)), yf = (float)(P.H0 + (int)(id / P.Wc));
+        const float dir[3] = {(xf - P.cx) / P.fx, P.raydir == 0 ? (xf - P.cy) / P.fy : -(yf - P.cy) / P.fy, -1.0f};
+        const float* g = P.d_rays + 6 * (size_t)i;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            acc[9 + r] += g[r];                                   // rays_o = t
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[3 * r + c] += g[3 + r] * dir[c];   // rays_d = R dir
+        }
+    }
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { const float v = warp_sum(acc[k]); if (l == 0) red[k][w] = v; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        float G[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) G[k] = warp_sum(l < nw ? red[k][l] : 0.0f);
+        if (l == 0) {
+            float gq[4];
+            quad2rotation_vjp(P.cam7, G, gq);
+            P.g_cam7[0] = gq[0]; P.g_cam7[1] = gq[1]; P.g_cam7[2] = gq[2]; P.g_cam7[3] = gq[3];
+            P.g_cam7[4] = G[9]; P.g_cam7[5] = G[10]; P.g_cam7[6] = G[11];
+        }
+    }
+}
+
+}  // namespace nsb

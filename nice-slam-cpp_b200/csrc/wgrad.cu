@@ -1,0 +1,118 @@
+// Split-K weight-gradient kernel for the colour decoder (the only decoder the reference optimises by default:
+// fix_fine = True, fix_color = False, Mapper.cpp:292-301).  The backward decoder kernel stashes, per sample, the
+// layer inputs X and the layer-output gradients G; every parameter gradient is then a tall-skinny product
+//     dW[a][b] = sum_s L[s][a] * R[s][b]
+// with the sample index as the contraction dimension.  Each CTA walks a contiguous range of samples, each warp
+// owns three groups of (one 16-row A tile) x (four 8-column B tiles) and keeps their accumulators in registers;
+// the per-CTA partial sums are added to the flat gradient with fp32 reductions at the end.
+#include "decode.cuh"
+#include "params.h"
+
+namespace nsb {
+
+constexpr int WG_WARPS = 16;
+constexpr int WG_GROUPS_PER_WARP = 3;
+constexpr int WG_MAX_GROUPS = WG_WARPS * WG_GROUPS_PER_WARP;   // 48 >= 45
+
+struct WGroup {
+    int L, R;          // stash column of row a0 of the A tile / of column b0 of the B tiles
+    int dst, ld;       // flat-gradient offset of element (a_lo, 0) and its row stride
+    int a_lo, a_hi;    // valid rows of the A tile (relative to L)
+    int nb;            // valid columns (relative to R), up to 32
+};
+struct WGTable { WGroup g[WG_MAX_GROUPS]; int n; };
+
+static WGTable build_table() {
+    WGTable T; T.n = 0;
+    const DecFlat f = DecFlat::make(32, 4);
+    auto add = [&](int L, int R, int dst, int ld, int a_lo, int a_hi, int nb) { T.g[T.n++] = WGroup{L, R, dst, ld, a_lo, a_hi, nb}; };
+    auto addmat = [&](int L, int na, int R, int nb, int dst, int ld) {   // dW[a][b], a < na, b < nb
+        for (int a0 = 0; a0 < na; a0 += 16)
+            for (int b0 = 0; b0 < nb; b0 += 32)
+                add(L + a0, R + b0, dst + a0 * ld + b0, ld, 0, (na - a0) < 16 ? (na - a0) : 16, (nb - b0) < 32 ? (nb - b0) : 32);
+    };
+    addmat(stash::GU + 0, 32, stash::E, EMB, f.W[0], EMB);
+    addmat(stash::GU + 32, 32, stash::H + 0, 32, f.W[1], 32);
+    addmat(stash::GU + 64, 32, stash::H + 32, 32, f.W[2], 32);
+    addmat(stash::GU + 96, 32, stash::E, EMB, f.W[3], EMB + HID);
+    addmat(stash::GU + 96, 32, stash::H + 64, 32, f.W[3] + EMB, EMB + HID);
+    addmat(stash::GU + 128, 32, stash::H + 96, 32, f.W[4], 32);
+    for (int i = 0; i < 5; ++i) addmat(stash::GH + 32 * i, 32, stash::Cc, 32, f.Fc[i], 32);
+    addmat(stash::GO, 4, stash::H + 128, 32, f.Wo, 32);
+    addmat(stash::Pp, 3, stash::GE, EMB, f.B, EMB);                       // dB[d][f] = sum p_d * g_e cos
+    for (int i = 0; i < 5; ++i) add(stash::Pp, stash::GU + 32 * i, f.b[i], 0, 3, 4, 32);    // bias = column sums (Pp[3] == 1)
+    for (int i = 0; i < 5; ++i) add(stash::Pp, stash::GH + 32 * i, f.bc[i], 0, 3, 4, 32);
+    add(stash::Pp, stash::GO, f.bo, 0, 3, 4, 4);
+    return T;
+}
+
+__constant__ WGTable c_wg;
+
+template <bool P3>
+__global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
+                                                         int P, int S, float* __restrict__ dflat) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float acc[WG_GROUPS_PER_WARP][4][4];
+#pragma unroll
+    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[q][j][0] = acc[q][j][1] = acc[q][j][2] = acc[q][j][3] = 0.0f;
+    int Lc[WG_GROUPS_PER_WARP], Rc[WG_GROUPS_PER_WARP]; bool on[WG_GROUPS_PER_WARP];
+#pragma unroll
+    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
+        const int gi = warp * WG_GROUPS_PER_WARP + q;
+        on[q] = gi < c_wg.n;
+        Lc[q] = on[q] ? c_wg.g[gi].L + 2 * g : 0;      // A rows g / g+8 <-> a0 + 2g, a0 + 2g + 1
+        Rc[q] = on[q] ? c_wg.g[gi].R + 4 * g : 0;      // B col g of tile j <-> b0 + 4g + j
+    }
+    const int nks = P / 8;
+    const int per = (nks + gridDim.x - 1) / gridDim.x;
+    const int k_lo = blockIdx.x * per, k_hi = min(nks, k_lo + per);
+    for (int ks = k_lo; ks < k_hi; ++ks) {
+        const int s0 = ks * 8;
+        if (valid && !valid[s0 / S]) continue;
+        const float* r0 = st + (size_t)(s0 + t) * stash::W;
+        const float* r1 = r0 + 4 * (size_t)stash::W;
+#pragma unroll
+        for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
+            if (!on[q]) continue;
+            const float2 a_lo = *reinterpret_cast<const float2*>(r0 + Lc[q]);   // k = t
+            const float2 a_hi = *reinterpret_cast<const float2*>(r1 + Lc[q]);   // k = t + 4
+            const float4 b_lo = *reinterpret_cast<const float4*>(r0 + Rc[q]);
+            const float4 b_hi = *reinterpret_cast<const float4*>(r1 + Rc[q]);
+            AFrag<P3> a;
+            a.set(a_lo.x, a_lo.y, a_hi.x, a_hi.y);
+            mma_acc<P3>(acc[q][0], a, b_lo.x, b_hi.x);
+            mma_acc<P3>(acc[q][1], a, b_lo.y, b_hi.y);
+            mma_acc<P3>(acc[q][2], a, b_lo.z, b_hi.z);
+            mma_acc<P3>(acc[q][3], a, b_lo.w, b_hi.w);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
+        if (!on[q]) continue;
+        const WGroup G = c_wg.g[warp * WG_GROUPS_PER_WARP + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int a = 2 * g + (e >> 1), b = 4 * (2 * t + (e & 1)) + j;
+                if (a >= G.a_lo && a < G.a_hi && b < G.nb) atomicAdd(dflat + G.dst + (a - G.a_lo) * G.ld + b, acc[q][j][e]);
+            }
+    }
+}
+
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st) {
+    static bool init = false;
+    if (!init) {
+        const WGTable T = build_table();
+        cudaError_t e = cudaMemcpyToSymbol(c_wg, &T, sizeof(T));
+        if (e != cudaSuccess) return e;
+        init = true;
+    }
+    if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, 0, st>>>(stash_buf, valid, P, S, dflat);
+    else k_wgrad<false><<<grid, WG_WARPS * 32, 0, st>>>(stash_buf, valid, P, S, dflat);
+    return cudaGetLastError();
+}
+
+}  // namespace nsb

@@ -1,0 +1,284 @@
+"""GPU parity tests (pytest -m gpu, run on a B200): every check calls the CUDA path through the C ABI
+(libnsb.so via the ctypes binding) and compares it with
+  * the golden vectors of oracle/_ref (the reference's own Renderer.cpp + utils.h), tests/golden/*.npz,
+  * the oracle restatement (oracle/nice_oracle.py) evaluated live on the same seeded inputs,
+  * size-independent properties at the BASELINE.json batch size (5000 rays x 48 samples).
+
+Tolerances (BASELINE.json north_star): pixel indices, rays and sample placement (z values) bit-exact;
+rgb / depth / var / weights within 1e-4 relative (max-norm); grid / decoder / pose gradients within 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+import nice_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4
+GRAD_TOL = 1e-3
+CAM = dict(H=480, W=640, fx=360.0, fy=360.0, cx=320.0, cy=240.0)
+
+
+@pytest.fixture(scope="module")
+def engine_factory(nsb, model_inputs, frames):
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    made = []
+
+    def make(t_samples=None, t_surface=None, **kw):
+        cfg = nsb.default_config()
+        cfg.max_rays = kw.pop("max_rays", 8192)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        e = nsb.Engine(cfg)
+        e.set_model(grids, decs)
+        if t_samples is None:
+            tt, ts = O.t_tables()
+            t_samples, t_surface = tt.numpy(), ts.numpy()
+        e.set_ttables(t_samples, t_surface)
+        for f in range(5):
+            e.set_frame(f, depths[f], colors[f], poses[f])
+        made.append(e)
+        return e
+
+    yield make
+    for e in made:
+        e.close()
+
+
+def filtered_rays(syn, frames, n, seed, f=0):
+    depths, colors, poses = frames
+    idx = syn.mt19937_indices(seed, n, CAM["H"] * CAM["W"])
+    ro, rd, gd, gc = O.ray_sampler(0, CAM["H"], 0, CAM["W"], idx, CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"],
+                                   torch.tensor(depths[f]), torch.tensor(colors[f]), torch.tensor(poses[f]), "reference")
+    m = O.inside_mask(ro, rd, gd, torch.tensor(O.BOUND)).numpy()
+    return ro.numpy()[m], rd.numpy()[m], gd.numpy()[m], gc.numpy()[m]
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+def test_get_samples_bit_exact_vs_reference(engine_factory, frames):
+    """get_samples / raySampler (utils.h:13-55,141-146) against oracle/_ref's output: indices, rays, gt gathers."""
+    g = load_golden("sampling.npz")
+    e = engine_factory()
+    ro, rd, gd, gc, ins, idx = e.get_samples(int(g["frame"]), int(g["H0"]), int(g["H1"]), int(g["W0"]), int(g["W1"]), 256, idx=g["idx"])
+    assert np.array_equal(ro, g["rays_o"]) and np.array_equal(rd, g["rays_d"])
+    assert np.array_equal(gd, g["gt_depth"]) and np.array_equal(gc, g["gt_color"])
+    want = O.inside_mask(torch.tensor(g["rays_o"]), torch.tensor(g["rays_d"]), torch.tensor(g["gt_depth"]), torch.tensor(O.BOUND)).numpy()
+    assert np.array_equal(ins, want)                                     # Mapper.cpp:416-427
+    e.seed(int(g["seed"]))                                               # utils.h:32: the library's own mt19937 stream
+    *_, idx2 = e.get_samples(int(g["frame"]), int(g["H0"]), int(g["H1"]), int(g["W0"]), int(g["W1"]), 256)
+    assert np.array_equal(idx2, g["idx"])
+
+
+def test_get_samples_pinhole_mode(engine_factory, frames, syn, nsb):
+    e = engine_factory(raydir=1)
+    depths, colors, poses = frames
+    idx = syn.mt19937_indices(5, 512, 440 * 600)
+    ro, rd, gd, gc, ins, _ = e.get_samples(3, 20, 460, 20, 620, 512, idx=idx)
+    a, b, c_, d = O.ray_sampler(20, 460, 20, 620, idx, 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[3]), torch.tensor(colors[3]), torch.tensor(poses[3]), "pinhole")
+    assert np.array_equal(rd, b.numpy()) and np.array_equal(ro, a.numpy()) and np.array_equal(gd, c_.numpy())
+
+
+# ------------------------------------------------------------------------------------------------- forward
+def test_render_forward_vs_reference_golden(engine_factory):
+    """Renderer::render_batch_ray (Renderer.cpp:44-125) against oracle/_ref: all stages + no-depth path."""
+    g = load_golden("render_forward.npz")
+    e = engine_factory(g["t_samples"], g["t_surface"])
+    for st in ("color", "fine", "middle", "coarse"):
+        o = e.render_batch_ray(g["rays_d"], g["rays_o"], st, g["gt_depth"])
+        for nm, x in zip(("rgb", "depth", "var", "weights"), o):
+            assert relerr(x, g["%s_%s" % (st, nm)]) < FWD_TOL, (st, nm)
+    o = e.render_batch_ray(g["rays_d"], g["rays_o"], "coarse", None)
+    for nm, x in zip(("rgb", "depth", "var", "weights"), o):
+        assert relerr(x, g["nodepth_coarse_%s" % nm]) < FWD_TOL, nm
+    for st in ("color", "coarse"):                                       # Renderer::eval_points (Renderer.cpp:19-42)
+        raw = e.eval_points(g["pts"], st)
+        ref = g["eval_%s" % st]
+        assert np.abs(raw - ref).max() < FWD_TOL * np.abs(ref[:, :3]).max() + 1e-4, st
+        assert np.array_equal(raw[:, 3] == 100.0, ref[:, 3] == 100.0)    # out-of-bound mask, Renderer.cpp:26-36
+
+
+def test_render_forward_vs_verbatim_reference(engine_factory):
+    """dist_norm = REFERENCE reproduces the UNPATCHED reference binary (utils.h:153 literal p=-1 norm)."""
+    g = load_golden("render_forward.npz")
+    e = engine_factory(g["t_samples"], g["t_surface"], dist_norm=1)
+    o = e.render_batch_ray(g["rays_d"], g["rays_o"], "color", g["gt_depth"])
+    for nm, x in zip(("rgb", "depth", "var", "weights"), o):
+        ref = g["verbatim_%s" % nm]
+        assert np.abs(x - ref).max() < FWD_TOL * max(1.0, np.abs(ref).max()), nm
+
+
+def test_sample_placement_bit_exact(engine_factory, frames, syn):
+    """z values of Renderer.cpp:61-119 (stratified + near-surface + sort), incl. zero-depth rays, vs the oracle."""
+    e = engine_factory()
+    ro, rd, gd, gc = filtered_rays(syn, frames, 1500, 13, f=2)
+    assert (gd == 0).sum() > 0
+    e.render_batch_ray(rd, ro, "middle", gd, want_weights=False)
+    z = e.last_zvals(rd.shape[0])
+    tt, ts = O.t_tables()
+    zo = O.z_values(torch.tensor(ro), torch.tensor(rd), torch.tensor(gd), torch.tensor(O.BOUND), tt, ts).numpy()
+    assert np.array_equal(z, zo)
+    assert np.all(np.diff(z, axis=1) >= 0)
+
+
+def test_render_forward_vs_oracle_live(engine_factory, frames, syn, model_inputs):
+    grids, decs, _ = model_inputs
+    e = engine_factory()
+    m = O.Model(grids, decs)
+    ro, rd, gd, gc = filtered_rays(syn, frames, 700, 3, f=4)
+    with torch.no_grad():
+        ref = O.render_batch_ray(m, torch.tensor(rd), torch.tensor(ro), "color", torch.tensor(gd))
+    got = e.render_batch_ray(rd, ro, "color", gd)
+    for nm, x, y in zip(("rgb", "depth", "var", "weights"), got, ref):
+        assert relerr(x, y.numpy()) < FWD_TOL, nm
+
+
+def test_occupancy_branch(engine_factory, frames, syn, model_inputs):
+    """Upstream's occupancy branch alpha = sigmoid(10 raw), behind the flag."""
+    grids, decs, _ = model_inputs
+    e = engine_factory(occupancy=1)
+    m = O.Model(grids, decs)
+    ro, rd, gd, gc = filtered_rays(syn, frames, 200, 4)
+    with torch.no_grad():
+        ref = O.render_batch_ray(m, torch.tensor(rd), torch.tensor(ro), "color", torch.tensor(gd), occupancy=True)
+    got = e.render_batch_ray(rd, ro, "color", gd)
+    for nm, x, y in zip(("rgb", "depth", "var", "weights"), got, ref):
+        assert relerr(x, y.numpy()) < 5e-4, nm   # sigmoid(10 x) amplifies the fp32 noise of raw tenfold
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def test_render_vjp_vs_reference_golden(engine_factory, nsb):
+    """loss.backward() through render_batch_ray against oracle/_ref's libtorch autograd."""
+    g = load_golden("render_vjp.npz")
+    e = engine_factory(g["t_samples"], g["t_surface"])
+    got = e.render_vjp(g["rays_d"], g["rays_o"], "color", g["gt_depth"], g["g_rgb"], g["g_depth"], g["g_var"])
+    assert relerr(got["rays_o"], g["d_rays_o"]) < GRAD_TOL and relerr(got["rays_d"], g["d_rays_d"]) < GRAD_TOL
+    assert relerr(got["dec_color"], g["d_dec_color"]) < GRAD_TOL
+    for lv in ("middle", "fine", "color"):
+        full = got["grid_" + lv]
+        assert np.abs(full.reshape(-1)[g["grid_%s_pos" % lv]] - g["grid_%s_val" % lv]).max() < GRAD_TOL * float(g["grid_%s_max" % lv]), lv
+        l2 = np.sqrt((full.astype(np.float64) ** 2).sum())
+        assert abs(l2 - float(g["grid_%s_l2" % lv])) < GRAD_TOL * float(g["grid_%s_l2" % lv]), lv   # nothing scattered elsewhere
+    for flags in (nsb.F_GRID, nsb.F_RAY, nsb.F_GRID | nsb.F_WGRAD, nsb.F_GRID | nsb.F_RAY):   # the other kernel instantiations
+        part = e.render_vjp(g["rays_d"], g["rays_o"], "color", g["gt_depth"], g["g_rgb"], g["g_depth"], g["g_var"], flags=flags)
+        if flags & nsb.F_GRID:
+            assert relerr(part["grid_fine"], got["grid_fine"]) < 1e-5
+        if flags & nsb.F_RAY:
+            assert relerr(part["rays_d"], got["rays_d"]) < 1e-5
+        if flags & nsb.F_WGRAD:
+            assert relerr(part["dec_color"], got["dec_color"]) < 1e-5
+
+
+def test_render_vjp_middle_and_fine_stage(engine_factory, frames, syn, model_inputs):
+    grids, decs, _ = model_inputs
+    e = engine_factory()
+    ro, rd, gd, gc = filtered_rays(syn, frames, 150, 8)
+    n = ro.shape[0]
+    rs = np.random.RandomState(2)
+    g_rgb = np.zeros((n, 3), np.float32); g_depth = rs.randn(n).astype(np.float32); g_var = (0.2 * rs.randn(n)).astype(np.float32)
+    for stage in ("middle", "fine"):
+        m = O.Model(grids, decs)
+        for k in ("middle", "fine"):
+            m.grids[k].requires_grad_(True)
+        tro = torch.tensor(ro, requires_grad=True); trd = torch.tensor(rd, requires_grad=True)
+        rgb, depth, var, _ = O.render_batch_ray(m, trd, tro, stage, torch.tensor(gd))
+        ((depth * torch.tensor(g_depth)).sum() + (var * torch.tensor(g_var)).sum()).backward()
+        got = e.render_vjp(rd, ro, stage, gd, g_rgb, g_depth, g_var, flags=1 | 4)
+        assert relerr(got["grid_middle"], m.grids["middle"].grad.numpy()) < GRAD_TOL
+        if stage == "fine":
+            assert relerr(got["grid_fine"], m.grids["fine"].grad.numpy()) < GRAD_TOL
+        else:
+            assert np.abs(got["grid_fine"]).max() == 0.0
+        assert relerr(got["rays_o"], tro.grad.numpy()) < GRAD_TOL and relerr(got["rays_d"], trd.grad.numpy()) < GRAD_TOL
+
+
+# --------------------------------------------------------------------------------- mapping / tracking loops
+def test_mapping_iterations_vs_reference(engine_factory, frames, syn, model_inputs):
+    """Mapper.cpp:330-465: sampling stream, inside filter, render, loss, backward, fused Adam -- four iterations
+    (two geometry, two colour) against oracle/_ref's libtorch autograd + torch::optim::Adam."""
+    grids, decs, _ = model_inputs
+    g = load_golden("mapping_iters.npz")
+    e = engine_factory(g["t_samples"], g["t_surface"], mapping_pixels=int(g["pixels"]), frustum_feature_selection=0)
+    it_of = {1: 0, 3: 59}          # iteration numbers of a 60-iteration schedule that select these stages
+    e.seed(int(g["seed"]))
+    e.mapping_begin(list(range(int(g["n_frames"]))), 60, 1.0)
+    losses = [e.mapping_iter(it_of[int(s)]) for s in g["stages"]]
+    assert np.allclose(losses, g["losses"], rtol=1e-3), (losses, g["losses"])
+    dec = e.get_decoder("color")
+    moved = np.abs(g["dec_color"] - decs["color"]).max()
+    assert moved > 1e-3 and np.abs(dec - g["dec_color"]).max() < 2e-2 * moved
+    for lv in ("middle", "fine", "color"):
+        pos = g["grid_%s_pos" % lv]
+        got = e.get_grid(lv).reshape(-1)[pos]; ref = g["grid_%s_val" % lv]; init = grids[lv].reshape(-1)[pos]
+        move_rms = np.sqrt(((ref - init) ** 2).mean())
+        # Adam normalises by sqrt(v): voxels whose gradient is at the fp32 noise level take +-lr steps of random
+        # sign in ANY implementation, so the comparison is in RMS relative to the RMS update
+        assert move_rms > 0 and np.sqrt(((got - ref) ** 2).mean()) < 5e-2 * move_rms, lv
+
+
+def test_tracking_iterations_vs_reference(engine_factory):
+    """Tracker.cpp:41-113: pose -> rays -> render -> median mask -> loss -> pose gradient -> Adam on 7 floats."""
+    t = load_golden("tracking_iters.npz")
+    e = engine_factory(t["t_samples"], t["t_surface"], tracking_pixels=int(t["pixels"]), tracking_lr=float(t["lr"]))
+    e.seed(int(t["seed"]))
+    e.tracking_begin(0, t["cam7_in"])
+    losses, g0 = [], None
+    for i in range(3):
+        l, g = e.tracking_iter()
+        losses.append(l)
+        if i == 0:
+            g0 = g
+    assert np.allclose(losses, t["losses"], rtol=1e-3)
+    assert relerr(g0, t["grad_first"]) < GRAD_TOL
+    assert np.abs(e.tracking_camera() - t["cam7_out"]).max() < 1e-5
+
+
+# ------------------------------------------------------------------ properties at the BASELINE.json batch size
+def test_full_size_properties(engine_factory, frames, syn, nsb):
+    e = engine_factory(max_rays=4096)      # 5000 rays > max_rays: also exercises the chunked render path
+    ro, rd, gd, gc = filtered_rays(syn, frames, 5700, 77, f=1)
+    ro, rd, gd = ro[:5000], rd[:5000], gd[:5000]
+    assert ro.shape[0] == 5000
+    rgb, depth, var, w = e.render_batch_ray(rd, ro, "color", gd)
+    z = None
+    assert np.all(np.isfinite(rgb)) and np.all(np.isfinite(depth)) and np.all(var >= -1e-6)
+    assert np.all(w >= 0) and np.all(w.sum(1) <= 1 + 1e-5)
+    # determinism and permutation equivariance (the batch statistics max(gt_depth) are order independent)
+    rgb2, depth2, var2, w2 = e.render_batch_ray(rd, ro, "color", gd)
+    assert np.array_equal(depth, depth2) and np.array_equal(w, w2)
+    perm = np.random.RandomState(0).permutation(5000)
+    rgb3, depth3, var3, w3 = e.render_batch_ray(rd[perm], ro[perm], "color", gd[perm])
+    assert np.array_equal(depth3, depth[perm]) and np.array_equal(rgb3, rgb[perm])
+    # one call == two half calls when the halves share the batch maximum
+    big = engine_factory(max_rays=8192)
+    rgb4, depth4, _, _ = big.render_batch_ray(rd, ro, "color", gd)
+    assert np.array_equal(depth4, depth) and np.array_equal(rgb4, rgb)
+    # linearity of the vjp in the cotangent, and zero cotangent -> zero gradient
+    rs = np.random.RandomState(1)
+    g_rgb = rs.randn(5000, 3).astype(np.float32); g_depth = rs.randn(5000).astype(np.float32); g_var = np.zeros(5000, np.float32)
+    g1 = big.render_vjp(rd, ro, "color", gd, g_rgb, g_depth, g_var)
+    g2 = big.render_vjp(rd, ro, "color", gd, 2 * g_rgb, 2 * g_depth, g_var)
+    for k in ("grid_middle", "grid_fine", "grid_color", "dec_color", "rays_o"):
+        assert relerr(g2[k], 2 * g1[k]) < 1e-4, k
+    g0 = big.render_vjp(rd, ro, "color", gd, 0 * g_rgb, 0 * g_depth, g_var)
+    assert all(np.abs(g0[k]).max() == 0.0 for k in ("grid_middle", "grid_fine", "grid_color", "dec_color"))
+
+
+def test_voxel_mask_limits_adam(engine_factory, model_inputs):
+    """frustum_feature_selection intent (Mapper.cpp:260-290,333-350): only masked voxels are optimised."""
+    grids, decs, _ = model_inputs
+    e = engine_factory(mapping_pixels=1000)
+    masks = {}
+    rs = np.random.RandomState(0)
+    for lv in ("middle", "fine", "color"):
+        masks[lv] = (rs.uniform(size=grids[lv].shape[2:]) < 0.5).astype(np.uint8)
+        e.set_voxel_mask(lv, masks[lv])
+    e.seed(1)
+    e.mapping_begin([0, 1], 60, 1.0)
+    for it in (0, 59):
+        e.mapping_iter(it)
+    for lv in ("middle", "fine", "color"):
+        d = np.abs(e.get_grid(lv) - grids[lv]).max(axis=(0, 1))
+        assert d[masks[lv] == 0].max() == 0.0 and d[masks[lv] == 1].max() > 0.0

@@ -1,0 +1,92 @@
+// Microbenchmarks that calibrate the roofline denominators MEASURED_PEAKS.json does not carry:
+//   * mma.sync m16n8k8 tf32 issue rate (the legacy warp-level tensor path the decoders use),
+//   * L2-resident gather bandwidth for 128-byte voxel lines (the grids are 11.2 MB, far below the 126 MB L2),
+//   * fp32 vector-reduction (red.global.add.v4.f32) throughput into an L2-resident buffer.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+
+__global__ void k_mma(float* out, int iters) {
+    float d[8][4];
+    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 7, b1 = a0 * 5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0; for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    if (s == 12345.f) out[0] = s;
+}
+
+__global__ void k_gather(const float4* __restrict__ buf, uint32_t nlines, float* out, int iters) {
+    // each quad (4 lanes x 2 float4) reads one random 128-byte line per step, like the trilinear corner fetch
+    uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, t = threadIdx.x & 3;
+    uint32_t s = quad * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t line = (s >> 8) % nlines;
+            const float4 v0 = __ldg(buf + line * 8 + 2 * t), v1 = __ldg(buf + line * 8 + 2 * t + 1);
+            acc += v0.x + v0.w + v1.y + v1.z;
+        }
+    }
+    if (acc == 12345.f) out[0] = acc;
+}
+
+__global__ void k_red(float* buf, uint32_t nlines, int iters) {
+    uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, t = threadIdx.x & 3;
+    uint32_t s = quad * 2654435761u + 777u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t line = (s >> 8) % nlines;
+            float* a = buf + line * 32 + 8 * t;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(a), "f"(1.0f) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(a + 4), "f"(1.0f) : "memory");
+        }
+    }
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz\": %d", p.name, p.multiProcessorCount, clk / 1000);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float* out; cudaMalloc(&out, 64);
+    float ms;
+    for (int warps : {4, 8, 16, 32}) {
+        const int iters = 20000, grid = p.multiProcessorCount;
+        k_mma<<<grid, warps * 32>>>(out, 100);
+        cudaEventRecord(e0); k_mma<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 16 * 8 * 8 * 8.0 * iters * warps * grid;
+        printf(", \"mma_tf32_tflops_w%d\": %.1f", warps, flop / ms * 1e-9);
+    }
+    const uint32_t nlines = 11 * 1024 * 1024 / 128;
+    float4* buf; cudaMalloc(&buf, (size_t)nlines * 128); cudaMemset(buf, 0, (size_t)nlines * 128);
+    for (int occ : {2, 4, 8}) {
+        const int grid = p.multiProcessorCount * occ, iters = 200;
+        k_gather<<<grid, 256>>>(buf, nlines, out, 10);
+        cudaEventRecord(e0); k_gather<<<grid, 256>>>(buf, nlines, out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 128.0 * 8 * iters * (double)grid * 256 / 4;
+        printf(", \"l2_gather_gbs_occ%d\": %.0f", occ, bytes / ms * 1e-6);
+    }
+    for (int occ : {2, 8}) {
+        const int grid = p.multiProcessorCount * occ, iters = 50;
+        k_red<<<grid, 256>>>((float*)buf, nlines, 5);
+        cudaEventRecord(e0); k_red<<<grid, 256>>>((float*)buf, nlines, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 128.0 * 8 * iters * (double)grid * 256 / 4;
+        printf(", \"l2_redv4_gbs_occ%d\": %.0f", occ, bytes / ms * 1e-6);
+    }
+    printf(", \"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
