@@ -105,6 +105,7 @@ struct nsb_ctx {
     float* stats = nullptr;       // [LOSS_RING][4]: max gt depth, n inside, sum 1/|d|, loss
     float* median = nullptr; int* count = nullptr;
     float* stash = nullptr; size_t stash_rows = 0;
+    uint32_t* masks = nullptr;   // relu masks of the last training forward
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
     int last_n = 0, last_S = 0;
     // host RNG (std::mt19937 == the CPU generator torch::randint uses, utils.h:32)
@@ -350,6 +351,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->o_rgb, 3 * (size_t)cap)); CK(dalloc(&ctx->o_depth, cap)); CK(dalloc(&ctx->o_var, cap)); CK(dalloc(&ctx->o_w, PS));
     CK(dalloc(&ctx->g_rgb, 3 * (size_t)cap)); CK(dalloc(&ctx->g_depth, cap)); CK(dalloc(&ctx->g_var, cap)); CK(dalloc(&ctx->d_rays, 6 * (size_t)cap));
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
+    CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
@@ -364,7 +366,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
-                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->scratch_ncdhw,
+                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->scratch_ncdhw,
                     c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -493,7 +495,7 @@ static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, cons
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
     P.S = S; P.P = n * S;
     P.out_rgb = ctx->raw_rgb; P.out_occ[0] = ctx->occ[0]; P.out_occ[1] = ctx->occ[1]; P.out_occ[2] = ctx->occ[2];
-    P.g_raw = ctx->g_raw; P.d_rays = ctx->d_rays; P.stash = ctx->stash;
+    P.g_raw = ctx->g_raw; P.d_rays = ctx->d_rays; P.stash = nullptr; P.masks = nullptr;
 }
 
 static int decode_grid_size(nsb_ctx* ctx, int P) {
@@ -513,7 +515,18 @@ static void stage_decoders(int stage, float w[4]) {
 
 // rays (ctx->rays_*, ctx->gt_depth or null, ctx->valid or null) -> z, raw, composite outputs in ctx buffers.
 // `off`/`n` select the slice of the ray batch this rank renders (ranks share the batch-global statistics).
-static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, bool want_weights) {
+static int ensure_stash(nsb_ctx* ctx, size_t rows) {
+    if (ctx->stash_rows >= rows) return 0;
+    if (ctx->stash) cudaFree(ctx->stash);
+    ctx->stash = nullptr; ctx->stash_rows = 0;
+    CK(dalloc(&ctx->stash, rows * stash::W + 64));
+    ctx->stash_rows = rows;
+    return 0;
+}
+
+// train: keep the relu masks for run_backward; stash_fwd: also write the colour decoder's activations to the wgrad stash.
+static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, bool want_weights,
+                       bool train = false, bool stash_fwd = false) {
     const nsb_config& c = ctx->cfg;
     const int S = have_depth ? c.n_samples + c.n_surface : c.n_samples;
     ctx->last_n = n; ctx->last_S = S;
@@ -530,6 +543,8 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
+        if (train) P.masks = ctx->masks;
+        if (train && stash_fwd && stage == NSB_COLOR) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
         float w[4]; stage_decoders(stage, w); env_weights("NSB_SPLIT_FWD", w);
         const int grid = decode_grid_size(ctx, n * S);
         partition(grid, w, P.cta_begin);
@@ -564,27 +579,19 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         CK(cudaGetLastError());
     }
     const bool wg = (flags & 2) && stage == NSB_COLOR && color_active;
-    if (wg) {
-        const size_t rows = (size_t)n * S;
-        if (ctx->stash_rows < rows) {
-            if (ctx->stash) cudaFree(ctx->stash);
-            ctx->stash = nullptr; ctx->stash_rows = 0;
-            CK(dalloc(&ctx->stash, rows * stash::W + 64));
-            ctx->stash_rows = rows;
-        }
-    }
+    if (wg && ctx->stash_rows < (size_t)n * S) return fail(ctx, "wgrad stash missing: the forward must run with stash_fwd");
     {
         Timer t(ctx, T_BWD);
         DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S; P.g_raw += 4 * (size_t)off * S; P.d_rays += 6 * (size_t)off;
-        P.stash = ctx->stash;
+        P.stash = ctx->stash; P.masks = ctx->masks;
         P.flags = (flags & 1) | (wg ? 2 : 0) | (flags & 4);
         if (P.flags == 0) return 0;
         float w[4] = {0, 0, 0, 0};
         const float ge = (flags & 4) ? 288.f : 0.f;
-        if (stage == NSB_MIDDLE) w[1] = 1164 + ge;
-        else if (stage == NSB_FINE) { w[1] = 1164 + ge; w[2] = 1404 + ge; }
-        else if (stage == NSB_COLOR) { w[1] = 1164 + ge; w[2] = 1404 + ge; if (color_active) w[3] = 1164 + (wg ? 288.f + 400.f : ge); }
+        if (stage == NSB_MIDDLE) w[1] = 480 + ge;
+        else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
+        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); }
         else return fail(ctx, "backward through the coarse stage is not implemented");
         env_weights("NSB_SPLIT_BWD", w);
         const int grid = decode_grid_size(ctx, n * S);
@@ -744,7 +751,7 @@ extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_
     if (upload_rays(ctx, n, rays_d, rays_o, gt_depth)) return -1;
     if (render_prepare_stats(ctx, n, hd)) return -1;
     if (zero_grads(ctx)) return -1;
-    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, false)) return -1;
+    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, false, true, (flags & 2) != 0)) return -1;
     CK(cudaMemcpyAsync(ctx->g_rgb, g_rgb, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->g_depth, g_depth, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->g_var, g_var, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -804,13 +811,7 @@ extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, i
     CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     if (!ctx->cfg.fix_color) {   // make sure the stash exists before the hot loop
-        const size_t rows = (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64;
-        if (ctx->stash_rows < rows) {
-            if (ctx->stash) cudaFree(ctx->stash);
-            ctx->stash = nullptr; ctx->stash_rows = 0;
-            CK(dalloc(&ctx->stash, rows * stash::W + 64));
-            ctx->stash_rows = rows;
-        }
+        if (ensure_stash(ctx, (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64)) return -1;
     }
     return 0;
 }
@@ -844,7 +845,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     const int per = cdiv(cdiv(n, ctx->world), 1), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
     const bool use_color = stage == NSB_COLOR;
     if (nl > 0) {
-        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false)) return -1;   // render is always called with "color" (Mapper.cpp:430)
+        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false, true, use_color && !c.fix_color)) return -1;   // render is always called with "color" (Mapper.cpp:430)
         {
             Timer t(ctx, T_COMP);
             LossParams L; memset(&L, 0, sizeof L);
@@ -945,7 +946,7 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
         if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
         CK(cudaGetLastError());
     }
-    if (run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false)) return -1;   // Tracker.cpp:61
+    if (run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false, true, false)) return -1;   // Tracker.cpp:61
     {
         Timer t(ctx, T_COMP);
         LossParams L; memset(&L, 0, sizeof L);

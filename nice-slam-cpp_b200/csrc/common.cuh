@@ -24,14 +24,14 @@ struct GridView {
 };
 
 // ---- tensor-core helpers: mma.sync m16n8k8 tf32, optional 3xTF32 split (fp32-grade accuracy) ------------
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// fp32 -> tf32 with round-to-nearest (ties away), as two integer ops: on sm_100a `cvt.rna.tf32.f32` expands to a
+// ~5-instruction FSETP/SEL/LOP3 sequence (NaN/Inf handling) that dominated the issue slots of the MMA loops.
+// The tensor core reads only the upper 19 bits of a tf32 operand, so the low part of the split is passed as raw
+// fp32 bits (truncation of an already 2^-11-scaled residual: ~2^-22 relative).
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = f2tf32(x);
-    lo = f2tf32(x - __uint_as_float(hi));
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {

@@ -1,5 +1,5 @@
-// Backward decoder kernel: recomputes the decoder forward for each 16-sample tile (only relu bit masks are
-// kept), then back-propagates the raw cotangent through the MLP on tensor cores, scatters the grid-feature
+// Backward decoder kernel: reads the relu bit masks the training forward saved for each 16-sample tile (no
+// forward recomputation), back-propagates the raw cotangent through the MLP on tensor cores, scatters the grid-feature
 // gradient with 128-bit vector reductions into the channel-last gradient grids, accumulates the ray (pose)
 // gradient, and -- for the colour decoder when its weights are being optimised -- stashes the per-layer
 // activations / gradients for the split-K weight-gradient kernel (wgrad.cu).
@@ -12,6 +12,10 @@
 namespace nsb {
 
 enum { F_GRID = 1, F_WGRAD = 2, F_RAY = 4 };
+
+#ifndef NSB_BWD_MIN_CTAS
+#define NSB_BWD_MIN_CTAS 2   // cap at 128 registers/thread so that two CTAs (16 warps) share an SM
+#endif
 
 __device__ __forceinline__ void zero_tile(float (&a)[4][4]) {
 #pragma unroll
@@ -202,19 +206,16 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
     }
     if (!WG && !__any_sync(0xffffffffu, any)) return;   // nothing flows into this tile
 
-    float c[2][C / 4];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        gather8(P.grid[dec], P.bnd, p[r], t, c[r]);
-        if (C == 64) gather8(P.grid[1], P.bnd, p[r], t, c[r] + 8);
+    // relu masks saved by the training forward (k_decode_fwd<.., TRAIN>): the data gradient needs nothing else
+    uint32_t masks[5];
+    {
+        const uint32_t* mb = P.masks + ((size_t)(dec - 1) * (P.P / TILE) + base / TILE) * 96 + lane;
+        const uint32_t m01 = mb[0], m23 = mb[32];
+        masks[0] = m01 & 0xffffu; masks[1] = m01 >> 16; masks[2] = m23 & 0xffffu; masks[3] = m23 >> 16; masks[4] = mb[64];
     }
     float* st0 = nullptr; float* st1 = nullptr;
-    if (WG) {
+    if (WG) {   // E / H / Cc columns of the stash rows were written by the forward; add the gradient side
         st0 = P.stash + (size_t)sidx[0] * stash::W; st1 = P.stash + (size_t)sidx[1] * stash::W;
-        *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t) = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
-        *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t + 4) = make_float4(c[0][4], c[0][5], c[0][6], c[0][7]);
-        *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t) = make_float4(c[1][0], c[1][1], c[1][2], c[1][3]);
-        *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t + 4) = make_float4(c[1][4], c[1][5], c[1][6], c[1][7]);
         if (t == 0) {
             *reinterpret_cast<float4*>(st0 + stash::GO) = make_float4(gout[0][0], gout[0][1], gout[0][2], 0.0f);
             *reinterpret_cast<float4*>(st1 + stash::GO) = make_float4(gout[1][0], gout[1][1], gout[1][2], 0.0f);
@@ -222,9 +223,6 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
             *reinterpret_cast<float4*>(st1 + stash::Pp) = make_float4(p[1][0], p[1][1], p[1][2], 1.0f);
         }
     }
-    float out[2][4], h[4][4]; uint32_t masks[5];
-    decoder_forward<C, O, P3, WG>(sm, p, c, g, t, out, masks, h, st0, st1);
-
     float gcf[2][8], gp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     decoder_backward<C, O, P3, GRID || RAY, RAY || WG, WG>(sm, p, g, t, gout, masks, gcf, gp, st0, st1);
     if (GRID || RAY) grid_backward<GRID, RAY>(P.grid[dec], P.bnd, p, gcf, t, gp);
@@ -248,7 +246,7 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
 }
 
 template <bool P3, bool GRID, bool RAY, bool WG>
-__global__ void __launch_bounds__(DECODE_THREADS) k_decode_bwd(const DecodeParams P) {
+__global__ void __launch_bounds__(DECODE_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd(const DecodeParams P) {
     extern __shared__ __align__(128) float sm[];
     int dec = 1;
 #pragma unroll

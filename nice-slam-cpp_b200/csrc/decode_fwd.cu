@@ -5,6 +5,10 @@
 
 namespace nsb {
 
+#ifndef NSB_FWD_MIN_CTAS
+#define NSB_FWD_MIN_CTAS 2   // 128 registers/thread: two CTAs (16 warps) per SM hide the gather and MMA latencies
+#endif
+
 // Positions of the thread's two samples (rows g and g+8 of the tile <-> samples base+2g, base+2g+1).
 // Returns false when the whole tile is to be skipped (ray dropped by the inside filter).
 __device__ __forceinline__ bool load_points(const DecodeParams& P, int base, int g, float (&p)[2][3], int (&sidx)[2]) {
@@ -31,8 +35,16 @@ __device__ __forceinline__ bool load_points(const DecodeParams& P, int base, int
     return true;
 }
 
-template <bool P3>
-__global__ void __launch_bounds__(DECODE_THREADS) k_decode_fwd(const DecodeParams P) {
+// Packed relu masks of one tile: 3 words per lane (layers 0|1, 2|3, 4), [decoder-1][tile][3][32 lanes].
+__device__ __forceinline__ void save_masks(const DecodeParams& P, int dec, int tile, int ntiles, int lane, const uint32_t (&m)[5]) {
+    uint32_t* mb = P.masks + ((size_t)(dec - 1) * ntiles + tile) * 96 + lane;
+    mb[0] = m[0] | (m[1] << 16); mb[32] = m[2] | (m[3] << 16); mb[64] = m[4];
+}
+
+// TRAIN: the launch is the forward half of a training step -- relu masks are kept for the backward kernel (which then
+// needs no forward recomputation) and, when P.stash is set, the colour decoder's activations go to the wgrad stash.
+template <bool P3, bool TRAIN>
+__global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(const DecodeParams P) {
     extern __shared__ __align__(128) float sm[];
     int dec = 0;
 #pragma unroll
@@ -63,12 +75,23 @@ __global__ void __launch_bounds__(DECODE_THREADS) k_decode_fwd(const DecodeParam
             gather8(P.grid[dec], P.bnd, p[1], t, c[1]);
             if (dec == 1) {
                 decoder_forward<32, 1, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+                if (TRAIN) save_masks(P, 1, tile, ntiles, lane, masks);
                 if (t == 0) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) if (sidx[r] < P.P) P.out_occ[1][sidx[r]] = out[r][0];
                 }
             } else {
-                decoder_forward<32, 4, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+                if (TRAIN && P.stash) {
+                    float* st0 = P.stash + (size_t)sidx[0] * stash::W; float* st1 = P.stash + (size_t)sidx[1] * stash::W;
+                    *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t) = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+                    *reinterpret_cast<float4*>(st0 + stash::Cc + 8 * t + 4) = make_float4(c[0][4], c[0][5], c[0][6], c[0][7]);
+                    *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t) = make_float4(c[1][0], c[1][1], c[1][2], c[1][3]);
+                    *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t + 4) = make_float4(c[1][4], c[1][5], c[1][6], c[1][7]);
+                    decoder_forward<32, 4, P3, TRAIN>(sm, p, c, g, t, out, masks, h, st0, st1);
+                } else {
+                    decoder_forward<32, 4, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+                }
+                if (TRAIN) save_masks(P, 3, tile, ntiles, lane, masks);
                 if (t == 0) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r)
@@ -83,6 +106,7 @@ __global__ void __launch_bounds__(DECODE_THREADS) k_decode_fwd(const DecodeParam
                 gather8(P.grid[1], P.bnd, p[r], t, c[r] + 8);      // ... cat middle features (MLP.cpp:79-84)
             }
             decoder_forward<64, 1, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+            if (TRAIN) save_masks(P, 2, tile, ntiles, lane, masks);
             if (t == 0) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) if (sidx[r] < P.P) P.out_occ[2][sidx[r]] = out[r][0];
@@ -93,28 +117,28 @@ __global__ void __launch_bounds__(DECODE_THREADS) k_decode_fwd(const DecodeParam
 
 size_t decode_fwd_smem() { return sizeof(float) * DecSmem<64>::TOTAL; }
 
-cudaError_t launch_decode_fwd(const DecodeParams& P, int precision, int grid, cudaStream_t st) {
+template <bool P3, bool TRAIN>
+static cudaError_t launch_fwd_one(const DecodeParams& P, int grid, cudaStream_t st) {
     const size_t smem = decode_fwd_smem();
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_decode_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_decode_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    if (precision == 0) k_decode_fwd<true><<<grid, DECODE_THREADS, smem, st>>>(P);
-    else k_decode_fwd<false><<<grid, DECODE_THREADS, smem, st>>>(P);
+    cudaError_t e = cudaFuncSetAttribute(k_decode_fwd<P3, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_decode_fwd<P3, TRAIN><<<grid, DECODE_THREADS, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+// P.masks != nullptr selects the training variant (relu masks saved, optional colour-decoder stash).
+cudaError_t launch_decode_fwd(const DecodeParams& P, int precision, int grid, cudaStream_t st) {
+    if (P.masks) return precision == 0 ? launch_fwd_one<true, true>(P, grid, st) : launch_fwd_one<false, true>(P, grid, st);
+    return precision == 0 ? launch_fwd_one<true, false>(P, grid, st) : launch_fwd_one<false, false>(P, grid, st);
 }
 
 int decode_fwd_occupancy(int precision) {
     int nb = 0;
     const size_t smem = decode_fwd_smem();
-    cudaFuncSetAttribute(k_decode_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_decode_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (precision == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<true>, DECODE_THREADS, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<false>, DECODE_THREADS, smem);
+    cudaFuncSetAttribute(k_decode_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_decode_fwd<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (precision == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<true, true>, DECODE_THREADS, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<false, true>, DECODE_THREADS, smem);
     return nb;
 }
 

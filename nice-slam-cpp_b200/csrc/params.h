@@ -30,6 +30,7 @@ struct DecodeParams {
     int flags;                     // bit0 grid grads, bit1 colour-decoder weight grads (stash), bit2 ray grads
     float* d_rays;                 // [N][6]: d L / d rays_o, d L / d rays_d (atomically accumulated)
     float* stash;                  // [P][STASH_W] colour-decoder activations / gradients for the wgrad kernel
+    uint32_t* masks;               // [3][P/16][3][32] packed relu masks written by the training forward, read by the backward
 };
 
 // Row layout of the colour-decoder weight-gradient stash (floats per sample).

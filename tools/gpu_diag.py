@@ -257,6 +257,9 @@ def check_timing(precision=0, pixels=5000):
 if __name__ == "__main__":
     rec("env", build=nsb.load_library(VARIANT).nsb_build_info().decode(), gpu=torch.cuda.get_device_name(0) if torch.cuda.is_available() else None,
         variant=VARIANT)
+    if "--timing-only" in sys.argv:
+        section(check_timing)
+        sys.exit(0)
     section(check_sampling)
     section(check_forward)
     section(check_reference_norm)
