@@ -21,7 +21,7 @@ BASE = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed
 
 UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("wgrad.cu", [])] + \
         [("decode_bwd_inst.cu", ["-DNSB_BWD_COMBO=%d" % k]) for k in range(6)]
-VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "occ1": ["-DNSB_FWD_MIN_CTAS=1", "-DNSB_BWD_MIN_CTAS=1"]}
+VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"]}
 
 
 def lib_path(variant=""):

@@ -68,6 +68,16 @@ __device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float
     }
 }
 
+// Same with a B operand that was split when the weights were staged (hi and lo planes in shared memory).
+template <bool P3>
+__device__ __forceinline__ void mma_acc_ps(float (&d)[4], const AFrag<P3>& a, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    if (P3) {
+        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], bh0, bh1);
+        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bl0, bl1);
+    }
+    mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bh0, bh1);
+}
+
 // Weight matrices W[out][in] live in shared memory with row stride ld (a multiple of 32 floats) and the
 // column index XOR-swizzled by the row:  col' = col ^ swz(row),  swz(row) = ((row ^ (row>>1)) & 3) << 3.
 // That makes BOTH access patterns bank-conflict free:
@@ -76,21 +86,29 @@ __device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float
 __host__ __device__ __forceinline__ int swz(int row) { return ((row ^ (row >> 1)) & 3) << 3; }
 
 // acc[j] += A(kk) * W[8j+g][8kk+2t..]^T for the NJ output tiles (forward: out = x W^T).
+// LO != 0: the matrix was staged pre-split, hi plane at W (tf32-rounded), lo plane at W + LO.
 template <bool P3, int NJ>
 __device__ __forceinline__ void kstep_fwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
-                                          int ld, int kk, int g, int t) {
+                                          int ld, int kk, int g, int t, int LO = 0) {
     const int col = (8 * kk + 2 * t) ^ swz(g);   // swz(8j+g) == swz(g)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const float2 w = *reinterpret_cast<const float2*>(W + (8 * j + g) * ld + col);
-        mma_acc<P3>(acc[j], a, w.x, w.y);
+        const float* wp = W + (8 * j + g) * ld + col;
+        const float2 w = *reinterpret_cast<const float2*>(wp);
+        if (LO) {
+            float2 wl = make_float2(0.f, 0.f);
+            if (P3) wl = *reinterpret_cast<const float2*>(wp + LO);
+            mma_acc_ps<P3>(acc[j], a, __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(wl.x), __float_as_uint(wl.y));
+        } else {
+            mma_acc<P3>(acc[j], a, w.x, w.y);
+        }
     }
 }
 
 // acc[j] += A(kk) * W[8kk+2t..][8(j0+j)+g] (backward data gradient: g_in = g_out W).
 template <bool P3, int NJ>
 __device__ __forceinline__ void kstep_bwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
-                                          int ld, int kk, int j0, int g, int t) {
+                                          int ld, int kk, int j0, int g, int t, int LO = 0) {
     const int r0 = 8 * kk + 2 * t, r1 = r0 + 1;
     const float* w0p = W + r0 * ld;
     const float* w1p = W + r1 * ld;
@@ -98,7 +116,14 @@ __device__ __forceinline__ void kstep_bwd(float (&acc)[NJ][4], const AFrag<P3>& 
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int c = 8 * (j0 + j) + g;
-        mma_acc<P3>(acc[j], a, w0p[c ^ s0], w1p[c ^ s1]);
+        if (LO) {
+            const uint32_t h0 = __float_as_uint(w0p[c ^ s0]), h1 = __float_as_uint(w1p[c ^ s1]);
+            uint32_t l0 = 0, l1 = 0;
+            if (P3) { l0 = __float_as_uint(w0p[(c ^ s0) + LO]); l1 = __float_as_uint(w1p[(c ^ s1) + LO]); }
+            mma_acc_ps<P3>(acc[j], a, h0, h1, l0, l1);
+        } else {
+            mma_acc<P3>(acc[j], a, w0p[c ^ s0], w1p[c ^ s1]);
+        }
     }
 }
 

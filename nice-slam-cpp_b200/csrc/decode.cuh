@@ -40,7 +40,11 @@ struct DecSmem {
     static constexpr int BIAS = WO + 4 * HID;           // b[5][32]
     static constexpr int BIASC = BIAS + 5 * HID;        // bc[5][32]
     static constexpr int BO = BIASC + 5 * HID;          // bo[4]
-    static constexpr int TOTAL = BO + 4;
+    static constexpr int HI_END = BO + 4;
+    // the MMA weight matrices [W0, WO) are staged pre-split for the 3xTF32 product: tf32-rounded hi plane in place,
+    // residual lo plane LO floats further (saves 6 ALU instructions per B fragment in the MMA loops)
+    static constexpr int LO = HI_END - W0;
+    static constexpr int TOTAL = HI_END + (WO - W0);
     __host__ __device__ static constexpr int w(int i) { return i == 0 ? W0 : i == 1 ? W1 : i == 2 ? W2 : i == 3 ? W3H : W4; }
 };
 
@@ -49,6 +53,12 @@ struct DecSmem {
 __host__ __device__ __forceinline__ int fc_channel(int ip) {
     const int blk = ip >> 5, i = ip & 31;
     return 32 * blk + 8 * ((i >> 1) & 3) + 2 * (i >> 3) + (i & 1);
+}
+
+__device__ __forceinline__ void put_split(float* sm, int idx, int lo_delta, float v) {
+    const float hi = __uint_as_float(f2tf32(v));
+    sm[idx] = hi;
+    sm[idx + lo_delta] = v - hi;
 }
 
 template <int C, int O>
@@ -61,19 +71,19 @@ __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid
     }
     for (int i = tid; i < HID * EMBP; i += nthr) {
         const int o = i / EMBP, c = i % EMBP;
-        sm[L::W0 + o * EMBP + (c ^ swz(o))] = c < EMB ? flat[f.W[0] + o * EMB + c] : 0.0f;
-        sm[L::W3E + o * EMBP + (c ^ swz(o))] = c < EMB ? flat[f.W[3] + o * (EMB + HID) + c] : 0.0f;
+        put_split(sm, L::W0 + o * EMBP + (c ^ swz(o)), L::LO, c < EMB ? flat[f.W[0] + o * EMB + c] : 0.0f);
+        put_split(sm, L::W3E + o * EMBP + (c ^ swz(o)), L::LO, c < EMB ? flat[f.W[3] + o * (EMB + HID) + c] : 0.0f);
     }
     for (int i = tid; i < HID * HID; i += nthr) {
         const int o = i / HID, c = i % HID, d = o * HID + (c ^ swz(o));
-        sm[L::W1 + d] = flat[f.W[1] + i];
-        sm[L::W2 + d] = flat[f.W[2] + i];
-        sm[L::W4 + d] = flat[f.W[4] + i];
-        sm[L::W3H + d] = flat[f.W[3] + o * (EMB + HID) + EMB + c];
+        put_split(sm, L::W1 + d, L::LO, flat[f.W[1] + i]);
+        put_split(sm, L::W2 + d, L::LO, flat[f.W[2] + i]);
+        put_split(sm, L::W4 + d, L::LO, flat[f.W[4] + i]);
+        put_split(sm, L::W3H + d, L::LO, flat[f.W[3] + o * (EMB + HID) + EMB + c]);
     }
     for (int i = tid; i < 5 * HID * C; i += nthr) {
         const int l = i / (HID * C), o = (i / C) % HID, ip = i % C;
-        sm[L::FC + l * HID * C + o * C + (ip ^ swz(o))] = flat[f.Fc[l] + o * C + fc_channel(ip)];
+        put_split(sm, L::FC + l * HID * C + o * C + (ip ^ swz(o)), L::LO, flat[f.Fc[l] + o * C + fc_channel(ip)]);
     }
     for (int i = tid; i < 4 * HID; i += nthr) sm[L::WO + i] = (i / HID) < O ? flat[f.Wo + i] : 0.0f;
     for (int i = tid; i < 5 * HID; i += nthr) {
@@ -137,21 +147,26 @@ __device__ __forceinline__ void embed_layers(const float* __restrict__ sm, const
         }
         AFrag<P3> a;
         a.set(e00, e10, e01, e11);
-        kstep_fwd<P3, 4>(acc0, a, sm + L::W0, EMBP, kk, g, t);
-        kstep_fwd<P3, 4>(accS, a, sm + L::W3E, EMBP, kk, g, t);
+        kstep_fwd<P3, 4>(acc0, a, sm + L::W0, EMBP, kk, g, t, L::LO);
+        kstep_fwd<P3, 4>(accS, a, sm + L::W3E, EMBP, kk, g, t, L::LO);
     }
 }
 
-// h += c . Fc_l^T   (c in the gather layout: c[r][2kk], c[r][2kk+1] are the k-step kk elements)
+// h += c . Fc_l^T   (c in the gather layout: c[r][2kk], c[r][2kk+1] are the k-step kk elements).
+// For C == 32 the four A fragments of c are split once (ca) and reused by all five layers.
 template <int C, bool P3>
-__device__ __forceinline__ void add_cterm(const float* __restrict__ sm, int l, const float (&c)[2][C / 4], int g, int t,
-                                          float (&h)[4][4]) {
+__device__ __forceinline__ void add_cterm(const float* __restrict__ sm, int l, const float (&c)[2][C / 4], const AFrag<P3>* ca,
+                                          int g, int t, float (&h)[4][4]) {
     using L = DecSmem<C>;
 #pragma unroll
     for (int kk = 0; kk < C / 8; ++kk) {
-        AFrag<P3> a;
-        a.set(c[0][2 * kk], c[1][2 * kk], c[0][2 * kk + 1], c[1][2 * kk + 1]);
-        kstep_fwd<P3, 4>(h, a, sm + L::FC + l * HID * C, C, kk, g, t);
+        if (C == 32) {
+            kstep_fwd<P3, 4>(h, ca[kk], sm + L::FC + l * HID * C, C, kk, g, t, L::LO);
+        } else {
+            AFrag<P3> a;
+            a.set(c[0][2 * kk], c[1][2 * kk], c[0][2 * kk + 1], c[1][2 * kk + 1]);
+            kstep_fwd<P3, 4>(h, a, sm + L::FC + l * HID * C, C, kk, g, t, L::LO);
+        }
     }
 }
 
@@ -186,6 +201,11 @@ __device__ __forceinline__ void decoder_forward(const float* __restrict__ sm, co
                                                 uint32_t (&masks)[5], float (&h)[4][4], float* st0, float* st1) {
     using L = DecSmem<C>;
     float acc[4][4], accS[4][4];
+    AFrag<P3> ca[C == 32 ? 4 : 1];
+    if (C == 32) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ca[kk].set(c[0][2 * kk], c[1][2 * kk], c[0][2 * kk + 1], c[1][2 * kk + 1]);
+    }
     embed_layers<C, P3, STASH>(sm, p, g, t, acc, accS, st0, st1);
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -202,12 +222,12 @@ __device__ __forceinline__ void decoder_forward(const float* __restrict__ sm, co
             for (int kk = 0; kk < 4; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, h[kk]);
-                kstep_fwd<P3, 4>(acc, a, sm + L::w(i), HID, kk, g, t);
+                kstep_fwd<P3, 4>(acc, a, sm + L::w(i), HID, kk, g, t, L::LO);
             }
         }
         masks[i] = relu_mask(h, acc);
         add_bias(h, sm + L::BIASC + i * HID, t);
-        add_cterm<C, P3>(sm, i, c, g, t, h);
+        add_cterm<C, P3>(sm, i, c, ca, g, t, h);
         if (STASH) stash_tile(st0, st1, stash::H + HID * i, h, t);
     }
     constexpr int NO = O == 4 ? 3 : 1;   // the colour decoder's 4th output is overwritten (NICE.cpp:49)

@@ -14,7 +14,7 @@ namespace nsb {
 enum { F_GRID = 1, F_WGRAD = 2, F_RAY = 4 };
 
 #ifndef NSB_BWD_MIN_CTAS
-#define NSB_BWD_MIN_CTAS 2   // cap at 128 registers/thread so that two CTAs (16 warps) share an SM
+#define NSB_BWD_MIN_CTAS 1   // 512 threads x 128 registers: one CTA of 16 warps per SM
 #endif
 
 __device__ __forceinline__ void zero_tile(float (&a)[4][4]) {
@@ -111,7 +111,7 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             for (int kk = 0; kk < 4; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, gh[kk]);
-                kstep_bwd<P3, 4>(gc, a, sm + L::FC + i * HID * C, C, kk, 0, g, t);
+                kstep_bwd<P3, 4>(gc, a, sm + L::FC + i * HID * C, C, kk, 0, g, t, L::LO);
             }
         }
         apply_mask(gu, gh, masks[i]);
@@ -135,7 +135,7 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             for (int kk = 0; kk < 4; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, gu[kk]);
-                kstep_bwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, 0, g, t);
+                kstep_bwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, 0, g, t, L::LO);
             }
         }
     }
@@ -156,8 +156,8 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             float ge[1][4] = {{0.0f, 0.0f, 0.0f, 0.0f}};
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                kstep_bwd<P3, 1>(ge, a0[kk], sm + L::W0, EMBP, kk, je, g, t);
-                kstep_bwd<P3, 1>(ge, a3[kk], sm + L::W3E, EMBP, kk, je, g, t);
+                kstep_bwd<P3, 1>(ge, a0[kk], sm + L::W0, EMBP, kk, je, g, t, L::LO);
+                kstep_bwd<P3, 1>(ge, a3[kk], sm + L::W3E, EMBP, kk, je, g, t, L::LO);
             }
             const int f0 = 8 * je + 2 * t;
             const float2 B0 = *reinterpret_cast<const float2*>(sm + L::B + f0);

@@ -6,7 +6,7 @@
 namespace nsb {
 
 #ifndef NSB_FWD_MIN_CTAS
-#define NSB_FWD_MIN_CTAS 2   // 128 registers/thread: two CTAs (16 warps) per SM hide the gather and MMA latencies
+#define NSB_FWD_MIN_CTAS 1   // 512 threads x 128 registers = the whole register file: one CTA of 16 warps per SM
 #endif
 
 // Positions of the thread's two samples (rows g and g+8 of the tile <-> samples base+2g, base+2g+1).

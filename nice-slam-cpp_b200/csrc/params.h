@@ -4,7 +4,7 @@
 
 namespace nsb {
 
-constexpr int DECODE_WARPS = 8;
+constexpr int DECODE_WARPS = 16;   // one 512-thread CTA per SM: the pre-split weights of a decoder take 130-167 KB of shared memory
 constexpr int DECODE_THREADS = DECODE_WARPS * 32;
 
 // Which decoders a launch evaluates and how the grid is split between them.
