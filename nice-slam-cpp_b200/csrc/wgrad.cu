@@ -48,9 +48,24 @@ static WGTable build_table() {
 
 __constant__ WGTable c_wg;
 
+constexpr int WG_STAGES = 4;                       // cp.async ring depth (k-steps in flight)
+constexpr int WG_KROWS = 8;                        // samples per k-step (MMA k = 8)
+constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B tile of a row may read past it (values unused)
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// The CTA streams its sample range through a 4-stage shared-memory ring (one stage = the 8 stash rows of a k-step,
+// 22.8 KB, fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA
+// fragments come from conflict-free LDS.64 / LDS.128 (row stride 712 = 8 mod 32 floats).
 template <bool P3>
 __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
                                                          int P, int S, float* __restrict__ dflat) {
+    extern __shared__ __align__(128) float ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float acc[WG_GROUPS_PER_WARP][4][4];
 #pragma unroll
@@ -65,14 +80,29 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
         Lc[q] = on[q] ? c_wg.g[gi].L + 2 * g : 0;      // A rows g / g+8 <-> a0 + 2g, a0 + 2g + 1
         Rc[q] = on[q] ? c_wg.g[gi].R + 4 * g : 0;      // B col g of tile j <-> b0 + 4g + j
     }
-    const int nks = P / 8;
+    const int nks = P / WG_KROWS;
     const int per = (nks + gridDim.x - 1) / gridDim.x;
     const int k_lo = blockIdx.x * per, k_hi = min(nks, k_lo + per);
-    for (int ks = k_lo; ks < k_hi; ++ks) {
-        const int s0 = ks * 8;
-        if (valid && !valid[s0 / S]) continue;
-        const float* r0 = st + (size_t)(s0 + t) * stash::W;
-        const float* r1 = r0 + 4 * (size_t)stash::W;
+    const int n_my = max(0, k_hi - k_lo);
+    constexpr int CHUNKS = WG_KROWS * stash::W / 4;    // 16-byte chunks per stage
+    auto issue = [&](int i) {                          // fetch k-step k_lo + i into ring slot i % WG_STAGES
+        if (i < n_my) {
+            const float* src = st + (size_t)(k_lo + i) * WG_KROWS * stash::W;
+            float* dst = ring + (i % WG_STAGES) * WG_STAGE_FLOATS;
+            for (int c = threadIdx.x; c < CHUNKS; c += blockDim.x) cp_async16(dst + 4 * c, src + 4 * c);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < WG_STAGES - 1; ++i) issue(i);
+    for (int i = 0; i < n_my; ++i) {
+        cp_async_wait<WG_STAGES - 2>();                // stage i has landed (for this thread's copies) ...
+        __syncthreads();                               // ... and for everybody's; also: slot (i-1) % STAGES is free again
+        issue(i + WG_STAGES - 1);
+        const int s0 = (k_lo + i) * WG_KROWS;
+        if (valid && !valid[s0 / S]) continue;         // rows of rays dropped by the inside filter were never written
+        const float* r0 = ring + (i % WG_STAGES) * WG_STAGE_FLOATS + t * stash::W;
+        const float* r1 = r0 + 4 * stash::W;
 #pragma unroll
         for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
             if (!on[q]) continue;
@@ -88,6 +118,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
             mma_acc<P3>(acc[q][3], a, b_lo.w, b_hi.w);
         }
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
         if (!on[q]) continue;
@@ -108,10 +139,16 @@ cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, in
         const WGTable T = build_table();
         cudaError_t e = cudaMemcpyToSymbol(c_wg, &T, sizeof(T));
         if (e != cudaSuccess) return e;
+    }
+    const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
+    if (!init) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         init = true;
     }
-    if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, 0, st>>>(stash_buf, valid, P, S, dflat);
-    else k_wgrad<false><<<grid, WG_WARPS * 32, 0, st>>>(stash_buf, valid, P, S, dflat);
+    if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
+    else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
     return cudaGetLastError();
 }
 

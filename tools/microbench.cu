@@ -22,6 +22,38 @@ __global__ void k_mma(float* out, int iters) {
     if (s == 12345.f) out[0] = s;
 }
 
+__global__ void k_mma_bf16(float* out, int iters) {
+    float d[8][4];
+    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 7, b1 = a0 * 5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0; for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    if (s == 12345.f) out[0] = s;
+}
+
+// mixed stream as the hybrid split would issue it: one tf32 m16n8k8 + one bf16 m16n8k16 per accumulator step
+__global__ void k_mma_mix(float* out, int iters) {
+    float d[8][4];
+    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 7, b1 = a0 * 5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+    }
+    float s = 0; for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    if (s == 12345.f) out[0] = s;
+}
+
 __global__ void k_gather(const float4* __restrict__ buf, uint32_t nlines, float* out, int iters) {
     // each quad (4 lanes x 2 float4) reads one random 128-byte line per step, like the trilinear corner fetch
     uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, t = threadIdx.x & 3;
@@ -68,6 +100,21 @@ int main() {
         cudaEventElapsedTime(&ms, e0, e1);
         const double flop = 2.0 * 16 * 8 * 8 * 8.0 * iters * warps * grid;
         printf(", \"mma_tf32_tflops_w%d\": %.1f", warps, flop / ms * 1e-9);
+    }
+    {
+        const int iters = 20000, grid = p.multiProcessorCount, warps = 16;
+        k_mma_bf16<<<grid, warps * 32>>>(out, 100);
+        cudaEventRecord(e0); k_mma_bf16<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf(", \"mma_bf16_k16_instr_per_clk_sm\": %.3f, \"mma_bf16_tflops\": %.1f", 8.0 * iters * warps / (ms * 1e-3 * clk * 1e3), 2.0 * 16 * 8 * 16 * 8.0 * iters * warps * grid / ms * 1e-9);
+        k_mma<<<grid, warps * 32>>>(out, 100);
+        cudaEventRecord(e0); k_mma<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf(", \"mma_tf32_k8_instr_per_clk_sm\": %.3f", 8.0 * iters * warps / (ms * 1e-3 * clk * 1e3));
+        k_mma_mix<<<grid, warps * 32>>>(out, 100);
+        cudaEventRecord(e0); k_mma_mix<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf(", \"mma_mix_pairs_per_clk_sm\": %.3f", 8.0 * iters * warps / (ms * 1e-3 * clk * 1e3));
     }
     const uint32_t nlines = 11 * 1024 * 1024 / 128;
     float4* buf; cudaMalloc(&buf, (size_t)nlines * 128); cudaMemset(buf, 0, (size_t)nlines * 128);
