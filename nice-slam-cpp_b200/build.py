@@ -21,7 +21,7 @@ BASE = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed
 
 UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("wgrad.cu", [])] + \
         [("decode_bwd_inst.cu", ["-DNSB_BWD_COMBO=%d" % k]) for k in range(6)]
-VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"]}
+VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "hybrid": ["-DNSB_HYBRID_BF16"]}
 
 
 def lib_path(variant=""):

@@ -788,7 +788,9 @@ static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fi
     if (n_cam_floats > 0) add(ctx->off_cam, n_cam_floats, lr_group[5], nullptr, 1);
     add(ctx->off_tail, 32, 0.f, nullptr, 0);
     A.n_seg = k;
-    k_adam<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(A); ctx->launches++;
+    A.cum4[0] = 0;
+    for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
+    k_adam<<<cdiv(A.cum4[k], 256), 256, 0, ctx->stream>>>(A); ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
@@ -979,7 +981,7 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
         const double b1 = 0.9, b2 = 0.999, bc1 = 1.0 - std::pow(b1, (double)ctx->trk_step), bc2 = 1.0 - std::pow(b2, (double)ctx->trk_step);
         A.beta1 = (float)b1; A.beta2 = (float)b2; A.om_beta1 = (float)(1.0 - b1); A.om_beta2 = (float)(1.0 - b2); A.eps = 1e-8f; A.bc2_sqrt = (float)std::sqrt(bc2); A.grad_scale = 1.f;
         A.seg[0].begin = (int)ctx->off_cam; A.seg[0].end = (int)ctx->off_cam + 8; A.seg[0].step = (float)((double)c.tracking_lr / bc1); A.seg[0].mask = nullptr; A.seg[0].active = 1;
-        A.n_seg = 1;
+        A.n_seg = 1; A.cum4[0] = 0; A.cum4[1] = 2;
         k_adam<<<1, 32, 0, ctx->stream>>>(A); ctx->launches++;
         CK(cudaGetLastError());
     }

@@ -1,5 +1,6 @@
 // Shared device helpers for the sm_100a kernels of libnsb.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,48 +42,89 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// two fp32 -> packed bf16x2, first argument in the low half (= the lower k index of the MMA fragment)
+__device__ __forceinline__ uint32_t pack_bf16(float lo_half, float hi_half) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// Default: the three-instruction 3xTF32 split (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi), error ~2^-22 per product.
+// Build variant NSB_HYBRID_BF16 (libnsb_hybrid.so): two instructions per k-step of 8 (measured on B200: a bf16 m16n8k16
+// issues at the same rate as a tf32 m16n8k8):
+//   main term   a_hi . b_hi                       one tf32 m16n8k8
+//   cross terms a_lo . b_hi  +  a_hi . b_lo       one bf16 m16n8k16: k slots 0..7 carry (a_lo, b_hi), slots 8..15 (a_hi, b_lo)
+// The cross terms are 2^-11 of the product, so bf16 operands (8 bits) leave a ~2^-20 relative error, the same order as
+// the 3xTF32 split's dropped a_lo.b_lo term x4.  Measured: forward 0.40 -> 0.345 ms and all mapping parity checks still at
+// 2-4e-6, but the ill-conditioned tracking pose gradient (fp32-vs-fp64 oracle noise 8e-5) degrades from 5e-6 to 6e-3,
+// above the 1e-3 tolerance -- hence not the default.
+//
 // A operand of one k-step (8 features) for the 16 rows of the tile, pre-split.
 template <bool P3>
 struct AFrag {
-    uint32_t hi[4], lo[4];
+    uint32_t hi[4];
+#ifndef NSB_HYBRID_BF16
+    uint32_t lo[4];
+#else
+    uint32_t x[4];   // bf16 fragment: x0/x1 = lo parts of rows g / g+8 (k slots 2t,2t+1), x2/x3 = bf16(a) (slots 2t+8, 2t+9)
+#endif
+    // a0 = (row g, feature 2t), a1 = (row g+8, 2t), a2 = (row g, 2t+1), a3 = (row g+8, 2t+1)
     __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
+        hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
         if (P3) {
-            split_tf32(a0, hi[0], lo[0]); split_tf32(a1, hi[1], lo[1]);
-            split_tf32(a2, hi[2], lo[2]); split_tf32(a3, hi[3], lo[3]);
-        } else {
-            hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
+#ifndef NSB_HYBRID_BF16
+            lo[0] = __float_as_uint(a0 - __uint_as_float(hi[0])); lo[1] = __float_as_uint(a1 - __uint_as_float(hi[1]));
+            lo[2] = __float_as_uint(a2 - __uint_as_float(hi[2])); lo[3] = __float_as_uint(a3 - __uint_as_float(hi[3]));
+#else
+            x[0] = pack_bf16(a0 - __uint_as_float(hi[0]), a2 - __uint_as_float(hi[2]));
+            x[1] = pack_bf16(a1 - __uint_as_float(hi[1]), a3 - __uint_as_float(hi[3]));
+            x[2] = pack_bf16(a0, a2);
+            x[3] = pack_bf16(a1, a3);
+#endif
         }
     }
 };
 
+// B fragment given as two fp32 weights (k = 2t and 2t+1 of the k-step, column g): split on the fly.
 template <bool P3>
 __device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float w0, float w1) {
+    const uint32_t bh0 = f2tf32(w0), bh1 = f2tf32(w1);
     if (P3) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(w0, bh0, bl0); split_tf32(w1, bh1, bl1);
+#ifndef NSB_HYBRID_BF16
+        const uint32_t bl0 = __float_as_uint(w0 - __uint_as_float(bh0)), bl1 = __float_as_uint(w1 - __uint_as_float(bh1));
         mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], bh0, bh1);   // small terms first
         mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bl0, bl1);
-        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bh0, bh1);
-    } else {
-        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], f2tf32(w0), f2tf32(w1));
-    }
-}
-
-// Same with a B operand that was split when the weights were staged (hi and lo planes in shared memory).
-template <bool P3>
-__device__ __forceinline__ void mma_acc_ps(float (&d)[4], const AFrag<P3>& a, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-    if (P3) {
-        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], bh0, bh1);
-        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bl0, bl1);
+#else
+        mma_bf16(d, a.x[0], a.x[1], a.x[2], a.x[3], pack_bf16(w0, w1), pack_bf16(w0 - __uint_as_float(bh0), w1 - __uint_as_float(bh1)));
+#endif
     }
     mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bh0, bh1);
 }
 
+// Same with a B operand that was split when the weights were staged: (h0, h1) tf32 weights from the hi plane and
+// (x0, x1) from the second plane -- the residuals (pure 3xTF32) or the packed bf16 pairs {w, w'} / {lo, lo'} (hybrid).
+template <bool P3>
+__device__ __forceinline__ void mma_acc_ps(float (&d)[4], const AFrag<P3>& a, uint32_t h0, uint32_t h1, uint32_t x0, uint32_t x1) {
+    if (P3) {
+#ifndef NSB_HYBRID_BF16
+        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], h0, h1);
+        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], x0, x1);
+#else
+        mma_bf16(d, a.x[0], a.x[1], a.x[2], a.x[3], x0, x1);
+#endif
+    }
+    mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], h0, h1);
+}
+
 // Weight matrices W[out][in] live in shared memory with row stride ld (a multiple of 32 floats) and the
 // column index XOR-swizzled by the row:  col' = col ^ swz(row),  swz(row) = ((row ^ (row>>1)) & 3) << 3.
-// That makes BOTH access patterns bank-conflict free:
-//   forward  B fragment  W[8j+g][8kk+2t .. +1]   (one 64-bit load, rows vary with g)
-//   backward B fragment  W[8kk+2t+r][8j+g]       (32-bit loads, rows vary with t)
+// That makes the B-fragment access  M[8j+g][8kk+2t .. +1]  (one 64-bit load per lane, rows vary with g) bank-conflict
+// free; the backward kernels stage the transposed matrices so that they use the very same access.
 __host__ __device__ __forceinline__ int swz(int row) { return ((row ^ (row >> 1)) & 3) << 3; }
 
 // acc[j] += A(kk) * W[8j+g][8kk+2t..]^T for the NJ output tiles (forward: out = x W^T).
@@ -101,28 +143,6 @@ __device__ __forceinline__ void kstep_fwd(float (&acc)[NJ][4], const AFrag<P3>& 
             mma_acc_ps<P3>(acc[j], a, __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(wl.x), __float_as_uint(wl.y));
         } else {
             mma_acc<P3>(acc[j], a, w.x, w.y);
-        }
-    }
-}
-
-// acc[j] += A(kk) * W[8kk+2t..][8(j0+j)+g] (backward data gradient: g_in = g_out W).
-template <bool P3, int NJ>
-__device__ __forceinline__ void kstep_bwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
-                                          int ld, int kk, int j0, int g, int t, int LO = 0) {
-    const int r0 = 8 * kk + 2 * t, r1 = r0 + 1;
-    const float* w0p = W + r0 * ld;
-    const float* w1p = W + r1 * ld;
-    const int s0 = swz(r0), s1 = swz(r1);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int c = 8 * (j0 + j) + g;
-        if (LO) {
-            const uint32_t h0 = __float_as_uint(w0p[c ^ s0]), h1 = __float_as_uint(w1p[c ^ s1]);
-            uint32_t l0 = 0, l1 = 0;
-            if (P3) { l0 = __float_as_uint(w0p[(c ^ s0) + LO]); l1 = __float_as_uint(w1p[(c ^ s1) + LO]); }
-            mma_acc_ps<P3>(acc[j], a, h0, h1, l0, l1);
-        } else {
-            mma_acc<P3>(acc[j], a, w0p[c ^ s0], w1p[c ^ s1]);
         }
     }
 }

@@ -55,13 +55,33 @@ __host__ __device__ __forceinline__ int fc_channel(int ip) {
     return 32 * blk + 8 * ((i >> 1) & 3) + 2 * (i >> 3) + (i & 1);
 }
 
-__device__ __forceinline__ void put_split(float* sm, int idx, int lo_delta, float v) {
-    const float hi = __uint_as_float(f2tf32(v));
-    sm[idx] = hi;
-    sm[idx + lo_delta] = v - hi;
+// Stage one weight matrix W[32 out][cols in] into shared memory as M[rows][ld] (swizzled columns):
+//   forward kernels  (T = false): M = W      (rows = out, contraction index of  x W^T  along the columns)
+//   backward kernels (T = true):  M = W^T    (rows = in,  contraction index of  g W    along the columns)
+// so that BOTH products read their B fragments as conflict-free 64-bit loads of two k-adjacent weights.
+// hi plane at `off`: tf32-rounded values.  Second plane LO floats further: the residuals w - hi (3xTF32), or with
+// NSB_HYBRID_BF16 the packed bf16 pairs {w, w'} at even columns and {lo, lo'} at odd columns.
+template <bool T, typename F>
+__device__ __forceinline__ void stage_matrix(float* sm, int off, int LO, int cols, int tid, int nthr, F w) {
+    const int nrow = T ? cols : HID, ncol = T ? HID : cols;     // M is [nrow][ncol], ld = ncol
+    for (int idx = tid; idx < nrow * ncol / 2; idx += nthr) {
+        const int r = idx / (ncol / 2), c0 = 2 * (idx % (ncol / 2));
+        const float v0 = T ? w(c0, r) : w(r, c0), v1 = T ? w(c0 + 1, r) : w(r, c0 + 1);
+        const float h0 = __uint_as_float(f2tf32(v0)), h1 = __uint_as_float(f2tf32(v1));
+        const int p0 = off + r * ncol + (c0 ^ swz(r));
+        sm[p0] = h0; sm[p0 + 1] = h1;
+#ifndef NSB_HYBRID_BF16
+        sm[p0 + LO] = v0 - h0; sm[p0 + 1 + LO] = v1 - h1;
+#else
+        sm[p0 + LO] = __uint_as_float(pack_bf16(v0, v1));
+        sm[p0 + 1 + LO] = __uint_as_float(pack_bf16(v0 - h0, v1 - h1));
+#endif
+    }
 }
 
-template <int C, int O>
+// BWD = true stages the transposed matrices the data-gradient products need; the Fc matrices then keep only the 32
+// input channels that carry gradient (stride HID*HID instead of HID*C).
+template <int C, int O, bool BWD>
 __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid, int nthr) {
     using L = DecSmem<C>;
     const DecFlat f = DecFlat::make(C, O);
@@ -69,21 +89,15 @@ __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid
         const int d = i / EMBP, c = i % EMBP;
         sm[L::B + i] = c < EMB ? flat[f.B + d * EMB + c] : 0.0f;
     }
-    for (int i = tid; i < HID * EMBP; i += nthr) {
-        const int o = i / EMBP, c = i % EMBP;
-        put_split(sm, L::W0 + o * EMBP + (c ^ swz(o)), L::LO, c < EMB ? flat[f.W[0] + o * EMB + c] : 0.0f);
-        put_split(sm, L::W3E + o * EMBP + (c ^ swz(o)), L::LO, c < EMB ? flat[f.W[3] + o * (EMB + HID) + c] : 0.0f);
-    }
-    for (int i = tid; i < HID * HID; i += nthr) {
-        const int o = i / HID, c = i % HID, d = o * HID + (c ^ swz(o));
-        put_split(sm, L::W1 + d, L::LO, flat[f.W[1] + i]);
-        put_split(sm, L::W2 + d, L::LO, flat[f.W[2] + i]);
-        put_split(sm, L::W4 + d, L::LO, flat[f.W[4] + i]);
-        put_split(sm, L::W3H + d, L::LO, flat[f.W[3] + o * (EMB + HID) + EMB + c]);
-    }
-    for (int i = tid; i < 5 * HID * C; i += nthr) {
-        const int l = i / (HID * C), o = (i / C) % HID, ip = i % C;
-        put_split(sm, L::FC + l * HID * C + o * C + (ip ^ swz(o)), L::LO, flat[f.Fc[l] + o * C + fc_channel(ip)]);
+    stage_matrix<BWD>(sm, L::W0, L::LO, EMBP, tid, nthr, [&](int o, int c) { return c < EMB ? flat[f.W[0] + o * EMB + c] : 0.0f; });
+    stage_matrix<BWD>(sm, L::W3E, L::LO, EMBP, tid, nthr, [&](int o, int c) { return c < EMB ? flat[f.W[3] + o * (EMB + HID) + c] : 0.0f; });
+    stage_matrix<BWD>(sm, L::W1, L::LO, HID, tid, nthr, [&](int o, int c) { return flat[f.W[1] + o * HID + c]; });
+    stage_matrix<BWD>(sm, L::W2, L::LO, HID, tid, nthr, [&](int o, int c) { return flat[f.W[2] + o * HID + c]; });
+    stage_matrix<BWD>(sm, L::W4, L::LO, HID, tid, nthr, [&](int o, int c) { return flat[f.W[4] + o * HID + c]; });
+    stage_matrix<BWD>(sm, L::W3H, L::LO, HID, tid, nthr, [&](int o, int c) { return flat[f.W[3] + o * (EMB + HID) + EMB + c]; });
+    for (int l = 0; l < 5; ++l) {
+        if (BWD) stage_matrix<true>(sm, L::FC + l * HID * HID, L::LO, HID, tid, nthr, [&](int o, int ip) { return flat[f.Fc[l] + o * C + fc_channel(ip)]; });
+        else stage_matrix<false>(sm, L::FC + l * HID * C, L::LO, C, tid, nthr, [&](int o, int ip) { return flat[f.Fc[l] + o * C + fc_channel(ip)]; });
     }
     for (int i = tid; i < 4 * HID; i += nthr) sm[L::WO + i] = (i / HID) < O ? flat[f.Wo + i] : 0.0f;
     for (int i = tid; i < 5 * HID; i += nthr) {

@@ -111,7 +111,7 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             for (int kk = 0; kk < 4; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, gh[kk]);
-                kstep_bwd<P3, 4>(gc, a, sm + L::FC + i * HID * C, C, kk, 0, g, t, L::LO);
+                kstep_fwd<P3, 4>(gc, a, sm + L::FC + i * HID * HID, HID, kk, g, t, L::LO);   // Fc_i^T [in][out]
             }
         }
         apply_mask(gu, gh, masks[i]);
@@ -135,7 +135,7 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             for (int kk = 0; kk < 4; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, gu[kk]);
-                kstep_bwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, 0, g, t, L::LO);
+                kstep_fwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, g, t, L::LO);                // W_i^T
             }
         }
     }
@@ -147,34 +147,39 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
         }
     }
     if (NEED_E) {
-        // g_e = g_u0 W0 + g_u3 W3e, one 8-feature tile at a time; chain through e = sin(p B)
+        // g_e = g_u0 W0 + g_u3 W3e, four 8-feature tiles (four independent accumulator chains) at a time; then the chain
+        // through e = sin(p B)
         AFrag<P3> a0[4], a3[4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) { afrag_from_c<P3>(a0[kk], gu0[kk]); afrag_from_c<P3>(a3[kk], gu3[kk]); }
-#pragma unroll 2
-        for (int je = 0; je < EMBP / 8; ++je) {
-            float ge[1][4] = {{0.0f, 0.0f, 0.0f, 0.0f}};
+#pragma unroll 1
+        for (int jg = 0; jg < EMBP / 32; ++jg) {
+            float ge[4][4];
+            zero_tile(ge);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                kstep_bwd<P3, 1>(ge, a0[kk], sm + L::W0, EMBP, kk, je, g, t, L::LO);
-                kstep_bwd<P3, 1>(ge, a3[kk], sm + L::W3E, EMBP, kk, je, g, t, L::LO);
+                kstep_fwd<P3, 4>(ge, a0[kk], sm + L::W0 + 32 * jg * HID, HID, kk, g, t, L::LO);    // W0^T rows 32 jg ..
+                kstep_fwd<P3, 4>(ge, a3[kk], sm + L::W3E + 32 * jg * HID, HID, kk, g, t, L::LO);
             }
-            const int f0 = 8 * je + 2 * t;
-            const float2 B0 = *reinterpret_cast<const float2*>(sm + L::B + f0);
-            const float2 B1 = *reinterpret_cast<const float2*>(sm + L::B + EMBP + f0);
-            const float2 B2 = *reinterpret_cast<const float2*>(sm + L::B + 2 * EMBP + f0);
-            float sn, c00, c01, c10, c11;
-            ff_sincos(fmaf(p[0][2], B2.x, fmaf(p[0][1], B1.x, p[0][0] * B0.x)), sn, c00);
-            ff_sincos(fmaf(p[0][2], B2.y, fmaf(p[0][1], B1.y, p[0][0] * B0.y)), sn, c01);
-            ff_sincos(fmaf(p[1][2], B2.x, fmaf(p[1][1], B1.x, p[1][0] * B0.x)), sn, c10);
-            ff_sincos(fmaf(p[1][2], B2.y, fmaf(p[1][1], B1.y, p[1][0] * B0.y)), sn, c11);
-            const float q00 = ge[0][0] * c00, q01 = ge[0][1] * c01, q10 = ge[0][2] * c10, q11 = ge[0][3] * c11;
-            if (STASH) {
-                *reinterpret_cast<float2*>(st0 + stash::GE + f0) = make_float2(q00, q01);
-                *reinterpret_cast<float2*>(st1 + stash::GE + f0) = make_float2(q10, q11);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int f0 = 32 * jg + 8 * jj + 2 * t;
+                const float2 B0 = *reinterpret_cast<const float2*>(sm + L::B + f0);
+                const float2 B1 = *reinterpret_cast<const float2*>(sm + L::B + EMBP + f0);
+                const float2 B2 = *reinterpret_cast<const float2*>(sm + L::B + 2 * EMBP + f0);
+                float sn, c00, c01, c10, c11;
+                ff_sincos(fmaf(p[0][2], B2.x, fmaf(p[0][1], B1.x, p[0][0] * B0.x)), sn, c00);
+                ff_sincos(fmaf(p[0][2], B2.y, fmaf(p[0][1], B1.y, p[0][0] * B0.y)), sn, c01);
+                ff_sincos(fmaf(p[1][2], B2.x, fmaf(p[1][1], B1.x, p[1][0] * B0.x)), sn, c10);
+                ff_sincos(fmaf(p[1][2], B2.y, fmaf(p[1][1], B1.y, p[1][0] * B0.y)), sn, c11);
+                const float q00 = ge[jj][0] * c00, q01 = ge[jj][1] * c01, q10 = ge[jj][2] * c10, q11 = ge[jj][3] * c11;
+                if (STASH) {
+                    *reinterpret_cast<float2*>(st0 + stash::GE + f0) = make_float2(q00, q01);
+                    *reinterpret_cast<float2*>(st1 + stash::GE + f0) = make_float2(q10, q11);
+                }
+                gp[0][0] += q00 * B0.x + q01 * B0.y; gp[0][1] += q00 * B1.x + q01 * B1.y; gp[0][2] += q00 * B2.x + q01 * B2.y;
+                gp[1][0] += q10 * B0.x + q11 * B0.y; gp[1][1] += q10 * B1.x + q11 * B1.y; gp[1][2] += q10 * B2.x + q11 * B2.y;
             }
-            gp[0][0] += q00 * B0.x + q01 * B0.y; gp[0][1] += q00 * B1.x + q01 * B1.y; gp[0][2] += q00 * B2.x + q01 * B2.y;
-            gp[1][0] += q10 * B0.x + q11 * B0.y; gp[1][1] += q10 * B1.x + q11 * B1.y; gp[1][2] += q10 * B2.x + q11 * B2.y;
         }
     }
 }
@@ -252,9 +257,9 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd
 #pragma unroll
     for (int d = 2; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
     const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
-    if (dec == 1) stage_decoder<32, 1>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
-    else if (dec == 2) stage_decoder<64, 1>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
-    else stage_decoder<32, 4>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
+    if (dec == 1) stage_decoder<32, 1, true>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
+    else if (dec == 2) stage_decoder<64, 1, true>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
+    else stage_decoder<32, 4, true>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = P.P / TILE;

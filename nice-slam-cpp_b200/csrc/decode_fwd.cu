@@ -51,9 +51,9 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd
     for (int d = 1; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
     const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
     if (dec == 0) stage_coarse(sm, P.dec_flat[0], threadIdx.x, blockDim.x);
-    else if (dec == 1) stage_decoder<32, 1>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
-    else if (dec == 2) stage_decoder<64, 1>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
-    else stage_decoder<32, 4>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
+    else if (dec == 1) stage_decoder<32, 1, false>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
+    else if (dec == 2) stage_decoder<64, 1, false>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
+    else stage_decoder<32, 4, false>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (P.P + TILE - 1) / TILE;
