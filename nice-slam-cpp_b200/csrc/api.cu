@@ -40,6 +40,9 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
 }
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
+cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
+cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
+int compose_floats(int which);
 }  // namespace nsb
 
 using namespace nsb;
@@ -106,6 +109,10 @@ struct nsb_ctx {
     float* median = nullptr; int* count = nullptr;
     float* stash = nullptr; size_t stash_rows = 0;
     uint32_t* masks = nullptr;   // relu masks of the last training forward
+    int mask_layout = 0, mask_stride = 0;
+    float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
+    int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
+    int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
     int last_n = 0, last_S = 0;
     // host RNG (std::mt19937 == the CPU generator torch::randint uses, utils.h:32)
@@ -352,6 +359,8 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->g_rgb, 3 * (size_t)cap)); CK(dalloc(&ctx->g_depth, cap)); CK(dalloc(&ctx->g_var, cap)); CK(dalloc(&ctx->d_rays, 6 * (size_t)cap));
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
+    for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
+    { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
@@ -366,7 +375,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
-                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->scratch_ncdhw,
+                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->scratch_ncdhw,
                     c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -416,6 +425,7 @@ extern "C" int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host, int64
     if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
     CK(cudaMemcpyAsync(ctx->param + ctx->off_dec[which], host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->comp_dirty |= 1 << which;
     return 0;
 }
 static int get_dec(nsb_ctx* ctx, const float* base, int which, float* host, int64_t n) {
@@ -546,9 +556,28 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         if (train) P.masks = ctx->masks;
         if (train && stash_fwd && stage == NSB_COLOR) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
         float w[4]; stage_decoders(stage, w); env_weights("NSB_SPLIT_FWD", w);
-        const int grid = decode_grid_size(ctx, n * S);
-        partition(grid, w, P.cta_begin);
-        CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_3XTF32 && stage != NSB_COARSE && P.stash == nullptr;
+        if (tc_ok) {
+            // tcgen05 path: one 320-thread CTA per SM, per-sample mask words, composed weights refreshed when stale
+            int need = 0;
+            for (int d = 1; d < 4; ++d) if (w[d] > 0 && ((ctx->comp_dirty >> d) & 1)) need |= 1 << d;
+            if (need) {
+                const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
+                CK(launch_compose(flat, ctx->comp, need, ctx->stream)); ctx->launches++;
+                ctx->comp_dirty &= ~need;
+            }
+            for (int d = 0; d < 4; ++d) P.comp[d] = ctx->comp[d];
+            P.mask_layout = 1; P.mask_stride = n * S;
+            if (train) { ctx->mask_layout = 1; ctx->mask_stride = n * S; }
+            float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
+            partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 256))), wt, P.cta_begin);
+            CK(launch_decode_fwd_tc(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        } else {
+            if (train) { ctx->mask_layout = 0; ctx->mask_stride = 0; }
+            const int grid = decode_grid_size(ctx, n * S);
+            partition(grid, w, P.cta_begin);
+            CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        }
     }
     {
         Timer t(ctx, T_COMP);
@@ -584,7 +613,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         Timer t(ctx, T_BWD);
         DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S; P.g_raw += 4 * (size_t)off * S; P.d_rays += 6 * (size_t)off;
-        P.stash = ctx->stash; P.masks = ctx->masks;
+        P.stash = ctx->stash; P.masks = ctx->masks; P.mask_layout = ctx->mask_layout; P.mask_stride = ctx->mask_stride;
         P.flags = (flags & 1) | (wg ? 2 : 0) | (flags & 4);
         if (P.flags == 0) return 0;
         float w[4] = {0, 0, 0, 0};
@@ -791,6 +820,8 @@ static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fi
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
     k_adam<<<cdiv(A.cum4[k], 256), 256, 0, ctx->stream>>>(A); ctx->launches++;
+    if (dec_fine && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 2;
+    if (dec_color && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 3;
     CK(cudaGetLastError());
     return 0;
 }

@@ -213,10 +213,20 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
 
     // relu masks saved by the training forward (k_decode_fwd<.., TRAIN>): the data gradient needs nothing else
     uint32_t masks[5];
-    {
+    if (P.mask_layout == 0) {
         const uint32_t* mb = P.masks + ((size_t)(dec - 1) * (P.P / TILE) + base / TILE) * 96 + lane;
         const uint32_t m01 = mb[0], m23 = mb[32];
         masks[0] = m01 & 0xffffu; masks[1] = m01 >> 16; masks[2] = m23 & 0xffffu; masks[3] = m23 >> 16; masks[4] = mb[64];
+    } else {   // one word per sample and layer (bit f = relu of feature f): pick this thread's fragment bits
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t* mb = P.masks + ((size_t)(dec - 1) * 5 + i) * P.mask_stride;
+            const uint32_t w0 = mb[sidx[0]] >> (2 * t), w1 = mb[sidx[1]] >> (2 * t);
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m |= (((w0 >> (8 * j)) & 3u) << (4 * j)) | (((w1 >> (8 * j)) & 3u) << (4 * j + 2));
+            masks[i] = m;
+        }
     }
     float* st0 = nullptr; float* st1 = nullptr;
     if (WG) {   // E / H / Cc columns of the stash rows were written by the forward; add the gradient side

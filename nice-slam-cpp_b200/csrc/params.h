@@ -30,7 +30,11 @@ struct DecodeParams {
     int flags;                     // bit0 grid grads, bit1 colour-decoder weight grads (stash), bit2 ray grads
     float* d_rays;                 // [N][6]: d L / d rays_o, d L / d rays_d (atomically accumulated)
     float* stash;                  // [P][STASH_W] colour-decoder activations / gradients for the wgrad kernel
-    uint32_t* masks;               // [3][P/16][3][32] packed relu masks written by the training forward, read by the backward
+    uint32_t* masks;               // relu masks written by the training forward, read by the backward:
+                                   //   mask_layout 0: [3][P/16][3][32] fragment-packed (mma.sync forward)
+                                   //   mask_layout 1: [3][5][mask_stride] one 32-bit word per sample and layer (tcgen05 forward)
+    int mask_layout, mask_stride;
+    const float* comp[4];          // composed weights of the tcgen05 forward (k_compose), per decoder
 };
 
 // Row layout of the colour-decoder weight-gradient stash (floats per sample).
