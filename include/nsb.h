@@ -190,6 +190,8 @@ int64_t nsb_launch_count(nsb_ctx* ctx, int reset);
  * [1] decode fwd, [2] composite/loss, [3] decode bwd, [4] wgrad, [5] adam, [6] allreduce. Enable with nsb_set_profiling. */
 int nsb_set_profiling(nsb_ctx* ctx, int on);
 int nsb_get_kernel_ms(nsb_ctx* ctx, float* ms7);
+/* Development aid: cycle counters of the tcgen05 forward kernel (filled only by the NSB_TC_TIMING build variant). */
+int nsb_debug_counters(nsb_ctx* ctx, unsigned long long* out32);
 
 #ifdef __cplusplus
 }

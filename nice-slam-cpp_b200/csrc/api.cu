@@ -113,6 +113,7 @@ struct nsb_ctx {
     float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
     int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
+    unsigned long long* dbg = nullptr;   // 32 cycle counters (NSB_TC_TIMING builds)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
     int last_n = 0, last_S = 0;
     // host RNG (std::mt19937 == the CPU generator torch::randint uses, utils.h:32)
@@ -361,6 +362,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
+    CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
@@ -375,7 +377,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
-                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->scratch_ncdhw,
+                    c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
                     c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -567,6 +569,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
                 ctx->comp_dirty &= ~need;
             }
             for (int d = 0; d < 4; ++d) P.comp[d] = ctx->comp[d];
+            P.dbg = ctx->dbg;
             P.mask_layout = 1; P.mask_stride = n * S;
             if (train) { ctx->mask_layout = 1; ctx->mask_stride = n * S; }
             float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
@@ -1047,6 +1050,14 @@ extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int worl
 extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }
 
 // ---- instrumentation ----------------------------------------------------------------------------------------------------
+// Cycle counters of the tcgen05 forward (only filled by the NSB_TC_TIMING build variant): 32 values, reset on read.
+extern "C" int nsb_debug_counters(nsb_ctx* ctx, unsigned long long* out32) {
+    CK(cudaMemcpyAsync(out32, ctx->dbg, 32 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int64_t nsb_launch_count(nsb_ctx* ctx, int reset) { const int64_t v = ctx->launches; if (reset) ctx->launches = 0; return v; }
 extern "C" int nsb_set_profiling(nsb_ctx* ctx, int on) { ctx->profiling = on != 0; ctx->ev_used = 0; return 0; }
 // Sum of the device times of every region timed since nsb_set_profiling(1), per category.

@@ -199,7 +199,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // (k < 2^10 so k*2PI_HI is exact in the fma), then the SFU.  Absolute error ~5e-7, far below the
 // ~3e-5 rad the fp32 argument p.B itself carries at |x| ~ 300.
 __device__ __forceinline__ float reduce_2pi(float x) {
-    const float k = rintf(x * 0.15915494309189535f);
+    // round-to-nearest-even via the 1.5 * 2^23 magic add (two FADDs on the FMA pipe) instead of rintf (FRND, on the
+    // quarter-rate XU pipe that also serves MUFU.SIN); exact for |x / 2pi| < 2^22
+    const float k = __fsub_rn(__fadd_rn(x * 0.15915494309189535f, 12582912.0f), 12582912.0f);
     float r = fmaf(-k, 6.2831854820251465f, x);
     return fmaf(-k, -1.7484555314695172e-07f, r);
 }

@@ -2,10 +2,10 @@
 //
 // One CTA per SM keeps ONE decoder's weights resident in shared memory in the UMMA canonical K-major SWIZZLE_128B layout
 // (tf32 hi plane + residual lo plane for the fp32-grade 3xTF32 product) and runs two 128-sample tiles concurrently:
-//   warps 0-3 / 4-7   one THREAD per sample: trilinear gather, Fourier features, per-layer epilogues (bias, relu, mask,
-//                     hi/lo split) -- activations go back to the tensor core through a 128x32 shared-memory A tile
+//   warps 0-7 / 8-15  TWO threads per sample (each owns 16 of the 32 columns): trilinear gather, Fourier features,
+//                     per-layer epilogues (bias, relu, mask, hi/lo split) -- activations go back to the tensor core through a 128x32 shared-memory A tile
 //                     (written with 16-byte swizzled stores), the grid features through tensor memory (A-from-TMEM MMA)
-//   warps 8 / 9       one elected lane each issues the tcgen05.mma stream of its tile and commits to an mbarrier
+//   warps 16 / 17     one elected lane each issues the tcgen05.mma stream of its tile and commits to an mbarrier
 // The two tiles ping-pong: while one tile's threads run an epilogue the other tile's MMAs execute.
 //
 // Algebra used to keep the chain to ONE accumulator read per layer: with h_{i+1} = relu(a_i) + Fc_i c + bc_i and
@@ -21,9 +21,18 @@
 namespace nsb {
 namespace tc {
 
+#ifdef NSB_TC_TIMING
+#define TC_T0() long long t_ = clock64()
+#define TC_ACC(k) do { const long long n_ = clock64(); tacc[k] += n_ - t_; t_ = n_; } while (0)
+#else
+#define TC_T0()
+#define TC_ACC(k)
+#endif
+
 constexpr int TM = 128;                       // samples per tile (UMMA M)
 constexpr int GROUPS = 2;                     // tiles in flight per CTA
-constexpr int CTHREADS = GROUPS * 128;        // compute threads (warps 0..7)
+constexpr int GTHREADS = 256;                 // compute threads per tile: TWO per sample, each owns 16 of the 32 columns
+constexpr int CTHREADS = GROUPS * GTHREADS;   // compute threads (warps 0..15)
 constexpr int THREADS = CTHREADS + 32 * GROUPS;   // + one issuer warp per tile group
 
 // ---- composed weights (global, per decoder): G[4][32][C] | bp[5][32] | woc[4][C] | boc[4] ---------------------------
@@ -97,7 +106,8 @@ struct Smem {
     static constexpr int BOC = WOC + 4 * C * 4;                   // const[4]
     static constexpr int BAR = BOC + 16;                          // mbarriers: full_A[2], mma_done[2]
     static constexpr int TMEMPTR = BAR + 4 * 8;
-    static constexpr int TOTAL = TMEMPTR + 16;
+    static constexpr int XCH = TMEMPTR + 16;                      // GROUPS x 128 x float4: output partial sums of column half 1
+    static constexpr int TOTAL = XCH + GROUPS * 128 * 16;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,6 +145,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
                    "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
                    "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                   "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
@@ -212,37 +235,37 @@ constexpr int ACC0 = 0, ACCS = 32, ACC1 = 64, ACH = 96;
 template <int C> constexpr int acl() { return ACH + C; }
 constexpr int GROUP_COLS = 256;
 
-// the thread's sample -> full 32-channel trilinear feature (all 8 corners x 8 float4)
-__device__ __forceinline__ void gather32(const GridView& G, const Bound& bnd, const float (&p)[3], float (&c)[32]) {
+// the thread's sample -> 16 channels [16h, 16h+16) of the trilinear feature (8 corners x 4 float4)
+__device__ __forceinline__ void gather16(const GridView& G, const Bound& bnd, const float (&p)[3], int h, float (&c)[16]) {
     Tri s;
     tri_setup(G, bnd, p, s);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) c[i] = 0.0f;
+    for (int i = 0; i < 16; ++i) c[i] = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int off;
         const float w = tri_corner(G, s, k, off);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 v = ldg4(G.data + off + 4 * q);
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = ldg4(G.data + off + 16 * h + 4 * q);
             c[4 * q] = fmaf(v.x, w, c[4 * q]); c[4 * q + 1] = fmaf(v.y, w, c[4 * q + 1]);
             c[4 * q + 2] = fmaf(v.z, w, c[4 * q + 2]); c[4 * q + 3] = fmaf(v.w, w, c[4 * q + 3]);
         }
     }
 }
 
-// write the thread's row (32 floats) of the A tile: hi plane at `hi_tile`, lo plane 4096 floats further
-__device__ __forceinline__ void store_row(float* hi_tile, int row, const float (&v)[32]) {
+// write columns [16h, 16h+16) of the thread's row of the A tile: hi plane at `hi_tile`, lo plane 4096 floats further
+__device__ __forceinline__ void store_half(float* hi_tile, int row, int h, const float (&v)[16]) {
     float* base = hi_tile + (row >> 3) * 256 + (row & 7) * 32;
     const int sw = row & 7;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 h, l;
-        h.x = __uint_as_float(f2tf32(v[4 * c])); h.y = __uint_as_float(f2tf32(v[4 * c + 1]));
-        h.z = __uint_as_float(f2tf32(v[4 * c + 2])); h.w = __uint_as_float(f2tf32(v[4 * c + 3]));
-        l.x = v[4 * c] - h.x; l.y = v[4 * c + 1] - h.y; l.z = v[4 * c + 2] - h.z; l.w = v[4 * c + 3] - h.w;
-        float* d = base + ((c ^ sw) << 2);
-        *reinterpret_cast<float4*>(d) = h;
+    for (int c = 0; c < 4; ++c) {
+        float4 hh, l;
+        hh.x = __uint_as_float(f2tf32(v[4 * c])); hh.y = __uint_as_float(f2tf32(v[4 * c + 1]));
+        hh.z = __uint_as_float(f2tf32(v[4 * c + 2])); hh.w = __uint_as_float(f2tf32(v[4 * c + 3]));
+        l.x = v[4 * c] - hh.x; l.y = v[4 * c + 1] - hh.y; l.z = v[4 * c + 2] - hh.z; l.w = v[4 * c + 3] - hh.w;
+        float* d = base + (((4 * h + c) ^ sw) << 2);
+        *reinterpret_cast<float4*>(d) = hh;
         *reinterpret_cast<float4*>(d + 4096) = l;
     }
 }
@@ -259,7 +282,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int g = 0; g < GROUPS; ++g) { mbar_init(bar0 + 8 * g, 128); mbar_init(bar0 + 16 + 8 * g, 1); }
+        for (int g = 0; g < GROUPS; ++g) { mbar_init(bar0 + 8 * g, GTHREADS); mbar_init(bar0 + 16 + 8 * g, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (dec == 1) stage<32, 1>(sm, P.dec_flat[1], P.comp[1], tid, THREADS);
@@ -271,9 +294,9 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
     fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    if (warp < 2 * 4) {
-        // ------------------------------------------------------------------ compute threads: one sample each
-        const int grp = warp >> 2, tg = tid & 127;
+    if (warp < GROUPS * 8) {
+        // ---------------------------------------------- compute threads: two per sample (h = column half), warp w -> TMEM lanes 32 (w & 3)
+        const int grp = warp >> 3, h = (warp >> 2) & 1, tg = ((warp & 3) << 5) | lane;
         const uint32_t tm = tmem + grp * GROUP_COLS + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t full_a = bar0 + 8 * grp, mma_done = bar0 + 16 + 8 * grp;
         float* a_hi = reinterpret_cast<float*>(sm + L::A + grp * 32768);
@@ -282,8 +305,14 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
         const float* wo = reinterpret_cast<const float*>(sm + L::WO);
         const float* woc = reinterpret_cast<const float*>(sm + L::WOC);
         const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
+        float* xch = reinterpret_cast<float*>(sm + L::XCH) + grp * 128 * 4;    // half-1 -> half-0 exchange of the output partial sums
+        constexpr int NO = O == 4 ? 3 : 1;
         uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
+#ifdef NSB_TC_TIMING
+        long long tacc[6] = {0, 0, 0, 0, 0, 0};   // gather, sin, wait(E), wait(layers), epilogue, tiles
+#endif
         for (int tile = cta * GROUPS + grp; tile < ntiles; tile += ncta * GROUPS) {
+            TC_T0();
             const int s = tile * TM + tg;
             bool active = s < P.P;
             float p[3] = {0.f, 0.f, 0.f};
@@ -299,43 +328,57 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
                     }
                 }
             }
-            // grid features -> tensor memory (A operand of the G_i c products) and the output-layer constant
-            float outc[O == 4 ? 3 : 1];
+            // grid features -> tensor memory (A operand of the G_i c products) and this half's share of the output-layer constant
+            float outc[NO];
 #pragma unroll
-            for (int o = 0; o < (O == 4 ? 3 : 1); ++o) outc[o] = boc[o];
+            for (int o = 0; o < NO; ++o) outc[o] = h == 0 ? boc[o] : 0.0f;
 #pragma unroll
             for (int cc = 0; cc < C / 32; ++cc) {
-                float c[32];
-                if (active) gather32(P.grid[cc == 0 ? dec : 1], P.bnd, p, c);     // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
+                float c[16];
+                if (active) gather16(P.grid[cc == 0 ? dec : 1], P.bnd, p, h, c);   // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
                 else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) c[i] = 0.0f;
+                    for (int i = 0; i < 16; ++i) c[i] = 0.0f;
                 }
 #pragma unroll
-                for (int o = 0; o < (O == 4 ? 3 : 1); ++o) {
+                for (int o = 0; o < NO; ++o) {
                     float acc = outc[o];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc = fmaf(c[i], woc[o * C + 32 * cc + i], acc);
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(woc + o * C + 32 * cc + 16 * h + 4 * q);
+                        acc = fmaf(c[4 * q], w4.x, acc); acc = fmaf(c[4 * q + 1], w4.y, acc); acc = fmaf(c[4 * q + 2], w4.z, acc); acc = fmaf(c[4 * q + 3], w4.w, acc);
+                    }
                     outc[o] = acc;
                 }
-                float lo[32];
+                float lo[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { const float h = __uint_as_float(f2tf32(c[i])); lo[i] = c[i] - h; c[i] = h; }
-                tmem_st32(tm + ACH + 32 * cc, c);
-                tmem_st32(tm + acl<C>() + 32 * cc, lo);
+                for (int i = 0; i < 16; ++i) { const float hh = __uint_as_float(f2tf32(c[i])); lo[i] = c[i] - hh; c[i] = hh; }
+                tmem_st16(tm + ACH + 32 * cc + 16 * h, c);
+                tmem_st16(tm + acl<C>() + 32 * cc + 16 * h, lo);
             }
             tmem_st_wait();
-            // Fourier features, 32 at a time, through the shared-memory A tile
+            TC_ACC(0);
+            // Fourier features, 32 per handshake (16 per thread), through the shared-memory A tile
 #pragma unroll 1
             for (int j = 0; j < 3; ++j) {
-                float e[32];
+                float e[16];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const int ft = 32 * j + k;
-                    e[k] = (active && ft < EMB) ? ff_sin(fmaf(p[2], bm[2 * EMBP + ft], fmaf(p[1], bm[EMBP + ft], p[0] * bm[ft]))) : 0.0f;
+                for (int q = 0; q < 4; ++q) {
+                    const int ft = 32 * j + 16 * h + 4 * q;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bm + ft), b1 = *reinterpret_cast<const float4*>(bm + EMBP + ft), b2 = *reinterpret_cast<const float4*>(bm + 2 * EMBP + ft);
+                    e[4 * q] = ff_sin(fmaf(p[2], b2.x, fmaf(p[1], b1.x, p[0] * b0.x)));
+                    e[4 * q + 1] = ff_sin(fmaf(p[2], b2.y, fmaf(p[1], b1.y, p[0] * b0.y)));
+                    e[4 * q + 2] = ff_sin(fmaf(p[2], b2.z, fmaf(p[1], b1.z, p[0] * b0.z)));
+                    e[4 * q + 3] = ff_sin(fmaf(p[2], b2.w, fmaf(p[1], b1.w, p[0] * b0.w)));   // padded columns of B are 0 -> sin(0) = 0
                 }
+                if (!active) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) e[k] = 0.0f;
+                }
+                TC_ACC(1);
                 if (j > 0) { mbar_wait(mma_done, (step - 1) & 1); }     // previous chunk's MMAs have consumed the A tile
-                store_row(a_hi, tg, e);
+                TC_ACC(2);
+                store_half(a_hi, tg, h, e);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 fence_before();
                 mbar_arrive(full_a);
@@ -344,52 +387,81 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
             // five layers: read the accumulator, bias + relu (+ mask), hand u_i back as the next A tile
 #pragma unroll 1
             for (int i = 0; i < 5; ++i) {
+                TC_ACC(4);
                 mbar_wait(mma_done, (step - 1) & 1);
+                TC_ACC(3);
                 fence_after();
-                float v[32];
-                tmem_ld32(tm + ((i & 1) ? ACC1 : ACC0), v);
+                float v[16];
+                tmem_ld16(tm + ((i & 1) ? ACC1 : ACC0) + 16 * h, v);
                 if (i == 3) {
-                    float sk[32];
-                    tmem_ld32(tm + ACCS, sk);
+                    float sk[16];
+                    tmem_ld16(tm + ACCS + 16 * h, sk);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] += sk[k];
+                    for (int k = 0; k < 16; ++k) v[k] += sk[k];
                 } else {
                     tmem_ld_wait();
                 }
                 uint32_t mask = 0;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float a = v[k] + bp[i * HID + k];
-                    const bool pos = a > 0.0f;
-                    mask |= (pos ? 1u : 0u) << k;
-                    v[k] = pos ? a : 0.0f;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bp + i * HID + 16 * h + 4 * q);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float a = v[4 * q + r] + bb[r];
+                        const bool pos = a > 0.0f;
+                        mask |= (pos ? 1u : 0u) << (4 * q + r);
+                        v[4 * q + r] = pos ? a : 0.0f;
+                    }
                 }
-                if (P.masks && active) P.masks[((size_t)(dec - 1) * 5 + i) * P.mask_stride + s] = mask;
+                if (P.masks && active)
+                    reinterpret_cast<uint16_t*>(P.masks + ((size_t)(dec - 1) * 5 + i) * P.mask_stride + s)[h] = (uint16_t)mask;
                 if (i < 4) {
-                    store_row(a_hi, tg, v);
+                    store_half(a_hi, tg, h, v);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     fence_before();
                     mbar_arrive(full_a);
                     ++step;
-                } else if (active) {
-                    float out[O == 4 ? 3 : 1];
+                } else {
+                    float out[NO];
 #pragma unroll
-                    for (int o = 0; o < (O == 4 ? 3 : 1); ++o) {
+                    for (int o = 0; o < NO; ++o) {
                         float acc = outc[o];
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) acc = fmaf(v[k], wo[o * HID + k], acc);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wo + o * HID + 16 * h + 4 * q);
+                            acc = fmaf(v[4 * q], w4.x, acc); acc = fmaf(v[4 * q + 1], w4.y, acc); acc = fmaf(v[4 * q + 2], w4.z, acc); acc = fmaf(v[4 * q + 3], w4.w, acc);
+                        }
                         out[o] = acc;
                     }
-                    if (O == 4) *reinterpret_cast<float4*>(P.out_rgb + 4 * (size_t)s) = make_float4(out[0], out[1], out[2], 0.0f);
-                    else P.out_occ[dec][s] = out[0];
+                    // the two halves of a row live in different warps: half 1 passes its partial sums through shared memory
+                    if (h == 1) {
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) xch[tg * 4 + o] = out[o];
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GTHREADS) : "memory");
+                    if (h == 0 && active) {
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) out[o] += xch[tg * 4 + o];
+                        if (O == 4) *reinterpret_cast<float4*>(P.out_rgb + 4 * (size_t)s) = make_float4(out[0], out[NO > 1 ? 1 : 0], out[NO > 2 ? 2 : 0], 0.0f);
+                        else P.out_occ[dec][s] = out[0];
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GTHREADS) : "memory");   // xch is reused by the next tile
                 }
             }
             fence_before();   // the accumulator reads above are ordered before the next tile's first arrive
+            TC_ACC(4);
+#ifdef NSB_TC_TIMING
+            tacc[5] += 1;
+#endif
         }
+#ifdef NSB_TC_TIMING
+        if (P.dbg && tg == 0 && h == 0) for (int k = 0; k < 6; ++k) atomicAdd(P.dbg + 8 * dec + k, (unsigned long long)tacc[k]);
+#endif
     } else if (lane == 0) {
         // ------------------------------------------------------------------ MMA issuer of tile group (warp - 8)
-        const int grp = warp - 8;
+        const int grp = warp - GROUPS * 8;
         const uint32_t tm = tmem + grp * GROUP_COLS;
         const uint32_t full_a = bar0 + 8 * grp, mma_done = bar0 + 16 + 8 * grp;
         const uint32_t sbase = smem_u32(sm);

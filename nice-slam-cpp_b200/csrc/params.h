@@ -35,6 +35,7 @@ struct DecodeParams {
                                    //   mask_layout 1: [3][5][mask_stride] one 32-bit word per sample and layer (tcgen05 forward)
     int mask_layout, mask_stride;
     const float* comp[4];          // composed weights of the tcgen05 forward (k_compose), per decoder
+    unsigned long long* dbg;       // optional cycle counters of the tcgen05 forward (NSB_TC_TIMING builds), or nullptr
 };
 
 // Row layout of the colour-decoder weight-gradient stash (floats per sample).
