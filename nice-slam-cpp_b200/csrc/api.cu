@@ -538,7 +538,7 @@ static int ensure_stash(nsb_ctx* ctx, size_t rows) {
 
 // train: keep the relu masks for run_backward; stash_fwd: also write the colour decoder's activations to the wgrad stash.
 static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, bool want_weights,
-                       bool train = false, bool stash_fwd = false) {
+                       bool train = false, bool stash_fwd = false, bool skip_composite = false) {
     const nsb_config& c = ctx->cfg;
     const int S = have_depth ? c.n_samples + c.n_surface : c.n_samples;
     ctx->last_n = n; ctx->last_S = S;
@@ -582,7 +582,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
         }
     }
-    {
+    if (!skip_composite) {
         Timer t(ctx, T_COMP);
         CompositeParams Q; memset(&Q, 0, sizeof Q);
         Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
@@ -596,10 +596,11 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
 }
 
 // cotangents in ctx->g_rgb / g_depth / g_var -> g_raw -> decoder backward (+ wgrad).  flags: F_GRID=1, F_WGRAD=2, F_RAY=4.
-static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, int flags, bool color_active) {
+static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, int flags, bool color_active,
+                        bool skip_composite = false) {
     const nsb_config& c = ctx->cfg;
     const int S = ctx->last_S;
-    {
+    if (!skip_composite) {
         Timer t(ctx, T_COMP);
         CompositeParams Q; memset(&Q, 0, sizeof Q);
         Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
@@ -822,7 +823,7 @@ static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fi
     A.n_seg = k;
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
-    k_adam<<<cdiv(A.cum4[k], 256), 256, 0, ctx->stream>>>(A); ctx->launches++;
+    k_adam<<<cdiv(A.cum4[k], 256 * ADAM_VEC), 256, 0, ctx->stream>>>(A); ctx->launches++;
     if (dec_fine && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 2;
     if (dec_color && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 3;
     CK(cudaGetLastError());
@@ -881,19 +882,25 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     const int per = cdiv(cdiv(n, ctx->world), 1), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
     const bool use_color = stage == NSB_COLOR;
     if (nl > 0) {
-        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false, true, use_color && !c.fix_color)) return -1;   // render is always called with "color" (Mapper.cpp:430)
+        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false, true, use_color && !c.fix_color, true)) return -1;   // render is always called with "color" (Mapper.cpp:430)
         {
+            // composite + loss (Mapper.cpp:435-442) + composite backward fused: the cotangents are local to each ray
             Timer t(ctx, T_COMP);
-            LossParams L; memset(&L, 0, sizeof L);
-            L.gt_depth = ctx->gt_depth + off; L.gt_color = ctx->gt_color + 3 * off; L.valid = ctx->valid + off;
-            L.rgb = ctx->o_rgb + 3 * off; L.depth = ctx->o_depth + off; L.var = ctx->o_var + off; L.n = nl; L.use_color = use_color; L.w_color = c.mapping_w_color_loss;
-            L.g_rgb = ctx->g_rgb + 3 * off; L.g_depth = ctx->g_depth + off; L.g_var = ctx->g_var + off;
-            L.loss = ctx->grad + ctx->off_tail;   // rides in the gradient arena so that the all-reduce sums it too
-            k_loss_mapping<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(L); ctx->launches++;
+            const int S = ctx->last_S;
+            CompositeParams Q; memset(&Q, 0, sizeof Q);
+            Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = ctx->valid + off;
+            Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
+            Q.stats = stats; Q.bnd = ctx->bnd; Q.n = nl; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+            Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = nullptr;
+            Q.g_raw = ctx->g_raw + 4 * (size_t)off * S;
+            // the loss rides in the tail of the gradient arena so that the all-reduce sums it too
+            k_composite_map<<<cdiv(nl * 32, 256), 256, 0, ctx->stream>>>(Q, ctx->gt_depth + off, ctx->gt_color + 3 * off, use_color ? 1 : 0,
+                                                                       c.mapping_w_color_loss, ctx->grad + ctx->off_tail);
+            ctx->launches++;
             CK(cudaGetLastError());
         }
         const int flags = 1 | (c.fix_color ? 0 : 2);
-        if (run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color)) return -1;
+        if (run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true)) return -1;
     }
     if (ctx->world > 1) {
         Timer t(ctx, T_COMM);

@@ -33,35 +33,52 @@ struct AdamParams {
     float grad_scale;        // 1 (single GPU) -- kept for mean-style reductions
 };
 
-// torch::optim::Adam::step (libtorch defaults, no amsgrad / weight decay) + zero_grad, one launch, one float4 per thread
-// over the concatenation of all segments (every load of the 90 MB pass is in flight at once):
+// torch::optim::Adam::step (libtorch defaults, no amsgrad / weight decay) + zero_grad, one launch over the concatenation
+// of all segments.  Each thread owns ADAM_VEC float4 slots and issues ALL its loads (g, m, v, p of every slot) before any
+// arithmetic, so that the 90 MB pass is bandwidth- rather than latency-bound:
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g g;  p -= (lr / bc1) * m / (sqrt(v)/sqrt(bc2) + eps);  g = 0
-__global__ void k_adam(AdamParams P) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= P.cum4[P.n_seg]) return;
-    int s = 0;
+constexpr int ADAM_VEC = 2;
+__global__ void __launch_bounds__(256) k_adam(AdamParams P) {
+    const int total = P.cum4[P.n_seg];
+    const int t0 = blockIdx.x * (blockDim.x * ADAM_VEC) + threadIdx.x;
+    int idx[ADAM_VEC]; bool live[ADAM_VEC], upd[ADAM_VEC]; float nstep[ADAM_VEC];
+    float4 g[ADAM_VEC], m[ADAM_VEC], v[ADAM_VEC], p[ADAM_VEC];
 #pragma unroll
-    for (int k = 1; k < ADAM_MAX_SEG; ++k) if (k < P.n_seg && tid >= P.cum4[k]) s = k;
-    const AdamSegment sg = P.seg[s];
-    const int i = sg.begin / 4 + (tid - P.cum4[s]);
-    const float nstep = -sg.step;
-    float4* gp = reinterpret_cast<float4*>(P.grad) + i;
-    float4 g = *gp;
-    *gp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!sg.active) return;
-    if (sg.mask && !sg.mask[(i * 4 - sg.begin) / CDIM]) return;
-    float4 m = reinterpret_cast<float4*>(P.m)[i], v = reinterpret_cast<float4*>(P.v)[i], p = reinterpret_cast<float4*>(P.param)[i];
-    float* gg = reinterpret_cast<float*>(&g); float* mm = reinterpret_cast<float*>(&m);
-    float* vv = reinterpret_cast<float*>(&v); float* pp = reinterpret_cast<float*>(&p);
+    for (int u = 0; u < ADAM_VEC; ++u) {
+        const int tid = t0 + u * blockDim.x;
+        live[u] = tid < total;
+        // compile-time indices only: a runtime index into the by-value parameter struct would go through local memory
+        AdamSegment sg = P.seg[0];
+        int base = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float gk = gg[k] * P.grad_scale;
-        mm[k] = __fadd_rn(__fmul_rn(mm[k], P.beta1), __fmul_rn(P.om_beta1, gk));                   // mul_(b1).add_(g, 1-b1)
-        vv[k] = __fadd_rn(__fmul_rn(vv[k], P.beta2), __fmul_rn(__fmul_rn(P.om_beta2, gk), gk));   // mul_(b2).addcmul_(g, g, 1-b2)
-        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), P.bc2_sqrt), P.eps);
-        pp[k] = __fadd_rn(pp[k], __fdiv_rn(__fmul_rn(nstep, mm[k]), denom));                      // addcdiv_(m, denom, -step)
+        for (int k = 1; k < ADAM_MAX_SEG; ++k)
+            if (k < P.n_seg && tid >= P.cum4[k]) { sg = P.seg[k]; base = P.cum4[k]; }
+        idx[u] = live[u] ? sg.begin / 4 + (tid - base) : 0;
+        nstep[u] = -sg.step;
+        upd[u] = live[u] && sg.active && !(sg.mask && !sg.mask[(idx[u] * 4 - sg.begin) / CDIM]);
     }
-    reinterpret_cast<float4*>(P.m)[i] = m; reinterpret_cast<float4*>(P.v)[i] = v; reinterpret_cast<float4*>(P.param)[i] = p;
+#pragma unroll
+    for (int u = 0; u < ADAM_VEC; ++u) {
+        if (live[u]) g[u] = reinterpret_cast<const float4*>(P.grad)[idx[u]];
+        if (upd[u]) { m[u] = reinterpret_cast<const float4*>(P.m)[idx[u]]; v[u] = reinterpret_cast<const float4*>(P.v)[idx[u]]; p[u] = reinterpret_cast<const float4*>(P.param)[idx[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_VEC; ++u) {
+        if (!live[u]) continue;
+        reinterpret_cast<float4*>(P.grad)[idx[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!upd[u]) continue;
+        float* gg = reinterpret_cast<float*>(&g[u]); float* mm = reinterpret_cast<float*>(&m[u]);
+        float* vv = reinterpret_cast<float*>(&v[u]); float* pp = reinterpret_cast<float*>(&p[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = gg[k] * P.grad_scale;
+            mm[k] = __fadd_rn(__fmul_rn(mm[k], P.beta1), __fmul_rn(P.om_beta1, gk));                   // mul_(b1).add_(g, 1-b1)
+            vv[k] = __fadd_rn(__fmul_rn(vv[k], P.beta2), __fmul_rn(__fmul_rn(P.om_beta2, gk), gk));   // mul_(b2).addcmul_(g, g, 1-b2)
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), P.bc2_sqrt), P.eps);
+            pp[k] = __fadd_rn(pp[k], __fdiv_rn(__fmul_rn(nstep[u], mm[k]), denom));                   // addcdiv_(m, denom, -step)
+        }
+        reinterpret_cast<float4*>(P.m)[idx[u]] = m[u]; reinterpret_cast<float4*>(P.v)[idx[u]] = v[u]; reinterpret_cast<float4*>(P.param)[idx[u]] = p[u];
+    }
 }
 
 __global__ void k_fill(float* p, float v, int n) {

@@ -288,18 +288,12 @@ __global__ void k_composite_fwd(CompositeParams P) {
     }
 }
 
-// Backward of the composite for per-ray cotangents (g_rgb, g_depth, g_var) -> g_raw (r,g,b,occ) per sample.
-__global__ void k_composite_bwd(CompositeParams P) {
-    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
-    if (ray >= P.n) return;
-    if (P.valid && !P.valid[ray]) return;   // tiles of dropped rays are skipped by the decoder kernels too
-    RaySamples s; float rgb[3], depth, var;
-    composite_forward(P, ray, l, s, rgb, depth, var);
-    const float gC[3] = {P.g_rgb[3 * ray], P.g_rgb[3 * ray + 1], P.g_rgb[3 * ray + 2]};
-    const float gV = P.g_var[ray];
+// Backward of the composite for the ray's cotangents (gC, gD0, gV) -> g_raw (r,g,b,occ) per sample.
+__device__ __forceinline__ void composite_backward(const CompositeParams& P, int ray, int l, const RaySamples& s, float depth,
+                                                   const float (&gC)[3], float gD0, float gV) {
     // var = sum w (z - D)^2  =>  dvar/dD = -2 sum w (z - D)
     const float sw = warp_sum(s.w[0] * (s.z[0] - depth) + s.w[1] * (s.z[1] - depth));
-    const float gD = P.g_depth[ray] - 2.0f * gV * sw;
+    const float gD = gD0 - 2.0f * gV * sw;
     float gw[2], gwsum[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -340,6 +334,46 @@ __global__ void k_composite_bwd(CompositeParams P) {
             atomicAdd(P.d_rays + 6 * (size_t)ray + 3 + l, g_norm * P.rays_d[3 * ray + l] / n2);
         }
     }
+}
+
+__global__ void k_composite_bwd(CompositeParams P) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) return;   // tiles of dropped rays are skipped by the decoder kernels too
+    RaySamples s; float rgb[3], depth, var;
+    composite_forward(P, ray, l, s, rgb, depth, var);
+    const float gC[3] = {P.g_rgb[3 * ray], P.g_rgb[3 * ray + 1], P.g_rgb[3 * ray + 2]};
+    composite_backward(P, ray, l, s, depth, gC, P.g_depth[ray], P.g_var[ray]);
+}
+
+// Mapping iteration: composite + loss of Mapper.cpp:435-442 + composite backward in ONE pass over the ray (the loss
+// cotangents are local to the ray).  Writes rgb / depth / var, accumulates the loss, leaves g_raw for the decoder backward.
+__global__ void k_composite_map(CompositeParams P, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                                int use_color, float w_color, float* loss_out) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) {
+        if (l == 0) { P.rgb[3 * ray] = P.rgb[3 * ray + 1] = P.rgb[3 * ray + 2] = 0.0f; P.depth[ray] = 0.0f; P.var[ray] = 0.0f; }
+        return;
+    }
+    RaySamples s; float rgb[3], depth, var;
+    composite_forward(P, ray, l, s, rgb, depth, var);
+    float loss = 0.0f, gD = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
+    const float g = gt_depth[ray];
+    if (g > 0.0f) { const float df = g - depth; loss += fabsf(df); gD = df > 0.0f ? -1.0f : (df < 0.0f ? 1.0f : 0.0f); }
+    if (use_color) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float df = gt_color[3 * ray + c] - rgb[c];
+            loss += w_color * fabsf(df);
+            gC[c] = df > 0.0f ? -w_color : (df < 0.0f ? w_color : 0.0f);
+        }
+    }
+    if (l == 0) {
+        P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var;
+        if (loss != 0.0f) atomicAdd(loss_out, loss);
+    }
+    composite_backward(P, ray, l, s, depth, gC, gD, 0.0f);
 }
 
 // ---- losses ------------------------------------------------------------------------------------------
