@@ -116,6 +116,10 @@ int nsb_set_ttables(nsb_ctx* ctx, const float* t_samples, const float* t_surface
 /* Optional frustum voxel mask per level (Z*Y*X bytes, NULL clears): Adam touches masked voxels only
  * (intent of Mapper.cpp:260-290,333-350,448-464). */
 int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host_mask_zyx);
+/* Mapper::get_mask_from_c2w (Mapper.h:23, Mapper.cpp:42-130): frustum voxel mask of grid `level` for the depth frame in
+ * `slot` seen from c2w16 (NULL = the slot's pose), computed on the GPU.  host_mask_zyx may be NULL; install != 0 makes it
+ * the level's Adam mask.  nsb_mapping_begin does this itself for the current frame when frustum_feature_selection is on. */
+int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int level, uint8_t* host_mask_zyx, int install);
 
 /* ---- frames (KeyFrame, Mapper.h:11-15) ------------------------------------------------------------ */
 /* Upload one RGB-D frame into resident slot `slot`: depth (H,W), colour (H,W,3), c2w row-major 4x4. */

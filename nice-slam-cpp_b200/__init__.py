@@ -92,6 +92,7 @@ def load_library(variant=""):
     L.nsb_get_decoder_grad.argtypes = [v, C.c_int, _fp, C.c_int64]
     L.nsb_set_ttables.argtypes = [v, _fp, _fp]
     L.nsb_set_voxel_mask.argtypes = [v, C.c_int, _u8p]
+    L.nsb_frustum_mask.argtypes = [v, C.c_int, _fp, C.c_int, _u8p, C.c_int]
     L.nsb_set_frame.argtypes = [v, C.c_int, _fp, _fp, _fp]
     L.nsb_set_frame_pose.argtypes = [v, C.c_int, _fp]
     L.nsb_seed.argtypes = [v, C.c_uint64]
@@ -124,7 +125,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_config_default", "nsb_config_load_yaml", "nsb_grid_dims", "nsb_decoder_count", "nsb_create", "nsb_destroy",
     "nsb_last_error", "nsb_abi_version", "nsb_build_info", "nsb_synchronize", "nsb_stream", "nsb_set_grid", "nsb_get_grid",
     "nsb_get_grid_grad", "nsb_set_decoder", "nsb_get_decoder", "nsb_get_decoder_grad", "nsb_set_ttables",
-    "nsb_set_voxel_mask", "nsb_set_frame", "nsb_set_frame_pose", "nsb_quad2rotation", "nsb_get_camera_from_tensor",
+    "nsb_set_voxel_mask", "nsb_frustum_mask", "nsb_set_frame", "nsb_set_frame_pose", "nsb_quad2rotation", "nsb_get_camera_from_tensor",
     "nsb_get_tensor_from_camera", "nsb_seed", "nsb_get_samples", "nsb_render_batch_ray", "nsb_render_batch_ray_dev",
     "nsb_eval_points", "nsb_get_last_zvals", "nsb_render_vjp", "nsb_mapping_begin", "nsb_mapping_iter",
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
@@ -261,6 +262,13 @@ class Engine:
     def set_voxel_mask(self, level, mask):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         self._ck(self.lib.nsb_set_voxel_mask(self.h, STAGE[level], None if m is None else m.ctypes.data_as(_u8p)))
+
+    def frustum_mask(self, slot, level, c2w=None, install=False):
+        """Mapper::get_mask_from_c2w (Mapper.cpp:42-130) on the GPU -> (Z, Y, X) bool."""
+        p = _c(c2w)
+        out = np.empty(self.grid_shape[level][2:], np.uint8)
+        self._ck(self.lib.nsb_frustum_mask(self.h, slot, _f(p), STAGE[level], out.ctypes.data_as(_u8p), int(install)))
+        return out.astype(bool)
 
     def set_frame(self, slot, depth, color, c2w):
         d, c, p = _c(depth), _c(color), _c(c2w)

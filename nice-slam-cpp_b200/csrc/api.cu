@@ -92,6 +92,7 @@ struct nsb_ctx {
     size_t nvox[4];
     int64_t dec_n[4];
     uint8_t* vmask[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t* vmask_tmp[4] = {nullptr, nullptr, nullptr, nullptr};
     float *t_samples = nullptr, *t_surface = nullptr;
     // frames
     float *f_depth = nullptr, *f_color = nullptr, *f_pose = nullptr;
@@ -378,7 +379,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3]};
+                    c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -452,6 +453,54 @@ extern "C" int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host) 
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+// Mapper::get_mask_from_c2w (Mapper.cpp:42-130): frustum voxel mask of grid `level` for the depth frame in `slot` seen from
+// c2w16 (NULL = the slot's pose).  host_mask_zyx (Z*Y*X bytes) may be NULL; install != 0 makes it the level's Adam mask.
+extern "C" int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int level, uint8_t* host_mask_zyx, int install) {
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    float c2w[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (c2w16) memcpy(c2w, c2w16, 12 * sizeof(float));
+    else { CK(cudaMemcpyAsync(c2w, ctx->f_pose + 12 * slot, 12 * 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    const size_t nv = ctx->nvox[level];
+    if (!ctx->vmask_tmp[level]) CK(dalloc(&ctx->vmask_tmp[level], nv));
+    if (ensure_scratch(ctx, nv)) return -1;
+    FrustumParams P; memset(&P, 0, sizeof P);
+    // general 4x4 inverse of [R|t; 0 0 0 1] in double (np.linalg.inv upstream): w2c = [R^-1 | -R^-1 t]
+    {
+        const double a[9] = {c2w[0], c2w[1], c2w[2], c2w[4], c2w[5], c2w[6], c2w[8], c2w[9], c2w[10]};
+        const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                         (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                         (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det};
+        const double t[3] = {c2w[3], c2w[7], c2w[11]};
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) P.w2c[4 * r + c] = (float)inv[3 * r + c];
+            P.w2c[4 * r + 3] = (float)(-(inv[3 * r] * t[0] + inv[3 * r + 1] * t[1] + inv[3 * r + 2] * t[2]));
+            P.cam_o[r] = (float)t[r];
+        }
+    }
+    P.depth = ctx->f_depth + (size_t)ctx->cfg.H * ctx->cfg.W * slot;
+    P.bnd = ctx->bnd; P.H = ctx->cfg.H; P.W = ctx->cfg.W; P.Z = ctx->gdim[level][0]; P.Y = ctx->gdim[level][1]; P.X = ctx->gdim[level][2];
+    P.fx = ctx->cfg.fx; P.fy = ctx->cfg.fy; P.cx = ctx->cfg.cx; P.cy = ctx->cfg.cy;
+    P.vdepth = ctx->scratch_ncdhw; P.stats = ctx->median; P.mask = ctx->vmask_tmp[level];
+    CK(cudaMemsetAsync(ctx->median, 0, 16, ctx->stream));
+    if (level == NSB_COARSE) {   // Mapper.cpp:54-59: the coarse grid is always fully selected
+        CK(cudaMemsetAsync(ctx->vmask_tmp[level], 1, nv, ctx->stream));
+    } else {
+        k_frustum_depth<<<cdiv((int)nv, 256), 256, 0, ctx->stream>>>(P);
+        k_frustum_mask<<<cdiv((int)nv, 256), 256, 0, ctx->stream>>>(P);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    if (host_mask_zyx) CK(cudaMemcpyAsync(host_mask_zyx, ctx->vmask_tmp[level], nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (install) {
+        if (!ctx->vmask[level]) CK(dalloc(&ctx->vmask[level], nv));
+        CK(cudaMemcpyAsync(ctx->vmask[level], ctx->vmask_tmp[level], nv, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (host_mask_zyx) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int nsb_set_frame_pose(nsb_ctx* ctx, int slot, const float* c2w16) {
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -847,6 +896,9 @@ extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, i
     CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    if (ctx->cfg.frustum_feature_selection) {   // Mapper.cpp:226-290: masks from the current frame (the last of optimize_frame)
+        for (int l = 1; l < 4; ++l) if (nsb_frustum_mask(ctx, slots[n_frames - 1], nullptr, l, nullptr, 1)) return -1;
+    }
     if (!ctx->cfg.fix_color) {   // make sure the stash exists before the hot loop
         if (ensure_stash(ctx, (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64)) return -1;
     }

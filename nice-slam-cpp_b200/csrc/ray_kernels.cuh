@@ -522,4 +522,78 @@ __global__ void k_pose_grad(PoseGradParams P) {
     }
 }
 
+
+// ---- frustum voxel mask: Mapper::get_mask_from_c2w (Mapper.cpp:42-130, upstream semantics -- the transliteration truncates
+// the bound to int and mixes up the memcpy directions / the sign of z) --------------------------------------
+struct FrustumParams {
+    const float* depth;      // (H, W) frame
+    float w2c[12];           // inverse pose, row-major 3x4
+    float cam_o[3];          // camera centre (c2w[:3, 3])
+    Bound bnd;
+    int H, W, Z, Y, X;
+    float fx, fy, cx, cy;
+    float* vdepth;           // [Z*Y*X] remapped depth per voxel
+    float* stats;            // [0] max remapped depth (int bits)
+    uint8_t* mask;           // [Z][Y][X]
+};
+
+// torch::linspace(lo, hi, n)[i] in fp32 (symmetric formula)
+__device__ __forceinline__ float linspace_at(float lo, float hi, int n, int i) {
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(n - 1));
+    return i < n / 2 ? __fadd_rn(lo, __fmul_rn(step, (float)i)) : __fsub_rn(hi, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__device__ __forceinline__ void frustum_project(const FrustumParams& P, int v, float (&pw)[3], float& u, float& vv, float& z) {
+    const int x = v % P.X, y = (v / P.X) % P.Y, zz = v / (P.X * P.Y);
+    pw[0] = linspace_at(P.bnd.lo[0], P.bnd.hi[0], P.X, x);
+    pw[1] = linspace_at(P.bnd.lo[1], P.bnd.hi[1], P.Y, y);
+    pw[2] = linspace_at(P.bnd.lo[2], P.bnd.hi[2], P.Z, zz);
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = P.w2c[4 * r] * pw[0] + P.w2c[4 * r + 1] * pw[1] + P.w2c[4 * r + 2] * pw[2] + P.w2c[4 * r + 3];
+    c[0] = -c[0];                                            // cam_cord[:, 0] *= -1
+    z = c[2] + 1e-5f;                                        // z = uv[:, -1:] + 1e-5
+    u = (P.fx * c[0] + P.cx * c[2]) / z;                     // uv = K @ cam_cord, uv[:, :2] / z
+    vv = (P.fy * c[1] + P.cy * c[2]) / z;
+}
+
+// cv::remap(depth, u, v, INTER_LINEAR, BORDER_CONSTANT 0) for one point: coordinates quantised to 1/32 pixel like OpenCV
+__device__ __forceinline__ float remap_bilinear(const FrustumParams& P, float u, float v) {
+    if (!(fabsf(u) < 1e6f) || !(fabsf(v) < 1e6f)) return 0.0f;
+    const int sx = __float2int_rn(u * 32.0f), sy = __float2int_rn(v * 32.0f);
+    const int ix = sx >> 5, iy = sy >> 5;
+    const float a = (float)(sx & 31) * (1.0f / 32.0f), b = (float)(sy & 31) * (1.0f / 32.0f);
+    auto at = [&](int yy, int xx) { return (xx >= 0 && xx < P.W && yy >= 0 && yy < P.H) ? P.depth[(size_t)yy * P.W + xx] : 0.0f; };
+    const float w0 = (1.0f - b) * (1.0f - a), w1 = (1.0f - b) * a, w2 = b * (1.0f - a), w3 = b * a;
+    return at(iy, ix) * w0 + at(iy, ix + 1) * w1 + at(iy + 1, ix) * w2 + at(iy + 1, ix + 1) * w3;
+}
+
+__global__ void k_frustum_depth(FrustumParams P) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 0.0f;
+    if (v < P.Z * P.Y * P.X) {
+        float pw[3], u, vv, z;
+        frustum_project(P, v, pw, u, vv, z);
+        d = remap_bilinear(P, u, vv);
+        P.vdepth[v] = d;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(P.stats), __float_as_int(fmaxf(d, 0.0f)));
+}
+
+__global__ void k_frustum_mask(FrustumParams P) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.Z * P.Y * P.X) return;
+    float pw[3], u, vv, z;
+    frustum_project(P, v, pw, u, vv, z);
+    float d = P.vdepth[v];
+    if (d == 0.0f) d = P.stats[0];                           // depths[zero_mask] = max(depths)
+    bool m = (u < (float)P.W) && (u > 0.0f) && (vv < (float)P.H) && (vv > 0.0f);   // edge = 0
+    m = m && (0.0f <= -z) && (-z <= d + 0.5f);               // depth test
+    const float dx = pw[0] - P.cam_o[0], dy = pw[1] - P.cam_o[1], dz = pw[2] - P.cam_o[2];
+    m = m || (dx * dx + dy * dy + dz * dz < 0.25f);          // features near the camera centre
+    P.mask[v] = m ? 1 : 0;
+}
+
 }  // namespace nsb

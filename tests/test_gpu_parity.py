@@ -282,3 +282,38 @@ def test_voxel_mask_limits_adam(engine_factory, model_inputs):
     for lv in ("middle", "fine", "color"):
         d = np.abs(e.get_grid(lv) - grids[lv]).max(axis=(0, 1))
         assert d[masks[lv] == 0].max() == 0.0 and d[masks[lv] == 1].max() > 0.0
+
+
+# ------------------------------------------------------------------ frustum voxel mask on the GPU
+def test_frustum_mask_vs_upstream_semantics(engine_factory, frames, syn):
+    """Mapper::get_mask_from_c2w (Mapper.cpp:42-130) restated with upstream's semantics + cv2.remap (oracle) vs the GPU
+    kernels.  A voxel whose projection lands within float rounding of a threshold may flip: <= 0.2 % mismatches."""
+    depths, colors, poses = frames
+    e = engine_factory()
+    # a piecewise-smooth depth image makes the depth test non-trivial
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float32)
+    depth = (1.5 + 0.8 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.float32)
+    depth[100:140, 200:260] = 0.0
+    for slot, pose in ((0, poses[1]), (1, poses[3])):
+        e.set_frame(slot, depth, colors[0], pose)
+        for lv in ("middle", "fine", "color"):
+            got = e.frustum_mask(slot, lv)
+            ref = O.get_mask_from_c2w(pose, depth, syn.grid_dims(lv), CAM)
+            assert got.shape == ref.shape and ref.sum() > 50
+            assert (got != ref).sum() <= max(2, int(0.002 * ref.size)), (lv, int((got != ref).sum()), int(ref.sum()))
+    assert e.frustum_mask(0, "coarse").all()                     # Mapper.cpp:54-59
+
+
+def test_mapping_with_frustum_feature_selection(engine_factory, model_inputs, frames):
+    """frustum_feature_selection = True (nice_slam.yaml:79): nsb_mapping_begin builds the masks from the current frame and
+    Adam leaves every voxel outside them untouched (Mapper.cpp:260-290, 333-350, 448-464)."""
+    grids, decs, _ = model_inputs
+    e = engine_factory(mapping_pixels=1000, frustum_feature_selection=1)
+    e.seed(2)
+    e.mapping_begin([1, 0], 60, 1.0)          # the last slot is the current frame
+    for it in (0, 59):
+        e.mapping_iter(it)
+    for lv in ("middle", "fine", "color"):
+        m = e.frustum_mask(0, lv)
+        d = np.abs(e.get_grid(lv) - grids[lv]).max(axis=(0, 1))
+        assert d[~m].max() == 0.0 and d[m].max() > 0.0
