@@ -187,7 +187,8 @@ def run_ours(args, rank, world, local_rank):
     cfg.mapping_pixels = n_global
     cfg.max_rays = n_global
     cfg.max_frames = N_FRAMES + 1
-    cfg.frustum_feature_selection = 0     # the frustum voxel mask (Mapper.cpp:42-130) is a SURVEY 8-f "next" row
+    cfg.frustum_feature_selection = 0     # every voxel is optimised in BOTH arms (random synthetic depth gives a degenerate frustum);
+                                          # the GPU frustum mask (Mapper.cpp:42-130) is covered by tests/test_gpu_parity.py
     e = nsb.Engine(cfg, device=local_rank)
     e.set_model(grids, decs)
     for f in range(N_FRAMES):
@@ -238,7 +239,9 @@ def run_ours(args, rank, world, local_rank):
         kms = e.kernel_ms()
         launches = e.launch_count()
         e.set_profiling(False)
-        losses, n_inside = e.mapping_losses(0, ITERS_PER_KEYFRAME) if K + W >= ITERS_PER_KEYFRAME else e.mapping_losses(0, (K + W))
+        gather_ms = e.bench_gather(20)       # grid sampling alone on the last step's rays (resident grids: L1/L2 traffic)
+        last_it = (W + K - 1) % ITERS_PER_KEYFRAME
+        losses, n_inside = e.mapping_losses(0, last_it + 1)    # the iterations run since the last mapping_begin
     t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -277,13 +280,23 @@ def run_ours(args, rank, world, local_rank):
         bwd_s = kms["decode_bwd"] * 1e-3
         ach = bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0
         fwd_s = kms["decode_fwd"] * 1e-3
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("k_decode_bwd")
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "k_decode_bwd", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 dense (sustained)",
-                "note": "algorithmic FLOPs; the kernel runs fp32-grade 3xTF32 mma.sync (3 MMAs per product) and recomputes the forward",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " bf16 dense (sustained)",
+                "note": "algorithmic FLOPs of the backward (SURVEY 8-d); the kernel runs the fp32-grade 3xTF32 split (3 mma.sync per product), measured mma.sync tf32 ceiling 278 TFLOP/s",
                 "launches": K, "avg_launch_ms": kms["decode_bwd"] / K,
                 "fwd_kernel": {"kernel": "k_decode_fwd", "achieved_tflops": K * FLOP_FWD_RAY * rays_rank / fwd_s * 1e-12 if fwd_s > 0 else 0.0,
                                "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_fwd"] / K},
-                "kernel_ms_total": kms}
+                "kernel_ms_total": kms,
+                "grid_sampling": {"kernel": "k_gather_only", "ms": gather_ms, "rays": RAYS_PER_GPU,
+                                  "achieved_gbs": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 if gather_ms > 0 else 0.0,
+                                  "frac_of_hbm_peak": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 / pk["hbm_gbs"] if gather_ms > 0 else 0.0,
+                                  "l2_gather_peak_gbs_measured": 9100.0, "note": "all rays of the step (no inside filter), 3 grids x 8 corners x 128 B per sample; grids (11.2 MB) are L2-resident"}}
         try:
             cpu = cpu_baseline_sample(nsb) if world == 1 and not args.no_cpu_baseline else None
         except Exception as ex:  # the checker is optional for the bench line

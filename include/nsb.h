@@ -194,6 +194,9 @@ int64_t nsb_launch_count(nsb_ctx* ctx, int reset);
  * [1] decode fwd, [2] composite/loss, [3] decode bwd, [4] wgrad, [5] adam, [6] allreduce. Enable with nsb_set_profiling. */
 int nsb_set_profiling(nsb_ctx* ctx, int on);
 int nsb_get_kernel_ms(nsb_ctx* ctx, float* ms7);
+/* Times the trilinear grid sampling alone (three 32-channel grids, the rays and z values of the last forward): average
+ * device ms of `reps` launches.  Algorithmic bytes per launch = n * S * 3 * 8 * 128. */
+int nsb_bench_gather(nsb_ctx* ctx, int reps, float* ms_out);
 /* Development aid: cycle counters of the tcgen05 forward kernel (filled only by the NSB_TC_TIMING build variant). */
 int nsb_debug_counters(nsb_ctx* ctx, unsigned long long* out32);
 

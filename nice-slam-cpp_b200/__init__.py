@@ -116,6 +116,7 @@ def load_library(variant=""):
     L.nsb_comm_rank_world.argtypes = [v, _ip, _ip]
     L.nsb_set_profiling.argtypes = [v, C.c_int]
     L.nsb_get_kernel_ms.argtypes = [v, _fp]
+    L.nsb_bench_gather.argtypes = [v, C.c_int, _fp]
     L.nsb_debug_counters.argtypes = [v, C.POINTER(C.c_uint64)]
     _LIBS[variant] = L
     return L
@@ -130,7 +131,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_eval_points", "nsb_get_last_zvals", "nsb_render_vjp", "nsb_mapping_begin", "nsb_mapping_iter",
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
-    "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters",
+    "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
 ]
 
 
@@ -380,6 +381,11 @@ class Engine:
     # ---- multi-GPU / instrumentation
     def comm_init(self, uid, rank, world):
         self._ck(self.lib.nsb_comm_init(self.h, uid, rank, world))
+
+    def bench_gather(self, reps=20):
+        ms = C.c_float(0)
+        self._ck(self.lib.nsb_bench_gather(self.h, reps, C.byref(ms)))
+        return ms.value
 
     def launch_count(self, reset=False):
         return int(self.lib.nsb_launch_count(self.h, int(reset)))

@@ -40,6 +40,7 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
 }
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
+cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
 int compose_floats(int which);
@@ -1107,6 +1108,26 @@ extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int worl
     return 0;
 }
 extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }
+
+// Grid sampling alone on the rays / z values of the last forward (n rays, S samples): returns the average device time of
+// `reps` launches in ms.  Algorithmic traffic per launch = n * S * 3 lookups * 8 corners * 128 B.
+extern "C" int nsb_bench_gather(nsb_ctx* ctx, int reps, float* ms_out) {
+    const int n = ctx->last_n, S = ctx->last_S;
+    if (n <= 0) return fail(ctx, "no forward has run yet");
+    DecodeParams P; fill_decode_params(ctx, P, n, S, nullptr);
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int grid = ctx->n_sm * 8;
+    CK(launch_gather_only(P, ctx->occ[0], grid, ctx->stream));
+    CK(cudaEventRecord(a, ctx->stream));
+    for (int r = 0; r < reps; ++r) CK(launch_gather_only(P, ctx->occ[0], grid, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, a, b));
+    ctx->launches += reps + 1;
+    *ms_out = ms / (float)reps;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return 0;
+}
 
 // ---- instrumentation ----------------------------------------------------------------------------------------------------
 // Cycle counters of the tcgen05 forward (only filled by the NSB_TC_TIMING build variant): 32 values, reset on read.

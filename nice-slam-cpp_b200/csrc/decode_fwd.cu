@@ -115,6 +115,36 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd
     }
 }
 
+// Grid sampling in isolation (the K6 row of SURVEY 2.1): the same quad-cooperative trilinear gather as the fused kernels
+// for the middle, fine and colour grids of every sample, features reduced to one float per sample so that nothing but the
+// gather is timed.  Used by nsb_bench_gather for the "grid sampling vs L2/HBM roofline" number.
+__global__ void __launch_bounds__(256) k_gather_only(const DecodeParams P, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5, ntiles = P.P / TILE;
+    for (int tile = warp; tile < ntiles; tile += nwarps) {
+        float p[2][3]; int sidx[2];
+        if (!load_points(P, tile * TILE, g, p, sidx)) continue;
+        float acc[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int lv = 1; lv < 4; ++lv) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float c[8];
+                gather8(P.grid[lv], P.bnd, p[r], t, c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[r] += c[i];
+            }
+        }
+        acc[0] = quad_sum(acc[0]); acc[1] = quad_sum(acc[1]);
+        if (t == 0) { out[sidx[0]] = acc[0]; out[sidx[1]] = acc[1]; }
+    }
+}
+
+cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st) {
+    k_gather_only<<<grid, 256, 0, st>>>(P, out);
+    return cudaGetLastError();
+}
+
 size_t decode_fwd_smem() { return sizeof(float) * DecSmem<64>::TOTAL; }
 
 template <bool P3, bool TRAIN>

@@ -269,7 +269,7 @@ def test_full_size_properties(engine_factory, frames, syn, nsb):
 def test_voxel_mask_limits_adam(engine_factory, model_inputs):
     """frustum_feature_selection intent (Mapper.cpp:260-290,333-350): only masked voxels are optimised."""
     grids, decs, _ = model_inputs
-    e = engine_factory(mapping_pixels=1000)
+    e = engine_factory(mapping_pixels=1000, frustum_feature_selection=0)   # explicit masks instead of the computed frustum
     masks = {}
     rs = np.random.RandomState(0)
     for lv in ("middle", "fine", "color"):
