@@ -52,43 +52,72 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms from a
+    thread (nvidia-smi -lms cannot start fast enough for a 60 ms region); nvidia-smi is the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, dev):
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.th = None
+        self.smi = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as N
+            import torch
+            N.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(dev).uuid)
+                h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = N.nvmlDeviceGetHandleByIndex(dev)
+            self.max_mhz = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        for k, b in bits.items():
+                            if r & b:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.th = threading.Thread(target=poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.th = None
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            try:
+                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._read_smi, daemon=True).start()
+            except Exception:
+                self.smi = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _read_smi(self):
+        for line in self.smi.stdout:
+            r = [x.strip() for x in line.split(",")]
+            if r and r[0].isdigit():
+                self.sm.append(int(r[0]))
+                if len(r) > 1 and r[1].isdigit():
+                    self.max_mhz = int(r[1])
+                for k, nm in enumerate(self.NAMES):
+                    if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                        self.reasons.add(nm)
 
     def stop(self):
-        if not self.proc:
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=1)
+        if self.smi:
+            self.smi.terminate()
+        if not self.sm:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        if not sm:
-            return None
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        return {"sm_mhz": int(statistics.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": int(statistics.median(self.sm)), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def synthetic_inputs(nsb):
@@ -172,6 +201,35 @@ def cpu_baseline_sample(nsb):
 
 
 # -------------------------------------------------------------------------------------------------- our arm
+def run_tracking(e, nsb, torch, ext, depths, colors, poses, frames=6, warm_frames=2):
+    """ms per tracking iteration (BASELINE configs[2], Tracker.cpp:41-113): 5000 rays in the edge-cropped window, render,
+    uncertainty-weighted loss with the median mask, backward to the 7-vector, Adam; 10 iterations per frame, the loss read
+    back every iteration as the reference prints it (Tracker.cpp:111).  Device time from events on the library's stream,
+    wall time through the host ABI (pixel indices drawn by the host mt19937 and copied H2D inside the timed region)."""
+    iters = e.cfg.tracking_iters
+    e.set_frame(0, depths[0], colors[0], poses[0])
+    cam0 = nsb.get_tensor_from_camera(poses[0])
+    cam0[4:] += 0.01     # start 1 cm off the ground-truth translation
+    dev_ms, wall = 0.0, 0.0
+    with torch.cuda.stream(ext):
+        for f in range(warm_frames + frames):
+            e.tracking_begin(0, cam0)
+            e.synchronize()
+            evs = []
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(ext); loss, _ = e.tracking_iter(None, want_grad=False); b.record(ext)
+                evs.append((a, b))
+            e.synchronize()
+            if f >= warm_frames:
+                wall += time.perf_counter() - t0
+                dev_ms += sum(a.elapsed_time(b) for a, b in evs)
+    n = frames * iters
+    return {"ms_per_iter": dev_ms / n, "e2e_ms_per_iter": wall / n * 1e3, "rays_per_iter": int(e.cfg.tracking_pixels), "iters_per_frame": int(iters),
+            "frames_timed": frames, "last_loss": float(loss), "note": "replicas only (one GPU per frame); loss D2H + sync every iteration"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     nsb = importlib.import_module("nice-slam-cpp_b200")
@@ -187,6 +245,7 @@ def run_ours(args, rank, world, local_rank):
     cfg.mapping_pixels = n_global
     cfg.max_rays = n_global
     cfg.max_frames = N_FRAMES + 1
+    cfg.tracking_pixels = RAYS_PER_GPU     # BASELINE configs[2]: 5000 rays per tracking iteration
     cfg.frustum_feature_selection = 0     # every voxel is optimised in BOTH arms (random synthetic depth gives a degenerate frustum);
                                           # the GPU frustum mask (Mapper.cpp:42-130) is covered by tests/test_gpu_parity.py
     e = nsb.Engine(cfg, device=local_rank)
@@ -270,6 +329,8 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": K * n_global / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": int(idx_all[0].nbytes + frame_bytes / ITERS_PER_KEYFRAME),
            "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / K * 1e3}
 
+    tracking = run_tracking(e, nsb, torch, ext, depths, colors, poses)   # replicas only: every rank tracks its own frame
+
     if rank == 0:
         pk = peaks()
         n_color = sum(1 for i in range(W, W + K) if (i % ITERS_PER_KEYFRAME) > 36)
@@ -277,21 +338,26 @@ def run_ours(args, rank, world, local_rank):
         frac_in = float(np.mean(n_inside[n_inside > 0])) / n_global if np.any(n_inside > 0) else 1.0
         rays_rank = RAYS_PER_GPU * frac_in                 # rays that survive the inside filter, per rank and step
         bwd_flop = (n_color * FLOP_BWD_COLOR_RAY + n_geom * FLOP_BWD_GEOM_RAY) * rays_rank
+        fwd_flop = K * FLOP_FWD_RAY * rays_rank
         bwd_s = kms["decode_bwd"] * 1e-3
-        ach = bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0
         fwd_s = kms["decode_fwd"] * 1e-3
-        traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        traffic = {}
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture (profiles/)
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("k_decode_bwd")
+                traffic = json.load(f)
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "k_decode_bwd", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + " bf16 dense (sustained)",
-                "note": "algorithmic FLOPs of the backward (SURVEY 8-d); the kernel runs the fp32-grade 3xTF32 split (3 mma.sync per product), measured mma.sync tf32 ceiling 278 TFLOP/s",
-                "launches": K, "avg_launch_ms": kms["decode_bwd"] / K,
-                "fwd_kernel": {"kernel": "k_decode_fwd", "achieved_tflops": K * FLOP_FWD_RAY * rays_rank / fwd_s * 1e-12 if fwd_s > 0 else 0.0,
-                               "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_fwd"] / K},
+        fwd_name = "k_decode_fwd_tc" if os.environ.get("NSB_TCGEN05", "0") not in ("", "0") else "k_decode_fwd"
+        kern = {fwd_name: {"achieved": fwd_flop / fwd_s * 1e-12 if fwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_fwd"] / K, "flop_per_launch": fwd_flop / K,
+                           "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0},
+                "k_decode_bwd": {"achieved": bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_bwd"] / K, "flop_per_launch": bwd_flop / K}}
+        dom = fwd_name if fwd_s >= bwd_s else "k_decode_bwd"       # the dominant kernel of the step
+        ach = kern[dom]["achieved"]
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic.get(dom), "peak_source": pk["source"] + " bf16 dense (sustained, kernel timed inside the step)",
+                "note": "algorithmic FLOPs (SURVEY 8-d: 2 x MACs of the three decoders x 48 samples x rays surviving the inside filter) / CUDA-event time of the kernel; "
+                        "the arithmetic is the fp32-grade 3xTF32 split (3 tensor-core MMAs per product), so the design ceiling is tf32 peak / 3",
+                "launches": K, "avg_launch_ms": kern[dom]["avg_launch_ms"], "kernels": kern,
                 "kernel_ms_total": kms,
                 "grid_sampling": {"kernel": "k_gather_only", "ms": gather_ms, "rays": RAYS_PER_GPU,
                                   "achieved_gbs": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 if gather_ms > 0 else 0.0,
@@ -308,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
                           "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "step i = iteration i%60 of optimize_map (37 geometry + 23 colour)",
                           "mma": "3xTF32 mma.sync (fp32-grade)", "l2": "256 MiB flush write between timed steps", "parallelism": "rays sharded x%d, NCCL all-reduce of grads" % world,
                           "inside_fraction": frac_in},
-               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking,
                "loss_first_last": [float(losses[0]), float(losses[len(losses) - 1])]}
         print(json.dumps(out), flush=True)
     e.close()

@@ -21,7 +21,7 @@ BASE = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed
 
 UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("decode_fwd_tc.cu", []), ("wgrad.cu", [])] + \
         [("decode_bwd_inst.cu", ["-DNSB_BWD_COMBO=%d" % k]) for k in range(6)]
-VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "hybrid": ["-DNSB_HYBRID_BF16"], "tctiming": ["-DNSB_TC_TIMING"]}
+VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC_TIMING"]}
 
 
 def lib_path(variant=""):

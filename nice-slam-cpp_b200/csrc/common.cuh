@@ -1,6 +1,6 @@
 // Shared device helpers for the sm_100a kernels of libnsb.so.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,133 +24,99 @@ struct GridView {
     int Z, Y, X;
 };
 
-// ---- tensor-core helpers: mma.sync m16n8k8 tf32, optional 3xTF32 split (fp32-grade accuracy) ------------
-// fp32 -> tf32 with round-to-nearest (ties away), as two integer ops: on sm_100a `cvt.rna.tf32.f32` expands to a
-// ~5-instruction FSETP/SEL/LOP3 sequence (NaN/Inf handling) that dominated the issue slots of the MMA loops.
-// The tensor core reads only the upper 19 bits of a tf32 operand, so the low part of the split is passed as raw
-// fp32 bits (truncation of an already 2^-11-scaled residual: ~2^-22 relative).
+// ---- tensor-core helpers: mma.sync m16n8k16 f16 with fp32 accumulation, fp16 two-way split (fp32-grade accuracy) ----
+// Every fp32 operand x is carried as the pair  hi = fp16(x),  lo = fp16(x - hi)  (22 significant bits; below 6e-5 the
+// fp16 subnormal spacing leaves an absolute error <= 3e-8, far under the fp32 rounding noise of the O(0.01..10)
+// activations).  A product is three tensor-core instructions  a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  accumulated in fp32 --
+// the same error (~2^-22 per product, measured 3-4e-7 on the decoder outputs against fp64) as the 3xTF32 split this
+// replaces, at half the instruction count: one m16n8k16 covers 16 contraction indices where the tf32 m16n8k8 covers 8,
+// and both issue at the same rate on sm_100a (tools/microbench).
+// f2tf32 is kept for the tcgen05 kernel (kind::tf32), which splits into tf32 hi/lo planes.
 __device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = f2tf32(x);
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 
-__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// two fp32 -> packed bf16x2, first argument in the low half (= the lower k index of the MMA fragment)
-__device__ __forceinline__ uint32_t pack_bf16(float lo_half, float hi_half) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);
+// two fp32 -> packed f16x2, first argument in the low half (= the lower k index of the MMA fragment)
+__device__ __forceinline__ uint32_t pack_f16(float lo_half, float hi_half) {
+    const __half2 v = __floats2half2_rn(lo_half, hi_half);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
+// (x0, x1) -> hi = f16x2(x0, x1), lo = f16x2(x0 - hi0, x1 - hi1)
+__device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_f16(x0 - hf.x, x1 - hf.y);
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
-// Default: the three-instruction 3xTF32 split (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi), error ~2^-22 per product.
-// Build variant NSB_HYBRID_BF16 (libnsb_hybrid.so): two instructions per k-step of 8 (measured on B200: a bf16 m16n8k16
-// issues at the same rate as a tf32 m16n8k8):
-//   main term   a_hi . b_hi                       one tf32 m16n8k8
-//   cross terms a_lo . b_hi  +  a_hi . b_lo       one bf16 m16n8k16: k slots 0..7 carry (a_lo, b_hi), slots 8..15 (a_hi, b_lo)
-// The cross terms are 2^-11 of the product, so bf16 operands (8 bits) leave a ~2^-20 relative error, the same order as
-// the 3xTF32 split's dropped a_lo.b_lo term x4.  Measured: forward 0.40 -> 0.345 ms and all mapping parity checks still at
-// 2-4e-6, but the ill-conditioned tracking pose gradient (fp32-vs-fp64 oracle noise 8e-5) degrades from 5e-6 to 6e-3,
-// above the 1e-3 tolerance -- hence not the default.
-//
-// A operand of one k-step (8 features) for the 16 rows of the tile, pre-split.
+// A operand of one k-step (16 contraction indices) for the 16 rows of the tile, pre-split.  The thread (g, t) holds, for
+// rows g and g+8, the four k slots 2t, 2t+1, 2t+8, 2t+9 of the instruction; `set` takes them in that order.
 template <bool P3>
 struct AFrag {
-    uint32_t hi[4];
-#ifndef NSB_HYBRID_BF16
-    uint32_t lo[4];
-#else
-    uint32_t x[4];   // bf16 fragment: x0/x1 = lo parts of rows g / g+8 (k slots 2t,2t+1), x2/x3 = bf16(a) (slots 2t+8, 2t+9)
-#endif
-    // a0 = (row g, feature 2t), a1 = (row g+8, 2t), a2 = (row g, 2t+1), a3 = (row g+8, 2t+1)
-    __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
-        hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
+    uint32_t hi[4], lo[4];
+    __device__ __forceinline__ void set(float r0s0, float r0s1, float r0s2, float r0s3, float r1s0, float r1s1, float r1s2, float r1s3) {
         if (P3) {
-#ifndef NSB_HYBRID_BF16
-            lo[0] = __float_as_uint(a0 - __uint_as_float(hi[0])); lo[1] = __float_as_uint(a1 - __uint_as_float(hi[1]));
-            lo[2] = __float_as_uint(a2 - __uint_as_float(hi[2])); lo[3] = __float_as_uint(a3 - __uint_as_float(hi[3]));
-#else
-            x[0] = pack_bf16(a0 - __uint_as_float(hi[0]), a2 - __uint_as_float(hi[2]));
-            x[1] = pack_bf16(a1 - __uint_as_float(hi[1]), a3 - __uint_as_float(hi[3]));
-            x[2] = pack_bf16(a0, a2);
-            x[3] = pack_bf16(a1, a3);
-#endif
+            split_f16(r0s0, r0s1, hi[0], lo[0]); split_f16(r1s0, r1s1, hi[1], lo[1]);
+            split_f16(r0s2, r0s3, hi[2], lo[2]); split_f16(r1s2, r1s3, hi[3], lo[3]);
+        } else {
+            hi[0] = pack_f16(r0s0, r0s1); hi[1] = pack_f16(r1s0, r1s1); hi[2] = pack_f16(r0s2, r0s3); hi[3] = pack_f16(r1s2, r1s3);
         }
     }
 };
 
-// B fragment given as two fp32 weights (k = 2t and 2t+1 of the k-step, column g): split on the fly.
+// acc += A . B for a B fragment given as four fp32 pairs: (k slots 2t, 2t+1) and (2t+8, 2t+9) of column g, split on the fly
 template <bool P3>
-__device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float w0, float w1) {
-    const uint32_t bh0 = f2tf32(w0), bh1 = f2tf32(w1);
+__device__ __forceinline__ void mma_acc(float (&d)[4], const AFrag<P3>& a, float w0, float w1, float w2, float w3) {
     if (P3) {
-#ifndef NSB_HYBRID_BF16
-        const uint32_t bl0 = __float_as_uint(w0 - __uint_as_float(bh0)), bl1 = __float_as_uint(w1 - __uint_as_float(bh1));
-        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], bh0, bh1);   // small terms first
-        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bl0, bl1);
-#else
-        mma_bf16(d, a.x[0], a.x[1], a.x[2], a.x[3], pack_bf16(w0, w1), pack_bf16(w0 - __uint_as_float(bh0), w1 - __uint_as_float(bh1)));
-#endif
+        uint32_t bh0, bl0, bh1, bl1;
+        split_f16(w0, w1, bh0, bl0); split_f16(w2, w3, bh1, bl1);
+        mma_f16(d, a.lo, bh0, bh1);   // small terms first
+        mma_f16(d, a.hi, bl0, bl1);
+        mma_f16(d, a.hi, bh0, bh1);
+    } else {
+        mma_f16(d, a.hi, pack_f16(w0, w1), pack_f16(w2, w3));
     }
-    mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], bh0, bh1);
 }
 
-// Same with a B operand that was split when the weights were staged: (h0, h1) tf32 weights from the hi plane and
-// (x0, x1) from the second plane -- the residuals (pure 3xTF32) or the packed bf16 pairs {w, w'} / {lo, lo'} (hybrid).
-template <bool P3>
-__device__ __forceinline__ void mma_acc_ps(float (&d)[4], const AFrag<P3>& a, uint32_t h0, uint32_t h1, uint32_t x0, uint32_t x1) {
-    if (P3) {
-#ifndef NSB_HYBRID_BF16
-        mma_tf32(d, a.lo[0], a.lo[1], a.lo[2], a.lo[3], h0, h1);
-        mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], x0, x1);
-#else
-        mma_bf16(d, a.x[0], a.x[1], a.x[2], a.x[3], x0, x1);
-#endif
-    }
-    mma_tf32(d, a.hi[0], a.hi[1], a.hi[2], a.hi[3], h0, h1);
+// Weight matrices live in shared memory pre-split as M[n][K] (n = output index of the product, K = contraction length,
+// a multiple of 16), one row = K 32-bit words + 16 words of padding: k-step kk of row n is the 16-word block
+//     word 16 kk + 4 t + {0, 1, 2, 3} = { hi(slots 2t,2t+1), hi(slots 2t+8,2t+9), lo(2t,2t+1), lo(2t+8,2t+9) }
+// so a lane fetches its whole B fragment (both planes) with ONE 128-bit load, and the row stride K + 16 = 16 (mod 32)
+// words makes the quarter-warp (rows g, g+1 x four t) hit 32 distinct banks.  "Position" pos = 16 kk + 4 t + i of a row
+// therefore holds k slot (2t, 2t+1, 2t+8, 2t+9)[i] of k-step kk; which input feature sits at a position is the staging
+// code's choice (identity for computed operands, perm16 for operands chained from accumulator fragments).
+__host__ __device__ constexpr int wstride(int K) { return K + 16; }
+// feature held at position pos when the A operand is an accumulator tile pair (tiles 2kk, 2kk+1) reused in place
+__host__ __device__ __forceinline__ int perm16(int pos) {
+    const int q = pos & 15, t = q >> 2, i = q & 3;
+    return (pos & ~15) + 2 * t + (i & 1) + 8 * (i >> 1);
 }
 
-// Weight matrices W[out][in] live in shared memory with row stride ld (a multiple of 32 floats) and the
-// column index XOR-swizzled by the row:  col' = col ^ swz(row),  swz(row) = ((row ^ (row>>1)) & 3) << 3.
-// That makes the B-fragment access  M[8j+g][8kk+2t .. +1]  (one 64-bit load per lane, rows vary with g) bank-conflict
-// free; the backward kernels stage the transposed matrices so that they use the very same access.
-__host__ __device__ __forceinline__ int swz(int row) { return ((row ^ (row >> 1)) & 3) << 3; }
-
-// acc[j] += A(kk) * W[8j+g][8kk+2t..]^T for the NJ output tiles (forward: out = x W^T).
-// LO != 0: the matrix was staged pre-split, hi plane at W (tf32-rounded), lo plane at W + LO.
+// acc[j] += A(kk) . M[8j+g][k-step kk]^T for the NJ output tiles.
 template <bool P3, int NJ>
-__device__ __forceinline__ void kstep_fwd(float (&acc)[NJ][4], const AFrag<P3>& a, const float* __restrict__ W,
-                                          int ld, int kk, int g, int t, int LO = 0) {
-    const int col = (8 * kk + 2 * t) ^ swz(g);   // swz(8j+g) == swz(g)
+__device__ __forceinline__ void kstep_fwd(float (&acc)[NJ][4], const AFrag<P3>& a, const uint32_t* __restrict__ M, int stride, int kk, int g, int t) {
+    const uint32_t* wp = M + g * stride + 16 * kk + 4 * t;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const float* wp = W + (8 * j + g) * ld + col;
-        const float2 w = *reinterpret_cast<const float2*>(wp);
-        if (LO) {
-            float2 wl = make_float2(0.f, 0.f);
-            if (P3) wl = *reinterpret_cast<const float2*>(wp + LO);
-            mma_acc_ps<P3>(acc[j], a, __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(wl.x), __float_as_uint(wl.y));
-        } else {
-            mma_acc<P3>(acc[j], a, w.x, w.y);
+        const uint4 b = *reinterpret_cast<const uint4*>(wp + 8 * j * stride);
+        if (P3) {
+            mma_f16(acc[j], a.lo, b.x, b.y);
+            mma_f16(acc[j], a.hi, b.z, b.w);
         }
+        mma_f16(acc[j], a.hi, b.x, b.y);
     }
 }
 
-// C-fragment (rows g, g+8; cols 2t, 2t+1 of tile kk) reused as the A operand of k-step kk: the k index of
-// the MMA is permuted (k=t <-> feature 2t, k=t+4 <-> feature 2t+1), which the B fragments above match.
+// Two adjacent accumulator tiles (rows g, g+8; features 16kk+2t,+1 and 16kk+8+2t,+1) reused as the A operand of
+// k-step kk: the fragment layouts coincide, no data movement.
 template <bool P3>
-__device__ __forceinline__ void afrag_from_c(AFrag<P3>& a, const float (&c)[4]) { a.set(c[0], c[2], c[1], c[3]); }
+__device__ __forceinline__ void afrag_from_c(AFrag<P3>& a, const float (&c0)[4], const float (&c1)[4]) {
+    a.set(c0[0], c0[1], c1[0], c1[1], c0[2], c0[3], c1[2], c1[3]);
+}
 
 // ---- trilinear sampling, identical arithmetic to ATen grid_sampler_3d (bilinear, border, align_corners) ----
 struct Tri {
@@ -190,6 +156,11 @@ __device__ __forceinline__ float tri_corner(const GridView& G, const Tri& s, int
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 256-bit read-only load (sm_100): the four lanes of a quad fetch one whole 128-byte voxel line in a single L1 wavefront
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -46,9 +46,10 @@ __device__ __forceinline__ void grid_backward(const GridView& G, const Bound& bn
             for (int k = 0; k < 8; ++k) {
                 int off;
                 tri_corner(G, s[r], k, off);
-                const float4 v0 = ldg4(G.data + off + 8 * t), v1 = ldg4(G.data + off + 8 * t + 4);
-                const float dot = gc[r][0] * v0.x + gc[r][1] * v0.y + gc[r][2] * v0.z + gc[r][3] * v0.w +
-                                  gc[r][4] * v1.x + gc[r][5] * v1.y + gc[r][6] * v1.z + gc[r][7] * v1.w;
+                float v[8];
+                ldg8(G.data + off + 8 * t, v);
+                const float dot = gc[r][0] * v[0] + gc[r][1] * v[1] + gc[r][2] * v[2] + gc[r][3] * v[3] +
+                                  gc[r][4] * v[4] + gc[r][5] * v[5] + gc[r][6] * v[6] + gc[r][7] * v[7];
                 const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
                 const float wx = dx ? s[r].w1[0] : s[r].w0[0], wy = dy ? s[r].w1[1] : s[r].w0[1], wz = dz ? s[r].w1[2] : s[r].w0[2];
                 gx += (dx ? dot : -dot) * wy * wz;
@@ -108,10 +109,10 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
         if (STASH) stash_tile(st0, st1, stash::GH + HID * i, gh, t);
         if (NEED_C) {   // g_c += g_h Fc_i  (only the first 32 input columns carry gradient)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 2; ++kk) {
                 AFrag<P3> a;
-                afrag_from_c<P3>(a, gh[kk]);
-                kstep_fwd<P3, 4>(gc, a, sm + L::FC + i * HID * HID, HID, kk, g, t, L::LO);   // Fc_i^T [in][out]
+                afrag_from_c<P3>(a, gh[2 * kk], gh[2 * kk + 1]);
+                kstep_fwd<P3, 4>(gc, a, wmat(sm, L::FC + i * HID * L::SH), L::SH, kk, g, t);   // Fc_i^T [in][out]
             }
         }
         apply_mask(gu, gh, masks[i]);
@@ -132,10 +133,10 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
         } else {   // g_h_i = g_u W_i
             zero_tile(gh);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 2; ++kk) {
                 AFrag<P3> a;
-                afrag_from_c<P3>(a, gu[kk]);
-                kstep_fwd<P3, 4>(gh, a, sm + L::w(i), HID, kk, g, t, L::LO);                // W_i^T
+                afrag_from_c<P3>(a, gu[2 * kk], gu[2 * kk + 1]);
+                kstep_fwd<P3, 4>(gh, a, wmat(sm, L::w(i)), L::SH, kk, g, t);                // W_i^T
             }
         }
     }
@@ -149,17 +150,17 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
     if (NEED_E) {
         // g_e = g_u0 W0 + g_u3 W3e, four 8-feature tiles (four independent accumulator chains) at a time; then the chain
         // through e = sin(p B)
-        AFrag<P3> a0[4], a3[4];
+        AFrag<P3> a0[2], a3[2];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { afrag_from_c<P3>(a0[kk], gu0[kk]); afrag_from_c<P3>(a3[kk], gu3[kk]); }
+        for (int kk = 0; kk < 2; ++kk) { afrag_from_c<P3>(a0[kk], gu0[2 * kk], gu0[2 * kk + 1]); afrag_from_c<P3>(a3[kk], gu3[2 * kk], gu3[2 * kk + 1]); }
 #pragma unroll 1
         for (int jg = 0; jg < EMBP / 32; ++jg) {
             float ge[4][4];
             zero_tile(ge);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                kstep_fwd<P3, 4>(ge, a0[kk], sm + L::W0 + 32 * jg * HID, HID, kk, g, t, L::LO);    // W0^T rows 32 jg ..
-                kstep_fwd<P3, 4>(ge, a3[kk], sm + L::W3E + 32 * jg * HID, HID, kk, g, t, L::LO);
+            for (int kk = 0; kk < 2; ++kk) {
+                kstep_fwd<P3, 4>(ge, a0[kk], wmat(sm, L::W0 + 32 * jg * L::SH), L::SH, kk, g, t);    // W0^T rows 32 jg ..
+                kstep_fwd<P3, 4>(ge, a3[kk], wmat(sm, L::W3E + 32 * jg * L::SH), L::SH, kk, g, t);
             }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {

@@ -48,8 +48,8 @@ static WGTable build_table() {
 
 __constant__ WGTable c_wg;
 
-constexpr int WG_STAGES = 4;                       // cp.async ring depth (k-steps in flight)
-constexpr int WG_KROWS = 8;                        // samples per k-step (MMA k = 8)
+constexpr int WG_STAGES = 3;                       // cp.async ring depth (k-steps in flight)
+constexpr int WG_KROWS = 16;                       // samples per k-step (MMA k = 16)
 constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B tile of a row may read past it (values unused)
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
@@ -59,9 +59,10 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// The CTA streams its sample range through a 4-stage shared-memory ring (one stage = the 8 stash rows of a k-step,
-// 22.8 KB, fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA
-// fragments come from conflict-free LDS.64 / LDS.128 (row stride 712 = 8 mod 32 floats).
+// The CTA streams its sample range through a shared-memory ring (one stage = the 16 stash rows of a k-step,
+// 45.6 KB, fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA
+// fragments come from conflict-free LDS.64 / LDS.128 (row stride 712 = 8 mod 32 floats).  k slots (2t, 2t+1, 2t+8, 2t+9)
+// of lane t <-> ring rows (t, t+4, t+8, t+12): any bijection works as long as both operands use it.
 template <bool P3>
 __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
                                                          int P, int S, float* __restrict__ dflat) {
@@ -102,20 +103,21 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
         const int s0 = (k_lo + i) * WG_KROWS;
         if (valid && !valid[s0 / S]) continue;         // rows of rays dropped by the inside filter were never written
         const float* r0 = ring + (i % WG_STAGES) * WG_STAGE_FLOATS + t * stash::W;
-        const float* r1 = r0 + 4 * stash::W;
 #pragma unroll
         for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
             if (!on[q]) continue;
-            const float2 a_lo = *reinterpret_cast<const float2*>(r0 + Lc[q]);   // k = t
-            const float2 a_hi = *reinterpret_cast<const float2*>(r1 + Lc[q]);   // k = t + 4
-            const float4 b_lo = *reinterpret_cast<const float4*>(r0 + Rc[q]);
-            const float4 b_hi = *reinterpret_cast<const float4*>(r1 + Rc[q]);
+            float2 av[4]; float4 bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                av[u] = *reinterpret_cast<const float2*>(r0 + 4 * u * stash::W + Lc[q]);
+                bv[u] = *reinterpret_cast<const float4*>(r0 + 4 * u * stash::W + Rc[q]);
+            }
             AFrag<P3> a;
-            a.set(a_lo.x, a_lo.y, a_hi.x, a_hi.y);
-            mma_acc<P3>(acc[q][0], a, b_lo.x, b_hi.x);
-            mma_acc<P3>(acc[q][1], a, b_lo.y, b_hi.y);
-            mma_acc<P3>(acc[q][2], a, b_lo.z, b_hi.z);
-            mma_acc<P3>(acc[q][3], a, b_lo.w, b_hi.w);
+            a.set(av[0].x, av[1].x, av[2].x, av[3].x, av[0].y, av[1].y, av[2].y, av[3].y);
+            mma_acc<P3>(acc[q][0], a, bv[0].x, bv[1].x, bv[2].x, bv[3].x);
+            mma_acc<P3>(acc[q][1], a, bv[0].y, bv[1].y, bv[2].y, bv[3].y);
+            mma_acc<P3>(acc[q][2], a, bv[0].z, bv[1].z, bv[2].z, bv[3].z);
+            mma_acc<P3>(acc[q][3], a, bv[0].w, bv[1].w, bv[2].w, bv[3].w);
         }
     }
     cp_async_wait<0>();

@@ -29,7 +29,7 @@ __global__ void k_mma_bf16(float* out, int iters) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
     }
     float s = 0; for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
@@ -106,7 +106,7 @@ int main() {
         k_mma_bf16<<<grid, warps * 32>>>(out, 100);
         cudaEventRecord(e0); k_mma_bf16<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
-        printf(", \"mma_bf16_k16_instr_per_clk_sm\": %.3f, \"mma_bf16_tflops\": %.1f", 8.0 * iters * warps / (ms * 1e-3 * clk * 1e3), 2.0 * 16 * 8 * 16 * 8.0 * iters * warps * grid / ms * 1e-9);
+        printf(", \"mma_f16_k16_instr_per_clk_sm\": %.3f, \"mma_f16_tflops\": %.1f", 8.0 * iters * warps / (ms * 1e-3 * clk * 1e3), 2.0 * 16 * 8 * 16 * 8.0 * iters * warps * grid / ms * 1e-9);
         k_mma<<<grid, warps * 32>>>(out, 100);
         cudaEventRecord(e0); k_mma<<<grid, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
