@@ -59,11 +59,12 @@ __host__ __device__ __forceinline__ int fc_channel_fwd(int pos) {
     const int blk = pos >> 5, q = pos & 31;
     return 32 * blk + 8 * ((q >> 2) & 3) + 4 * (q >> 4) + (q & 3);
 }
-// Backward: row n = 8j + 2t + b of Fc^T (an accumulator column) <-> channel 8t + 2j + b, so that lane t ends up with the
-// gradient of the eight channels 8t..8t+7 it scatters.
+// Backward: row n = 8j + 2t + b of Fc^T (an accumulator column) <-> channel 4t + 2(j&1) + b + 16(j>>1), so that lane t ends
+// up with the gradient of channels 4t..4t+3 and 16+4t..16+4t+3: each of its two vector reductions then lands, together
+// with the other three lanes of the quad, on 64 contiguous bytes (two whole 32-byte sectors) of the voxel's gradient line.
 __host__ __device__ __forceinline__ int fc_channel_bwd(int n) {
-    const int i = n & 31;
-    return 8 * ((i >> 1) & 3) + 2 * (i >> 3) + (i & 1);
+    const int j = (n >> 3) & 3, t = (n >> 1) & 3, b = n & 1;
+    return 4 * t + 2 * (j & 1) + b + 16 * (j >> 1);
 }
 
 // Stage M[n][pos] = w(n, pos), n < nrow, pos < K, pre-split into fp16 hi/lo (layout: common.cuh).

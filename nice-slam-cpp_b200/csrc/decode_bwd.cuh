@@ -30,7 +30,7 @@ __device__ __forceinline__ void apply_mask(float (&gu)[4][4], const float (&gh)[
         for (int q = 0; q < 4; ++q) gu[j][q] = ((m >> (4 * j + q)) & 1u) ? gh[j][q] : 0.0f;
 }
 
-// Scatter the feature gradient of the thread's two samples into grid G (channels 8t..8t+7), and/or
+// Scatter the feature gradient of the thread's two samples into grid G (channels 4t..4t+3 and 16+4t..16+4t+3), and/or
 // accumulate d c / d p (coordinate derivative of the trilinear sample) into gp.  gc[r][8].
 template <bool DO_GRID, bool DO_RAY>
 __device__ __forceinline__ void grid_backward(const GridView& G, const Bound& bnd, const float (&p)[2][3],
@@ -46,10 +46,9 @@ __device__ __forceinline__ void grid_backward(const GridView& G, const Bound& bn
             for (int k = 0; k < 8; ++k) {
                 int off;
                 tri_corner(G, s[r], k, off);
-                float v[8];
-                ldg8(G.data + off + 8 * t, v);
-                const float dot = gc[r][0] * v[0] + gc[r][1] * v[1] + gc[r][2] * v[2] + gc[r][3] * v[3] +
-                                  gc[r][4] * v[4] + gc[r][5] * v[5] + gc[r][6] * v[6] + gc[r][7] * v[7];
+                const float4 v0 = ldg4(G.data + off + 4 * t), v1 = ldg4(G.data + off + 16 + 4 * t);
+                const float dot = gc[r][0] * v0.x + gc[r][1] * v0.y + gc[r][2] * v0.z + gc[r][3] * v0.w +
+                                  gc[r][4] * v1.x + gc[r][5] * v1.y + gc[r][6] * v1.z + gc[r][7] * v1.w;
                 const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
                 const float wx = dx ? s[r].w1[0] : s[r].w0[0], wy = dy ? s[r].w1[1] : s[r].w0[1], wz = dz ? s[r].w1[2] : s[r].w0[2];
                 gx += (dx ? dot : -dot) * wy * wz;
@@ -67,16 +66,16 @@ __device__ __forceinline__ void grid_backward(const GridView& G, const Bound& bn
             int off0, off1;
             const float w0 = tri_corner(G, s[0], k, off0);
             const float w1 = tri_corner(G, s[1], k, off1);
-            float* a0 = G.grad + off0 + 8 * t;
+            float* a0 = G.grad + off0 + 4 * t;
             if (same) {
                 red_add_v4(a0, w0 * gc[0][0] + w1 * gc[1][0], w0 * gc[0][1] + w1 * gc[1][1], w0 * gc[0][2] + w1 * gc[1][2], w0 * gc[0][3] + w1 * gc[1][3]);
-                red_add_v4(a0 + 4, w0 * gc[0][4] + w1 * gc[1][4], w0 * gc[0][5] + w1 * gc[1][5], w0 * gc[0][6] + w1 * gc[1][6], w0 * gc[0][7] + w1 * gc[1][7]);
+                red_add_v4(a0 + 16, w0 * gc[0][4] + w1 * gc[1][4], w0 * gc[0][5] + w1 * gc[1][5], w0 * gc[0][6] + w1 * gc[1][6], w0 * gc[0][7] + w1 * gc[1][7]);
             } else {
-                float* a1 = G.grad + off1 + 8 * t;
+                float* a1 = G.grad + off1 + 4 * t;
                 red_add_v4(a0, w0 * gc[0][0], w0 * gc[0][1], w0 * gc[0][2], w0 * gc[0][3]);
-                red_add_v4(a0 + 4, w0 * gc[0][4], w0 * gc[0][5], w0 * gc[0][6], w0 * gc[0][7]);
+                red_add_v4(a0 + 16, w0 * gc[0][4], w0 * gc[0][5], w0 * gc[0][6], w0 * gc[0][7]);
                 red_add_v4(a1, w1 * gc[1][0], w1 * gc[1][1], w1 * gc[1][2], w1 * gc[1][3]);
-                red_add_v4(a1 + 4, w1 * gc[1][4], w1 * gc[1][5], w1 * gc[1][6], w1 * gc[1][7]);
+                red_add_v4(a1 + 16, w1 * gc[1][4], w1 * gc[1][5], w1 * gc[1][6], w1 * gc[1][7]);
             }
         }
     }
@@ -192,13 +191,27 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
 #pragma unroll
     for (int r = 0; r < 2; ++r) sidx[r] = base + 2 * g + r;
     const int ray = base / P.S;
-    if (P.valid && !P.valid[ray]) return;
+    // every global input of the tile is requested before the first use (one exposed memory latency instead of a chain of four)
+    const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
     const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
     const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
-    float zz[2];
+    const float zz[2] = {P.z[sidx[0]], P.z[sidx[1]]};
+    const float4 gr[2] = {*reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[0]), *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[1])};
+    // relu masks saved by the training forward (k_decode_fwd<.., TRAIN>): the data gradient needs nothing else
+    uint32_t mw[10];
+    if (P.mask_layout == 0) {
+        const uint32_t* mb = P.masks + ((size_t)(dec - 1) * (P.P / TILE) + base / TILE) * 96 + lane;
+        mw[0] = mb[0]; mw[1] = mb[32]; mw[2] = mb[64];
+    } else {   // one word per sample and layer (bit f = relu of feature f)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t* mb = P.masks + ((size_t)(dec - 1) * 5 + i) * P.mask_stride;
+            mw[2 * i] = mb[sidx[0]]; mw[2 * i + 1] = mb[sidx[1]];
+        }
+    }
+    if (!ok) return;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        zz[r] = P.z[sidx[r]];
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], zz[r]));
     }
@@ -206,23 +219,18 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
     bool any = false;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const float4 gr = *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[r]);
-        if (O == 4) { gout[r][0] = gr.x; gout[r][1] = gr.y; gout[r][2] = gr.z; gout[r][3] = 0.0f; any = any || gr.x != 0.0f || gr.y != 0.0f || gr.z != 0.0f; }
-        else { gout[r][0] = gr.w; gout[r][1] = gout[r][2] = gout[r][3] = 0.0f; any = any || gr.w != 0.0f; }
+        if (O == 4) { gout[r][0] = gr[r].x; gout[r][1] = gr[r].y; gout[r][2] = gr[r].z; gout[r][3] = 0.0f; any = any || gr[r].x != 0.0f || gr[r].y != 0.0f || gr[r].z != 0.0f; }
+        else { gout[r][0] = gr[r].w; gout[r][1] = gout[r][2] = gout[r][3] = 0.0f; any = any || gr[r].w != 0.0f; }
     }
     if (!WG && !__any_sync(0xffffffffu, any)) return;   // nothing flows into this tile
 
-    // relu masks saved by the training forward (k_decode_fwd<.., TRAIN>): the data gradient needs nothing else
     uint32_t masks[5];
     if (P.mask_layout == 0) {
-        const uint32_t* mb = P.masks + ((size_t)(dec - 1) * (P.P / TILE) + base / TILE) * 96 + lane;
-        const uint32_t m01 = mb[0], m23 = mb[32];
-        masks[0] = m01 & 0xffffu; masks[1] = m01 >> 16; masks[2] = m23 & 0xffffu; masks[3] = m23 >> 16; masks[4] = mb[64];
-    } else {   // one word per sample and layer (bit f = relu of feature f): pick this thread's fragment bits
+        masks[0] = mw[0] & 0xffffu; masks[1] = mw[0] >> 16; masks[2] = mw[1] & 0xffffu; masks[3] = mw[1] >> 16; masks[4] = mw[2];
+    } else {   // pick this thread's fragment bits out of the per-sample words
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const uint32_t* mb = P.masks + ((size_t)(dec - 1) * 5 + i) * P.mask_stride;
-            const uint32_t w0 = mb[sidx[0]] >> (2 * t), w1 = mb[sidx[1]] >> (2 * t);
+            const uint32_t w0 = mw[2 * i] >> (2 * t), w1 = mw[2 * i + 1] >> (2 * t);
             uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) m |= (((w0 >> (8 * j)) & 3u) << (4 * j)) | (((w1 >> (8 * j)) & 3u) << (4 * j + 2));

@@ -23,14 +23,16 @@ __device__ __forceinline__ bool load_points(const DecodeParams& P, int base, int
         return true;
     }
     const int ray = base / P.S;
-    if (P.valid && !P.valid[ray]) return false;
+    // all loads are requested before the first use: one exposed latency instead of valid -> rays -> z
+    const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
     const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
     const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
+    const float z[2] = {P.z[sidx[0]], P.z[sidx[1]]};
+    if (!ok) return false;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const float z = P.z[sidx[r]];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], z));   // Renderer.cpp:121
+        for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], z[r]));   // Renderer.cpp:121
     }
     return true;
 }

@@ -86,6 +86,34 @@ __global__ void k_red(float* buf, uint32_t nlines, int iters) {
     }
 }
 
+// variants of the scatter pattern: MODE 0 = lane t adds floats 8t..8t+7 (two v4: each touches half of four sectors),
+// MODE 1 = lane t adds floats 4t..4t+3 then 16+4t..16+4t+3 (each v4 instruction of a quad fills two whole sectors);
+// SAME = all eight quads of a warp hit the same line (neighbouring samples of a ray in one voxel cell)
+template <int MODE, bool SAME>
+__global__ void k_red2(float* buf, uint32_t nlines, int iters) {
+    uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> (SAME ? 5 : 2), t = threadIdx.x & 3;
+    uint32_t s = quad * 2654435761u + 777u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t line = (s >> 8) % nlines;
+            float* a = buf + line * 32 + (MODE == 0 ? 8 * t : 4 * t);
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(a), "f"(1.0f) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(a + (MODE == 0 ? 4 : 16)), "f"(1.0f) : "memory");
+        }
+    }
+}
+template <int MODE, bool SAME>
+static void run_red2(float* buf, uint32_t nlines, int sms, const char* name, cudaEvent_t e0, cudaEvent_t e1) {
+    const int grid = sms * 8, iters = 50; float ms;
+    k_red2<MODE, SAME><<<grid, 256>>>(buf, nlines, 5);
+    cudaEventRecord(e0); k_red2<MODE, SAME><<<grid, 256>>>(buf, nlines, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = 128.0 * 8 * iters * (double)grid * 256 / 4;
+    printf(", \"%s\": %.0f", name, bytes / ms * 1e-6);
+}
+
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
@@ -134,6 +162,10 @@ int main() {
         const double bytes = 128.0 * 8 * iters * (double)grid * 256 / 4;
         printf(", \"l2_redv4_gbs_occ%d\": %.0f", occ, bytes / ms * 1e-6);
     }
+    run_red2<0, false>((float*)buf, nlines, p.multiProcessorCount, "red_mode0_gbs", e0, e1);
+    run_red2<1, false>((float*)buf, nlines, p.multiProcessorCount, "red_mode1_gbs", e0, e1);
+    run_red2<0, true>((float*)buf, nlines, p.multiProcessorCount, "red_mode0_sameline_gbs", e0, e1);
+    run_red2<1, true>((float*)buf, nlines, p.multiProcessorCount, "red_mode1_sameline_gbs", e0, e1);
     printf(", \"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
