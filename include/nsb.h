@@ -161,10 +161,28 @@ int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_d, const fl
                    const float* g_rgb, const float* g_depth, const float* g_var, int flags,
                    float* d_rays_d, float* d_rays_o);
 
+/* Mapper::keyframe_selection_overlap (Mapper.cpp:132-196): samples `pixels` (reference: 100) pixels of the current frame
+ * (slot cur_slot, pose cur_c2w16 or the slot's own when NULL; pixel indices from `idx` or the context's mt19937 stream),
+ * places n_samples (16) vertices per ray between 0.8 d and d + 0.5, projects them into each of the n_kf keyframe poses
+ * (kf_c2w16: [n_kf][16] row-major 4x4) and returns the indices of the k_overlap keyframes that see the largest fraction
+ * (> 0) of them, best first.  percent_out ([n_kf], may be NULL) receives every keyframe's fraction. */
+int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const float* cur_c2w16, int n_kf, const float* kf_c2w16, int k_overlap,
+                                   const int64_t* idx, int pixels, int n_samples, int* selected, int* n_selected, float* percent_out);
+
 /* ---- mapping: Mapper::optimize_map inner loop (Mapper.cpp:330-465) ------------------------------------ */
 /* begin = the per-call setup of Mapper.cpp:198-330: chooses the frame slots to optimise (optimize_frame),
  * resets Adam (a fresh torch::optim::Adam is built at :330).  lr_factor as Mapper::run passes it. */
 int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor);
+/* Bundle adjustment (Mapper.cpp:305-329,366-368,382-399,467-489): like nsb_mapping_begin, and the poses of the frames whose
+ * bit is set in ba_mask (bit f <-> slots[f]; the reference: every frame of optimize_frame except the oldest keyframe) are
+ * optimised together with the map as 7-vectors (quaternion w,x,y,z + translation), lr = mapping.BA_cam_lr in the colour
+ * stage and 0 before.  nsb_mapping_end writes the optimised poses back into the frame slots (est_c2w) and optionally
+ * returns the 7-vectors ([n_frames][7]); nsb_get_frame_pose reads a slot's current [R|t] (3x4 row-major). */
+int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask);
+int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out);
+/* d L / d (q, t) per frame at the last BA iteration, [n_frames][7] (parity checks of the pose-gradient chain). */
+int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s);
+int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12);
 /* One joint iteration.  idx: host int64 [n_frames * (mapping_pixels / n_frames)] flat pixel indices, or NULL to
  * draw them from the context's mt19937 stream.  loss (host, may be NULL; reading it synchronises). */
 int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss);

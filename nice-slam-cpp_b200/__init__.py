@@ -117,6 +117,11 @@ def load_library(variant=""):
     L.nsb_set_profiling.argtypes = [v, C.c_int]
     L.nsb_get_kernel_ms.argtypes = [v, _fp]
     L.nsb_bench_gather.argtypes = [v, C.c_int, _fp]
+    L.nsb_mapping_begin_ba.argtypes = [v, C.c_int, _ip, C.c_int, C.c_float, C.c_uint32]
+    L.nsb_mapping_end.argtypes = [v, _fp]
+    L.nsb_mapping_cam_grads.argtypes = [v, _fp]
+    L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
+    L.nsb_get_frame_pose.argtypes = [v, C.c_int, _fp]
     L.nsb_debug_counters.argtypes = [v, C.POINTER(C.c_uint64)]
     _LIBS[variant] = L
     return L
@@ -132,6 +137,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
+    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap",
 ]
 
 
@@ -329,9 +335,38 @@ class Engine:
         return out
 
     # ---- Mapper::optimize_map inner loop (Mapper.cpp:330-465)
-    def mapping_begin(self, slots, n_iters, lr_factor=1.0):
+    def mapping_begin(self, slots, n_iters, lr_factor=1.0, ba_mask=0):
+        """ba_mask: bit f set -> the pose of slots[f] is optimised with the map (bundle adjustment, Mapper.cpp:305-329)."""
         s = np.ascontiguousarray(slots, np.int32)
-        self._ck(self.lib.nsb_mapping_begin(self.h, len(s), s.ctypes.data_as(_ip), n_iters, C.c_float(lr_factor)))
+        self._n_map_frames = len(s)
+        self._ck(self.lib.nsb_mapping_begin_ba(self.h, len(s), s.ctypes.data_as(_ip), n_iters, C.c_float(lr_factor), C.c_uint32(ba_mask)))
+
+    def mapping_end(self):
+        """BA write-back (Mapper.cpp:467-489); returns the (n_frames, 7) camera vectors."""
+        cams = np.zeros((self._n_map_frames, 7), np.float32)
+        self._ck(self.lib.nsb_mapping_end(self.h, _f(cams)))
+        return cams
+
+    def mapping_cam_grads(self):
+        g = np.zeros((self._n_map_frames, 7), np.float32)
+        self._ck(self.lib.nsb_mapping_cam_grads(self.h, _f(g)))
+        return g
+
+    def keyframe_selection_overlap(self, cur_slot, kf_c2ws, k_overlap, cur_c2w=None, idx=None, pixels=100, n_samples=16):
+        """Mapper::keyframe_selection_overlap (Mapper.cpp:132-196) -> (selected keyframe indices, per-keyframe fractions)."""
+        kf = _c(np.asarray(kf_c2ws, np.float32).reshape(-1, 16))
+        n_kf = kf.shape[0]
+        sel = np.zeros(max(n_kf, 1), np.int32); n_sel = C.c_int(0); pct = np.zeros(max(n_kf, 1), np.float32)
+        ix = None if idx is None else np.ascontiguousarray(idx, np.int64)
+        cur = None if cur_c2w is None else _c(np.asarray(cur_c2w, np.float32).reshape(-1))
+        self._ck(self.lib.nsb_keyframe_selection_overlap(self.h, cur_slot, _f(cur), n_kf, _f(kf), k_overlap, None if ix is None else ix.ctypes.data_as(_i64p),
+                                                         pixels, n_samples, sel.ctypes.data_as(_ip), C.byref(n_sel), _f(pct)))
+        return sel[:n_sel.value].tolist(), pct[:n_kf]
+
+    def get_frame_pose(self, slot):
+        m = np.empty((3, 4), np.float32)
+        self._ck(self.lib.nsb_get_frame_pose(self.h, slot, _f(m)))
+        return m
 
     def mapping_iter(self, it, idx=None, sync=True):
         ix = None if idx is None else np.ascontiguousarray(idx, np.int64)

@@ -123,6 +123,8 @@ struct nsb_ctx {
     std::vector<int64_t> h_idx;
     // mapping state
     int map_frames = 0, map_slots[MAX_OPT_FRAMES], map_iters = 0, map_step = 0; float map_lr_factor = 1.0f;
+    float* cam_grad_last = nullptr;   // [MAX_OPT_FRAMES][8] camera gradients of the last BA iteration (Adam zeroes the arena)
+    uint32_t map_ba_mask = 0;      // bundle adjustment: frames (bit f) whose 7-vector pose is optimised with the map (Mapper.cpp:305-329)
     // tracking state
     int trk_slot = 0, trk_step = 0;
     // comm
@@ -319,7 +321,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     if (cfg->n_samples != 32 || (cfg->n_surface != 16 && cfg->n_surface != 0)) return fail(ctx, "n_samples/n_surface %d/%d unsupported (32 / 16|0)", cfg->n_samples, cfg->n_surface);
     if (cfg->max_frames < 1 || cfg->max_rays < 16) return fail(ctx, "max_frames / max_rays too small");
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; }
+    for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
     auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
     for (int l = 0; l < 4; ++l) {
@@ -365,6 +367,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
@@ -380,7 +383,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -698,7 +701,7 @@ static int zero_grads(nsb_ctx* ctx) {
 static void fill_sample_params(nsb_ctx* ctx, SampleParams& P, int n, int H0, int H1, int W0, int W1, float* stats, int apply_filter) {
     const nsb_config& c = ctx->cfg;
     memset(&P, 0, sizeof P);
-    P.depth = ctx->f_depth; P.color = ctx->f_color; P.poses = ctx->f_pose; P.cam7 = nullptr; P.idx = ctx->idx;
+    P.depth = ctx->f_depth; P.color = ctx->f_color; P.poses = ctx->f_pose; P.cams = ctx->param + ctx->off_cam; P.cam_mask = 0; P.idx = ctx->idx;
     P.H = c.H; P.W = c.W; P.H0 = H0; P.W0 = W0; P.Wc = W1 - W0;
     P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.raydir = c.raydir; P.bnd = ctx->bnd; P.n = n;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.gt_depth = ctx->gt_depth; P.gt_color = ctx->gt_color; P.valid = ctx->valid;
@@ -888,7 +891,14 @@ static int stage_of_iter(const nsb_config& c, int it, int n_iters) {   // Mapper
 }
 
 extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor) {
+    return nsb_mapping_begin_ba(ctx, n_frames, slots, n_iters, lr_factor, 0u);
+}
+
+// ba_mask bit f: frame f's pose joins the optimisation as a 7-vector (Mapper.cpp:305-329: every frame of optimize_frame but
+// the oldest one when BA is on); its lr is BA_cam_lr in the colour stage and 0 before (Mapper.cpp:366-368).
+extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask) {
     if (n_frames < 1 || n_frames > MAX_OPT_FRAMES) return fail(ctx, "n_frames %d out of range", n_frames);
+    if (n_frames > ctx->cfg.max_frames) return fail(ctx, "n_frames %d exceeds max_frames %d", n_frames, ctx->cfg.max_frames);
     const int pix = ctx->cfg.mapping_pixels / n_frames;   // Mapper.cpp:223
     if (pix * n_frames > ctx->cap) return fail(ctx, "mapping_pixels %d exceeds max_rays %d", ctx->cfg.mapping_pixels, ctx->cap);
     for (int f = 0; f < n_frames; ++f) { if (slots[f] < 0 || slots[f] >= ctx->cfg.max_frames) return fail(ctx, "bad slot %d", slots[f]); ctx->map_slots[f] = slots[f]; }
@@ -897,6 +907,19 @@ extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, i
     CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    ctx->map_ba_mask = ba_mask & ((n_frames >= 32) ? 0xffffffffu : ((1u << n_frames) - 1u));
+    if (ctx->map_ba_mask) {   // camera_tensor = get_tensor_from_camera(c2w) per optimised frame (Mapper.cpp:322-325)
+        std::vector<float> hp(12 * (size_t)ctx->cfg.max_frames), cams(8 * (size_t)n_frames, 0.f);
+        CK(cudaMemcpyAsync(hp.data(), ctx->f_pose, hp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int f = 0; f < n_frames; ++f) {
+            float m16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+            memcpy(m16, hp.data() + 12 * slots[f], 12 * sizeof(float));
+            nsb_get_tensor_from_camera(m16, cams.data() + 8 * f);
+        }
+        CK(cudaMemcpyAsync(ctx->param + ctx->off_cam, cams.data(), cams.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (ctx->cfg.frustum_feature_selection) {   // Mapper.cpp:226-290: masks from the current frame (the last of optimize_frame)
         for (int l = 1; l < 4; ++l) if (nsb_frustum_mask(ctx, slots[n_frames - 1], nullptr, l, nullptr, 1)) return -1;
     }
@@ -924,7 +947,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         }
         CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
         SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
-        P.idx = d_idx;
+        P.idx = d_idx; P.cam_mask = ctx->map_ba_mask;
         for (int f = 0; f < ctx->map_frames; ++f) P.slots[f] = ctx->map_slots[f];
         P.n_frames = ctx->map_frames; P.pix_per_frame = pix;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
@@ -946,14 +969,29 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             Q.stats = stats; Q.bnd = ctx->bnd; Q.n = nl; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
             Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = nullptr;
             Q.g_raw = ctx->g_raw + 4 * (size_t)off * S;
+            if (ctx->map_ba_mask) {   // bundle adjustment: ray gradients (d L / d rays_o, rays_d) are accumulated for the pose chain
+                CK(cudaMemsetAsync(ctx->d_rays + 6 * (size_t)off, 0, 6 * (size_t)nl * 4, ctx->stream));
+                Q.d_rays = ctx->d_rays + 6 * (size_t)off;
+            }
             // the loss rides in the tail of the gradient arena so that the all-reduce sums it too
             k_composite_map<<<cdiv(nl * 32, 256), 256, 0, ctx->stream>>>(Q, ctx->gt_depth + off, ctx->gt_color + 3 * off, use_color ? 1 : 0,
                                                                        c.mapping_w_color_loss, ctx->grad + ctx->off_tail);
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        const int flags = 1 | (c.fix_color ? 0 : 2);
+        const int flags = 1 | (c.fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
         if (run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true)) return -1;
+        if (ctx->map_ba_mask) {   // chain to (q, t) of every optimised frame; other ranks' partial sums arrive through the all-reduce
+            Timer t(ctx, T_COMP);
+            PoseGradParams G; memset(&G, 0, sizeof G);
+            G.d_rays = ctx->d_rays; G.idx = ctx->idx_pool && ctx->pool_n == n && !idx ? ctx->idx_pool + (size_t)((ctx->pool_cursor - 1) % ctx->pool_iters) * n : ctx->idx;
+            G.valid = ctx->valid; G.cams = ctx->param + ctx->off_cam; G.cam_mask = ctx->map_ba_mask;
+            G.pix_per_frame = pix; G.n_frames = ctx->map_frames; G.lo = off; G.hi = off + nl;
+            G.H0 = 0; G.W0 = 0; G.Wc = c.W; G.raydir = c.raydir; G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy;
+            G.g_cams = ctx->grad + ctx->off_cam;
+            k_pose_grad<<<ctx->map_frames, 1024, 0, ctx->stream>>>(G); ctx->launches++;
+            CK(cudaGetLastError());
+        }
     }
     if (ctx->world > 1) {
         Timer t(ctx, T_COMM);
@@ -962,12 +1000,46 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         if (rc != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
     CK(cudaMemcpyAsync(stats + 3, ctx->grad + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->map_step++;
     float lr[6];
     for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
-    lr[5] = 0.f;
+    lr[5] = (ctx->map_ba_mask && stage == NSB_COLOR) ? c.BA_cam_lr : 0.f;   // Mapper.cpp:366-368 (not scaled by lr_factor)
     // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups
-    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, 0)) return -1;
+    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, ctx->map_ba_mask ? 8 * ctx->map_frames : 0)) return -1;
+    return 0;
+}
+
+// Bundle-adjustment write-back (Mapper.cpp:467-489): est_c2w of every optimised frame <- get_camera_from_tensor(camera_tensor).
+// cam7s_out ([n_frames][7], may be NULL) receives the optimised 7-vectors (frames outside the mask: their initial pose).
+extern "C" int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out) {
+    if (!ctx->map_ba_mask) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+    const int nf = ctx->map_frames;
+    std::vector<float> cams(8 * (size_t)nf);
+    CK(cudaMemcpyAsync(cams.data(), ctx->param + ctx->off_cam, cams.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < nf; ++f) {
+        if (cam7s_out) memcpy(cam7s_out + 7 * f, cams.data() + 8 * f, 7 * sizeof(float));
+        if (!((ctx->map_ba_mask >> f) & 1u)) continue;
+        float RT[12];
+        nsb_get_camera_from_tensor(cams.data() + 8 * f, RT);
+        CK(cudaMemcpyAsync(ctx->f_pose + 12 * ctx->map_slots[f], RT, sizeof RT, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // RT is a stack buffer
+    }
+    return 0;
+}
+// d L / d (q, t) of the optimised frames at the last bundle-adjustment iteration ([n_frames][7]; zeros outside the mask).
+extern "C" int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s) {
+    std::vector<float> h(8 * (size_t)ctx->map_frames);
+    CK(cudaMemcpyAsync(h.data(), ctx->cam_grad_last, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < ctx->map_frames; ++f) for (int k = 0; k < 7; ++k) g7s[7 * f + k] = ((ctx->map_ba_mask >> f) & 1u) ? h[8 * f + k] : 0.f;
+    return 0;
+}
+extern "C" int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12) {
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    CK(cudaMemcpyAsync(c2w12, ctx->f_pose + 12 * slot, 12 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1009,6 +1081,61 @@ extern "C" int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, in
     return 0;
 }
 
+// ---- keyframe selection (Mapper.cpp:132-196) ------------------------------------------------------------------------------
+// 3x4 inverse of a rigid-or-not [A|t; 0 0 0 1] in double (Eigen's Matrix4f::inverse() upstream): [A^-1 | -A^-1 t]
+static void invert_pose(const float* c2w12, float* w2c12) {
+    const double a = c2w12[0], b = c2w12[1], cc = c2w12[2], d = c2w12[4], e = c2w12[5], f = c2w12[6], g = c2w12[8], h = c2w12[9], i = c2w12[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + cc * (d * h - e * g);
+    const double inv[9] = {(e * i - f * h) / det, (cc * h - b * i) / det, (b * f - cc * e) / det,
+                           (f * g - d * i) / det, (a * i - cc * g) / det, (cc * d - a * f) / det,
+                           (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
+    const double t[3] = {c2w12[3], c2w12[7], c2w12[11]};
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) w2c12[4 * r + k] = (float)inv[3 * r + k];
+        w2c12[4 * r + 3] = (float)-(inv[3 * r] * t[0] + inv[3 * r + 1] * t[1] + inv[3 * r + 2] * t[2]);
+    }
+}
+
+extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const float* cur_c2w16, int n_kf, const float* kf_c2w16, int k_overlap,
+                                              const int64_t* idx, int pixels, int n_samples, int* selected, int* n_selected, float* percent_out) {
+    *n_selected = 0;
+    if (n_kf <= 0) return 0;
+    if (cur_slot < 0 || cur_slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", cur_slot);
+    if (pixels > ctx->cap) return fail(ctx, "pixels %d exceeds max_rays %d", pixels, ctx->cap);
+    if (n_samples != 16) return fail(ctx, "n_samples %d unsupported (the reference hard-codes 16, Mapper.cpp:136)", n_samples);
+    const nsb_config& c = ctx->cfg;
+    // get_samples(0, H, 0, W, pixels, ...) on the current frame (:137): consumes the host RNG stream like the reference
+    ctx->h_idx.resize(pixels);
+    if (idx) memcpy(ctx->h_idx.data(), idx, pixels * sizeof(int64_t)); else draw_indices(ctx, pixels, (int64_t)c.H * c.W, ctx->h_idx.data());
+    CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), pixels * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (cur_c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * cur_slot, cur_c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
+    SampleParams S; fill_sample_params(ctx, S, pixels, 0, c.H, 0, c.W, ctx->stats, 0);
+    S.slots[0] = cur_slot; S.n_frames = 1; S.pix_per_frame = pixels;
+    k_sample<<<cdiv(pixels, 128), 128, 0, ctx->stream>>>(S); ctx->launches++;
+    std::vector<float> w2c(12 * (size_t)n_kf);
+    for (int k = 0; k < n_kf; ++k) invert_pose(kf_c2w16 + 16 * k, w2c.data() + 12 * k);
+    if (ensure_scratch(ctx, 13 * (size_t)n_kf)) return -1;
+    CK(cudaMemcpyAsync(ctx->scratch_ncdhw, w2c.data(), w2c.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    OverlapParams P; memset(&P, 0, sizeof P);
+    P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.gt_depth = ctx->gt_depth; P.t_vals = ctx->t_surface; P.w2c = ctx->scratch_ncdhw;
+    P.pixels = pixels; P.n_samples = n_samples; P.n_kf = n_kf; P.H = c.H; P.W = c.W; P.edge = 20;
+    P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.percent = ctx->scratch_ncdhw + 12 * (size_t)n_kf;
+    k_kf_overlap<<<n_kf, 256, 0, ctx->stream>>>(P); ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<float> pct(n_kf);
+    CK(cudaMemcpyAsync(pct.data(), P.percent, n_kf * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (percent_out) memcpy(percent_out, pct.data(), n_kf * sizeof(float));
+    std::vector<int> order;
+    for (int k = 0; k < n_kf; ++k) if (pct[k] > 0.f) order.push_back(k);                        // :178-179
+    std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return pct[l] > pct[r]; });   // :182-191 (ties: lower index first)
+    const int take = std::min((int)order.size(), std::max(0, k_overlap));                       // :193-194 (intent: the first k_overlap)
+    for (int k = 0; k < take; ++k) selected[k] = order[k];
+    *n_selected = take;
+    return 0;
+}
+
 // ---- tracking -----------------------------------------------------------------------------------------------------------
 extern "C" int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7) {
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
@@ -1037,7 +1164,7 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
         CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
         CK(cudaMemsetAsync(ctx->count, 0, 16, ctx->stream));
         SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, stats, 1);
-        P.slots[0] = ctx->trk_slot; P.n_frames = 1; P.pix_per_frame = n; P.cam7 = cam;
+        P.slots[0] = ctx->trk_slot; P.n_frames = 1; P.pix_per_frame = n; P.cam_mask = 1u;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
         if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
         CK(cudaGetLastError());
@@ -1061,8 +1188,9 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
     {
         Timer t(ctx, T_COMP);
         PoseGradParams G; memset(&G, 0, sizeof G);
-        G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.valid = ctx->valid; G.cam7 = cam; G.n = n; G.H0 = H0; G.W0 = W0; G.Wc = W1 - W0; G.raydir = c.raydir;
-        G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy; G.g_cam7 = ctx->grad + ctx->off_cam;
+        G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.valid = ctx->valid; G.cams = cam; G.cam_mask = 1u; G.pix_per_frame = n; G.n_frames = 1; G.lo = 0; G.hi = n;
+        G.H0 = H0; G.W0 = W0; G.Wc = W1 - W0; G.raydir = c.raydir;
+        G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy; G.g_cams = ctx->grad + ctx->off_cam;
         k_pose_grad<<<1, 1024, 0, ctx->stream>>>(G); ctx->launches++;
         CK(cudaGetLastError());
     }

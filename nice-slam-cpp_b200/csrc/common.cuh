@@ -15,6 +15,8 @@ constexpr int TILE = 16;      // samples per warp tile (MMA m16)
 // Scene bound and derived constants, all in fp32 exactly as the reference computes them.
 struct Bound {
     float lo[3], hi[3], len[3];   // len = hi - lo in fp32 (utils.h:135-137)
+    float inv_len[3];             // 1 / len: the normalisation multiplies by it (<= 1 ulp from the reference's division; the trilinear
+                                  // sample is continuous in the coordinate, so this is far inside the 1e-4 tolerance)
 };
 
 // One feature grid, channel-last [Z][Y][X][32] fp32: a voxel corner is one 128-byte line.
@@ -130,10 +132,10 @@ __device__ __forceinline__ void tri_setup(const GridView& G, const Bound& B, con
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         // utils.h:135-137: ((p - lo) / (hi - lo)) * 2 - 1, each op rounded separately
-        float pn = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p[a], B.lo[a]), B.len[a]), 2.0f), 1.0f);
+        float pn = __fsub_rn(__fmul_rn(__fmul_rn(__fsub_rn(p[a], B.lo[a]), B.inv_len[a]), 2.0f), 1.0f);
         // grid_sampler_unnormalize(align_corners): ((x + 1) / 2) * (size - 1)
         const float sm1 = (float)(dim[a] - 1);
-        float ix = __fmul_rn(__fdiv_rn(__fadd_rn(pn, 1.0f), 2.0f), sm1);
+        float ix = __fmul_rn(__fmul_rn(__fadd_rn(pn, 1.0f), 0.5f), sm1);
         const bool clipped = !(ix > 0.0f && ix < sm1);
         ix = fminf(sm1, fmaxf(ix, 0.0f));
         const float f = floorf(ix);
@@ -142,7 +144,7 @@ __device__ __forceinline__ void tri_setup(const GridView& G, const Bound& B, con
         s.i1[a] = min(i + 1, dim[a] - 1);
         s.w1[a] = __fsub_rn(ix, f);
         s.w0[a] = __fsub_rn(__fadd_rn(f, 1.0f), ix);
-        s.gm[a] = clipped ? 0.0f : __fdiv_rn(sm1, B.len[a]);
+        s.gm[a] = clipped ? 0.0f : __fmul_rn(sm1, B.inv_len[a]);
     }
 }
 

@@ -41,7 +41,8 @@ struct SampleParams {
     const float* depth;      // [max_frames][H*W]
     const float* color;      // [max_frames][H*W*3]
     const float* poses;      // [max_frames][12]  row-major [R|t]
-    const float* cam7;       // non-null: every ray uses this 7-vector pose (tracking), R via quad2rotation
+    const float* cams;       // [n_frames][8] 7-vector poses being optimised (tracking: one; bundle adjustment: one per frame)
+    uint32_t cam_mask;       // bit f set: frame f takes its pose from cams + 8 f (R via quad2rotation) instead of poses[slot]
     const int64_t* idx;      // [n] flat index into the crop
     int slots[MAX_OPT_FRAMES];
     int n_frames, pix_per_frame;
@@ -80,9 +81,10 @@ __global__ void k_sample(SampleParams P) {
         P.gt_color[3 * i + 0] = c[0]; P.gt_color[3 * i + 1] = c[1]; P.gt_color[3 * i + 2] = c[2];
         P.gt_depth[i] = gd;
         float R[9], tr[3];
-        if (P.cam7) {
-            quad2rotation(P.cam7, R);
-            tr[0] = P.cam7[4]; tr[1] = P.cam7[5]; tr[2] = P.cam7[6];
+        if ((P.cam_mask >> f) & 1u) {
+            const float* q = P.cams + 8 * f;
+            quad2rotation(q, R);
+            tr[0] = q[4]; tr[1] = q[5]; tr[2] = q[6];
         } else {
             const float* m = P.poses + slot * 12;
             for (int r = 0; r < 3; ++r) { R[3 * r] = m[4 * r]; R[3 * r + 1] = m[4 * r + 1]; R[3 * r + 2] = m[4 * r + 2]; tr[r] = m[4 * r + 3]; }
@@ -478,20 +480,28 @@ __global__ void k_loss_tracking(LossParams P, int handle_dynamic) {
 
 // ---- pose gradient: d L / d (q, t) from the per-ray gradients (block reduction, one block) -------------
 struct PoseGradParams {
-    const float* d_rays;     // [n][6]: d_o, d_d
+    const float* d_rays;     // [n][6]: d L / d rays_o, d L / d rays_d
     const int64_t* idx; const uint8_t* valid;
-    const float* cam7;
-    int n, H0, W0, Wc, raydir;
+    const float* cams;       // [n_frames][8] current 7-vectors
+    uint32_t cam_mask;       // frames whose pose is optimised
+    int pix_per_frame, n_frames;
+    int lo, hi;              // rays [lo, hi) carry gradient on this rank (the others' partial sums arrive through the all-reduce)
+    int H0, W0, Wc, raydir;
     float fx, fy, cx, cy;
-    float* g_cam7;           // [7]
+    float* g_cams;           // [n_frames][8]
 };
 
+// One block per frame: d L / d (q, t) of that frame's pose from the ray gradients of its pixels
+// (rays_o = t, rays_d = R(q) dir: utils.h:44-52, 174-210).
 __global__ void k_pose_grad(PoseGradParams P) {
+    const int f = blockIdx.x;
+    if (!((P.cam_mask >> f) & 1u)) return;
     __shared__ float red[12][32];
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
-    for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+    const int r_lo = max(P.lo, f * P.pix_per_frame), r_hi = min(P.hi, (f + 1) * P.pix_per_frame);
+    for (int i = r_lo + threadIdx.x; i < r_hi; i += blockDim.x) {
         if (P.valid && !P.valid[i]) continue;
         const int64_t id = P.idx[i];
         const float xf = (float)(P.W0 + (int)(id % P.Wc)), yf = (float)(P.H0 + (int)(id / P.Wc));
@@ -515,13 +525,60 @@ __global__ void k_pose_grad(PoseGradParams P) {
         for (int k = 0; k < 12; ++k) G[k] = warp_sum(l < nw ? red[k][l] : 0.0f);
         if (l == 0) {
             float gq[4];
-            quad2rotation_vjp(P.cam7, G, gq);
-            P.g_cam7[0] = gq[0]; P.g_cam7[1] = gq[1]; P.g_cam7[2] = gq[2]; P.g_cam7[3] = gq[3];
-            P.g_cam7[4] = G[9]; P.g_cam7[5] = G[10]; P.g_cam7[6] = G[11];
+            quad2rotation_vjp(P.cams + 8 * f, G, gq);
+            float* o = P.g_cams + 8 * f;
+            o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3]; o[4] = G[9]; o[5] = G[10]; o[6] = G[11];
         }
     }
 }
 
+
+// ---- keyframe selection by view overlap: Mapper::keyframe_selection_overlap (Mapper.cpp:132-196) ------------------------
+struct OverlapParams {
+    const float* rays_o; const float* rays_d; const float* gt_depth;   // the `pixels` rays sampled from the current frame
+    const float* t_vals;     // linspace(0, 1, n_samples)
+    const float* w2c;        // [n_kf][12] inverse keyframe poses, row-major 3x4
+    int pixels, n_samples, n_kf;
+    int H, W, edge;
+    float fx, fy, cx, cy;
+    float* percent;          // [n_kf] fraction of the pixels x n_samples vertices that project inside the keyframe
+};
+
+// One block per keyframe.  Vertices z = 0.8 d (1 - t) + (d + 0.5) t along each ray (:142-146) are projected with
+// K [-x, y, z] (:166-170) and counted when 20 px inside the image and in front of the camera (z < 0, :172-174).
+__global__ void k_kf_overlap(OverlapParams P) {
+    const int kf = blockIdx.x;
+    const float* M = P.w2c + 12 * kf;
+    const int nv = P.pixels * P.n_samples;
+    int cnt = 0;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const int r = v / P.n_samples, k = v % P.n_samples;
+        const float d = P.gt_depth[r], t = P.t_vals[k];
+        const float nearv = __fmul_rn(d, 0.8f), farv = __fadd_rn(d, 0.5f);
+        const float z = __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.0f, t)), __fmul_rn(farv, t));
+        float p[3], c[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(P.rays_o[3 * r + a], __fmul_rn(P.rays_d[3 * r + a], z));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c[a] = M[4 * a] * p[0] + M[4 * a + 1] * p[1] + M[4 * a + 2] * p[2] + M[4 * a + 3];
+        c[0] = -c[0];
+        const float zz = c[2] + 1e-5f;
+        const float u = (P.fx * c[0] + P.cx * c[2]) / zz, w = (P.fy * c[1] + P.cy * c[2]) / zz;
+        const bool in = u < (float)(P.W - P.edge) && u > (float)P.edge && w < (float)(P.H - P.edge) && w > (float)P.edge && zz < 0.0f;
+        cnt += in ? 1 : 0;
+    }
+    __shared__ int red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) P.percent[kf] = (float)v / (float)nv;
+    }
+}
 
 // ---- frustum voxel mask: Mapper::get_mask_from_c2w (Mapper.cpp:42-130, upstream semantics -- the transliteration truncates
 // the bound to int and mixes up the memcpy directions / the sign of z) --------------------------------------

@@ -317,3 +317,65 @@ def test_mapping_with_frustum_feature_selection(engine_factory, model_inputs, fr
         m = e.frustum_mask(0, lv)
         d = np.abs(e.get_grid(lv) - grids[lv]).max(axis=(0, 1))
         assert d[~m].max() == 0.0 and d[m].max() > 0.0
+
+
+def test_bundle_adjustment_vs_oracle(engine_factory, model_inputs, frames, syn):
+    """Mapper.cpp:305-329,366-368,382-399,467-489: the poses of the non-oldest frames are optimised with the map as
+    7-vectors.  Camera gradients of the first iteration, the loss trajectory, the optimised vectors and the pose
+    write-back against the autograd oracle on the same pixel stream."""
+    import torch
+    import nice_oracle as O
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    nf, pix = 3, 600
+    e = engine_factory(mapping_pixels=pix, frustum_feature_selection=0, BA_cam_lr=0.001)
+    stages = ["middle", "color", "color"]
+    it_of = {"middle": 0, "color": 59}
+    e.seed(11)
+    e.mapping_begin(list(range(nf)), 60, 1.0, ba_mask=0b110)      # frame 0 = the oldest keyframe stays fixed
+    losses, g_first = [], None
+    for st in stages:
+        losses.append(e.mapping_iter(it_of[st]))
+        if g_first is None:
+            g_first = e.mapping_cam_grads()
+    cams = e.mapping_end()
+    m = O.Model(grids, decs)
+    go, co = {}, []
+    ref_losses, _ = O.mapping_iters(m, depths[:nf], colors[:nf], poses[:nf], syn.CAM, pix, stages, seed=11, ba_frames=[1, 2],
+                                    ba_cam_lr=0.001, grads_out=go, cams_out=co)
+    assert np.allclose(losses, ref_losses, rtol=1e-3), (losses, ref_losses)
+    assert np.all(g_first[0] == 0)
+    for f in (1, 2):
+        assert relerr(g_first[f], go["cam_%d" % f].numpy()) < GRAD_TOL, f
+    ref_cams = co[0].numpy()
+    init = np.stack([O.get_tensor_from_camera(poses[f]) for f in range(nf)])
+    moved = np.abs(ref_cams - init).max()
+    assert moved > 1e-3 and np.abs(cams - ref_cams).max() < 5e-2 * moved, (cams, ref_cams)
+    assert np.array_equal(cams[0], init[0])
+    for f in (1, 2):   # est_c2w <- get_camera_from_tensor(camera_tensor)
+        assert np.abs(e.get_frame_pose(f) - O.get_camera_from_tensor(torch.tensor(cams[f])).numpy()).max() < 1e-6
+    assert np.abs(e.get_frame_pose(0) - poses[0][:3]).max() == 0
+
+
+def test_keyframe_selection_overlap(engine_factory, frames, syn):
+    """Mapper.cpp:132-196: fraction of the current frame's 100 x 16 depth-guided vertices that each keyframe sees, and the
+    resulting ranking, against the numpy restatement on the same pixel indices."""
+    import nice_oracle as O
+    depths, colors, poses = frames
+    e = engine_factory()
+    rs = np.random.RandomState(5)
+    kfs = []
+    for k in range(7):   # keyframes around the current pose: growing yaw and a sideways offset, one looking away
+        yaw = np.deg2rad([0, 10, 25, 40, 60, 90, 180][k])
+        R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]], np.float32)
+        m = np.eye(4, dtype=np.float32); m[:3, :3] = poses[0][:3, :3] @ R; m[:3, 3] = poses[0][:3, 3] + rs.uniform(-0.3, 0.3, 3).astype(np.float32)
+        kfs.append(m)
+    idx = syn.mt19937_indices(3, 100, 480 * 640)
+    sel, pct = e.keyframe_selection_overlap(0, kfs, 3, idx=idx)
+    _, ts = O.t_tables()
+    ref_sel, ref_pct = O.keyframe_selection_overlap(depths[0], colors[0], poses[0], kfs, 3, syn.CAM, idx, ts=ts.numpy())
+    assert np.abs(pct - ref_pct).max() <= 2.0 / 1600 + 1e-7, (pct, ref_pct)      # a vertex exactly on the 20 px border may flip
+    assert ref_pct.max() > 0.3 and (ref_pct == 0).any()
+    if np.abs(pct - ref_pct).max() == 0:
+        assert sel == ref_sel
+    assert len(sel) == 3 and all(pct[sel[i]] >= pct[sel[i + 1]] for i in range(2))
