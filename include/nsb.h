@@ -150,6 +150,11 @@ int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const float* d_rays
                              const float* d_gt_depth, float* d_rgb, float* d_depth, float* d_var, float* d_weights);
 /* Renderer::eval_points (Renderer.h:12, Renderer.cpp:19-42): raw (P,4) for P points. */
 int nsb_eval_points(nsb_ctx* ctx, int stage, int P, const float* pts, float* raw);
+/* Dense render of all H*W pixels of the frame in `slot` seen from c2w16 (NULL: the slot's pose) -- upstream's
+ * Renderer::render_img, of which the reference keeps only ray_batch_size (Renderer.cpp:5); equals ONE render_batch_ray over
+ * the H*W rays in row-major pixel order.  use_gt_depth != 0: depth-guided with the frame's depth image (48 samples/ray);
+ * 0: the no-depth path (32 samples/ray, e.g. the coarse level).  Outputs are host arrays (H*W*3, H*W, H*W), any may be NULL. */
+int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int stage, int use_gt_depth, float* rgb, float* depth, float* var);
 /* z_vals of the last render (n, S) -- the "sample placement" intermediate of Renderer.cpp:61-119. */
 int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z_vals);
 

@@ -11,6 +11,7 @@
 // paths, torch::optim::Adam& -> nsb::Adam (the optimiser state lives in the engine), c10::Error -> std::runtime_error.
 // Header-only; link with libnsb.so.
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -203,6 +204,14 @@ struct KeyFrame { Tensor est_c2w, gt_c2w, color, depth; int idx = 0; int slot = 
 class Mapper {
   public:
     Mapper(EnginePtr engine, bool coarse_mapper = false) : e_(std::move(engine)), coarse_mapper_(coarse_mapper) {}
+    // Mapper.cpp:132-196 (member form): indices into keyframes() of the k_overlap keyframes that see most of the current view.
+    void keyframe_selection_overlap(Tensor gt_color, Tensor gt_depth, Tensor c2w, const std::vector<KeyFrame>& keyframe_vector, int k_overlap,
+                                    std::vector<int>& selected_kf) {
+        const int cur_slot = e_->cfg().max_frames - 1;
+        float m[16] = {0}; m[15] = 1.f; std::memcpy(m, c2w.data(), sizeof(float) * std::min<int64_t>(16, c2w.numel()));
+        e_->check(nsb_set_frame(e_->ctx(), cur_slot, gt_depth.data(), gt_color.data(), m));
+        select_overlap(cur_slot, keyframe_vector, k_overlap, selected_kf);
+    }
     // Mapper.cpp:198-491.  The current frame is uploaded to the last resident slot; keyframes keep their slots.
     void optimize_map(int num_joint_iters, Dict& c, Tensor cur_gt_color, Tensor cur_gt_depth, Tensor gt_cur_c2w, Tensor& cur_c2w, NICE& decoders,
                       float lr_factor = 1.f, std::vector<float>* losses = nullptr) {
@@ -212,23 +221,51 @@ class Mapper {
         const int cur_slot = e_->cfg().max_frames - 1;
         float m[16] = {0}; m[15] = 1.f; std::memcpy(m, cur_c2w.data(), sizeof(float) * std::min<int64_t>(16, cur_c2w.numel()));
         e_->check(nsb_set_frame(e_->ctx(), cur_slot, cur_gt_depth.data(), cur_gt_color.data(), m));
-        std::vector<int> slots;                                      // optimize_frame, Mapper.cpp:200-216
-        const int window = e_->cfg().mapping_window_size - 2;
-        for (int k = (int)keyframes_.size() - 1; k >= 0 && (int)slots.size() < window + 1; --k) slots.insert(slots.begin(), keyframes_[k].slot);
-        slots.push_back(cur_slot);
+        // optimize_frame (Mapper.cpp:200-216): overlap-selected keyframes, the latest keyframe, then the current frame (-1)
+        std::vector<int> optimize_frame;
+        if (!keyframes_.empty()) select_overlap(cur_slot, keyframes_, e_->cfg().mapping_window_size - 2, optimize_frame);
+        int oldest_frame = -1;
+        if (!keyframes_.empty()) {
+            optimize_frame.push_back((int)keyframes_.size() - 1);
+            oldest_frame = *std::min_element(optimize_frame.begin(), optimize_frame.end());
+        }
+        optimize_frame.push_back(-1);
+        if ((int)optimize_frame.size() > 16) throw std::runtime_error("optimize_frame exceeds the 16 frames a mapping call supports");
+        std::vector<int> slots;
+        uint32_t ba_mask = 0;
+        for (size_t f = 0; f < optimize_frame.size(); ++f) {
+            const int fr = optimize_frame[f];
+            slots.push_back(fr == -1 ? cur_slot : keyframes_[(size_t)fr].slot);
+            if (BA && fr != oldest_frame) ba_mask |= 1u << f;          // Mapper.cpp:305-329 (the current frame always joins)
+        }
         std::vector<float> l((size_t)num_joint_iters);
-        e_->check(nsb_optimize_map(e_->ctx(), (int)slots.size(), slots.data(), num_joint_iters, lr_factor, l.data()));
+        e_->check(nsb_mapping_begin_ba(e_->ctx(), (int)slots.size(), slots.data(), num_joint_iters, lr_factor, ba_mask));
+        for (int it = 0; it < num_joint_iters; ++it) e_->check(nsb_mapping_iter_async(e_->ctx(), it, nullptr));
+        for (int o = 0; o < num_joint_iters; o += 4096) e_->check(nsb_mapping_losses(e_->ctx(), o, std::min(4096, num_joint_iters - o), l.data() + o, nullptr));
+        e_->check(nsb_mapping_end(e_->ctx(), nullptr));
         if (losses) *losses = l;
+        if (ba_mask) {                                               // Mapper.cpp:467-489: est_c2w / cur_c2w <- optimised cameras
+            for (size_t f = 0; f < optimize_frame.size(); ++f) {
+                if (!((ba_mask >> f) & 1u)) continue;
+                Tensor pose({4, 4});
+                e_->check(nsb_get_frame_pose(e_->ctx(), slots[f], pose.data()));
+                pose.data()[12] = pose.data()[13] = pose.data()[14] = 0.f; pose.data()[15] = 1.f;
+                if (optimize_frame[f] == -1) cur_c2w = pose; else keyframes_[(size_t)optimize_frame[f]].est_c2w = pose;
+            }
+        }
         e_->sync_grids_to_host(c);                                   // Mapper.cpp:448-464 write-back
     }
-    // Mapper.cpp:493-552 (keyframe policy: every keyframe_every-th frame becomes a keyframe)
+    // Mapper.cpp:493-552.  The transliteration hard-codes `init = true` (:495); the intent (upstream) is the first frame only.
     void run(NICE& decoders, Dict& c, std::vector<Tensor>& estimate_c2w_vec, Tensor gt_color_t, Tensor gt_depth_t, Tensor gt_c2w_t, int idx, int n_imgs) {
         const bool first = keyframes_.empty() && idx == 0;
         const int iters = first ? e_->cfg().mapping_iters_first : e_->cfg().mapping_iters;
         const float lrf = first ? e_->cfg().lr_first_factor : e_->cfg().lr_factor;
         Tensor cur = estimate_c2w_vec[(size_t)idx];
+        BA = keyframes_.size() > 4 && e_->cfg().BA && !coarse_mapper_;                                  // Mapper.cpp:530
         optimize_map(iters, c, gt_color_t, gt_depth_t, gt_c2w_t, cur, decoders, lrf);
+        if (BA) estimate_c2w_vec[(size_t)idx] = cur;                                                    // Mapper.cpp:533-534
         if ((idx % e_->cfg().keyframe_every == 0 || idx == n_imgs - 2) && (int)keyframes_.size() < e_->cfg().max_frames - 1) {
+            for (const KeyFrame& k : keyframes_) if (k.idx == idx) return;                              // Mapper.cpp:539
             KeyFrame kf; kf.idx = idx; kf.gt_c2w = gt_c2w_t; kf.est_c2w = cur; kf.color = gt_color_t; kf.depth = gt_depth_t; kf.slot = (int)keyframes_.size();
             float m[16] = {0}; m[15] = 1.f; std::memcpy(m, cur.data(), sizeof(float) * std::min<int64_t>(16, cur.numel()));
             e_->check(nsb_set_frame(e_->ctx(), kf.slot, gt_depth_t.data(), gt_color_t.data(), m));
@@ -236,8 +273,19 @@ class Mapper {
         }
     }
     const std::vector<KeyFrame>& keyframes() const { return keyframes_; }
+    bool BA = false;
 
   private:
+    void select_overlap(int cur_slot, const std::vector<KeyFrame>& kfs, int k_overlap, std::vector<int>& selected_kf) {
+        std::vector<float> poses(16 * kfs.size(), 0.f);
+        for (size_t k = 0; k < kfs.size(); ++k) {
+            poses[16 * k + 15] = 1.f;
+            std::memcpy(poses.data() + 16 * k, kfs[k].est_c2w.data(), sizeof(float) * std::min<int64_t>(16, kfs[k].est_c2w.numel()));
+        }
+        std::vector<int> sel(kfs.size() + 1); int n_sel = 0;
+        e_->check(nsb_keyframe_selection_overlap(e_->ctx(), cur_slot, nullptr, (int)kfs.size(), poses.data(), k_overlap, nullptr, 100, 16, sel.data(), &n_sel, nullptr));
+        selected_kf.assign(sel.begin(), sel.begin() + n_sel);
+    }
     EnginePtr e_;
     bool coarse_mapper_;
     std::vector<KeyFrame> keyframes_;

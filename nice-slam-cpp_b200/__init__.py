@@ -120,6 +120,7 @@ def load_library(variant=""):
     L.nsb_mapping_begin_ba.argtypes = [v, C.c_int, _ip, C.c_int, C.c_float, C.c_uint32]
     L.nsb_mapping_end.argtypes = [v, _fp]
     L.nsb_mapping_cam_grads.argtypes = [v, _fp]
+    L.nsb_render_img.argtypes = [v, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _fp]
     L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
     L.nsb_get_frame_pose.argtypes = [v, C.c_int, _fp]
     L.nsb_debug_counters.argtypes = [v, C.POINTER(C.c_uint64)]
@@ -137,7 +138,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
-    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap",
+    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img",
 ]
 
 
@@ -306,6 +307,14 @@ class Engine:
         w = np.empty((n, S), np.float32) if want_weights else None
         self._ck(self.lib.nsb_render_batch_ray(self.h, STAGE[stage], n, _f(rd), _f(ro), _f(gd), _f(rgb), _f(depth), _f(var), _f(w)))
         return rgb, depth, var, w
+
+    def render_img(self, slot, stage, use_gt_depth=True, c2w=None):
+        """Dense render of every pixel of a resident frame (upstream render_img) -> rgb (H,W,3), depth (H,W), var (H,W)."""
+        H, W = self.cfg.H, self.cfg.W
+        rgb = np.empty((H, W, 3), np.float32); depth = np.empty((H, W), np.float32); var = np.empty((H, W), np.float32)
+        p = None if c2w is None else _c(np.asarray(c2w, np.float32).reshape(-1))
+        self._ck(self.lib.nsb_render_img(self.h, slot, _f(p), STAGE[stage], int(use_gt_depth), _f(rgb), _f(depth), _f(var)))
+        return rgb, depth, var
 
     def last_zvals(self, n, S=None):
         S = S or self.S

@@ -791,6 +791,48 @@ extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float*
     return 0;
 }
 
+// Dense render of every pixel of a resident frame (upstream Renderer.render_img; the reference keeps only its chunk constant,
+// Renderer.cpp:5): rays of all H*W pixels in row-major order, optionally depth-guided by the frame's own depth image,
+// rendered in chunks of max_rays.  The batch-global scalars of Renderer.cpp:76,93 (and utils.h:153 in reference mode) are
+// taken over the whole image in a first pass, exactly as one render_batch_ray call over all pixels would.
+extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int stage, int use_gt_depth, float* rgb, float* depth, float* var) {
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    const nsb_config& c = ctx->cfg;
+    const int HW = c.H * c.W;
+    if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float* stats = ctx->stats + 4 * (LOSS_RING - 1);     // whole-image scalars (kept apart from the per-chunk scratch in stats[0..3])
+    CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
+    const bool ref_norm = c.dist_norm == NSB_DISTNORM_REFERENCE;
+    auto sample_chunk = [&](int o, int m) -> int {
+        k_iota<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->idx, (int64_t)o, m);
+        CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
+        SampleParams P; fill_sample_params(ctx, P, m, 0, c.H, 0, c.W, ctx->stats, 0);
+        P.slots[0] = slot; P.n_frames = 1; P.pix_per_frame = m;
+        k_sample<<<cdiv(m, 128), 128, 0, ctx->stream>>>(P); ctx->launches += 2;
+        CK(cudaGetLastError());
+        return 0;
+    };
+    if (use_gt_depth) { k_depth_max<<<cdiv(HW, 256), 256, 0, ctx->stream>>>(ctx->f_depth + (size_t)HW * slot, HW, stats); ctx->launches++; }
+    if (ref_norm) {
+        for (int o = 0; o < HW; o += ctx->cap) {
+            const int m = std::min(ctx->cap, HW - o);
+            if (sample_chunk(o, m)) return -1;
+            k_dirnorm_ref<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, m, stats); ctx->launches++;
+        }
+    }
+    for (int o = 0; o < HW; o += ctx->cap) {
+        const int m = std::min(ctx->cap, HW - o);
+        if (sample_chunk(o, m)) return -1;
+        if (run_forward(ctx, stage, 0, m, use_gt_depth != 0, nullptr, stats, false)) return -1;
+        if (rgb) CK(cudaMemcpyAsync(rgb + 3 * (size_t)o, ctx->o_rgb, 12 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (depth) CK(cudaMemcpyAsync(depth + o, ctx->o_depth, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (var) CK(cudaMemcpyAsync(var + o, ctx->o_var, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z) {
     if (n != ctx->last_n || S != ctx->last_S) return fail(ctx, "last render was %d x %d, asked %d x %d", ctx->last_n, ctx->last_S, n, S);
     CK(cudaMemcpyAsync(z, ctx->z, 4 * (size_t)n * S, cudaMemcpyDeviceToHost, ctx->stream));

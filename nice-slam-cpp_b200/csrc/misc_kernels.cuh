@@ -14,6 +14,11 @@ __global__ void k_cl_to_ncdhw(const float* __restrict__ src, float* __restrict__
     if (i < C * nvox) { const int c = i / nvox, v = i % nvox; dst[i] = src[(size_t)v * C + c]; }
 }
 
+__global__ void k_iota(int64_t* __restrict__ dst, int64_t base, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = base + i;
+}
+
 // One contiguous run of the parameter arena that shares a learning rate (an Adam "param group" of
 // Mapper.cpp:330: decoders, coarse, middle, fine, color grids, camera tensors).
 struct AdamSegment {

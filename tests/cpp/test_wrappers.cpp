@@ -1,6 +1,7 @@
 // Exercises the C++ wrapper classes of include/nsb/nsb.hpp exactly the way a caller of the reference would use
 // Renderer / Mapper / Tracker (same method names and argument order).  Inputs are raw fp32 files written by
 // tests/test_cpp_wrappers.py; outputs go back the same way.  usage: test_wrappers <dir>
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -60,6 +61,37 @@ int main(int argc, char** argv) {
         nsb::Tensor cam = tracker.run(decoders, color_t, depth_t, c2w_t, 0, &tl);
         wr(d + "out_trk_losses.bin", tl.data(), tl.size());
         wr(d + "out_cam.bin", cam.data(), 7);
+        // Mapper::run over a short sequence (Mapper.cpp:493-552): every frame becomes a keyframe, so from the sixth frame on
+        // bundle adjustment is active (keyframes > 4, :530), the overlap selection picks the window and poses are written back
+        {
+            nsb_config cfg2 = cfg; cfg2.mapping_iters = 6; cfg2.mapping_iters_first = 6; cfg2.keyframe_every = 1; cfg2.max_frames = 8; cfg2.mapping_window_size = 5;
+            cfg2.middle_iter_ratio = 0.2f; cfg2.fine_iter_ratio = 0.2f; cfg2.BA_cam_lr = 0.002f;
+            auto engine2 = std::make_shared<nsb::Engine>(cfg2, 0);
+            nsb::Dict c2; nsb::NICE dec2(engine2);
+            for (int l = 0; l < 4; ++l) {
+                int Z, Y, X; nsb_grid_dims(&cfg2, l, &Z, &Y, &X);
+                auto g = rd(d + "grid_" + lv[l] + ".bin");
+                c2.insert(nsb::grid_key(l), nsb::Tensor({1, 32, Z, Y, X}, g.data()));
+                dec2.load(lv[l], rd(d + "dec_" + lv[l] + ".bin"));
+            }
+            engine2->check(nsb_set_ttables(engine2->ctx(), tt.data(), ts.data()));
+            engine2->check(nsb_seed(engine2->ctx(), 9));
+            nsb::Mapper mapper2(engine2, false);
+            const int n_imgs = 7;
+            std::vector<nsb::Tensor> est;
+            for (int i = 0; i < n_imgs; ++i) { nsb::Tensor p = c2w_t.clone(); p.data()[3] += 0.01f * (float)i; est.push_back(p); }
+            std::vector<float> ba_flags, pose_delta;
+            for (int i = 0; i < n_imgs; ++i) {
+                nsb::Tensor before = est[(size_t)i].clone();
+                mapper2.run(dec2, c2, est, color_t, depth_t, est[(size_t)i], i, n_imgs);
+                float dmax = 0.f;
+                for (int k = 0; k < 12; ++k) dmax = std::max(dmax, std::fabs(est[(size_t)i].data()[k] - before.data()[k]));
+                ba_flags.push_back(mapper2.BA ? 1.f : 0.f); pose_delta.push_back(dmax);
+            }
+            std::vector<float> seq = {(float)mapper2.keyframes().size()};
+            seq.insert(seq.end(), ba_flags.begin(), ba_flags.end()); seq.insert(seq.end(), pose_delta.begin(), pose_delta.end());
+            wr(d + "out_run_seq.bin", seq.data(), seq.size());
+        }
         // error behaviour: exceptions, like the reference's c10::Error
         bool threw = false;
         try { renderer.render_batch_ray(c, decoders, nsb::Tensor({n, 3}, rdv.data()), nsb::Tensor({n, 3}, ro.data()), "bogus", nsb::Tensor(), rgb, depth, var, w); }

@@ -64,4 +64,9 @@ def test_wrappers_match_ctypes_and_oracle(nsb, syn, model_inputs, frames, tmp_pa
     assert np.allclose(out["map_losses"], l_or, rtol=1e-3)
     assert np.abs(out["grid_middle"] - grids["middle"].reshape(-1)).max() > 0.05      # the dict got the optimised grid back
     assert len(out["trk_losses"]) == 2 and np.all(np.isfinite(out["cam"])) and abs(np.linalg.norm(out["cam"][:4]) - 1) < 1e-2
+    # Mapper::run over 7 frames with keyframe_every = 1: seven keyframes, BA from the sixth frame on (keyframes > 4), and the
+    # bundle-adjusted current pose is written back into estimate_c2w (Mapper.cpp:530-534)
+    seq = np.fromfile(os.path.join(d, "out_run_seq.bin"), np.float32)
+    assert seq[0] == 7 and list(seq[1:8]) == [0, 0, 0, 0, 0, 1, 1]
+    assert np.all(seq[8:13] == 0) and np.all(seq[13:15] > 1e-4) and np.all(seq[13:15] < 0.1)
     e.close()

@@ -379,3 +379,31 @@ def test_keyframe_selection_overlap(engine_factory, frames, syn):
     if np.abs(pct - ref_pct).max() == 0:
         assert sel == ref_sel
     assert len(sel) == 3 and all(pct[sel[i]] >= pct[sel[i + 1]] for i in range(2))
+
+
+def test_dense_render_img(engine_factory, frames, model_inputs, syn):
+    """BASELINE configs[3]: every pixel of a 640x480 frame through render_batch_ray (upstream render_img).  The chunked dense
+    render equals single render_batch_ray calls on the same rays (batch-global scalars taken over the whole image), a strip
+    of it matches the oracle, and the no-depth coarse level runs over the full image."""
+    import torch
+    import nice_oracle as O
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    e = engine_factory(max_rays=65536)
+    rgb, depth, var = e.render_img(0, "color", True)
+    assert rgb.shape == (480, 640, 3) and np.isfinite(rgb).all() and np.isfinite(depth).all() and (var >= 0).all()
+    # rows 200..201 against the oracle, with the whole-image maxima of Renderer.cpp:76,93 injected through an extra ray
+    rows = np.arange(200 * 640, 202 * 640)
+    ro, rd, gd, _ = O.ray_sampler(0, 480, 0, 640, rows, 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]))
+    imax = int(np.argmax(depths[0]))
+    ro2, rd2, gd2, _ = O.ray_sampler(0, 480, 0, 640, np.array([imax]), 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]))
+    tt, ts = O.t_tables()
+    with torch.no_grad():
+        ref = O.render_batch_ray(O.Model(grids, decs), torch.cat([rd, rd2]), torch.cat([ro, ro2]), "color", torch.cat([gd, gd2]), tt, ts)
+    assert relerr(depth.reshape(-1)[rows], ref[1].numpy()[:-1]) < FWD_TOL and relerr(rgb.reshape(-1, 3)[rows], ref[0].numpy()[:-1]) < FWD_TOL
+    # the same rays through render_batch_ray in one call: identical bits
+    got = e.render_batch_ray(torch.cat([rd, rd2]).numpy(), torch.cat([ro, ro2]).numpy(), "color", torch.cat([gd, gd2]).numpy(), want_weights=False)
+    assert np.array_equal(got[1][:-1], depth.reshape(-1)[rows])
+    # coarse level, no depth guidance (Renderer.cpp:54-58): 32 samples per ray over all 307 200 pixels
+    _, dc, vc = e.render_img(0, "coarse", False)
+    assert np.isfinite(dc).all() and dc.min() > 0 and (vc >= 0).all()
