@@ -208,6 +208,9 @@ int nsb_tracking_get_camera(nsb_ctx* ctx, float* cam7);
 /* ---- multi-GPU: rays sharded over ranks, one fp32 SUM all-reduce of the gradient arena per iteration ---- */
 int nsb_comm_unique_id(char* id128);                                       /* ncclGetUniqueId */
 int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world);  /* ncclCommInitRank on the ctx device */
+/* Multi-GPU ray order (rank-major interleave of the reference's frame-major batch, see RayOrder in ray_kernels.cuh): returns
+ * the reference batch element that ray i of the rendered order is, and its frame.  Rank r renders rays [r*n/world, (r+1)*n/world). */
+int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, int i, int* frame);
 int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world);
 
 /* ---- instrumentation ----------------------------------------------------------------------------------- */

@@ -120,6 +120,7 @@ def load_library(variant=""):
     L.nsb_mapping_begin_ba.argtypes = [v, C.c_int, _ip, C.c_int, C.c_float, C.c_uint32]
     L.nsb_mapping_end.argtypes = [v, _fp]
     L.nsb_mapping_cam_grads.argtypes = [v, _fp]
+    L.nsb_ray_order_source.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip]
     L.nsb_render_img.argtypes = [v, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _fp]
     L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
     L.nsb_get_frame_pose.argtypes = [v, C.c_int, _fp]
@@ -138,7 +139,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
-    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img",
+    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source",
 ]
 
 

@@ -58,6 +58,8 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     bool load() {
         if (h) return true;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -69,6 +71,8 @@ struct NcclApi {
         AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
         CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
         GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+        GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
         return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
     }
 };
@@ -129,6 +133,8 @@ struct nsb_ctx {
     int trk_slot = 0, trk_step = 0;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
+    bool ar_request = false, ar_overlapped = false;
     // instrumentation
     int64_t launches = 0; bool profiling = false;
     struct EvRec { int id; cudaEvent_t a, b; };
@@ -321,6 +327,8 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     if (cfg->n_samples != 32 || (cfg->n_surface != 16 && cfg->n_surface != 0)) return fail(ctx, "n_samples/n_surface %d/%d unsupported (32 / 16|0)", cfg->n_samples, cfg->n_surface);
     if (cfg->max_frames < 1 || cfg->max_rays < 16) return fail(ctx, "max_frames / max_rays too small");
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_bwd, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
     auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
@@ -333,10 +341,11 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     ctx->off_grid[0] = seg(ctx->nvox[0] * CDIM);
     ctx->off_dec[0] = seg(ctx->dec_n[0]); ctx->off_dec[1] = seg(ctx->dec_n[1]);
     ctx->off_train = off;
+    ctx->off_tail = seg(32);          // the loss scalar rides at the HEAD of the all-reduced range, so that a geometry-stage
+                                      // iteration (no colour / decoder / camera gradients) reduces one short contiguous prefix
     for (int l = 1; l < 4; ++l) ctx->off_grid[l] = seg(ctx->nvox[l] * CDIM);
     ctx->off_dec[2] = seg(ctx->dec_n[2]); ctx->off_dec[3] = seg(ctx->dec_n[3]);
     ctx->off_cam = seg(8 * (size_t)cfg->max_frames);
-    ctx->off_tail = seg(32);
     ctx->arena_n = off;
     CK(dalloc(&ctx->param, off)); CK(dalloc(&ctx->grad, off)); CK(dalloc(&ctx->m, off)); CK(dalloc(&ctx->v, off));
     CK(cudaMemsetAsync(ctx->param, 0, off * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->grad, 0, off * 4, ctx->stream));
@@ -386,6 +395,9 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
                     c->cam_grad_last, c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -648,6 +660,14 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
     return 0;
 }
 
+// Sum all-reduce of the gradient-arena floats [begin, end) over the ranks, on stream st.
+static int allreduce_range(nsb_ctx* ctx, size_t begin, size_t end, cudaStream_t st) {
+    if (end <= begin) return 0;
+    const int rc = g_nccl.AllReduce(ctx->grad + begin, ctx->grad + begin, end - begin, NCCL_FLOAT32, NCCL_SUM, ctx->comm, st);
+    if (rc != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
 // cotangents in ctx->g_rgb / g_depth / g_var -> g_raw -> decoder backward (+ wgrad).  flags: F_GRID=1, F_WGRAD=2, F_RAY=4.
 static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, int flags, bool color_active,
                         bool skip_composite = false) {
@@ -684,6 +704,16 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         partition(grid, w, P.cta_begin);
         P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
         CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+    }
+    ctx->ar_overlapped = false;
+    if (wg && ctx->ar_request && ctx->world > 1) {
+        // multi-GPU colour iteration: the grid gradients are final once k_decode_bwd has run, so their all-reduce goes to the
+        // communication stream now and overlaps the weight-gradient kernel; the decoder / camera gradients follow after it
+        CK(cudaEventRecord(ctx->ev_bwd, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_bwd, 0));
+        if (allreduce_range(ctx, ctx->off_train, ctx->off_dec[2], ctx->comm_stream)) return -1;
+        CK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+        ctx->ar_overlapped = true;
     }
     if (wg) {
         Timer t(ctx, T_WGRAD);
@@ -971,6 +1001,21 @@ extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots
     return 0;
 }
 
+// Ray order of a mapping iteration: identity on one GPU, rank-major interleave when the frames divide evenly over the ranks.
+static RayOrder map_order(const nsb_ctx* ctx, int n, int pix) {
+    RayOrder o; o.world = 1; o.per = n; o.pix = pix; o.ppr = pix;
+    if (ctx->world > 1 && pix % ctx->world == 0 && n % ctx->world == 0) { o.world = ctx->world; o.per = n / ctx->world; o.ppr = pix / ctx->world; }
+    return o;
+}
+
+// Host-visible copy of the ray-order rule (tests): which reference batch element, and which frame, ray i of the rendered order is.
+extern "C" int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, int i, int* frame) {
+    RayOrder o; o.world = 1; o.per = n_rays; o.pix = pix_per_frame; o.ppr = pix_per_frame;
+    if (world > 1 && pix_per_frame % world == 0 && n_rays % world == 0) { o.world = world; o.per = n_rays / world; o.ppr = pix_per_frame / world; }
+    if (frame) *frame = o.frame(i, pix_per_frame);
+    return o.source(i);
+}
+
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
     const nsb_config& c = ctx->cfg;
     if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
@@ -990,13 +1035,14 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
         SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
         P.idx = d_idx; P.cam_mask = ctx->map_ba_mask;
+        P.order = map_order(ctx, n, pix);
         for (int f = 0; f < ctx->map_frames; ++f) P.slots[f] = ctx->map_slots[f];
         P.n_frames = ctx->map_frames; P.pix_per_frame = pix;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
         if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
         CK(cudaGetLastError());
     }
-    // this rank's slice of the (already filtered, batch-global) ray list
+    // this rank's slice of the (already filtered, batch-global) ray list (rank-major order, see RayOrder)
     const int per = cdiv(cdiv(n, ctx->world), 1), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
     const bool use_color = stage == NSB_COLOR;
     if (nl > 0) {
@@ -1022,13 +1068,16 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             CK(cudaGetLastError());
         }
         const int flags = 1 | (c.fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
-        if (run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true)) return -1;
+        ctx->ar_request = ctx->world > 1;
+        const int rb = run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true);
+        ctx->ar_request = false;
+        if (rb) return -1;
         if (ctx->map_ba_mask) {   // chain to (q, t) of every optimised frame; other ranks' partial sums arrive through the all-reduce
             Timer t(ctx, T_COMP);
             PoseGradParams G; memset(&G, 0, sizeof G);
             G.d_rays = ctx->d_rays; G.idx = ctx->idx_pool && ctx->pool_n == n && !idx ? ctx->idx_pool + (size_t)((ctx->pool_cursor - 1) % ctx->pool_iters) * n : ctx->idx;
             G.valid = ctx->valid; G.cams = ctx->param + ctx->off_cam; G.cam_mask = ctx->map_ba_mask;
-            G.pix_per_frame = pix; G.n_frames = ctx->map_frames; G.lo = off; G.hi = off + nl;
+            G.pix_per_frame = pix; G.n_frames = ctx->map_frames; G.lo = off; G.hi = off + nl; G.order = map_order(ctx, n, pix);
             G.H0 = 0; G.W0 = 0; G.Wc = c.W; G.raydir = c.raydir; G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy;
             G.g_cams = ctx->grad + ctx->off_cam;
             k_pose_grad<<<ctx->map_frames, 1024, 0, ctx->stream>>>(G); ctx->launches++;
@@ -1037,9 +1086,17 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     }
     if (ctx->world > 1) {
         Timer t(ctx, T_COMM);
-        const size_t cnt = ctx->arena_n - ctx->off_train;
-        const int rc = g_nccl.AllReduce(ctx->grad + ctx->off_train, ctx->grad + ctx->off_train, cnt, NCCL_FLOAT32, NCCL_SUM, ctx->comm, ctx->stream);
-        if (rc != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        if (nl > 0 && ctx->ar_overlapped) {   // colour iteration: grids went out under the wgrad kernel, the small remainder follows
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+            if (allreduce_range(ctx, ctx->off_dec[2], ctx->arena_n, ctx->stream)) return -1;
+        } else if (!use_color && !ctx->map_ba_mask) {
+            // geometry iteration: colour-grid, decoder and camera gradients are exact zeros on every rank (Mapper.cpp:435-442
+            // adds the colour term only in stage "color"), so only [loss | grid_middle | grid_fine] is exchanged
+            if (allreduce_range(ctx, ctx->off_train, ctx->off_grid[3], ctx->stream)) return -1;
+        } else {
+            if (allreduce_range(ctx, ctx->off_train, ctx->arena_n, ctx->stream)) return -1;
+        }
+        ctx->ar_overlapped = false;
     }
     CK(cudaMemcpyAsync(stats + 3, ctx->grad + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));

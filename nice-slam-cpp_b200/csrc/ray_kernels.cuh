@@ -37,6 +37,22 @@ __host__ __device__ inline void quad2rotation_vjp(const float* q, const float* G
     gq[0] = two_s * dqr - k * qr; gq[1] = two_s * dqi - k * qi; gq[2] = two_s * dqj - k * qj; gq[3] = two_s * dqk - k * qk;
 }
 
+// Multi-GPU ray order.  The reference's batch is frame-major: ray q of frame f is element f * pix + q (Mapper.cpp:404-414).
+// With `world` ranks each rank renders a contiguous block of `per` rays; to give every rank the same mix of frames (same
+// inside fraction, same scatter footprint) the blocks are cut rank-major: element i of the rendered order is
+//   rank r = i / per, j = i % per, frame f = j / ppr, k = j % ppr   ->   reference element  f * pix + r * ppr + k,   ppr = pix / world.
+// The loss and every gradient are sums over rays, so the order only changes the association of fp32 additions.
+struct RayOrder {
+    int world, per, pix, ppr;    // world <= 1 (incl. a zeroed struct): identity, frame = i / pix_per_frame
+    __host__ __device__ __forceinline__ bool identity() const { return world <= 1; }
+    __host__ __device__ __forceinline__ int frame(int i, int pix_per_frame) const { return identity() ? i / pix_per_frame : (i % per) / ppr; }
+    __host__ __device__ __forceinline__ int source(int i) const {
+        if (identity()) return i;
+        const int r = i / per, j = i % per;
+        return (j / ppr) * pix + r * ppr + (j % ppr);
+    }
+};
+
 struct SampleParams {
     const float* depth;      // [max_frames][H*W]
     const float* color;      // [max_frames][H*W*3]
@@ -46,6 +62,7 @@ struct SampleParams {
     const int64_t* idx;      // [n] flat index into the crop
     int slots[MAX_OPT_FRAMES];
     int n_frames, pix_per_frame;
+    RayOrder order;          // which reference batch element ray i is (identity on one GPU)
     int H, W, H0, W0, Wc;
     float fx, fy, cx, cy;
     int raydir;
@@ -71,9 +88,9 @@ __global__ void k_sample(SampleParams P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float gd = 0.0f; bool ok = false;
     if (i < P.n) {
-        const int f = min(i / P.pix_per_frame, P.n_frames - 1);
+        const int f = min(P.order.frame(i, P.pix_per_frame), P.n_frames - 1);
         const int slot = P.slots[f];
-        const int64_t id = P.idx[i];
+        const int64_t id = P.idx[P.order.source(i)];
         const int x = P.W0 + (int)(id % P.Wc), y = P.H0 + (int)(id / P.Wc);
         const size_t pix = (size_t)slot * P.H * P.W + (size_t)y * P.W + x;
         gd = P.depth[pix];
@@ -485,6 +502,7 @@ struct PoseGradParams {
     const float* cams;       // [n_frames][8] current 7-vectors
     uint32_t cam_mask;       // frames whose pose is optimised
     int pix_per_frame, n_frames;
+    RayOrder order;
     int lo, hi;              // rays [lo, hi) carry gradient on this rank (the others' partial sums arrive through the all-reduce)
     int H0, W0, Wc, raydir;
     float fx, fy, cx, cy;
@@ -500,10 +518,12 @@ __global__ void k_pose_grad(PoseGradParams P) {
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
-    const int r_lo = max(P.lo, f * P.pix_per_frame), r_hi = min(P.hi, (f + 1) * P.pix_per_frame);
+    // this rank's rays of frame f: a contiguous run in either ray order
+    const int r_lo = P.order.identity() ? max(P.lo, f * P.pix_per_frame) : P.lo + f * P.order.ppr;
+    const int r_hi = P.order.identity() ? min(P.hi, (f + 1) * P.pix_per_frame) : min(P.hi, P.lo + (f + 1) * P.order.ppr);
     for (int i = r_lo + threadIdx.x; i < r_hi; i += blockDim.x) {
         if (P.valid && !P.valid[i]) continue;
-        const int64_t id = P.idx[i];
+        const int64_t id = P.idx[P.order.source(i)];
         const float xf = (float)(P.W0 + (int)(id % P.Wc)), yf = (float)(P.H0 + (int)(id / P.Wc));
         const float dir[3] = {(xf - P.cx) / P.fx, P.raydir == 0 ? (xf - P.cy) / P.fy : -(yf - P.cy) / P.fy, -1.0f};
         const float* g = P.d_rays + 6 * (size_t)i;
