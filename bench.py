@@ -294,7 +294,11 @@ def run_ours(args, rank, world, local_rank):
             evs.append((a, b))
         barrier()
         clk = clocks.stop() if clocks else None
-        t_dev = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        t_dev = sum(step_ms) * 1e-3
+        is_color = [((W + k) % ITERS_PER_KEYFRAME) > 36 for k in range(K)]
+        ms_geom = float(np.mean([m for m, c_ in zip(step_ms, is_color) if not c_])) if not all(is_color) else None
+        ms_color = float(np.mean([m for m, c_ in zip(step_ms, is_color) if c_])) if any(is_color) else None
         kms = e.kernel_ms()
         launches = e.launch_count()
         e.set_profiling(False)
@@ -368,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # the checker is optional for the bench line
             cpu = {"error": repr(ex)}
         out = {"metric": "mapping rays/s (fwd+bwd, 48 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "ms_per_step": t_dev / K * 1e3, "ms_per_step_by_stage": {"geometry": ms_geom, "color": ms_color}, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": n_global,
                           "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "step i = iteration i%60 of optimize_map (37 geometry + 23 colour)",

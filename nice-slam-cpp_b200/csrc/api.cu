@@ -135,6 +135,9 @@ struct nsb_ctx {
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
     bool ar_request = false, ar_overlapped = false;
+    int ar_mode = 1;               // NSB_AR_MODE: 0 = one full all-reduce per iteration; 1 (default) = short prefix in geometry iterations;
+                                   // 2 = additionally the grid all-reduce of colour iterations on a second stream under the wgrad kernel
+                                   // (measured: fine on 2 GPUs, pathological on 8 -- NCCL's NVLS kernel and k_wgrad fight for SM residency)
     // instrumentation
     int64_t launches = 0; bool profiling = false;
     struct EvRec { int id; cudaEvent_t a, b; };
@@ -375,6 +378,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
+    { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
@@ -1068,7 +1072,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             CK(cudaGetLastError());
         }
         const int flags = 1 | (c.fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
-        ctx->ar_request = ctx->world > 1;
+        ctx->ar_request = ctx->world > 1 && ctx->ar_mode == 2;
         const int rb = run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true);
         ctx->ar_request = false;
         if (rb) return -1;
@@ -1089,7 +1093,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         if (nl > 0 && ctx->ar_overlapped) {   // colour iteration: grids went out under the wgrad kernel, the small remainder follows
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
             if (allreduce_range(ctx, ctx->off_dec[2], ctx->arena_n, ctx->stream)) return -1;
-        } else if (!use_color && !ctx->map_ba_mask) {
+        } else if (!use_color && !ctx->map_ba_mask && ctx->ar_mode != 0) {
             // geometry iteration: colour-grid, decoder and camera gradients are exact zeros on every rank (Mapper.cpp:435-442
             // adds the colour term only in stage "color"), so only [loss | grid_middle | grid_fine] is exchanged
             if (allreduce_range(ctx, ctx->off_train, ctx->off_grid[3], ctx->stream)) return -1;
