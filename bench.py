@@ -258,6 +258,12 @@ def run_ours(args, rank, world, local_rank):
             uid = torch.tensor(list(nsb.comm_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         e.comm_init(bytes(uid.cpu().tolist()), rank, world)
+        if args.comm == "p2p":   # peer-memory optimiser step: gather every rank's CUDA IPC handles, import, barrier
+            mine = torch.tensor(list(e.p2p_export()), dtype=torch.uint8, device="cuda")
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            e.p2p_import(b"".join(bytes(h.cpu().tolist()) for h in allh), rank, world)
+            dist.barrier()
     pix = n_global // N_FRAMES
     K, W = args.steps, args.warmup
     idx_all = nsb.synthetic.mt19937_indices(0, (K + W) * N_FRAMES * pix, cfg.H * cfg.W).reshape(K + W, N_FRAMES * pix)
@@ -376,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
                "data": "synthetic",
                "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": n_global,
                           "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "step i = iteration i%60 of optimize_map (37 geometry + 23 colour)",
-                          "mma": "3xTF32 mma.sync (fp32-grade)", "l2": "256 MiB flush write between timed steps", "parallelism": "rays sharded x%d, NCCL all-reduce of grads" % world,
+                          "mma": "3xTF32 mma.sync (fp32-grade)", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
                           "inside_fraction": frac_in},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking,
                "loss_first_last": [float(losses[0]), float(losses[len(losses) - 1])]}
@@ -393,6 +399,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU optimiser step: fused peer-memory kernel (default) or ncclAllReduce + Adam")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))

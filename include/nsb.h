@@ -208,6 +208,14 @@ int nsb_tracking_get_camera(nsb_ctx* ctx, float* cam7);
 /* ---- multi-GPU: rays sharded over ranks, one fp32 SUM all-reduce of the gradient arena per iteration ---- */
 int nsb_comm_unique_id(char* id128);                                       /* ncclGetUniqueId */
 int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world);  /* ncclCommInitRank on the ctx device */
+/* Peer-memory mode (NVLink / NVSwitch, one process per GPU): every rank exports the CUDA IPC handles of its gradient arena,
+ * parameter arena and flag block (192 bytes), the host gathers them in rank order ([world][192]) and every rank imports them.
+ * From then on a mapping iteration replaces "ncclAllReduce(gradients) + Adam" by ONE kernel: each rank sums its slice of all
+ * ranks' gradients with P2P loads, applies Adam to that slice and stores the updated parameters into every rank's arena, with
+ * two flag barriers in peer memory.  nsb_comm_init is still required first (rank / world; NCCL stays the fallback path).
+ * Put a host barrier between the imports and the first nsb_mapping_iter. */
+int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192);
+int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world);
 /* Multi-GPU ray order (rank-major interleave of the reference's frame-major batch, see RayOrder in ray_kernels.cuh): returns
  * the reference batch element that ray i of the rendered order is, and its frame.  Rank r renders rays [r*n/world, (r+1)*n/world). */
 int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, int i, int* frame);

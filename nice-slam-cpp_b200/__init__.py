@@ -113,6 +113,8 @@ def load_library(variant=""):
     L.nsb_tracking_get_camera.argtypes = [v, _fp]
     L.nsb_comm_unique_id.argtypes = [C.c_char_p]
     L.nsb_comm_init.argtypes = [v, C.c_char_p, C.c_int, C.c_int]
+    L.nsb_comm_p2p_export.argtypes = [v, C.c_char_p]
+    L.nsb_comm_p2p_import.argtypes = [v, C.c_char_p, C.c_int, C.c_int]
     L.nsb_comm_rank_world.argtypes = [v, _ip, _ip]
     L.nsb_set_profiling.argtypes = [v, C.c_int]
     L.nsb_get_kernel_ms.argtypes = [v, _fp]
@@ -139,7 +141,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
-    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source",
+    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source", "nsb_comm_p2p_export", "nsb_comm_p2p_import",
 ]
 
 
@@ -426,6 +428,17 @@ class Engine:
     # ---- multi-GPU / instrumentation
     def comm_init(self, uid, rank, world):
         self._ck(self.lib.nsb_comm_init(self.h, uid, rank, world))
+
+    def p2p_export(self):
+        """192 bytes: CUDA IPC handles of this rank's gradient arena, parameter arena and flag block."""
+        buf = C.create_string_buffer(192)
+        self._ck(self.lib.nsb_comm_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_import(self, all_handles, rank, world):
+        """all_handles: the ranks' p2p_export() bytes concatenated in rank order; host-barrier afterwards."""
+        assert len(all_handles) == 192 * world
+        self._ck(self.lib.nsb_comm_p2p_import(self.h, all_handles, rank, world))
 
     def bench_gather(self, reps=20):
         ms = C.c_float(0)

@@ -15,6 +15,7 @@
 
 #include "../../include/nsb.h"
 #include "misc_kernels.cuh"
+#include "p2p_kernels.cuh"
 #include "params.h"
 #include "ray_kernels.cuh"
 
@@ -128,6 +129,7 @@ struct nsb_ctx {
     // mapping state
     int map_frames = 0, map_slots[MAX_OPT_FRAMES], map_iters = 0, map_step = 0; float map_lr_factor = 1.0f;
     float* cam_grad_last = nullptr;   // [MAX_OPT_FRAMES][8] camera gradients of the last BA iteration (Adam zeroes the arena)
+    bool map_color_touched = false;   // a colour iteration has run since nsb_mapping_begin (see run_adam)
     uint32_t map_ba_mask = 0;      // bundle adjustment: frames (bit f) whose 7-vector pose is optimised with the map (Mapper.cpp:305-329)
     // tracking state
     int trk_slot = 0, trk_step = 0;
@@ -135,6 +137,9 @@ struct nsb_ctx {
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
     bool ar_request = false, ar_overlapped = false;
+    // peer-memory optimiser step (nsb_comm_p2p_import): every rank's gradient / parameter arena and flag block, opened through CUDA IPC
+    bool p2p = false; uint32_t p2p_epoch = 0; uint32_t* p2p_flags = nullptr;
+    float* peer_grad[P2P_MAX_WORLD] = {nullptr}; float* peer_param[P2P_MAX_WORLD] = {nullptr}; uint32_t* peer_flags[P2P_MAX_WORLD] = {nullptr};
     int ar_mode = 1;               // NSB_AR_MODE: 0 = one full all-reduce per iteration; 1 (default) = short prefix in geometry iterations;
                                    // 2 = additionally the grid all-reduce of colour iterations on a second stream under the wgrad kernel
                                    // (measured: fine on 2 GPUs, pathological on 8 -- NCCL's NVLS kernel and k_wgrad fight for SM residency)
@@ -380,6 +385,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
@@ -393,6 +399,8 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->p2p) for (int w = 0; w < c->world; ++w) if (w != c->rank) { cudaIpcCloseMemHandle(c->peer_grad[w]); cudaIpcCloseMemHandle(c->peer_param[w]); cudaIpcCloseMemHandle(c->peer_flags[w]); }
+    if (c->p2p_flags) cudaFree(c->p2p_flags);
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
@@ -932,9 +940,11 @@ extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_
 }
 
 // ---- Adam -----------------------------------------------------------------------------------------------------------
-static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats) {
-    Timer t(ctx, T_ADAM);
-    AdamParams A; memset(&A, 0, sizeof A);
+// color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first
+// colour iteration): gradient, m and v of the colour grid / colour decoder are all exactly zero, the Adam update is the identity
+// (p - step * 0 / (0 + eps) = p), so those segments are left out of the launch.
+static void build_adam(nsb_ctx* ctx, AdamParams& A, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine) {
+    memset(&A, 0, sizeof A);
     A.param = ctx->param; A.grad = ctx->grad; A.m = ctx->m; A.v = ctx->v;
     const double b1 = 0.9, b2 = 0.999;
     const double bc1 = 1.0 - std::pow(b1, (double)step), bc2 = 1.0 - std::pow(b2, (double)step);
@@ -944,18 +954,42 @@ static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fi
     auto add = [&](size_t begin, size_t n, float lr, const uint8_t* mask, int active) {
         AdamSegment& s = A.seg[k++]; s.begin = (int)begin; s.end = (int)(begin + pad32(n)); s.step = (float)((double)lr / bc1); s.mask = mask; s.active = active;
     };
-    for (int l = 1; l < 4; ++l) add(ctx->off_grid[l], ctx->nvox[l] * CDIM, lr_group[1 + l], ctx->vmask[l], 1);   // groups 2,3,4 = middle, fine, color
+    for (int l = 1; l < (color_pristine ? 3 : 4); ++l) add(ctx->off_grid[l], ctx->nvox[l] * CDIM, lr_group[1 + l], ctx->vmask[l], 1);   // groups 2,3,4 = middle, fine, color
     add(ctx->off_dec[2], ctx->dec_n[2], lr_group[0], nullptr, dec_fine ? 1 : 0);
-    add(ctx->off_dec[3], ctx->dec_n[3], lr_group[0], nullptr, dec_color ? 1 : 0);
+    if (!color_pristine) add(ctx->off_dec[3], ctx->dec_n[3], lr_group[0], nullptr, dec_color ? 1 : 0);
     if (n_cam_floats > 0) add(ctx->off_cam, n_cam_floats, lr_group[5], nullptr, 1);
     add(ctx->off_tail, 32, 0.f, nullptr, 0);
     A.n_seg = k;
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
-    k_adam<<<cdiv(A.cum4[k], 256 * ADAM_VEC), 256, 0, ctx->stream>>>(A); ctx->launches++;
     if (dec_fine && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 2;
     if (dec_color && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 3;
+}
+
+// color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first
+// colour iteration): gradient, m and v of the colour grid / colour decoder are all exactly zero, the Adam update is the identity
+// (p - step * 0 / (0 + eps) = p), so those segments are left out of the launch.
+static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine = false) {
+    Timer t(ctx, T_ADAM);
+    AdamParams A; build_adam(ctx, A, step, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
+    k_adam<<<cdiv(A.cum4[A.n_seg], 256 * ADAM_VEC), 256, 0, ctx->stream>>>(A); ctx->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// Multi-GPU optimiser step over peer memory (p2p_kernels.cuh): floats [begin, end) of the arena are exchanged and stepped.
+static int run_reduce_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine,
+                           size_t begin, size_t end) {
+    Timer t(ctx, T_COMM);
+    P2PParams P; memset(&P, 0, sizeof P);
+    build_adam(ctx, P.A, step, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
+    for (int w = 0; w < ctx->world; ++w) { P.peer_grad[w] = ctx->peer_grad[w]; P.peer_param[w] = ctx->peer_param[w]; P.peer_flags[w] = ctx->peer_flags[w]; }
+    P.rank = ctx->rank; P.world = ctx->world; P.lo4 = (int)(begin / 4); P.hi4 = (int)(end / 4); P.loss4 = (int)(ctx->off_tail / 4);
+    P.epoch = ++ctx->p2p_epoch;
+    k_reduce_adam<<<ctx->n_sm * 2, 256, 0, ctx->stream>>>(P); ctx->launches++;
+    CK(cudaGetLastError());
+    // every peer has finished reading this rank's gradients when the kernel retires: clear them for the next iteration
+    CK(cudaMemsetAsync(ctx->grad + ctx->off_train, 0, (ctx->arena_n - ctx->off_train) * 4, ctx->stream));
     return 0;
 }
 
@@ -978,7 +1012,7 @@ extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots
     const int pix = ctx->cfg.mapping_pixels / n_frames;   // Mapper.cpp:223
     if (pix * n_frames > ctx->cap) return fail(ctx, "mapping_pixels %d exceeds max_rays %d", ctx->cfg.mapping_pixels, ctx->cap);
     for (int f = 0; f < n_frames; ++f) { if (slots[f] < 0 || slots[f] >= ctx->cfg.max_frames) return fail(ctx, "bad slot %d", slots[f]); ctx->map_slots[f] = slots[f]; }
-    ctx->map_frames = n_frames; ctx->map_iters = n_iters; ctx->map_step = 0; ctx->map_lr_factor = lr_factor;
+    ctx->map_frames = n_frames; ctx->map_iters = n_iters; ctx->map_step = 0; ctx->map_lr_factor = lr_factor; ctx->map_color_touched = false;
     // a fresh torch::optim::Adam is constructed per optimize_map (Mapper.cpp:330): state starts at zero
     CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
@@ -1088,14 +1122,29 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             CK(cudaGetLastError());
         }
     }
+    ctx->map_step++;
+    float lr[6];
+    for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
+    lr[5] = (ctx->map_ba_mask && stage == NSB_COLOR) ? c.BA_cam_lr : 0.f;   // Mapper.cpp:366-368 (not scaled by lr_factor)
+    if (use_color) ctx->map_color_touched = true;
+    const bool pristine = !ctx->map_color_touched;   // colour grid / decoder: gradient, m, v all exactly zero so far
+    const int n_cam = ctx->map_ba_mask ? 8 * ctx->map_frames : 0;
+    // geometry iteration before any colour iteration, no BA: colour-grid, decoder and camera gradients are exact zeros on every
+    // rank (Mapper.cpp:435-442 adds the colour term only in stage "color"), so only [loss | grid_middle | grid_fine] is exchanged
+    const bool prefix_only = pristine && !ctx->map_ba_mask && ctx->ar_mode != 0;
+    if (ctx->world > 1 && ctx->p2p) {
+        // peer-memory mode: reduce-scatter + Adam + all-gather in one kernel (p2p_kernels.cuh); the summed loss lands in the parameter arena
+        if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));   // this rank's partial sums
+        if (run_reduce_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine, ctx->off_train, prefix_only ? ctx->off_grid[3] : ctx->arena_n)) return -1;
+        CK(cudaMemcpyAsync(stats + 3, ctx->param + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
     if (ctx->world > 1) {
         Timer t(ctx, T_COMM);
         if (nl > 0 && ctx->ar_overlapped) {   // colour iteration: grids went out under the wgrad kernel, the small remainder follows
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
             if (allreduce_range(ctx, ctx->off_dec[2], ctx->arena_n, ctx->stream)) return -1;
-        } else if (!use_color && !ctx->map_ba_mask && ctx->ar_mode != 0) {
-            // geometry iteration: colour-grid, decoder and camera gradients are exact zeros on every rank (Mapper.cpp:435-442
-            // adds the colour term only in stage "color"), so only [loss | grid_middle | grid_fine] is exchanged
+        } else if (prefix_only) {
             if (allreduce_range(ctx, ctx->off_train, ctx->off_grid[3], ctx->stream)) return -1;
         } else {
             if (allreduce_range(ctx, ctx->off_train, ctx->arena_n, ctx->stream)) return -1;
@@ -1104,12 +1153,8 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     }
     CK(cudaMemcpyAsync(stats + 3, ctx->grad + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->map_step++;
-    float lr[6];
-    for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
-    lr[5] = (ctx->map_ba_mask && stage == NSB_COLOR) ? c.BA_cam_lr : 0.f;   // Mapper.cpp:366-368 (not scaled by lr_factor)
     // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups
-    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, ctx->map_ba_mask ? 8 * ctx->map_frames : 0)) return -1;
+    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine)) return -1;
     return 0;
 }
 
@@ -1336,6 +1381,32 @@ extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int worl
     const int rc = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
     if (rc != 0) return fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     ctx->rank = rank; ctx->world = world;
+    return 0;
+}
+// ---- peer-memory mode: CUDA IPC handles of {gradient arena, parameter arena, flag block} ----------------------------------------
+extern "C" int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192) {
+    cudaIpcMemHandle_t h[3];
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcGetMemHandle(&h[0], ctx->grad)); CK(cudaIpcGetMemHandle(&h[1], ctx->param)); CK(cudaIpcGetMemHandle(&h[2], ctx->p2p_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles192, h, sizeof h);
+    return 0;
+}
+// all_handles: [world][192] gathered from every rank's nsb_comm_p2p_export (rank order).  After this call the mapping iteration
+// replaces ncclAllReduce + Adam by k_reduce_adam.  The caller must put a host barrier between the imports and the first iteration.
+extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world) {
+    if (world < 2 || world > P2P_MAX_WORLD) return fail(ctx, "peer-memory mode supports 2..%d ranks, got %d", P2P_MAX_WORLD, world);
+    if (ctx->comm && (rank != ctx->rank || world != ctx->world)) return fail(ctx, "rank/world differ from nsb_comm_init");
+    CK(cudaSetDevice(ctx->device));
+    for (int w = 0; w < world; ++w) {
+        if (w == rank) { ctx->peer_grad[w] = ctx->grad; ctx->peer_param[w] = ctx->param; ctx->peer_flags[w] = ctx->p2p_flags; continue; }
+        cudaIpcMemHandle_t h[3]; memcpy(h, all_handles + 192 * (size_t)w, sizeof h);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h[0], cudaIpcMemLazyEnablePeerAccess)); ctx->peer_grad[w] = (float*)p;
+        CK(cudaIpcOpenMemHandle(&p, h[1], cudaIpcMemLazyEnablePeerAccess)); ctx->peer_param[w] = (float*)p;
+        CK(cudaIpcOpenMemHandle(&p, h[2], cudaIpcMemLazyEnablePeerAccess)); ctx->peer_flags[w] = (uint32_t*)p;
+    }
+    ctx->rank = rank; ctx->world = world; ctx->p2p = true; ctx->p2p_epoch = 0;
     return 0;
 }
 extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }

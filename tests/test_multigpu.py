@@ -1,5 +1,6 @@
 """Two-GPU mapping: rays sharded over the ranks, gradients summed with NCCL (grids under the wgrad kernel in
-colour iterations, the [loss | middle | fine] prefix in geometry iterations), identical Adam on every rank.  The result
+colour iterations, the [loss | middle | fine] prefix in geometry iterations), identical Adam on every rank -- or, in
+peer-memory mode, one reduce-scatter + Adam + all-gather kernel over NVLink (p2p_kernels.cuh).  The result
 must equal the one-GPU run on the same global batch up to the association of the fp32 sums.  Needs 2 GPUs (skipped else)."""
 import importlib
 import os
@@ -15,7 +16,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(rank, world, uid, q, ba):
+def _run(rank, world, uid, q, ba, p2p=False, port=0):
     sys.path.insert(0, ROOT)
     nsb = importlib.import_module("nice-slam-cpp_b200")
     syn = nsb.synthetic
@@ -28,6 +29,13 @@ def _run(rank, world, uid, q, ba):
         e.set_frame(f, depths[f], colors[f], poses[f])
     if world > 1:
         e.comm_init(uid, rank, world)
+        if p2p:   # peer-memory mode: exchange the CUDA IPC handles over gloo, host barrier before the first iteration
+            import torch.distributed as dist
+            dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+            hs = [None] * world
+            dist.all_gather_object(hs, e.p2p_export())
+            e.p2p_import(b"".join(hs), rank, world)
+            dist.barrier()
     e.seed(21)
     e.mapping_begin([0, 1], 60, 1.0, ba_mask=0b10 if ba else 0)
     losses = [e.mapping_iter(it) for it in (0, 30, 59, 59)]
@@ -41,15 +49,16 @@ def _run(rank, world, uid, q, ba):
     return out
 
 
-@pytest.mark.parametrize("ba", [False, True])
-def test_two_gpu_mapping_equals_one_gpu(nsb, ba):
+@pytest.mark.parametrize("ba,p2p", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_gpu_mapping_equals_one_gpu(nsb, ba, p2p):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ref = _run(0, 1, None, None, ba)
     uid = nsb.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, 2, uid, q, ba)) for r in range(2)]
+    port = 29600 + 2 * int(ba) + int(p2p)
+    procs = [ctx.Process(target=_run, args=(r, 2, uid, q, ba, p2p, port)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=300) for _ in range(2))
@@ -58,7 +67,7 @@ def test_two_gpu_mapping_equals_one_gpu(nsb, ba):
     grids0 = nsb.synthetic.make_grids(0)
     for r in range(2):
         o = got[r]
-        assert np.allclose(o["losses"], ref["losses"], rtol=1e-4), (o["losses"], ref["losses"])
+        assert np.allclose(o["losses"], ref["losses"], rtol=5e-4), (o["losses"], ref["losses"])
         for lv in ("middle", "fine", "color"):
             move = np.sqrt(((ref[lv] - grids0[lv]) ** 2).mean())
             assert move > 0 and np.sqrt(((o[lv] - ref[lv]) ** 2).mean()) < 2e-2 * move, lv     # Adam sign noise on ~zero gradients
