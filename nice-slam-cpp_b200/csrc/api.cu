@@ -42,6 +42,8 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
+cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st);
+size_t wimg_floats(int which);
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
 int compose_floats(int which);
@@ -119,6 +121,9 @@ struct nsb_ctx {
     int mask_layout = 0, mask_stride = 0;
     float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
+    float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
+    float* wimg_bwd[4] = {nullptr, nullptr, nullptr, nullptr};
+    int wimg_dirty = 0xE;        // bit d: decoder d's images are stale
     int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
     unsigned long long* dbg = nullptr;   // 32 cycle counters (NSB_TC_TIMING builds)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
@@ -382,6 +387,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
+    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); }
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
@@ -404,7 +410,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
@@ -456,7 +462,7 @@ extern "C" int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host, int64
     if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
     CK(cudaMemcpyAsync(ctx->param + ctx->off_dec[which], host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->comp_dirty |= 1 << which;
+    ctx->comp_dirty |= 1 << which; ctx->wimg_dirty |= 1 << which;
     return 0;
 }
 static int get_dec(nsb_ctx* ctx, const float* base, int which, float* host, int64_t n) {
@@ -579,7 +585,11 @@ static void env_weights(const char* name, float w[4]) {
 
 static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
     memset(&P, 0, sizeof P);
-    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); }
+    if (ctx->wimg_dirty) {   // decoder weights changed (set_decoder / an Adam step with a decoder learning rate): rebuild the pre-split images
+        const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
+        if (launch_build_wimg(flat, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_dirty, ctx->stream) == cudaSuccess) { ctx->launches++; ctx->wimg_dirty = 0; }
+    }
+    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; }
     P.bnd = ctx->bnd;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
     P.S = S; P.P = n * S;
@@ -962,8 +972,8 @@ static void build_adam(nsb_ctx* ctx, AdamParams& A, int step, const float lr_gro
     A.n_seg = k;
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
-    if (dec_fine && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 2;
-    if (dec_color && lr_group[0] != 0.f) ctx->comp_dirty |= 1 << 3;
+    if (dec_fine && lr_group[0] != 0.f) { ctx->comp_dirty |= 1 << 2; ctx->wimg_dirty |= 1 << 2; }
+    if (dec_color && lr_group[0] != 0.f && !color_pristine) { ctx->comp_dirty |= 1 << 3; ctx->wimg_dirty |= 1 << 3; }
 }
 
 // color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first

@@ -47,7 +47,7 @@ struct DecSmem {
     static constexpr int BIAS = WO + 4 * HID;           // b[5][32]
     static constexpr int BIASC = BIAS + 5 * HID;        // bc[5][32]
     static constexpr int BO = BIASC + 5 * HID;          // bo[4]
-    static constexpr int TOTAL = BO + 4;
+    static constexpr int TOTAL = (BO + 4 + 3) & ~3;     // multiple of 4 words: the image is copied with 16-byte loads
     __host__ __device__ static constexpr int w(int i) { return i == 0 ? W0 : i == 1 ? W1 : i == 2 ? W2 : i == 3 ? W3H : W4; }
 };
 static_assert(EMBP * wstride(HID) >= HID * wstride(EMBP), "W0 slot must hold both orientations");
@@ -120,6 +120,15 @@ __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid
         sm[L::BIASC + i] = flat[f.bc[i / HID] + i % HID];
     }
     if (tid < 4) sm[L::BO + tid] = tid < O ? flat[f.bo + tid] : 0.0f;
+}
+
+// Copy a decoder's pre-split image (built once per weight update by k_build_wimg, same layout as stage_decoder writes) from
+// global into shared memory: coalesced 16-byte loads instead of ~60 scattered fp32 loads + splits per thread and launch.
+template <int C>
+__device__ __forceinline__ void load_decoder_image(float* sm, const float* __restrict__ img, int tid, int nthr) {
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    for (int i = tid; i < DecSmem<C>::TOTAL / 4; i += nthr) dst[i] = __ldg(src + i);
 }
 
 __device__ __forceinline__ const uint32_t* wmat(const float* sm, int off) { return reinterpret_cast<const uint32_t*>(sm + off); }

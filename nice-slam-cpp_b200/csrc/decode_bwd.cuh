@@ -276,9 +276,8 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd
 #pragma unroll
     for (int d = 2; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
     const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
-    if (dec == 1) stage_decoder<32, 1, true>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
-    else if (dec == 2) stage_decoder<64, 1, true>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
-    else stage_decoder<32, 4, true>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
+    if (dec == 2) load_decoder_image<64>(sm, P.wimg_bwd[2], threadIdx.x, blockDim.x);
+    else load_decoder_image<32>(sm, P.wimg_bwd[dec], threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = P.P / TILE;

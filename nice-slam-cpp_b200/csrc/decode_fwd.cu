@@ -53,9 +53,8 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd
     for (int d = 1; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
     const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
     if (dec == 0) stage_coarse(sm, P.dec_flat[0], threadIdx.x, blockDim.x);
-    else if (dec == 1) stage_decoder<32, 1, false>(sm, P.dec_flat[1], threadIdx.x, blockDim.x);
-    else if (dec == 2) stage_decoder<64, 1, false>(sm, P.dec_flat[2], threadIdx.x, blockDim.x);
-    else stage_decoder<32, 4, false>(sm, P.dec_flat[3], threadIdx.x, blockDim.x);
+    else if (dec == 2) load_decoder_image<64>(sm, P.wimg_fwd[2], threadIdx.x, blockDim.x);
+    else load_decoder_image<32>(sm, P.wimg_fwd[dec], threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (P.P + TILE - 1) / TILE;
@@ -146,6 +145,22 @@ cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cuda
     k_gather_only<<<grid, 256, 0, st>>>(P, out);
     return cudaGetLastError();
 }
+
+// Builds the pre-split shared-memory images of the decoders in `mask` (bit d), both orientations: blockIdx.y = 2 (d - 1) + orientation.
+__global__ void __launch_bounds__(512) k_build_wimg(const float* f1, const float* f2, const float* f3, float* o1f, float* o1b, float* o2f, float* o2b,
+                                                    float* o3f, float* o3b, int mask) {
+    const int d = 1 + blockIdx.y / 2, bwd = blockIdx.y & 1;
+    if (!((mask >> d) & 1)) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (d == 1) { if (bwd) stage_decoder<32, 1, true>(o1b, f1, tid, nthr); else stage_decoder<32, 1, false>(o1f, f1, tid, nthr); }
+    else if (d == 2) { if (bwd) stage_decoder<64, 1, true>(o2b, f2, tid, nthr); else stage_decoder<64, 1, false>(o2f, f2, tid, nthr); }
+    else { if (bwd) stage_decoder<32, 4, true>(o3b, f3, tid, nthr); else stage_decoder<32, 4, false>(o3f, f3, tid, nthr); }
+}
+cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st) {
+    k_build_wimg<<<dim3(8, 6), 512, 0, st>>>(flat[1], flat[2], flat[3], img_fwd[1], img_bwd[1], img_fwd[2], img_bwd[2], img_fwd[3], img_bwd[3], mask);
+    return cudaGetLastError();
+}
+size_t wimg_floats(int which) { return which == 2 ? DecSmem<64>::TOTAL : DecSmem<32>::TOTAL; }
 
 size_t decode_fwd_smem() { return sizeof(float) * DecSmem<64>::TOTAL; }
 

@@ -10,6 +10,8 @@ constexpr int DECODE_THREADS = DECODE_WARPS * 32;
 // Which decoders a launch evaluates and how the grid is split between them.
 struct DecodeParams {
     const float* dec_flat[4];      // coarse, middle, fine, color flat parameter vectors (device)
+    const float* wimg_fwd[4];      // pre-split shared-memory images of decoders 1..3 (k_build_wimg): forward orientation ...
+    const float* wimg_bwd[4];      // ... and transposed for the backward kernel; a CTA copies its decoder's image with 16-byte loads
     GridView grid[4];
     Bound bnd;
     // sample source: ray mode (rays + z) or points mode (pts != nullptr)
