@@ -262,7 +262,16 @@ def run_ours(args, rank, world, local_rank):
             mine = torch.tensor(list(e.p2p_export()), dtype=torch.uint8, device="cuda")
             allh = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allh, mine)
-            e.p2p_import(b"".join(bytes(h.cpu().tolist()) for h in allh), rank, world)
+            ok = torch.ones(1, device="cuda")
+            try:
+                e.p2p_import(b"".join(bytes(h.cpu().tolist()) for h in allh), rank, world)
+            except RuntimeError as ex:       # e.g. CUDA IPC not permitted in this container: every rank falls back to NCCL together
+                print("rank %d: peer-memory mode unavailable (%s)" % (rank, ex), file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                e.p2p_import(None, rank, world)
+                args.comm = "nccl"
             dist.barrier()
     pix = n_global // N_FRAMES
     K, W = args.steps, args.warmup

@@ -213,7 +213,7 @@ int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world);  /* ncc
  * From then on a mapping iteration replaces "ncclAllReduce(gradients) + Adam" by ONE kernel: each rank sums its slice of all
  * ranks' gradients with P2P loads, applies Adam to that slice and stores the updated parameters into every rank's arena, with
  * two flag barriers in peer memory.  nsb_comm_init is still required first (rank / world; NCCL stays the fallback path).
- * Put a host barrier between the imports and the first nsb_mapping_iter. */
+ * Put a host barrier between the imports and the first nsb_mapping_iter.  all_handles == NULL switches back to the NCCL path. */
 int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192);
 int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world);
 /* Multi-GPU ray order (rank-major interleave of the reference's frame-major batch, see RayOrder in ray_kernels.cuh): returns

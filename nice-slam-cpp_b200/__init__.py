@@ -437,6 +437,8 @@ class Engine:
 
     def p2p_import(self, all_handles, rank, world):
         """all_handles: the ranks' p2p_export() bytes concatenated in rank order; host-barrier afterwards."""
+        if all_handles is None:          # back to the NCCL path
+            self._ck(self.lib.nsb_comm_p2p_import(self.h, None, rank, world)); return
         assert len(all_handles) == 192 * world
         self._ck(self.lib.nsb_comm_p2p_import(self.h, all_handles, rank, world))
 

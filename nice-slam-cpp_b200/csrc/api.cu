@@ -1405,6 +1405,7 @@ extern "C" int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192) {
 // all_handles: [world][192] gathered from every rank's nsb_comm_p2p_export (rank order).  After this call the mapping iteration
 // replaces ncclAllReduce + Adam by k_reduce_adam.  The caller must put a host barrier between the imports and the first iteration.
 extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world) {
+    if (!all_handles) { ctx->p2p = false; return 0; }   // back to the NCCL path (e.g. another rank could not open the handles)
     if (world < 2 || world > P2P_MAX_WORLD) return fail(ctx, "peer-memory mode supports 2..%d ranks, got %d", P2P_MAX_WORLD, world);
     if (ctx->comm && (rank != ctx->rank || world != ctx->world)) return fail(ctx, "rank/world differ from nsb_comm_init");
     CK(cudaSetDevice(ctx->device));

@@ -2,47 +2,72 @@
 // fix_fine = True, fix_color = False, Mapper.cpp:292-301).  The backward decoder kernel stashes, per sample, the
 // layer inputs X and the layer-output gradients G; every parameter gradient is then a tall-skinny product
 //     dW[a][b] = sum_s L[s][a] * R[s][b]
-// with the sample index as the contraction dimension.  Each CTA walks a contiguous range of samples, each warp
-// owns three groups of (one 16-row A tile) x (four 8-column B tiles) and keeps their accumulators in registers;
+// with the sample index as the contraction dimension.  Each CTA walks a contiguous range of samples; each warp owns one
+// task = up to four 16-row A tiles x ONE 32-column B block (accumulators in registers), one warp sums the bias columns;
 // the per-CTA partial sums are added to the flat gradient with fp32 reductions at the end.
 #include "decode.cuh"
 #include "params.h"
+#include <cstring>
+#include <initializer_list>
 
 namespace nsb {
 
 constexpr int WG_WARPS = 16;
-constexpr int WG_GROUPS_PER_WARP = 3;
-constexpr int WG_MAX_GROUPS = WG_WARPS * WG_GROUPS_PER_WARP;   // 48 >= 45
+constexpr int WG_MAXL = 4;          // A tiles (16 stash columns each) a warp multiplies with its one B block (32 stash columns)
+constexpr int WG_NBIAS = 11;        // column-sum blocks of the bias warp
 
 struct WGroup {
-    int L, R;          // stash column of row a0 of the A tile / of column b0 of the B tiles
+    int L;             // stash column of row 0 of the A tile
     int dst, ld;       // flat-gradient offset of element (a_lo, 0) and its row stride
     int a_lo, a_hi;    // valid rows of the A tile (relative to L)
-    int nb;            // valid columns (relative to R), up to 32
 };
-struct WGTable { WGroup g[WG_MAX_GROUPS]; int n; };
+// One task per warp: dW[L rows][R cols] += sum_s stash[s][L + a] * stash[s][R + b] for up to four A tiles that share ONE B
+// block, so that the B operand is split into fp16 hi/lo once per k-step and reused (the split, not the MMA, dominates the
+// instruction count).  kind 1 is the bias warp: plain fp32 column sums of eleven blocks (b_i = sum GU_i, bc_i = sum GH_i, bo = sum GO).
+struct WTask {
+    int kind;          // 0 idle, 1 bias sums, 2 MMA task
+    int nL, R, nb;     // number of A tiles, stash column of the B block, valid B columns (<= 32)
+    WGroup g[WG_MAXL];
+    int bias_col[WG_NBIAS], bias_dst[WG_NBIAS], bias_n[WG_NBIAS];
+};
+struct WGTable { WTask t[WG_WARPS]; };
 
 static WGTable build_table() {
-    WGTable T; T.n = 0;
+    WGTable T; memset(&T, 0, sizeof T);
     const DecFlat f = DecFlat::make(32, 4);
-    auto add = [&](int L, int R, int dst, int ld, int a_lo, int a_hi, int nb) { T.g[T.n++] = WGroup{L, R, dst, ld, a_lo, a_hi, nb}; };
-    auto addmat = [&](int L, int na, int R, int nb, int dst, int ld) {   // dW[a][b], a < na, b < nb
-        for (int a0 = 0; a0 < na; a0 += 16)
-            for (int b0 = 0; b0 < nb; b0 += 32)
-                add(L + a0, R + b0, dst + a0 * ld + b0, ld, 0, (na - a0) < 16 ? (na - a0) : 16, (nb - b0) < 32 ? (nb - b0) : 32);
+    auto mma = [&](int warp, int R, int nb, std::initializer_list<WGroup> gs) {
+        WTask& t = T.t[warp]; t.kind = 2; t.R = R; t.nb = nb; t.nL = 0;
+        for (const WGroup& g : gs) t.g[t.nL++] = g;
     };
-    addmat(stash::GU + 0, 32, stash::E, EMB, f.W[0], EMB);
-    addmat(stash::GU + 32, 32, stash::H + 0, 32, f.W[1], 32);
-    addmat(stash::GU + 64, 32, stash::H + 32, 32, f.W[2], 32);
-    addmat(stash::GU + 96, 32, stash::E, EMB, f.W[3], EMB + HID);
-    addmat(stash::GU + 96, 32, stash::H + 64, 32, f.W[3] + EMB, EMB + HID);
-    addmat(stash::GU + 128, 32, stash::H + 96, 32, f.W[4], 32);
-    for (int i = 0; i < 5; ++i) addmat(stash::GH + 32 * i, 32, stash::Cc, 32, f.Fc[i], 32);
-    addmat(stash::GO, 4, stash::H + 128, 32, f.Wo, 32);
-    addmat(stash::Pp, 3, stash::GE, EMB, f.B, EMB);                       // dB[d][f] = sum p_d * g_e cos
-    for (int i = 0; i < 5; ++i) add(stash::Pp, stash::GU + 32 * i, f.b[i], 0, 3, 4, 32);    // bias = column sums (Pp[3] == 1)
-    for (int i = 0; i < 5; ++i) add(stash::Pp, stash::GH + 32 * i, f.bc[i], 0, 3, 4, 32);
-    add(stash::Pp, stash::GO, f.bo, 0, 3, 4, 4);
+    auto G = [&](int L, int dst, int ld, int a_hi = 16, int a_lo = 0) { return WGroup{L, dst, ld, a_lo, a_hi}; };
+    const int GU = stash::GU, GH = stash::GH, LD3 = EMB + HID;
+    // warps are spread over the four schedulers (warp & 3) so that each gets ~600 instructions per k-step
+    // scheduler 0: bias sums, Cc x GH4, H0 x GU1 (W1), H4 x GO (Wo)
+    {
+        WTask& t = T.t[0]; t.kind = 1;
+        for (int i = 0; i < 5; ++i) { t.bias_col[i] = GU + 32 * i; t.bias_dst[i] = f.b[i]; t.bias_n[i] = 32; }
+        for (int i = 0; i < 5; ++i) { t.bias_col[5 + i] = GH + 32 * i; t.bias_dst[5 + i] = f.bc[i]; t.bias_n[5 + i] = 32; }
+        t.bias_col[10] = stash::GO; t.bias_dst[10] = f.bo; t.bias_n[10] = 4;
+    }
+    mma(4, stash::Cc, 32, {G(GH + 128, f.Fc[4], 32), G(GH + 144, f.Fc[4] + 16 * 32, 32)});
+    mma(8, stash::H + 0, 32, {G(GU + 32, f.W[1], 32), G(GU + 48, f.W[1] + 16 * 32, 32)});
+    mma(12, stash::H + 128, 32, {G(stash::GO, f.Wo, 32, 4)});
+    // scheduler 1: E0 / E1 x {GU0 (W0), GU3 (W3 embedding columns)}, H1 x GU2 (W2)
+    for (int j = 0; j < 2; ++j)
+        mma(1 + 4 * j, stash::E + 32 * j, 32, {G(GU + 0, f.W[0] + 32 * j, EMB), G(GU + 16, f.W[0] + 16 * EMB + 32 * j, EMB),
+                                               G(GU + 96, f.W[3] + 32 * j, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 32 * j, LD3)});
+    mma(9, stash::H + 32, 32, {G(GU + 64, f.W[2], 32), G(GU + 80, f.W[2] + 16 * 32, 32)});
+    // scheduler 2: E2 x {GU0, GU3}, Cc x {GH0, GH1}, GE0 / GE1 x p (dB)
+    mma(2, stash::E + 64, EMB - 64, {G(GU + 0, f.W[0] + 64, EMB), G(GU + 16, f.W[0] + 16 * EMB + 64, EMB),
+                                     G(GU + 96, f.W[3] + 64, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 64, LD3)});
+    mma(6, stash::Cc, 32, {G(GH + 0, f.Fc[0], 32), G(GH + 16, f.Fc[0] + 16 * 32, 32), G(GH + 32, f.Fc[1], 32), G(GH + 48, f.Fc[1] + 16 * 32, 32)});
+    mma(10, stash::GE + 0, 32, {G(stash::Pp, f.B, EMB, 3)});
+    mma(14, stash::GE + 32, 32, {G(stash::Pp, f.B + 32, EMB, 3)});
+    // scheduler 3: Cc x {GH2, GH3}, H2 x GU3 (W3 hidden columns), H3 x GU4 (W4), GE2 x p
+    mma(3, stash::Cc, 32, {G(GH + 64, f.Fc[2], 32), G(GH + 80, f.Fc[2] + 16 * 32, 32), G(GH + 96, f.Fc[3], 32), G(GH + 112, f.Fc[3] + 16 * 32, 32)});
+    mma(7, stash::H + 64, 32, {G(GU + 96, f.W[3] + EMB, LD3), G(GU + 112, f.W[3] + 16 * LD3 + EMB, LD3)});
+    mma(11, stash::H + 96, 32, {G(GU + 128, f.W[4], 32), G(GU + 144, f.W[4] + 16 * 32, 32)});
+    mma(15, stash::GE + 64, EMB - 64, {G(stash::Pp, f.B + 64, EMB, 3)});
     return T;
 }
 
@@ -50,7 +75,7 @@ __constant__ WGTable c_wg;
 
 constexpr int WG_STAGES = 3;                       // cp.async ring depth (k-steps in flight)
 constexpr int WG_KROWS = 16;                       // samples per k-step (MMA k = 16)
-constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B tile of a row may read past it (values unused)
+constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B block of a row may read past it (values unused)
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -59,28 +84,26 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// The CTA streams its sample range through a shared-memory ring (one stage = the 16 stash rows of a k-step,
-// 45.6 KB, fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA
-// fragments come from conflict-free LDS.64 / LDS.128 (row stride 712 = 8 mod 32 floats).  k slots (2t, 2t+1, 2t+8, 2t+9)
-// of lane t <-> ring rows (t, t+4, t+8, t+12): any bijection works as long as both operands use it.
+// The CTA streams its sample range through a shared-memory ring (one stage = the 16 stash rows of a k-step, 45.6 KB,
+// fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA fragments come from
+// conflict-free LDS.64 / LDS.128 (row stride 712 = 8 mod 32 floats).  k slots (2t, 2t+1, 2t+8, 2t+9) of lane t <-> ring
+// rows (t, t+4, t+8, t+12): any bijection works as long as both operands use it.  A rows g / g+8 <-> stash columns L + 2g,
+// L + 2g + 1; B column g of n-tile j <-> stash column R + 4g + j (one float4 per row serves the four n-tiles).
 template <bool P3>
 __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
                                                          int P, int S, float* __restrict__ dflat) {
     extern __shared__ __align__(128) float ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    float acc[WG_GROUPS_PER_WARP][4][4];
+    const int kind = c_wg.t[warp].kind, nL = c_wg.t[warp].nL;
+    float acc[WG_MAXL][4][4];     // bias warp: acc[q][j][e] doubles as 44 column-sum accumulators
 #pragma unroll
-    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q)
+    for (int q = 0; q < WG_MAXL; ++q)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[q][j][0] = acc[q][j][1] = acc[q][j][2] = acc[q][j][3] = 0.0f;
-    int Lc[WG_GROUPS_PER_WARP], Rc[WG_GROUPS_PER_WARP]; bool on[WG_GROUPS_PER_WARP];
+    int Lc[WG_MAXL];
 #pragma unroll
-    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
-        const int gi = warp * WG_GROUPS_PER_WARP + q;
-        on[q] = gi < c_wg.n;
-        Lc[q] = on[q] ? c_wg.g[gi].L + 2 * g : 0;      // A rows g / g+8 <-> a0 + 2g, a0 + 2g + 1
-        Rc[q] = on[q] ? c_wg.g[gi].R + 4 * g : 0;      // B col g of tile j <-> b0 + 4g + j
-    }
+    for (int q = 0; q < WG_MAXL; ++q) Lc[q] = c_wg.t[warp].g[q < nL ? q : 0].L + 2 * g;
+    const int Rc = c_wg.t[warp].R + 4 * g;
     const int nks = P / WG_KROWS;
     const int per = (nks + gridDim.x - 1) / gridDim.x;
     const int k_lo = blockIdx.x * per, k_hi = min(nks, k_lo + per);
@@ -103,35 +126,76 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
         const int s0 = (k_lo + i) * WG_KROWS;
         if (valid && !valid[s0 / S]) continue;         // rows of rays dropped by the inside filter were never written
         const float* r0 = ring + (i % WG_STAGES) * WG_STAGE_FLOATS + t * stash::W;
+        if (kind == 2) {
+            float4 bv[4];
 #pragma unroll
-        for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
-            if (!on[q]) continue;
-            float2 av[4]; float4 bv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                av[u] = *reinterpret_cast<const float2*>(r0 + 4 * u * stash::W + Lc[q]);
-                bv[u] = *reinterpret_cast<const float4*>(r0 + 4 * u * stash::W + Rc[q]);
+            for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(r0 + 4 * u * stash::W + Rc);
+            uint32_t bh[4][2], bl[4][2];               // the B block, split once for all A tiles of the task
+            if (P3) {
+                split_f16(bv[0].x, bv[1].x, bh[0][0], bl[0][0]); split_f16(bv[2].x, bv[3].x, bh[0][1], bl[0][1]);
+                split_f16(bv[0].y, bv[1].y, bh[1][0], bl[1][0]); split_f16(bv[2].y, bv[3].y, bh[1][1], bl[1][1]);
+                split_f16(bv[0].z, bv[1].z, bh[2][0], bl[2][0]); split_f16(bv[2].z, bv[3].z, bh[2][1], bl[2][1]);
+                split_f16(bv[0].w, bv[1].w, bh[3][0], bl[3][0]); split_f16(bv[2].w, bv[3].w, bh[3][1], bl[3][1]);
+            } else {
+                bh[0][0] = pack_f16(bv[0].x, bv[1].x); bh[0][1] = pack_f16(bv[2].x, bv[3].x);
+                bh[1][0] = pack_f16(bv[0].y, bv[1].y); bh[1][1] = pack_f16(bv[2].y, bv[3].y);
+                bh[2][0] = pack_f16(bv[0].z, bv[1].z); bh[2][1] = pack_f16(bv[2].z, bv[3].z);
+                bh[3][0] = pack_f16(bv[0].w, bv[1].w); bh[3][1] = pack_f16(bv[2].w, bv[3].w);
             }
-            AFrag<P3> a;
-            a.set(av[0].x, av[1].x, av[2].x, av[3].x, av[0].y, av[1].y, av[2].y, av[3].y);
-            mma_acc<P3>(acc[q][0], a, bv[0].x, bv[1].x, bv[2].x, bv[3].x);
-            mma_acc<P3>(acc[q][1], a, bv[0].y, bv[1].y, bv[2].y, bv[3].y);
-            mma_acc<P3>(acc[q][2], a, bv[0].z, bv[1].z, bv[2].z, bv[3].z);
-            mma_acc<P3>(acc[q][3], a, bv[0].w, bv[1].w, bv[2].w, bv[3].w);
+#pragma unroll
+            for (int q = 0; q < WG_MAXL; ++q) {
+                if (q >= nL) break;
+                float2 av[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const float2*>(r0 + 4 * u * stash::W + Lc[q]);
+                AFrag<P3> a;
+                a.set(av[0].x, av[1].x, av[2].x, av[3].x, av[0].y, av[1].y, av[2].y, av[3].y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (P3) { mma_f16(acc[q][j], a.lo, bh[j][0], bh[j][1]); mma_f16(acc[q][j], a.hi, bl[j][0], bl[j][1]); }
+                    mma_f16(acc[q][j], a.hi, bh[j][0], bh[j][1]);
+                }
+            }
+        } else if (kind == 1) {
+            float* sums = &acc[0][0][0];
+#pragma unroll
+            for (int b = 0; b < WG_NBIAS; ++b) {
+                const int col = c_wg.t[warp].bias_col[b] + 4 * g;
+                if (4 * g < c_wg.t[warp].bias_n[b]) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 v = *reinterpret_cast<const float4*>(r0 + 4 * u * stash::W + col);
+                        sums[4 * b] += v.x; sums[4 * b + 1] += v.y; sums[4 * b + 2] += v.z; sums[4 * b + 3] += v.w;
+                    }
+                }
+            }
         }
     }
     cp_async_wait<0>();
+    if (kind == 2) {
+        const int nb = c_wg.t[warp].nb;
 #pragma unroll
-    for (int q = 0; q < WG_GROUPS_PER_WARP; ++q) {
-        if (!on[q]) continue;
-        const WGroup G = c_wg.g[warp * WG_GROUPS_PER_WARP + q];
+        for (int q = 0; q < WG_MAXL; ++q) {
+            if (q >= nL) break;
+            const WGroup G = c_wg.t[warp].g[q];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int a = 2 * g + (e >> 1), b = 4 * (2 * t + (e & 1)) + j;
-                if (a >= G.a_lo && a < G.a_hi && b < G.nb) atomicAdd(dflat + G.dst + (a - G.a_lo) * G.ld + b, acc[q][j][e]);
+                for (int e = 0; e < 4; ++e) {
+                    const int a = 2 * g + (e >> 1), b = 4 * (2 * t + (e & 1)) + j;
+                    if (a >= G.a_lo && a < G.a_hi && b < nb) atomicAdd(dflat + G.dst + (a - G.a_lo) * G.ld + b, acc[q][j][e]);
+                }
+        }
+    } else if (kind == 1) {
+        float* sums = &acc[0][0][0];
+#pragma unroll
+        for (int b = 0; b < WG_NBIAS; ++b) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float v = quad_sum(sums[4 * b + k]);          // the four lanes of a quad hold different sample rows
+                if (t == 0 && 4 * g + k < c_wg.t[warp].bias_n[b]) atomicAdd(dflat + c_wg.t[warp].bias_dst[b] + 4 * g + k, v);
             }
+        }
     }
 }
 
