@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(512) k_build_wimg(const float* f1, const float
     else { if (bwd) stage_decoder<32, 4, true>(o3b, f3, tid, nthr); else stage_decoder<32, 4, false>(o3f, f3, tid, nthr); }
 }
 cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st) {
-    k_build_wimg<<<dim3(8, 6), 512, 0, st>>>(flat[1], flat[2], flat[3], img_fwd[1], img_bwd[1], img_fwd[2], img_bwd[2], img_fwd[3], img_bwd[3], mask);
+    k_build_wimg<<<dim3(24, 6), 512, 0, st>>>(flat[1], flat[2], flat[3], img_fwd[1], img_bwd[1], img_fwd[2], img_bwd[2], img_fwd[3], img_bwd[3], mask);
     return cudaGetLastError();
 }
 size_t wimg_floats(int which) { return which == 2 ? DecSmem<64>::TOTAL : DecSmem<32>::TOTAL; }

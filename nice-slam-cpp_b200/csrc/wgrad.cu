@@ -73,7 +73,7 @@ static WGTable build_table() {
 
 __constant__ WGTable c_wg;
 
-constexpr int WG_STAGES = 3;                       // cp.async ring depth (k-steps in flight)
+constexpr int WG_STAGES = 4;                       // cp.async ring depth (k-steps in flight)
 constexpr int WG_KROWS = 16;                       // samples per k-step (MMA k = 16)
 constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B block of a row may read past it (values unused)
 
