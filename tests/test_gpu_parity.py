@@ -407,3 +407,50 @@ def test_dense_render_img(engine_factory, frames, model_inputs, syn):
     # coarse level, no depth guidance (Renderer.cpp:54-58): 32 samples per ray over all 307 200 pixels
     _, dc, vc = e.render_img(0, "coarse", False)
     assert np.isfinite(dc).all() and dc.min() > 0 and (vc >= 0).all()
+
+
+def test_edge_cases(engine_factory, frames, model_inputs, syn, nsb):
+    """Empty, tiny and ragged batches, zero-depth pixels, axis-parallel rays, batches larger than max_rays (chunked with
+    whole-call batch scalars), point counts that are not a multiple of the 16-sample tile, and the error behaviour."""
+    import torch
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    e = engine_factory(max_rays=512)
+    tt, ts = O.t_tables()
+    model = O.Model(grids, decs)
+    idx = syn.mt19937_indices(7, 1200, 480 * 640)
+    ro, rd, gd, _ = O.ray_sampler(0, 480, 0, 640, idx, 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]))
+    keep = O.inside_mask(ro, rd, gd, torch.tensor(O.BOUND))
+    ro, rd, gd = ro[keep].numpy(), rd[keep].numpy(), gd[keep].numpy().copy()
+    gd[::7] = 0.0                                             # zero-depth pixels: the 0.001 .. max(depth) surface branch (Renderer.cpp:93-98)
+    # empty batch: a no-op
+    rgb, depth, var, w = e.render_batch_ray(rd[:0], ro[:0], "color", gd[:0])
+    assert rgb.shape == (0, 3) and depth.shape == (0,) and w.shape == (0, 48)
+    for n in (1, 17, 33, 700):                                # 700 > max_rays: three chunks, batch scalars over the whole call
+        with torch.no_grad():
+            ref = O.render_batch_ray(model, torch.tensor(rd[:n]), torch.tensor(ro[:n]), "color", torch.tensor(gd[:n]), tt, ts)
+        rgb, depth, var, w = e.render_batch_ray(rd[:n], ro[:n], "color", gd[:n])
+        assert relerr(depth, ref[1].numpy()) < FWD_TOL and relerr(rgb, ref[0].numpy()) < FWD_TOL and relerr(w, ref[3].numpy()) < FWD_TOL, n
+    # axis-parallel rays: a zero direction component gives +-inf in the AABB test (Renderer.cpp:69-73); results stay finite
+    o = np.tile(np.array([[-0.34, 0.26, -0.12]], np.float32), (16, 1)); d = np.zeros((16, 3), np.float32); d[:, 0] = 1.0
+    g = np.linspace(0.5, 3.0, 16).astype(np.float32)
+    with torch.no_grad():
+        ref = O.render_batch_ray(model, torch.tensor(d), torch.tensor(o), "color", torch.tensor(g), tt, ts)
+    rgb, depth, var, _ = e.render_batch_ray(d, o, "color", g)
+    assert np.isfinite(depth).all() and relerr(depth, ref[1].numpy()) < FWD_TOL
+    # eval_points with a point count that is not a multiple of the tile, incl. points outside the bound (occupancy 100)
+    pts = np.random.RandomState(3).uniform(-5, 4, (37, 3)).astype(np.float32)
+    raw = e.eval_points(pts, "color")
+    with torch.no_grad():
+        ref = model.eval_points(torch.tensor(pts), "color").numpy()
+    bnd = np.asarray(O.BOUND, np.float32)
+    inside = np.all((pts < bnd[:, 1]) & (pts > bnd[:, 0]), axis=1)
+    assert (raw[~inside, 3] == 100).all() and np.abs(raw - ref).max() < 1e-3
+    # error behaviour: status + message, never a crash
+    with pytest.raises(RuntimeError, match="stage"):
+        e._ck(e.lib.nsb_render_batch_ray(e.h, 9, 1, None, None, None, None, None, None, None))
+    with pytest.raises(RuntimeError, match="exceeds max_rays"):
+        n = 600
+        e.render_vjp(rd[:n], ro[:n], "color", gd[:n], np.ones((n, 3), np.float32), np.ones(n, np.float32), np.zeros(n, np.float32))
+    with pytest.raises(RuntimeError, match="slot"):
+        e.set_frame(99, depths[0], colors[0], poses[0])
