@@ -125,6 +125,17 @@ int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int level, uint
 /* Upload one RGB-D frame into resident slot `slot`: depth (H,W), colour (H,W,3), c2w row-major 4x4. */
 int nsb_set_frame(nsb_ctx* ctx, int slot, const float* host_depth, const float* host_color, const float* c2w16);
 int nsb_set_frame_pose(nsb_ctx* ctx, int slot, const float* c2w16);
+/* Asynchronous frame ingest: the H2D copy runs on its own stream while the optimiser keeps iterating; the next call that reads
+ * frames waits for it on the device.  Pass buffers from nsb_host_alloc (pinned) for a truly asynchronous copy and keep them alive
+ * until nsb_frames_ready returns (host-side wait) or another frame-reading call has been made and synchronised. */
+int nsb_set_frame_async(nsb_ctx* ctx, int slot, const float* host_depth, const float* host_color, const float* c2w16);
+int nsb_frames_ready(nsb_ctx* ctx);
+int nsb_host_alloc(void** p, size_t bytes);
+int nsb_host_free(void* p);
+/* Checkpoint of the map (nice_slam.yaml mapping.ckpt_freq): the four grids in the reference's (1,C,Z,Y,X) layout and the four
+ * flat decoder vectors, in one little-endian file; load validates the grid dimensions / decoder sizes against the context. */
+int nsb_save_checkpoint(nsb_ctx* ctx, const char* path);
+int nsb_load_checkpoint(nsb_ctx* ctx, const char* path);
 
 /* ---- camera utilities (utils.h:174-231) ------------------------------------------------------------- */
 void nsb_quad2rotation(const float* q4, float* R9);                    /* utils.h:174-195 */

@@ -122,6 +122,12 @@ def load_library(variant=""):
     L.nsb_mapping_begin_ba.argtypes = [v, C.c_int, _ip, C.c_int, C.c_float, C.c_uint32]
     L.nsb_mapping_end.argtypes = [v, _fp]
     L.nsb_mapping_cam_grads.argtypes = [v, _fp]
+    L.nsb_set_frame_async.argtypes = [v, C.c_int, _fp, _fp, _fp]
+    L.nsb_frames_ready.argtypes = [v]
+    L.nsb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.nsb_host_free.argtypes = [C.c_void_p]
+    L.nsb_save_checkpoint.argtypes = [v, C.c_char_p]
+    L.nsb_load_checkpoint.argtypes = [v, C.c_char_p]
     L.nsb_ray_order_source.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip]
     L.nsb_render_img.argtypes = [v, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _fp]
     L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
@@ -141,7 +147,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_mapping_iter_async", "nsb_mapping_losses", "nsb_mapping_set_index_pool", "nsb_optimize_map", "nsb_tracking_begin", "nsb_tracking_iter",
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
-    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source", "nsb_comm_p2p_export", "nsb_comm_p2p_import",
+    "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source", "nsb_set_frame_async", "nsb_frames_ready", "nsb_host_alloc", "nsb_host_free", "nsb_save_checkpoint", "nsb_load_checkpoint", "nsb_comm_p2p_export", "nsb_comm_p2p_import",
 ]
 
 
@@ -284,6 +290,22 @@ class Engine:
     def set_frame(self, slot, depth, color, c2w):
         d, c, p = _c(depth), _c(color), _c(c2w)
         self._ck(self.lib.nsb_set_frame(self.h, slot, _f(d), _f(c), _f(p)))
+
+    def set_frame_async(self, slot, depth, color, c2w):
+        """Asynchronous ingest (own copy stream); the arrays must stay alive until frames_ready() or the next synchronising call."""
+        d, c, p = _c(depth), _c(color), _c(c2w)
+        self._pending_frames = (d, c, p)
+        self._ck(self.lib.nsb_set_frame_async(self.h, slot, _f(d), _f(c), _f(p)))
+
+    def frames_ready(self):
+        self._ck(self.lib.nsb_frames_ready(self.h))
+        self._pending_frames = None
+
+    def save_checkpoint(self, path):
+        self._ck(self.lib.nsb_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        self._ck(self.lib.nsb_load_checkpoint(self.h, str(path).encode()))
 
     def seed(self, s):
         self._ck(self.lib.nsb_seed(self.h, C.c_uint64(s)))

@@ -134,6 +134,7 @@ struct nsb_ctx {
     // mapping state
     int map_frames = 0, map_slots[MAX_OPT_FRAMES], map_iters = 0, map_step = 0; float map_lr_factor = 1.0f;
     float* cam_grad_last = nullptr;   // [MAX_OPT_FRAMES][8] camera gradients of the last BA iteration (Adam zeroes the arena)
+    cudaStream_t upload_stream = nullptr; cudaEvent_t ev_upload = nullptr; bool upload_pending = false;   // nsb_set_frame_async
     bool map_color_touched = false;   // a colour iteration has run since nsb_mapping_begin (see run_adam)
     uint32_t map_ba_mask = 0;      // bundle adjustment: frames (bit f) whose 7-vector pose is optimised with the map (Mapper.cpp:305-329)
     // tracking state
@@ -176,6 +177,11 @@ struct Timer {
     ~Timer() { if (c->profiling) cudaEventRecord(c->ev_pool[slot].b, c->stream); }
 };
 
+// Makes the compute stream wait (on the device) for pending asynchronous frame uploads; called by every sampling entry point.
+static int wait_uploads(nsb_ctx* ctx) {
+    if (ctx->upload_pending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_upload, 0)); ctx->upload_pending = false; }
+    return 0;
+}
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static size_t pad32(size_t n) { return (n + 31) / 32 * 32; }
 
@@ -341,6 +347,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     if (cfg->max_frames < 1 || cfg->max_rays < 16) return fail(ctx, "max_frames / max_rays too small");
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_bwd, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
@@ -413,6 +420,8 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
                     c->cam_grad_last, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -490,6 +499,7 @@ extern "C" int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host) 
 // Mapper::get_mask_from_c2w (Mapper.cpp:42-130): frustum voxel mask of grid `level` for the depth frame in `slot` seen from
 // c2w16 (NULL = the slot's pose).  host_mask_zyx (Z*Y*X bytes) may be NULL; install != 0 makes it the level's Adam mask.
 extern "C" int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int level, uint8_t* host_mask_zyx, int install) {
+    if (wait_uploads(ctx)) return -1;
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     float c2w[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -550,6 +560,71 @@ extern "C" int nsb_set_frame(nsb_ctx* ctx, int slot, const float* depth, const f
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+// Frame ingest without stalling the optimiser: the copy runs on a separate stream from (ideally pinned, see
+// nsb_host_alloc) host buffers while the compute stream keeps iterating; the next call that samples frames waits for it on the
+// device (event), not on the host.  The caller keeps the buffers alive until nsb_frames_ready or the next synchronising call.
+extern "C" int nsb_set_frame_async(nsb_ctx* ctx, int slot, const float* depth, const float* color, const float* c2w16) {
+    if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
+    const size_t hw = (size_t)ctx->cfg.H * ctx->cfg.W;
+    CK(cudaMemcpyAsync(ctx->f_depth + hw * slot, depth, hw * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    CK(cudaMemcpyAsync(ctx->f_color + 3 * hw * slot, color, 3 * hw * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    CK(cudaEventRecord(ctx->ev_upload, ctx->upload_stream));
+    ctx->upload_pending = true;
+    return 0;
+}
+extern "C" int nsb_frames_ready(nsb_ctx* ctx) { CK(cudaStreamSynchronize(ctx->upload_stream)); return 0; }
+extern "C" int nsb_host_alloc(void** p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? 0 : -1; }
+extern "C" int nsb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? 0 : -1; }
+
+// ---- checkpoint (nice_slam.yaml mapping.ckpt_freq; upstream saves the grids and the decoders): flat little-endian file,
+// grids in the reference's (1,C,Z,Y,X) layout, decoders as the flat vectors of nsb_set_decoder -------------------------------------
+struct CkptHeader { char magic[8]; int32_t abi, c_dim, gdim[4][3]; int64_t dec_n[4]; };
+extern "C" int nsb_save_checkpoint(nsb_ctx* ctx, const char* path) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ctx, "cannot open %s for writing", path);
+    CkptHeader h; memset(&h, 0, sizeof h); memcpy(h.magic, "NSBCKPT1", 8); h.abi = NSB_ABI_VERSION; h.c_dim = CDIM;
+    for (int l = 0; l < 4; ++l) { for (int a = 0; a < 3; ++a) h.gdim[l][a] = ctx->gdim[l][a]; h.dec_n[l] = ctx->dec_n[l]; }
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    std::vector<float> buf;
+    for (int l = 0; l < 4 && ok; ++l) {
+        buf.resize(ctx->nvox[l] * CDIM);
+        if (nsb_get_grid(ctx, l, buf.data())) { fclose(f); return -1; }
+        ok = fwrite(buf.data(), 4, buf.size(), f) == buf.size();
+    }
+    for (int d = 0; d < 4 && ok; ++d) {
+        buf.resize((size_t)ctx->dec_n[d]);
+        if (nsb_get_decoder(ctx, d, buf.data(), ctx->dec_n[d])) { fclose(f); return -1; }
+        ok = fwrite(buf.data(), 4, buf.size(), f) == buf.size();
+    }
+    fclose(f);
+    return ok ? 0 : fail(ctx, "short write to %s", path);
+}
+extern "C" int nsb_load_checkpoint(nsb_ctx* ctx, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, "cannot open %s", path);
+    CkptHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "NSBCKPT1", 8) != 0) { fclose(f); return fail(ctx, "%s is not an nsb checkpoint", path); }
+    for (int l = 0; l < 4; ++l) {
+        if (h.dec_n[l] != ctx->dec_n[l] || h.gdim[l][0] != ctx->gdim[l][0] || h.gdim[l][1] != ctx->gdim[l][1] || h.gdim[l][2] != ctx->gdim[l][2] || h.c_dim != CDIM) {
+            fclose(f); return fail(ctx, "checkpoint %s was written for another configuration (level %d)", path, l);
+        }
+    }
+    std::vector<float> buf;
+    for (int l = 0; l < 4; ++l) {
+        buf.resize(ctx->nvox[l] * CDIM);
+        if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { fclose(f); return fail(ctx, "checkpoint %s is truncated", path); }
+        if (nsb_set_grid(ctx, l, buf.data())) { fclose(f); return -1; }
+    }
+    for (int d = 0; d < 4; ++d) {
+        buf.resize((size_t)ctx->dec_n[d]);
+        if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { fclose(f); return fail(ctx, "checkpoint %s is truncated", path); }
+        if (nsb_set_decoder(ctx, d, buf.data(), ctx->dec_n[d])) { fclose(f); return -1; }
+    }
+    fclose(f);
+    return 0;
+}
+
 extern "C" int nsb_seed(nsb_ctx* ctx, uint64_t seed) { ctx->rng.seed((uint32_t)seed); return 0; }
 
 // ---- shared pipeline pieces ---------------------------------------------------------------------------------------
@@ -762,6 +837,7 @@ static void fill_sample_params(nsb_ctx* ctx, SampleParams& P, int n, int H0, int
 
 extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H0, int H1, int W0, int W1, int n, const int64_t* idx,
                                float* rays_o, float* rays_d, float* gt_depth, float* gt_color, uint8_t* inside, int64_t* idx_out) {
+    if (wait_uploads(ctx)) return -1;
     if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     ctx->h_idx.resize(n);
@@ -848,6 +924,7 @@ extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float*
 // rendered in chunks of max_rays.  The batch-global scalars of Renderer.cpp:76,93 (and utils.h:153 in reference mode) are
 // taken over the whole image in a first pass, exactly as one render_batch_ray call over all pixels would.
 extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int stage, int use_gt_depth, float* rgb, float* depth, float* var) {
+    if (wait_uploads(ctx)) return -1;
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     const nsb_config& c = ctx->cfg;
@@ -1017,6 +1094,7 @@ extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, i
 // ba_mask bit f: frame f's pose joins the optimisation as a 7-vector (Mapper.cpp:305-329: every frame of optimize_frame but
 // the oldest one when BA is on); its lr is BA_cam_lr in the colour stage and 0 before (Mapper.cpp:366-368).
 extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask) {
+    if (wait_uploads(ctx)) return -1;
     if (n_frames < 1 || n_frames > MAX_OPT_FRAMES) return fail(ctx, "n_frames %d out of range", n_frames);
     if (n_frames > ctx->cfg.max_frames) return fail(ctx, "n_frames %d exceeds max_frames %d", n_frames, ctx->cfg.max_frames);
     const int pix = ctx->cfg.mapping_pixels / n_frames;   // Mapper.cpp:223
@@ -1067,6 +1145,7 @@ extern "C" int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, in
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
     const nsb_config& c = ctx->cfg;
     if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
+    if (wait_uploads(ctx)) return -1;
     const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
     const int stage = stage_of_iter(c, iter, ctx->map_iters);
     float* stats = ctx->stats + 4 * (iter % LOSS_RING);
@@ -1258,6 +1337,7 @@ extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const 
                                               const int64_t* idx, int pixels, int n_samples, int* selected, int* n_selected, float* percent_out) {
     *n_selected = 0;
     if (n_kf <= 0) return 0;
+    if (wait_uploads(ctx)) return -1;
     if (cur_slot < 0 || cur_slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", cur_slot);
     if (pixels > ctx->cap) return fail(ctx, "pixels %d exceeds max_rays %d", pixels, ctx->cap);
     if (n_samples != 16) return fail(ctx, "n_samples %d unsupported (the reference hard-codes 16, Mapper.cpp:136)", n_samples);
@@ -1296,6 +1376,7 @@ extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const 
 
 // ---- tracking -----------------------------------------------------------------------------------------------------------
 extern "C" int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7) {
+    if (wait_uploads(ctx)) return -1;
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     if (ctx->cfg.tracking_pixels > ctx->cap) return fail(ctx, "tracking_pixels %d exceeds max_rays %d", ctx->cfg.tracking_pixels, ctx->cap);
     ctx->trk_slot = slot; ctx->trk_step = 0;

@@ -454,3 +454,34 @@ def test_edge_cases(engine_factory, frames, model_inputs, syn, nsb):
         e.render_vjp(rd[:n], ro[:n], "color", gd[:n], np.ones((n, 3), np.float32), np.ones(n, np.float32), np.zeros(n, np.float32))
     with pytest.raises(RuntimeError, match="slot"):
         e.set_frame(99, depths[0], colors[0], poses[0])
+
+
+def test_async_frame_ingest_and_checkpoint(engine_factory, frames, model_inputs, nsb, tmp_path):
+    """a frame uploaded on the copy stream is what the next sampling call sees (device-side wait), and a
+    checkpoint written after some mapping iterations restores grids and decoders bit-exactly into a fresh context."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    e = engine_factory(mapping_pixels=500, frustum_feature_selection=0)
+    idx = np.arange(0, 480 * 640, 4801)[:60]
+    ref = e.get_samples(3, 0, 480, 0, 640, 60, idx=idx)
+    e.set_frame_async(1, depths[3], colors[3], poses[3])                 # slot 1 <- frame 3, no host wait
+    got = e.get_samples(1, 0, 480, 0, 640, 60, idx=idx)
+    e.frames_ready()
+    for a, b in zip(ref[:4], got[:4]):
+        assert np.array_equal(a, b)
+    e.seed(4)
+    e.mapping_begin([0, 1], 60, 1.0)
+    for it in (0, 59, 59):
+        e.mapping_iter(it)
+    path = tmp_path / "map.nsbckpt"
+    e.save_checkpoint(path)
+    e2 = engine_factory()
+    e2.load_checkpoint(path)
+    for lv in ("coarse", "middle", "fine", "color"):
+        assert np.array_equal(e2.get_grid(lv), e.get_grid(lv)) and np.array_equal(e2.get_decoder(lv), e.get_decoder(lv))
+    assert not np.array_equal(e.get_grid("color"), grids["color"]) and not np.array_equal(e.get_decoder("color"), decs["color"])
+    rd, ro, gd = got[1], got[0], got[2]
+    assert np.array_equal(e2.render_batch_ray(rd, ro, "color", gd)[1], e.render_batch_ray(rd, ro, "color", gd)[1])
+    with pytest.raises(RuntimeError, match="not an nsb checkpoint"):
+        bad = tmp_path / "bad.bin"; bad.write_bytes(b"x" * 400)
+        e2.load_checkpoint(bad)
