@@ -55,6 +55,8 @@ _LIBS = {}
 
 def load_library(variant=""):
     """dlopen libnsb.so and declare the prototypes.  Raises if the library is missing: no fallback."""
+    if variant == "":
+        variant = os.environ.get("NSB_VARIANT", "")       # build-variant experiments (build.py VARIANTS)
     if variant in _LIBS:
         return _LIBS[variant]
     path = lib_path(variant)

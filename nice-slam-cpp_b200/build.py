@@ -21,7 +21,10 @@ BASE = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed
 
 UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("decode_fwd_tc.cu", []), ("wgrad.cu", [])] + \
         [("decode_bwd_inst.cu", ["-DNSB_BWD_COMBO=%d" % k]) for k in range(6)]
-VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC_TIMING"]}
+VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC_TIMING"],
+            # occupancy experiments: warps per CTA of the forward / backward decoder kernels
+            "f20b20": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=20"], "f16b24": ["-DNSB_BWD_WARPS=24"], "f20b24": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=24"],
+            "f24b24": ["-DNSB_FWD_WARPS=24", "-DNSB_BWD_WARPS=24"], "f16b20": ["-DNSB_BWD_WARPS=20"]}
 
 
 def lib_path(variant=""):

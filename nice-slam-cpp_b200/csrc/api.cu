@@ -675,7 +675,7 @@ static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, cons
 static int decode_grid_size(nsb_ctx* ctx, int P) {
     const int occ = std::max(1, ctx->occ_blocks[ctx->cfg.precision ? 1 : 0]);
     const int tiles = cdiv(P, TILE);
-    return std::max(1, std::min(ctx->n_sm * occ, cdiv(tiles, DECODE_WARPS)));
+    return std::max(1, std::min(ctx->n_sm * occ, cdiv(tiles, std::min(FWD_WARPS, BWD_WARPS))));
 }
 
 // Decoders a stage evaluates (NICE.cpp:16-51).
@@ -719,7 +719,9 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
         if (train) P.masks = ctx->masks;
         if (train && stash_fwd && stage == NSB_COLOR) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
-        float w[4]; stage_decoders(stage, w); env_weights("NSB_SPLIT_FWD", w);
+        float w[4]; stage_decoders(stage, w);
+        if (P.stash) { w[1] = 700; w[2] = 972; w[3] = 860; }   // the colour decoder also writes its activations to the wgrad stash (measured split, tools/sweep_split.sh)
+        env_weights("NSB_SPLIT_FWD", w);
         const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_3XTF32 && stage != NSB_COARSE && P.stash == nullptr;
         if (tc_ok) {
             // tcgen05 path: one 320-thread CTA per SM, per-sample mask words, composed weights refreshed when stale
@@ -794,7 +796,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         const float ge = (flags & 4) ? 288.f : 0.f;
         if (stage == NSB_MIDDLE) w[1] = 480 + ge;
         else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
-        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); }
+        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); if (wg && !ge) { w[1] = 460; w[2] = 500; w[3] = 1400; } }   // measured (tools/sweep_split.sh)
         else return fail(ctx, "backward through the coarse stage is not implemented");
         env_weights("NSB_SPLIT_BWD", w);
         const int grid = decode_grid_size(ctx, n * S);

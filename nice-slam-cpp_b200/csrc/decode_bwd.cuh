@@ -270,7 +270,7 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
 }
 
 template <bool P3, bool GRID, bool RAY, bool WG>
-__global__ void __launch_bounds__(DECODE_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd(const DecodeParams P) {
+__global__ void __launch_bounds__(BWD_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd(const DecodeParams P) {
     extern __shared__ __align__(128) float sm[];
     int dec = 1;
 #pragma unroll
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = P.P / TILE;
-    for (int tile = cta * DECODE_WARPS + warp; tile < ntiles; tile += ncta * DECODE_WARPS) {
+    for (int tile = cta * BWD_WARPS + warp; tile < ntiles; tile += ncta * BWD_WARPS) {
         if (dec == 1) backward_tile<32, 1, P3, GRID, RAY, false>(P, sm, 1, tile * TILE, g, t, lane);
         else if (dec == 2) backward_tile<64, 1, P3, GRID, RAY, false>(P, sm, 2, tile * TILE, g, t, lane);
         else backward_tile<32, 4, P3, GRID, RAY, WG>(P, sm, 3, tile * TILE, g, t, lane);

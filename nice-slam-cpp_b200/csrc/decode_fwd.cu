@@ -46,7 +46,7 @@ __device__ __forceinline__ void save_masks(const DecodeParams& P, int dec, int t
 // TRAIN: the launch is the forward half of a training step -- relu masks are kept for the backward kernel (which then
 // needs no forward recomputation) and, when P.stash is set, the colour decoder's activations go to the wgrad stash.
 template <bool P3, bool TRAIN>
-__global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(const DecodeParams P) {
+__global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(const DecodeParams P) {
     extern __shared__ __align__(128) float sm[];
     int dec = 0;
 #pragma unroll
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(DECODE_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (P.P + TILE - 1) / TILE;
-    for (int tile = cta * DECODE_WARPS + warp; tile < ntiles; tile += ncta * DECODE_WARPS) {
+    for (int tile = cta * FWD_WARPS + warp; tile < ntiles; tile += ncta * FWD_WARPS) {
         float p[2][3]; int sidx[2];
         if (!load_points(P, tile * TILE, g, p, sidx)) continue;
         if (dec == 0) {
@@ -169,7 +169,7 @@ static cudaError_t launch_fwd_one(const DecodeParams& P, int grid, cudaStream_t 
     const size_t smem = decode_fwd_smem();
     cudaError_t e = cudaFuncSetAttribute(k_decode_fwd<P3, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_decode_fwd<P3, TRAIN><<<grid, DECODE_THREADS, smem, st>>>(P);
+    k_decode_fwd<P3, TRAIN><<<grid, FWD_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -184,8 +184,8 @@ int decode_fwd_occupancy(int precision) {
     const size_t smem = decode_fwd_smem();
     cudaFuncSetAttribute(k_decode_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_decode_fwd<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (precision == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<true, true>, DECODE_THREADS, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<false, true>, DECODE_THREADS, smem);
+    if (precision == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<true, true>, FWD_THREADS, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode_fwd<false, true>, FWD_THREADS, smem);
     return nb;
 }
 

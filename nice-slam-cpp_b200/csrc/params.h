@@ -4,8 +4,16 @@
 
 namespace nsb {
 
-constexpr int DECODE_WARPS = 16;   // one 512-thread CTA per SM: the pre-split weights of a decoder take 130-167 KB of shared memory
-constexpr int DECODE_THREADS = DECODE_WARPS * 32;
+// Warps per CTA of the decoder kernels (one CTA per SM: a decoder's pre-split weights take 84-117 KB of shared memory).  The
+// register file (64 K) divided by the thread count caps the registers per thread: 16 warps -> 128, 20 -> 96, 24 -> 80.
+#ifndef NSB_FWD_WARPS
+#define NSB_FWD_WARPS 16
+#endif
+#ifndef NSB_BWD_WARPS
+#define NSB_BWD_WARPS 16
+#endif
+constexpr int FWD_WARPS = NSB_FWD_WARPS, FWD_THREADS = FWD_WARPS * 32;
+constexpr int BWD_WARPS = NSB_BWD_WARPS, BWD_THREADS = BWD_WARPS * 32;
 
 // Which decoders a launch evaluates and how the grid is split between them.
 struct DecodeParams {
