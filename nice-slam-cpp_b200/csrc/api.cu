@@ -124,6 +124,8 @@ struct nsb_ctx {
     float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
     float* wimg_bwd[4] = {nullptr, nullptr, nullptr, nullptr};
     int wimg_dirty = 0xE;        // bit d: decoder d's images are stale
+    unsigned long long* tile_ctr = nullptr;          // [4] ticket counters of the decoder kernels' tile scheduler (never reset)
+    unsigned long long tile_ticket[4] = {0, 0, 0, 0};   // host mirror: tickets handed out by the launches enqueued so far
     int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
     unsigned long long* dbg = nullptr;   // 32 cycle counters (NSB_TC_TIMING builds)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
@@ -398,6 +400,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(dalloc(&ctx->tile_ctr, 4)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
@@ -417,7 +420,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -672,6 +675,18 @@ static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, cons
     P.g_raw = ctx->g_raw; P.d_rays = ctx->d_rays; P.stash = nullptr; P.masks = nullptr;
 }
 
+// Reserves this launch's tickets of the tile scheduler: each of decoder d's warps draws tickets until one is past the last tile,
+// so a launch consumes exactly ntiles + (number of warps of d) tickets of counter d.
+static void reserve_tiles(nsb_ctx* ctx, DecodeParams& P, int warps_per_cta) {
+    const int ntiles = cdiv(P.P, TILE);
+    P.tile_ctr = ctx->tile_ctr;
+    for (int d = 0; d < 4; ++d) {
+        P.tile_base[d] = ctx->tile_ticket[d];
+        const int nc = P.cta_begin[d + 1] - P.cta_begin[d];
+        if (nc > 0) ctx->tile_ticket[d] += (unsigned long long)ntiles + (unsigned long long)nc * warps_per_cta;
+    }
+}
+
 static int decode_grid_size(nsb_ctx* ctx, int P) {
     const int occ = std::max(1, ctx->occ_blocks[ctx->cfg.precision ? 1 : 0]);
     const int tiles = cdiv(P, TILE);
@@ -743,6 +758,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             if (train) { ctx->mask_layout = 0; ctx->mask_stride = 0; }
             const int grid = decode_grid_size(ctx, n * S);
             partition(grid, w, P.cta_begin);
+            reserve_tiles(ctx, P, FWD_WARPS);
             CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
         }
     }
@@ -802,6 +818,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         const int grid = decode_grid_size(ctx, n * S);
         partition(grid, w, P.cta_begin);
         P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
+        reserve_tiles(ctx, P, BWD_WARPS);
         CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
     }
     ctx->ar_overlapped = false;
@@ -983,6 +1000,7 @@ extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts
         P.pts = ctx->pts; P.P = m;
         float w[4]; stage_decoders(stage, w);
         partition(decode_grid_size(ctx, m), w, P.cta_begin);
+        reserve_tiles(ctx, P, FWD_WARPS);
         CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
         h_rgb.resize(4 * (size_t)m); for (int k = 0; k < 3; ++k) h_occ[k].resize(m);
         CK(cudaMemcpyAsync(h_rgb.data(), ctx->raw_rgb, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));

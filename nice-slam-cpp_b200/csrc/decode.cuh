@@ -131,6 +131,21 @@ __device__ __forceinline__ void load_decoder_image(float* sm, const float* __res
     for (int i = tid; i < DecSmem<C>::TOTAL / 4; i += nthr) dst[i] = __ldg(src + i);
 }
 
+// Ticket-based tile scheduler of the decoder kernels: lane 0 draws the next ticket while the current tile is processed.
+struct TileQueue {
+    unsigned long long* ctr; unsigned long long base; int ntiles; unsigned long long pending;
+    __device__ __forceinline__ void init(unsigned long long* c, unsigned long long b, int n, int lane) { ctr = c; base = b; ntiles = n; prefetch(lane); }
+    __device__ __forceinline__ void prefetch(int lane) { if (lane == 0) pending = atomicAdd(ctr, 1ull); }
+    // tile index of the pending ticket (or -1 when the decoder's tiles are exhausted); draws the one after it
+    __device__ __forceinline__ int next(int lane) {
+        const unsigned long long tk = __shfl_sync(0xffffffffu, pending, 0);
+        const long long tile = (long long)(tk - base);
+        if (tile >= ntiles) return -1;
+        prefetch(lane);
+        return (int)tile;
+    }
+};
+
 __device__ __forceinline__ const uint32_t* wmat(const float* sm, int off) { return reinterpret_cast<const uint32_t*>(sm + off); }
 
 // Gather the thread's 8 channels (8t..8t+7) of the trilinear feature for one sample: one 256-bit load per corner, the four

@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(BWD_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd(co
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = P.P / TILE;
-    for (int tile = cta * BWD_WARPS + warp; tile < ntiles; tile += ncta * BWD_WARPS) {
+    (void)cta; (void)ncta; (void)warp;
+    TileQueue q; q.init(P.tile_ctr + dec, P.tile_base[dec], ntiles, lane);
+    for (int tile = q.next(lane); tile >= 0; tile = q.next(lane)) {
         if (dec == 1) backward_tile<32, 1, P3, GRID, RAY, false>(P, sm, 1, tile * TILE, g, t, lane);
         else if (dec == 2) backward_tile<64, 1, P3, GRID, RAY, false>(P, sm, 2, tile * TILE, g, t, lane);
         else backward_tile<32, 4, P3, GRID, RAY, WG>(P, sm, 3, tile * TILE, g, t, lane);
