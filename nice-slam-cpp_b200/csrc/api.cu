@@ -812,7 +812,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         const float ge = (flags & 4) ? 288.f : 0.f;
         if (stage == NSB_MIDDLE) w[1] = 480 + ge;
         else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
-        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); if (wg && !ge) { w[1] = 460; w[2] = 500; w[3] = 1400; } }   // measured (tools/sweep_split.sh)
+        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); if (wg && !ge) { w[1] = 460; w[2] = 500; w[3] = 1250; } }   // measured (tools/sweep_split.sh)
         else return fail(ctx, "backward through the coarse stage is not implemented");
         env_weights("NSB_SPLIT_BWD", w);
         const int grid = decode_grid_size(ctx, n * S);
