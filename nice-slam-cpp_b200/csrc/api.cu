@@ -45,6 +45,7 @@ cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cuda
 cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st);
 size_t wimg_floats(int which);
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
+cudaError_t launch_decode_fwd_tc16(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
 int compose_floats(int which);
 }  // namespace nsb
@@ -752,8 +753,13 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             P.mask_layout = 1; P.mask_stride = n * S;
             if (train) { ctx->mask_layout = 1; ctx->mask_stride = n * S; }
             float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
-            partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 256))), wt, P.cta_begin);
-            CK(launch_decode_fwd_tc(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+            if (ctx->use_tc == 2) {   // kind::f16 kernel: three 128-sample tiles per CTA
+                partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 384))), wt, P.cta_begin);
+                CK(launch_decode_fwd_tc16(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+            } else {
+                partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 256))), wt, P.cta_begin);
+                CK(launch_decode_fwd_tc(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+            }
         } else {
             if (train) { ctx->mask_layout = 0; ctx->mask_stride = 0; }
             const int grid = decode_grid_size(ctx, n * S);
