@@ -202,9 +202,10 @@ int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12);
 /* One joint iteration.  idx: host int64 [n_frames * (mapping_pixels / n_frames)] flat pixel indices, or NULL to
  * draw them from the context's mt19937 stream.  loss (host, may be NULL; reading it synchronises). */
 int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss);
-/* Enqueue only (no host sync); the loss of iteration i is later read with nsb_mapping_losses. */
+/* Enqueue only (no host sync); losses are later read with nsb_mapping_losses, indexed by STEP: the k-th nsb_mapping_iter* call
+ * since nsb_mapping_begin is step k - 1, whatever `iter` it was given (a ring of the last 4096 steps is kept). */
 int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx);
-int nsb_mapping_losses(nsb_ctx* ctx, int first_iter, int n, float* losses, int* n_inside);
+int nsb_mapping_losses(nsb_ctx* ctx, int first_step, int n, float* losses, int* n_inside);
 /* Optional: park the pixel indices of n_iters iterations ([n_iters][n] int64) in device memory; iterations called
  * with idx = NULL then consume the rows in order (wrapping) instead of drawing/uploading (device-resident benchmarking). */
 int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n);

@@ -1082,9 +1082,11 @@ static void build_adam(nsb_ctx* ctx, AdamParams& A, int step, const float lr_gro
 // color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first
 // colour iteration): gradient, m and v of the colour grid / colour decoder are all exactly zero, the Adam update is the identity
 // (p - step * 0 / (0 + eps) = p), so those segments are left out of the launch.
-static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine = false) {
+static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine = false,
+                    float* loss_dst = nullptr) {
     Timer t(ctx, T_ADAM);
     AdamParams A; build_adam(ctx, A, step, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
+    A.loss_dst = loss_dst; A.loss_idx4 = (int)(ctx->off_tail / 4);
     k_adam<<<cdiv(A.cum4[A.n_seg], 256 * ADAM_VEC), 256, 0, ctx->stream>>>(A); ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1174,7 +1176,10 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     if (wait_uploads(ctx)) return -1;
     const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
     const int stage = stage_of_iter(c, iter, ctx->map_iters);
-    float* stats = ctx->stats + 4 * (iter % LOSS_RING);
+    // statistics / loss slot of this step (the k-th iteration since nsb_mapping_begin, whatever its `iter` argument): the ring was
+    // cleared by nsb_mapping_begin, so no per-iteration memset is needed until it wraps
+    if (ctx->map_step > 0 && ctx->map_step % LOSS_RING == 0) CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    float* stats = ctx->stats + 4 * (ctx->map_step % LOSS_RING);
     {
         Timer t(ctx, T_SAMPLE);
         const int64_t* d_idx = ctx->idx;
@@ -1185,7 +1190,6 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
             CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         }
-        CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
         SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
         P.idx = d_idx; P.cam_mask = ctx->map_ba_mask;
         P.order = map_order(ctx, n, pix);
@@ -1266,10 +1270,10 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         }
         ctx->ar_overlapped = false;
     }
-    CK(cudaMemcpyAsync(stats + 3, ctx->grad + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups
-    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine)) return -1;
+    // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups;
+    // the Adam kernel also moves the (all-reduced) loss out of the gradient arena into the step's statistics slot
+    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine, stats + 3)) return -1;
     return 0;
 }
 
@@ -1332,7 +1336,7 @@ extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses,
 
 extern "C" int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss) {
     if (nsb_mapping_iter_async(ctx, iter, idx)) return -1;
-    if (loss) return nsb_mapping_losses(ctx, iter, 1, loss, nullptr);
+    if (loss) return nsb_mapping_losses(ctx, ctx->map_step - 1, 1, loss, nullptr);
     return 0;
 }
 

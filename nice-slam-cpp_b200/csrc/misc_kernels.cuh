@@ -36,6 +36,8 @@ struct AdamParams {
     float beta1, beta2, om_beta1, om_beta2, eps;   // om_* = (float)(1.0 - beta) as libtorch passes them
     float bc2_sqrt;          // (float)sqrt(1 - beta2^t), double arithmetic on the host
     float grad_scale;        // 1 (single GPU) -- kept for mean-style reductions
+    float* loss_dst;         // optional: receives the loss scalar that rides at float4 slot loss_idx4 of the gradient arena
+    int loss_idx4;
 };
 
 // torch::optim::Adam::step (libtorch defaults, no amsgrad / weight decay) + zero_grad, one launch over the concatenation
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
 #pragma unroll
     for (int u = 0; u < ADAM_VEC; ++u) {
         if (!live[u]) continue;
+        if (P.loss_dst && idx[u] == P.loss_idx4) *P.loss_dst = g[u].x;
         reinterpret_cast<float4*>(P.grad)[idx[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!upd[u]) continue;
         float* gg = reinterpret_cast<float*>(&g[u]); float* mm = reinterpret_cast<float*>(&m[u]);
