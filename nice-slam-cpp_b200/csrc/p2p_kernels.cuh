@@ -17,7 +17,7 @@ struct P2PParams {
     float* peer_param[P2P_MAX_WORLD];      // every rank's parameter arena
     uint32_t* peer_flags[P2P_MAX_WORLD];   // every rank's flag block: [0..7] ready epochs, [8..15] done epochs, [16] CTA counter
     int rank, world;
-    int lo4, hi4;                          // the exchanged range of the arena in float4 units; rank r owns an equal share of it
+    int lo4, hi4;                          // the exchanged range of the arena in float4 units (ownership: see the kernel)
     int loss4;                             // float4 index of the loss slot (summed, written to param arenas, no Adam), or -1
     uint32_t epoch;
 };
@@ -35,10 +35,16 @@ __global__ void __launch_bounds__(256) k_reduce_adam(P2PParams P) {
     if (threadIdx.x < P.world) { while (ld_acquire_sys(my_flags + threadIdx.x) < P.epoch) { } }
     __syncthreads();
 
-    const int span = P.hi4 - P.lo4;
-    const int chunk = ((span + P.world - 1) / P.world + 7) & ~7;          // whole voxels (32 floats) per rank
-    const int my_lo = P.lo4 + P.rank * chunk, my_hi = min(P.hi4, my_lo + chunk);
-    for (int i4 = my_lo + blockIdx.x * blockDim.x + threadIdx.x; i4 < my_hi; i4 += gridDim.x * blockDim.x) {
+    // Ownership is static and interleaved: block b of 256 float4 (4 KB) of the arena belongs to rank b % world, whatever range
+    // an iteration exchanges -- the owner alone keeps Adam's m and v of a block, so it must never change, and any exchanged
+    // range (the short geometry-stage prefix or the whole arena) is spread evenly over the ranks.
+    constexpr int BLK4 = 256;
+    const int b_lo = P.lo4 / BLK4;
+    const int first = b_lo + ((P.rank - b_lo % P.world) + P.world) % P.world;      // first block >= b_lo owned by this rank
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; ; j += gridDim.x * blockDim.x) {
+        const int i4 = (first + (j / BLK4) * P.world) * BLK4 + (j % BLK4);
+        if (i4 >= P.hi4) break;
+        if (i4 < P.lo4) continue;
         // segment of this element (compile-time indices only, as in k_adam)
         AdamSegment sg = P.A.seg[0];
 #pragma unroll
