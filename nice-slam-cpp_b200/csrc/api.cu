@@ -117,6 +117,8 @@ struct nsb_ctx {
     float* pts = nullptr;
     float* stats = nullptr;       // [LOSS_RING][4]: max gt depth, n inside, sum 1/|d|, loss
     float* median = nullptr; int* count = nullptr;
+    float* trk_scratch = nullptr;   // [32] per-iteration tracking scratch (see nsb_tracking_iter)
+    bool trk_hook = false; int* trk_count = nullptr;   // set around the tracking forward: the composite compacts |gt - depth|
     float* stash = nullptr; size_t stash_rows = 0;
     uint32_t* masks = nullptr;   // relu masks of the last training forward
     int mask_layout = 0, mask_stride = 0;
@@ -405,6 +407,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
+    CK(dalloc(&ctx->trk_scratch, 32)); CK(cudaMemsetAsync(ctx->trk_scratch, 0, 32 * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -421,7 +424,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -775,6 +778,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
         Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
         Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = want_weights ? ctx->o_w + (size_t)off * S : nullptr;
+        if (ctx->trk_hook) { Q.trk_gt_depth = ctx->gt_depth + off; Q.trk_absdiff = ctx->absdiff; Q.trk_count = ctx->trk_count; }
         k_composite_fwd<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q); ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -1420,8 +1424,11 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
     const nsb_config& c = ctx->cfg;
     const int n = c.tracking_pixels;
     const int H0 = c.ignore_edge_H, H1 = c.H - c.ignore_edge_H, W0 = c.ignore_edge_W, W1 = c.W - c.ignore_edge_W;   // Tracker.cpp:46
-    float* stats = ctx->stats;
+    // per-iteration scratch, cleared with one memset: [0..3] batch statistics + loss, [4] survivor count, [8..20] pose-gradient partial sums
+    float* stats = ctx->trk_scratch;
+    int* count = reinterpret_cast<int*>(ctx->trk_scratch + 4);
     float* cam = ctx->param + ctx->off_cam;
+    if (wait_uploads(ctx)) return -1;
     {
         Timer t(ctx, T_SAMPLE);
         if (idx) CK(cudaMemcpyAsync(ctx->idx, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1430,52 +1437,51 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
             draw_indices(ctx, n, (int64_t)(H1 - H0) * (W1 - W0), ctx->h_idx.data());
             CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         }
-        CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
-        CK(cudaMemsetAsync(ctx->count, 0, 16, ctx->stream));
+        CK(cudaMemsetAsync(ctx->trk_scratch, 0, 32 * 4, ctx->stream));
         SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, stats, 1);
         P.slots[0] = ctx->trk_slot; P.n_frames = 1; P.pix_per_frame = n; P.cam_mask = 1u;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
         if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
         CK(cudaGetLastError());
     }
-    if (run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false, true, false)) return -1;   // Tracker.cpp:61
+    // render (Tracker.cpp:61); with handle_dynamic the composite also compacts |gt - depth| of the surviving rays for the median (:69)
+    ctx->trk_hook = c.handle_dynamic != 0; ctx->trk_count = count;
+    const int rf = run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false, true, false);
+    ctx->trk_hook = false;
+    if (rf) return -1;
+    const int S = ctx->last_S;
     {
         Timer t(ctx, T_COMP);
-        LossParams L; memset(&L, 0, sizeof L);
-        L.gt_depth = ctx->gt_depth; L.gt_color = ctx->gt_color; L.valid = ctx->valid; L.rgb = ctx->o_rgb; L.depth = ctx->o_depth; L.var = ctx->o_var;
-        L.n = n; L.use_color = c.use_color_in_tracking; L.w_color = c.w_color_loss;
-        L.g_rgb = ctx->g_rgb; L.g_depth = ctx->g_depth; L.g_var = ctx->g_var; L.loss = stats + 3; L.median = ctx->median; L.absdiff = ctx->absdiff;
-        if (c.handle_dynamic) {
-            k_track_absdiff<<<cdiv(n, 256), 256, 0, ctx->stream>>>(L, ctx->count);
-            k_median<<<1, 1024, 0, ctx->stream>>>(ctx->absdiff, ctx->count, ctx->median);
-            ctx->launches += 2;
-        }
-        k_loss_tracking<<<cdiv(n, 256), 256, 0, ctx->stream>>>(L, c.handle_dynamic); ctx->launches++;
+        if (c.handle_dynamic) { k_median<<<1, 1024, 0, ctx->stream>>>(ctx->absdiff, count, ctx->median); ctx->launches++; }
+        // loss (Tracker.cpp:67-82) + composite backward in one pass over the rays
+        CK(cudaMemsetAsync(ctx->d_rays, 0, 6 * (size_t)n * 4, ctx->stream));
+        CompositeParams Q; memset(&Q, 0, sizeof Q);
+        Q.rays_o = ctx->rays_o; Q.rays_d = ctx->rays_d; Q.z = ctx->z; Q.valid = ctx->valid;
+        Q.raw_rgb = ctx->raw_rgb; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k];
+        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.g_raw = ctx->g_raw; Q.d_rays = ctx->d_rays;
+        k_composite_track<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q, ctx->gt_depth, ctx->gt_color, ctx->median, c.handle_dynamic, c.use_color_in_tracking,
+                                                                     c.w_color_loss, stats + 3);
+        ctx->launches++;
         CK(cudaGetLastError());
     }
-    if (run_backward(ctx, NSB_COLOR, 0, n, ctx->valid, stats, 4, true)) return -1;
-    {
-        Timer t(ctx, T_COMP);
-        PoseGradParams G; memset(&G, 0, sizeof G);
-        G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.valid = ctx->valid; G.cams = cam; G.cam_mask = 1u; G.pix_per_frame = n; G.n_frames = 1; G.lo = 0; G.hi = n;
-        G.H0 = H0; G.W0 = W0; G.Wc = W1 - W0; G.raydir = c.raydir;
-        G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy; G.g_cams = ctx->grad + ctx->off_cam;
-        k_pose_grad<<<1, 1024, 0, ctx->stream>>>(G); ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    if (cam_grad7) CK(cudaMemcpyAsync(cam_grad7, ctx->grad + ctx->off_cam, 28, cudaMemcpyDeviceToHost, ctx->stream));
+    if (run_backward(ctx, NSB_COLOR, 0, n, ctx->valid, stats, 4, true, true)) return -1;
     ctx->trk_step++;
     {
+        // chain to (q, t) (utils.h:174-210) and the Adam step on the 7-vector (Tracker.cpp:85), fused: the last block applies it
         Timer t(ctx, T_ADAM);
-        AdamParams A; memset(&A, 0, sizeof A);
-        A.param = ctx->param; A.grad = ctx->grad; A.m = ctx->m; A.v = ctx->v;
+        TrackStepParams T; memset(&T, 0, sizeof T);
+        PoseGradParams& G = T.G;
+        G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.valid = ctx->valid; G.cams = cam; G.cam_mask = 1u; G.pix_per_frame = n; G.n_frames = 1; G.lo = 0; G.hi = n;
+        G.H0 = H0; G.W0 = W0; G.Wc = W1 - W0; G.raydir = c.raydir; G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy;
+        T.partial = ctx->trk_scratch + 8; T.cam = cam; T.m = ctx->m + ctx->off_cam; T.v = ctx->v + ctx->off_cam; T.g_out = ctx->cam_grad_last;
         const double b1 = 0.9, b2 = 0.999, bc1 = 1.0 - std::pow(b1, (double)ctx->trk_step), bc2 = 1.0 - std::pow(b2, (double)ctx->trk_step);
-        A.beta1 = (float)b1; A.beta2 = (float)b2; A.om_beta1 = (float)(1.0 - b1); A.om_beta2 = (float)(1.0 - b2); A.eps = 1e-8f; A.bc2_sqrt = (float)std::sqrt(bc2); A.grad_scale = 1.f;
-        A.seg[0].begin = (int)ctx->off_cam; A.seg[0].end = (int)ctx->off_cam + 8; A.seg[0].step = (float)((double)c.tracking_lr / bc1); A.seg[0].mask = nullptr; A.seg[0].active = 1;
-        A.n_seg = 1; A.cum4[0] = 0; A.cum4[1] = 2;
-        k_adam<<<1, 32, 0, ctx->stream>>>(A); ctx->launches++;
+        T.beta1 = (float)b1; T.beta2 = (float)b2; T.om_beta1 = (float)(1.0 - b1); T.om_beta2 = (float)(1.0 - b2); T.eps = 1e-8f;
+        T.bc2_sqrt = (float)std::sqrt(bc2); T.step = (float)((double)c.tracking_lr / bc1);
+        k_track_step<<<std::max(1, std::min(32, cdiv(n, 256))), 256, 0, ctx->stream>>>(T); ctx->launches++;
         CK(cudaGetLastError());
     }
+    if (cam_grad7) CK(cudaMemcpyAsync(cam_grad7, ctx->cam_grad_last, 28, cudaMemcpyDeviceToHost, ctx->stream));
     if (loss) CK(cudaMemcpyAsync(loss, stats + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (loss || cam_grad7) CK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -210,6 +210,8 @@ struct CompositeParams {
     const float* g_rgb; const float* g_depth; const float* g_var;   // per-ray cotangents
     float* g_raw;             // [P][4]
     float* d_rays;            // [n][6] or null: receives d L / d rays_d through dists * |rays_d| (utils.h:153)
+    // tracking (Tracker.cpp:69): the forward also compacts |gt_depth - depth| of the surviving rays for the median
+    const float* trk_gt_depth; float* trk_absdiff; int* trk_count;
 };
 
 struct RaySamples {   // lane l owns samples l and l+32
@@ -300,7 +302,10 @@ __global__ void k_composite_fwd(CompositeParams P) {
     }
     RaySamples s; float rgb[3], depth, var;
     composite_forward(P, ray, l, s, rgb, depth, var);
-    if (l == 0) { P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var; }
+    if (l == 0) {
+        P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var;
+        if (P.trk_absdiff) P.trk_absdiff[atomicAdd(P.trk_count, 1)] = fabsf(P.trk_gt_depth[ray] - depth);
+    }
     if (P.weights) {
         P.weights[ray * P.S + l] = s.w[0];
         if (s.has[1]) P.weights[ray * P.S + 32 + l] = s.w[1];
@@ -395,49 +400,38 @@ __global__ void k_composite_map(CompositeParams P, const float* __restrict__ gt_
     composite_backward(P, ray, l, s, depth, gC, gD, 0.0f);
 }
 
-// ---- losses ------------------------------------------------------------------------------------------
-struct LossParams {
-    const float* gt_depth; const float* gt_color; const uint8_t* valid;
-    const float* rgb; const float* depth; const float* var;
-    int n, use_color; float w_color;
-    float* g_rgb; float* g_depth; float* g_var;
-    float* loss;              // scalar accumulator
-    const float* median;      // tracking: [0] = median |gt - depth| (handle_dynamic), null otherwise
-    float* absdiff;           // tracking pass 1 output
-};
-
-__device__ __forceinline__ float sgn(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
-
-// Mapper.cpp:435-442: sum_{gt>0} |gt - depth| + w * sum |gt_color - color|
-__global__ void k_loss_mapping(LossParams P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float loss = 0.0f;
-    if (i < P.n) {
-        float gd = 0.0f, gc[3] = {0.0f, 0.0f, 0.0f};
-        if (!P.valid || P.valid[i]) {
-            const float g = P.gt_depth[i];
-            if (g > 0.0f) { const float df = g - P.depth[i]; loss += fabsf(df); gd = -sgn(df); }
-            if (P.use_color) {
+// Tracking iteration: loss of Tracker.cpp:67-82 (median mask, uncertainty-weighted depth term, colour term) + composite backward
+// in one pass over the ray, from the rgb / depth / var the forward left (the cotangents are local to the ray).
+__global__ void k_composite_track(CompositeParams P, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                                  const float* __restrict__ median, int handle_dynamic, int use_color, float w_color, float* loss_out) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (ray >= P.n) return;
+    if (P.valid && !P.valid[ray]) return;
+    RaySamples s; float rgb[3], depth, var;
+    composite_forward(P, ray, l, s, rgb, depth, var);
+    float loss = 0.0f, gD = 0.0f, gV = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
+    const float g = gt_depth[ray], df = g - depth;
+    bool m = g > 0.0f;
+    if (handle_dynamic) m = m && (fabsf(df) < 10.0f * median[0]);
+    if (m) {
+        const float vv = var + 1e-10f, r = 1.0f / sqrtf(vv);
+        loss += fabsf(df) * r;
+        gD = -(df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) * r;
+        gV = -0.5f * fabsf(df) * r / vv;
+        if (use_color) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { const float df = P.gt_color[3 * i + c] - P.rgb[3 * i + c]; loss += P.w_color * fabsf(df); gc[c] = -P.w_color * sgn(df); }
+            for (int c = 0; c < 3; ++c) {
+                const float dc = gt_color[3 * ray + c] - rgb[c];
+                loss += w_color * fabsf(dc);
+                gC[c] = dc > 0.0f ? -w_color : (dc < 0.0f ? w_color : 0.0f);
             }
         }
-        P.g_depth[i] = gd; P.g_var[i] = 0.0f;
-        P.g_rgb[3 * i] = gc[0]; P.g_rgb[3 * i + 1] = gc[1]; P.g_rgb[3 * i + 2] = gc[2];
     }
-    loss = warp_sum(loss);
-    if ((threadIdx.x & 31) == 0 && loss != 0.0f) atomicAdd(P.loss, loss);
+    if (l == 0 && loss != 0.0f) atomicAdd(loss_out, loss);
+    composite_backward(P, ray, l, s, depth, gC, gD, gV);
 }
 
-// Tracker.cpp:69: |gt - depth| of the rays that passed the filter (compacted for the median)
-__global__ void k_track_absdiff(LossParams P, int* count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n && (!P.valid || P.valid[i])) {
-        const int slot = atomicAdd(count, 1);
-        P.absdiff[slot] = fabsf(P.gt_depth[i] - P.depth[i]);
-    }
-}
-
+// ---- lower median of the tracking residuals (Tracker.cpp:70) ------------------------------------------
 // torch.median (lower median) of n non-negative floats by 4-pass radix select on the bit pattern; one block.
 __global__ void k_median(const float* __restrict__ v, const int* __restrict__ count, float* out) {
     __shared__ unsigned hist[256];
@@ -465,34 +459,6 @@ __global__ void k_median(const float* __restrict__ v, const int* __restrict__ co
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = __uint_as_float(prefix_s);
-}
-
-// Tracker.cpp:67-82: mask = (|gt-depth| < 10 median) & (gt > 0); loss = sum_mask |gt-depth|/sqrt(var+1e-10) + w sum_mask |dc|
-__global__ void k_loss_tracking(LossParams P, int handle_dynamic) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float loss = 0.0f;
-    if (i < P.n) {
-        float gd = 0.0f, gv = 0.0f, gc[3] = {0.0f, 0.0f, 0.0f};
-        if (!P.valid || P.valid[i]) {
-            const float g = P.gt_depth[i], df = g - P.depth[i];
-            bool m = g > 0.0f;
-            if (handle_dynamic) m = m && (fabsf(df) < 10.0f * P.median[0]);
-            if (m) {
-                const float vv = P.var[i] + 1e-10f, r = 1.0f / sqrtf(vv);
-                loss += fabsf(df) * r;
-                gd = -sgn(df) * r;
-                gv = -0.5f * fabsf(df) * r / vv;
-                if (P.use_color) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { const float dc = P.gt_color[3 * i + c] - P.rgb[3 * i + c]; loss += P.w_color * fabsf(dc); gc[c] = -P.w_color * sgn(dc); }
-                }
-            }
-        }
-        P.g_depth[i] = gd; P.g_var[i] = gv;
-        P.g_rgb[3 * i] = gc[0]; P.g_rgb[3 * i + 1] = gc[1]; P.g_rgb[3 * i + 2] = gc[2];
-    }
-    loss = warp_sum(loss);
-    if ((threadIdx.x & 31) == 0 && loss != 0.0f) atomicAdd(P.loss, loss);
 }
 
 // ---- pose gradient: d L / d (q, t) from the per-ray gradients (block reduction, one block) -------------
@@ -597,6 +563,69 @@ __global__ void k_kf_overlap(OverlapParams P) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (threadIdx.x == 0) P.percent[kf] = (float)v / (float)nv;
+    }
+}
+
+// Tracking variant: several blocks reduce the rays, the last block to finish turns the 12 sums into d L / d (q, t) and applies
+// the Adam step to the 7-vector in place (torch::optim::Adam on one tiny parameter, Tracker.cpp:85,103) -- one launch instead
+// of a single-block reduction plus an optimiser launch.
+struct TrackStepParams {
+    PoseGradParams G;
+    float* partial;          // [13]: 12 sums + block counter (as int), zero on entry, left zero on exit
+    float* cam; float* m; float* v;   // the 7-vector and its Adam moments
+    float* g_out;            // [7] gradient copy for the caller (may alias the gradient arena)
+    float beta1, beta2, om_beta1, om_beta2, eps, bc2_sqrt, step;   // step = lr / (1 - beta1^t)
+};
+
+__global__ void __launch_bounds__(256) k_track_step(TrackStepParams T) {
+    const PoseGradParams& P = T.G;
+    __shared__ float red[12][8];
+    __shared__ int s_last;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+    for (int i = P.lo + blockIdx.x * blockDim.x + threadIdx.x; i < P.hi; i += gridDim.x * blockDim.x) {
+        if (P.valid && !P.valid[i]) continue;
+        const int64_t id = P.idx[i];
+        const float xf = (float)(P.W0 + (int)(id % P.Wc)), yf = (float)(P.H0 + (int)(id / P.Wc));
+        const float dir[3] = {(xf - P.cx) / P.fx, P.raydir == 0 ? (xf - P.cy) / P.fy : -(yf - P.cy) / P.fy, -1.0f};
+        const float* g = P.d_rays + 6 * (size_t)i;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            acc[9 + r] += g[r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[3 * r + c] += g[3 + r] * dir[c];
+        }
+    }
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { const float v = warp_sum(acc[k]); if (l == 0) red[k][w] = v; }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.0f;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) v += red[threadIdx.x][q];
+        atomicAdd(T.partial + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<int*>(T.partial + 12), 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    float G[12];
+    for (int k = 0; k < 12; ++k) { G[k] = __ldcg(T.partial + k); T.partial[k] = 0.0f; }
+    reinterpret_cast<int*>(T.partial)[12] = 0;
+    float gq[7];
+    quad2rotation_vjp(T.cam, G, gq);
+    gq[4] = G[9]; gq[5] = G[10]; gq[6] = G[11];
+    for (int k = 0; k < 7; ++k) {      // same operation order as k_adam / libtorch
+        const float gk = gq[k];
+        if (T.g_out) T.g_out[k] = gk;
+        const float mm = __fadd_rn(__fmul_rn(T.m[k], T.beta1), __fmul_rn(T.om_beta1, gk));
+        const float vv = __fadd_rn(__fmul_rn(T.v[k], T.beta2), __fmul_rn(__fmul_rn(T.om_beta2, gk), gk));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), T.bc2_sqrt), T.eps);
+        T.m[k] = mm; T.v[k] = vv;
+        T.cam[k] = __fadd_rn(T.cam[k], __fdiv_rn(__fmul_rn(-T.step, mm), denom));
     }
 }
 
