@@ -375,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic.get(dom), "peak_source": pk["source"] + " bf16 dense (sustained, kernel timed inside the step)",
                 "note": "algorithmic FLOPs (SURVEY 8-d: 2 x MACs of the three decoders x 48 samples x rays surviving the inside filter) / CUDA-event time of the kernel; "
-                        "the arithmetic is the fp32-grade 3xTF32 split (3 tensor-core MMAs per product), so the design ceiling is tf32 peak / 3",
+                        "the arithmetic is the fp32-grade fp16 two-way split (3 tensor-core MMAs per product, measured warp-MMA ceiling 556 TFLOP/s), so the design ceiling is 185 TFLOP/s algorithmic",
                 "launches": K, "avg_launch_ms": kern[dom]["avg_launch_ms"], "kernels": kern,
                 "kernel_ms_total": kms,
                 "grid_sampling": {"kernel": "k_gather_only", "ms": gather_ms, "rays": RAYS_PER_GPU,
@@ -391,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
                "data": "synthetic",
                "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": n_global,
                           "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "step i = iteration i%60 of optimize_map (37 geometry + 23 colour)",
-                          "mma": "3xTF32 mma.sync (fp32-grade)", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
+                          "mma": "fp16 two-way split (3 products) on mma.sync m16n8k16, fp32 accumulate: fp32-grade", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
                           "inside_fraction": frac_in},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking,
                "loss_first_last": [float(losses[0]), float(losses[len(losses) - 1])]}

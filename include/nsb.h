@@ -41,7 +41,10 @@ extern "C" {
 #define NSB_ABI_VERSION 1
 
 enum { NSB_COARSE = 0, NSB_MIDDLE = 1, NSB_FINE = 2, NSB_COLOR = 3 }; /* grid level / decoder / stage id */
-enum { NSB_PREC_3XTF32 = 0, NSB_PREC_TF32 = 1 };   /* decoder MMA precision: fp32-grade split / plain TF32 */
+/* decoder MMA precision.  0 (default): fp32-grade -- every operand is split into fp16 hi + lo and a product is three tensor-core
+ * instructions (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate, ~2^-22 per product; it replaced a 3xTF32 split of the same
+ * accuracy, hence the historical name).  1: one fp16 product (~2^-11), fast mode, outside the 1e-4 parity target. */
+enum { NSB_PREC_3XTF32 = 0, NSB_PREC_FP32_GRADE = 0, NSB_PREC_TF32 = 1, NSB_PREC_SINGLE = 1 };
 enum { NSB_RAYDIR_REFERENCE = 0, NSB_RAYDIR_PINHOLE = 1 }; /* utils.h:44-47 as written / upstream pinhole */
 enum { NSB_DISTNORM_PER_RAY = 0, NSB_DISTNORM_REFERENCE = 1 }; /* upstream intent / utils.h:153 as written */
 
