@@ -27,9 +27,10 @@ struct GridView {
 };
 
 // ---- tensor-core helpers: mma.sync m16n8k16 f16 with fp32 accumulation, fp16 two-way split (fp32-grade accuracy) ----
-// Every fp32 operand x is carried as the pair  hi = fp16(x),  lo = fp16(x - hi)  (22 significant bits; below 6e-5 the
-// fp16 subnormal spacing leaves an absolute error <= 3e-8, far under the fp32 rounding noise of the O(0.01..10)
-// activations).  A product is three tensor-core instructions  a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  accumulated in fp32 --
+// Every fp32 operand x is carried as the pair  hi = fp16(x),  lo = fp16(x - hi):  |hi + lo - x| <= max(2^-22 |x|, 2^-25)
+// -- 22 significant bits while lo is a normal fp16 (|x| >= 0.125), and below that the half-spacing of the fp16 subnormal
+// grid, 3e-8 ABSOLUTE, far under the fp32 rounding noise of the O(0.1..10) sums these operands enter
+// (tests/test_split_numerics.py).  A product is three tensor-core instructions  a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  accumulated in fp32 --
 // the same error (~2^-22 per product, measured 3-4e-7 on the decoder outputs against fp64) as the 3xTF32 split this
 // replaces, at half the instruction count: one m16n8k16 covers 16 contraction indices where the tf32 m16n8k8 covers 8,
 // and both issue at the same rate on sm_100a (tools/microbench).
