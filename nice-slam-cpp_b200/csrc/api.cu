@@ -42,7 +42,8 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
-cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st);
+cudaError_t launch_build_wimg(const float* const flat[4], const float* const comp[4], float* const img_fwd[4], float* const img_bwd[4], float* const img_cmp[4],
+                              int mask, int cmp_mask, cudaStream_t st);
 size_t wimg_floats(int which);
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_decode_fwd_tc16(const DecodeParams& P, int grid, cudaStream_t st);
@@ -126,7 +127,10 @@ struct nsb_ctx {
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
     float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
     float* wimg_bwd[4] = {nullptr, nullptr, nullptr, nullptr};
-    int wimg_dirty = 0xE;        // bit d: decoder d's images are stale
+    float* wimg_cmp[4] = {nullptr, nullptr, nullptr, nullptr};
+    int wimg_dirty = 0xE;        // bit d: decoder d's plain forward / backward images are stale
+    int wimg_cmp_dirty = 0xE;    // bit d: decoder d's composed forward image is stale (rebuilt lazily: a colour decoder that is being
+                                 // trained changes every iteration but runs on the plain image while its stash is needed)
     unsigned long long* tile_ctr = nullptr;          // [4] ticket counters of the decoder kernels' tile scheduler (never reset)
     unsigned long long tile_ticket[4] = {0, 0, 0, 0};   // host mirror: tickets handed out by the launches enqueued so far
     int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
@@ -399,7 +403,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
-    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); }
+    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); }
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
@@ -424,7 +428,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -478,7 +482,7 @@ extern "C" int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host, int64
     if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
     CK(cudaMemcpyAsync(ctx->param + ctx->off_dec[which], host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->comp_dirty |= 1 << which; ctx->wimg_dirty |= 1 << which;
+    ctx->comp_dirty |= 1 << which; ctx->wimg_dirty |= 1 << which; ctx->wimg_cmp_dirty |= 1 << which;
     return 0;
 }
 static int get_dec(nsb_ctx* ctx, const float* base, int which, float* host, int64_t n) {
@@ -665,13 +669,22 @@ static void env_weights(const char* name, float w[4]) {
     if (sscanf(e, "%f,%f,%f,%f", &a, &b, &c, &d) == 4) { if (w[0] > 0) w[0] = a; if (w[1] > 0) w[1] = b; if (w[2] > 0) w[2] = c; if (w[3] > 0) w[3] = d; }
 }
 
-static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
+// cmp_mask: decoders whose COMPOSED forward image the coming launch reads (the plain / backward images are always kept fresh).
+static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid, int cmp_mask = 0) {
     memset(&P, 0, sizeof P);
-    if (ctx->wimg_dirty) {   // decoder weights changed (set_decoder / an Adam step with a decoder learning rate): rebuild the pre-split images
+    const int cmp_need = ctx->wimg_cmp_dirty & cmp_mask;
+    if (ctx->wimg_dirty || cmp_need) {   // decoder weights changed (set_decoder / an Adam step with a decoder learning rate): rebuild the pre-split images
         const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
-        if (launch_build_wimg(flat, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_dirty, ctx->stream) == cudaSuccess) { ctx->launches++; ctx->wimg_dirty = 0; }
+        bool ok = true;
+        if (ctx->comp_dirty & cmp_need) {   // the composed images are built from k_compose's output
+            ok = launch_compose(flat, ctx->comp, ctx->comp_dirty & cmp_need, ctx->stream) == cudaSuccess;
+            if (ok) { ctx->launches++; ctx->comp_dirty &= ~cmp_need; }
+        }
+        if (ok && launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, ctx->wimg_dirty, cmp_need, ctx->stream) == cudaSuccess) {
+            ctx->launches++; ctx->wimg_dirty = 0; ctx->wimg_cmp_dirty &= ~cmp_need;
+        }
     }
-    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; }
+    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; }
     P.bnd = ctx->bnd;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
     P.S = S; P.P = n * S;
@@ -733,7 +746,9 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
     }
     {
         Timer t(ctx, T_FWD);
-        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
+        // the forward runs on the composed images, except for a colour decoder whose activations are stashed for the weight gradient
+        const bool will_stash = train && stash_fwd && stage == NSB_COLOR;
+        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr, will_stash ? 0x6 : 0xE);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
         if (train) P.masks = ctx->masks;
@@ -1006,7 +1021,7 @@ extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts
     for (size_t o = 0; o < (size_t)Pn; o += cap_pts) {
         const int m = (int)std::min(cap_pts, (size_t)Pn - o);
         CK(cudaMemcpyAsync(ctx->pts, pts + 3 * o, 12 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr);
+        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr, 0xE);
         P.pts = ctx->pts; P.P = m;
         float w[4]; stage_decoders(stage, w);
         partition(decode_grid_size(ctx, m), w, P.cta_begin);
@@ -1079,8 +1094,8 @@ static void build_adam(nsb_ctx* ctx, AdamParams& A, int step, const float lr_gro
     A.n_seg = k;
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
-    if (dec_fine && lr_group[0] != 0.f) { ctx->comp_dirty |= 1 << 2; ctx->wimg_dirty |= 1 << 2; }
-    if (dec_color && lr_group[0] != 0.f && !color_pristine) { ctx->comp_dirty |= 1 << 3; ctx->wimg_dirty |= 1 << 3; }
+    if (dec_fine && lr_group[0] != 0.f) { ctx->comp_dirty |= 1 << 2; ctx->wimg_dirty |= 1 << 2; ctx->wimg_cmp_dirty |= 1 << 2; }
+    if (dec_color && lr_group[0] != 0.f && !color_pristine) { ctx->comp_dirty |= 1 << 3; ctx->wimg_dirty |= 1 << 3; ctx->wimg_cmp_dirty |= 1 << 3; }
 }
 
 // color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first

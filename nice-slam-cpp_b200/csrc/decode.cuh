@@ -46,8 +46,9 @@ struct DecSmem {
     static constexpr int WO = FC + 5 * FCS;             // [4][32] fp32
     static constexpr int BIAS = WO + 4 * HID;           // b[5][32]
     static constexpr int BIASC = BIAS + 5 * HID;        // bc[5][32]
-    static constexpr int BO = BIASC + 5 * HID;          // bo[4]
-    static constexpr int TOTAL = (BO + 4 + 3) & ~3;     // multiple of 4 words: the image is copied with 16-byte loads
+    static constexpr int BO = BIASC + 5 * HID;          // bo[4]   (composed image: Wo bc_4 + bo)
+    static constexpr int WOC = BO + 4;                  // composed image only: (Wo Fc_4)[4][C] fp32, natural channel order
+    static constexpr int TOTAL = (WOC + 4 * C + 3) & ~3;   // multiple of 4 words: the image is copied with 16-byte loads
     __host__ __device__ static constexpr int w(int i) { return i == 0 ? W0 : i == 1 ? W1 : i == 2 ? W2 : i == 3 ? W3H : W4; }
 };
 static_assert(EMBP * wstride(HID) >= HID * wstride(EMBP), "W0 slot must hold both orientations");
@@ -145,6 +146,33 @@ struct TileQueue {
         return (int)tile;
     }
 };
+
+// Composed forward image (k_compose, the algebra of the tcgen05 kernels): with h_{i+1} = relu(a_i) + Fc_i c + bc_i and
+// a_{i+1} = W_{i+1} h_{i+1} + b_{i+1} the grid-feature term moves into the NEXT layer's pre-activation,
+//     a_{i+1} = W_{i+1} relu(a_i) + G_i c + b'_{i+1},   G_i = W_{i+1} Fc_i,   b'_{i+1} = b_{i+1} + W_{i+1} bc_i,
+// so that the c-term MMAs of layer i+1 no longer depend on layer i's relu and overlap its epilogue.  FC slot l holds G_l
+// (l = 0..3), BIAS holds b', WOC / BO the grid-feature part and the constant of the output layer.  comp: layout of k_compose.
+template <int C, int O>
+__device__ void stage_decoder_composed(float* sm, const float* __restrict__ flat, const float* __restrict__ comp, int tid, int nthr) {
+    using L = DecSmem<C>;
+    const DecFlat f = DecFlat::make(C, O);
+    for (int i = tid; i < 3 * EMBP; i += nthr) {
+        const int d = i / EMBP, c = i % EMBP;
+        sm[L::B + i] = c < EMB ? flat[f.B + d * EMB + c] : 0.0f;
+    }
+    stage_matrix(sm, L::W0, EMBP, HID, tid, nthr, [&](int o, int pos) { return pos < EMB ? flat[f.W[0] + o * EMB + pos] : 0.0f; });
+    stage_matrix(sm, L::W3E, EMBP, HID, tid, nthr, [&](int o, int pos) { return pos < EMB ? flat[f.W[3] + o * (EMB + HID) + pos] : 0.0f; });
+    stage_matrix(sm, L::W1, HID, HID, tid, nthr, [&](int o, int pos) { return flat[f.W[1] + o * HID + perm16(pos)]; });
+    stage_matrix(sm, L::W2, HID, HID, tid, nthr, [&](int o, int pos) { return flat[f.W[2] + o * HID + perm16(pos)]; });
+    stage_matrix(sm, L::W3H, HID, HID, tid, nthr, [&](int o, int pos) { return flat[f.W[3] + o * (EMB + HID) + EMB + perm16(pos)]; });
+    stage_matrix(sm, L::W4, HID, HID, tid, nthr, [&](int o, int pos) { return flat[f.W[4] + o * HID + perm16(pos)]; });
+    for (int l = 0; l < 4; ++l)      // G_l [32][C] at comp[l * 32 * C]
+        stage_matrix(sm, L::FC + l * L::FCS, C, HID, tid, nthr, [&](int o, int pos) { return comp[(l * HID + o) * C + fc_channel_fwd(pos)]; });
+    for (int i = tid; i < 4 * HID; i += nthr) sm[L::WO + i] = (i / HID) < O ? flat[f.Wo + i] : 0.0f;
+    for (int i = tid; i < 5 * HID; i += nthr) { sm[L::BIAS + i] = comp[4 * HID * C + i]; sm[L::BIASC + i] = 0.0f; }       // b'[5][32]
+    for (int i = tid; i < 4 * C; i += nthr) sm[L::WOC + i] = comp[4 * HID * C + 5 * HID + i];                            // woc[4][C]
+    if (tid < 4) sm[L::BO + tid] = comp[4 * HID * C + 5 * HID + 4 * C + tid];                                            // boc[4]
+}
 
 __device__ __forceinline__ const uint32_t* wmat(const float* sm, int off) { return reinterpret_cast<const uint32_t*>(sm + off); }
 
@@ -286,6 +314,71 @@ __device__ __forceinline__ void decoder_forward(const float* __restrict__ sm, co
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
         float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 w = *reinterpret_cast<const float2*>(sm + L::WO + o * HID + 8 * j + 2 * t);
+            s0 = fmaf(h[j][0], w.x, s0); s0 = fmaf(h[j][1], w.y, s0);
+            s1 = fmaf(h[j][2], w.x, s1); s1 = fmaf(h[j][3], w.y, s1);
+        }
+        out[0][o] = quad_sum(s0) + sm[L::BO + o];
+        out[1][o] = quad_sum(s1) + sm[L::BO + o];
+    }
+}
+
+// Same on the composed image (stage_decoder_composed): the grid-feature term of every layer is accumulated into that layer's
+// pre-activation BEFORE the previous layer's relu is needed, so those MMAs run while the relu / fp16 split of the previous layer
+// occupies the ALUs.  No stash variant: the weight gradient needs the uncomposed block outputs.
+template <int C, int O, bool P3>
+__device__ __forceinline__ void decoder_forward_composed(const float* __restrict__ sm, const float (&p)[2][3],
+                                                         const float (&c)[2][C / 4], int g, int t, float (&out)[2][4],
+                                                         uint32_t (&masks)[5]) {
+    using L = DecSmem<C>;
+    float acc[4][4], accS[4][4], nxt[4][4], h[4][4];
+    AFrag<P3> ca[C / 16];
+#pragma unroll
+    for (int kk = 0; kk < C / 16; ++kk)
+        ca[kk].set(c[0][4 * kk], c[0][4 * kk + 1], c[0][4 * kk + 2], c[0][4 * kk + 3], c[1][4 * kk], c[1][4 * kk + 1], c[1][4 * kk + 2], c[1][4 * kk + 3]);
+    // grid-feature part of the output layer, per lane over its channels (finished by the quad sum below)
+    constexpr int NO = O == 4 ? 3 : 1;
+    float oc[2][NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        oc[0][o] = oc[1][o] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < C / 32; ++b)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float w = sm[L::WOC + o * C + 32 * b + 8 * t + i];
+                oc[0][o] = fmaf(c[0][8 * b + i], w, oc[0][o]); oc[1][o] = fmaf(c[1][8 * b + i], w, oc[1][o]);
+            }
+    }
+    embed_layers<C, P3, false>(sm, p, g, t, acc, accS, nullptr, nullptr);      // acc = b'_0 + W0 e, accS = b'_3 + W3e e
+    add_cterm<C, P3>(sm, 2, ca, g, t, accS);                                    // + G_2 c
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        // pre-activation of the NEXT layer starts with its bias and grid-feature term: independent of this layer's relu
+        if (i == 0 || i == 1 || i == 3) {
+            init_bias(nxt, sm + L::BIAS + (i + 1) * HID, t);
+            add_cterm<C, P3>(sm, i, ca, g, t, nxt);                             // G_i c
+        }
+        masks[i] = relu_mask(h, acc);
+        if (i < 4) {
+            float (&dst)[4][4] = (i == 2) ? accS : nxt;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                AFrag<P3> a;
+                afrag_from_c<P3>(a, h[2 * kk], h[2 * kk + 1]);
+                kstep_fwd<P3, 4>(dst, a, wmat(sm, L::w(i + 1)), L::SH, kk, g, t);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[j][q] = dst[j][q];
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        float s0 = oc[0][o], s1 = oc[1][o];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 w = *reinterpret_cast<const float2*>(sm + L::WO + o * HID + 8 * j + 2 * t);

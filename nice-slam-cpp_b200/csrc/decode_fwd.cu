@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
     for (int d = 1; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
     const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
     if (dec == 0) stage_coarse(sm, P.dec_flat[0], threadIdx.x, blockDim.x);
-    else if (dec == 2) load_decoder_image<64>(sm, P.wimg_fwd[2], threadIdx.x, blockDim.x);
-    else load_decoder_image<32>(sm, P.wimg_fwd[dec], threadIdx.x, blockDim.x);
+    // decoders 1 / 2 and the colour decoder without a stash run on the composed image (decoder_forward_composed)
+    else if (dec == 2) load_decoder_image<64>(sm, P.wimg_cmp[2], threadIdx.x, blockDim.x);
+    else load_decoder_image<32>(sm, (dec == 3 && TRAIN && P.stash) ? P.wimg_fwd[3] : P.wimg_cmp[dec], threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (P.P + TILE - 1) / TILE;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
             gather8(P.grid[dec], P.bnd, p[0], t, c[0]);
             gather8(P.grid[dec], P.bnd, p[1], t, c[1]);
             if (dec == 1) {
-                decoder_forward<32, 1, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+                decoder_forward_composed<32, 1, P3>(sm, p, c, g, t, out, masks);
                 if (TRAIN) save_masks(P, 1, tile, ntiles, lane, masks);
                 if (t == 0) {
 #pragma unroll
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
                     *reinterpret_cast<float4*>(st1 + stash::Cc + 8 * t + 4) = make_float4(c[1][4], c[1][5], c[1][6], c[1][7]);
                     decoder_forward<32, 4, P3, TRAIN>(sm, p, c, g, t, out, masks, h, st0, st1);
                 } else {
-                    decoder_forward<32, 4, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+                    decoder_forward_composed<32, 4, P3>(sm, p, c, g, t, out, masks);
                 }
                 if (TRAIN) save_masks(P, 3, tile, ntiles, lane, masks);
                 if (t == 0) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
                 gather8(P.grid[2], P.bnd, p[r], t, c[r]);          // fine features ...
                 gather8(P.grid[1], P.bnd, p[r], t, c[r] + 8);      // ... cat middle features (MLP.cpp:79-84)
             }
-            decoder_forward<64, 1, P3, false>(sm, p, c, g, t, out, masks, h, nullptr, nullptr);
+            decoder_forward_composed<64, 1, P3>(sm, p, c, g, t, out, masks);
             if (TRAIN) save_masks(P, 2, tile, ntiles, lane, masks);
             if (t == 0) {
 #pragma unroll
@@ -148,18 +149,28 @@ cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cuda
     return cudaGetLastError();
 }
 
-// Builds the pre-split shared-memory images of the decoders in `mask` (bit d), both orientations: blockIdx.y = 2 (d - 1) + orientation.
-__global__ void __launch_bounds__(512) k_build_wimg(const float* f1, const float* f2, const float* f3, float* o1f, float* o1b, float* o2f, float* o2b,
-                                                    float* o3f, float* o3b, int mask) {
-    const int d = 1 + blockIdx.y / 2, bwd = blockIdx.y & 1;
-    if (!((mask >> d) & 1)) return;
+// Builds the pre-split shared-memory images of the decoders in `mask` (bit d): blockIdx.y = 3 (d - 1) + kind, kind 0 = forward
+// (plain, only the colour decoder needs it: stash iterations), 1 = backward (transposed), 2 = forward composed (reads k_compose's output).
+struct WimgParams { const float* flat[4]; const float* comp[4]; float* fwd[4]; float* bwd[4]; float* cmp[4]; int mask, cmp_mask; };
+__global__ void __launch_bounds__(512) k_build_wimg(WimgParams W) {
+    const int d = 1 + blockIdx.y / 3, kind = blockIdx.y % 3;
+    if (!(((kind == 2 ? W.cmp_mask : W.mask) >> d) & 1)) return;
+    if (kind == 0 && d != 3) return;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    if (d == 1) { if (bwd) stage_decoder<32, 1, true>(o1b, f1, tid, nthr); else stage_decoder<32, 1, false>(o1f, f1, tid, nthr); }
-    else if (d == 2) { if (bwd) stage_decoder<64, 1, true>(o2b, f2, tid, nthr); else stage_decoder<64, 1, false>(o2f, f2, tid, nthr); }
-    else { if (bwd) stage_decoder<32, 4, true>(o3b, f3, tid, nthr); else stage_decoder<32, 4, false>(o3f, f3, tid, nthr); }
+    if (d == 1) { if (kind == 1) stage_decoder<32, 1, true>(W.bwd[1], W.flat[1], tid, nthr); else stage_decoder_composed<32, 1>(W.cmp[1], W.flat[1], W.comp[1], tid, nthr); }
+    else if (d == 2) { if (kind == 1) stage_decoder<64, 1, true>(W.bwd[2], W.flat[2], tid, nthr); else stage_decoder_composed<64, 1>(W.cmp[2], W.flat[2], W.comp[2], tid, nthr); }
+    else {
+        if (kind == 0) stage_decoder<32, 4, false>(W.fwd[3], W.flat[3], tid, nthr);
+        else if (kind == 1) stage_decoder<32, 4, true>(W.bwd[3], W.flat[3], tid, nthr);
+        else stage_decoder_composed<32, 4>(W.cmp[3], W.flat[3], W.comp[3], tid, nthr);
+    }
 }
-cudaError_t launch_build_wimg(const float* const flat[4], float* const img_fwd[4], float* const img_bwd[4], int mask, cudaStream_t st) {
-    k_build_wimg<<<dim3(24, 6), 512, 0, st>>>(flat[1], flat[2], flat[3], img_fwd[1], img_bwd[1], img_fwd[2], img_bwd[2], img_fwd[3], img_bwd[3], mask);
+cudaError_t launch_build_wimg(const float* const flat[4], const float* const comp[4], float* const img_fwd[4], float* const img_bwd[4], float* const img_cmp[4],
+                              int mask, int cmp_mask, cudaStream_t st) {
+    WimgParams W;
+    for (int d = 0; d < 4; ++d) { W.flat[d] = flat[d]; W.comp[d] = comp[d]; W.fwd[d] = img_fwd[d]; W.bwd[d] = img_bwd[d]; W.cmp[d] = img_cmp[d]; }
+    W.mask = mask; W.cmp_mask = cmp_mask;
+    k_build_wimg<<<dim3(24, 9), 512, 0, st>>>(W);
     return cudaGetLastError();
 }
 size_t wimg_floats(int which) { return which == 2 ? DecSmem<64>::TOTAL : DecSmem<32>::TOTAL; }
