@@ -112,8 +112,16 @@ __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid
         stage_matrix(sm, L::W2, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[2] + perm16(pos) * HID + n]; });
         stage_matrix(sm, L::W3H, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[3] + perm16(pos) * (EMB + HID) + EMB + n]; });
         stage_matrix(sm, L::W4, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[4] + perm16(pos) * HID + n]; });
-        for (int l = 0; l < 5; ++l)
-            stage_matrix(sm, L::FC + l * HID * L::SH, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.Fc[l] + perm16(pos) * C + fc_channel_bwd(n)]; });
+        // the FC slots of the backward image hold the composed matrices G_l^T: written by stage_backward_G (block-cooperative)
+        for (int i = tid; i < 4 * C; i += nthr) {        // (Wo Fc_4)[o][ch]
+            const int o = i / C, ch = i % C;
+            float acc = 0.0f;
+            if (o < O) {
+#pragma unroll 8
+                for (int m = 0; m < HID; ++m) acc = fmaf(__ldg(flat + f.Wo + o * HID + m), __ldg(flat + f.Fc[4] + m * C + ch), acc);
+            }
+            sm[L::WOC + i] = acc;
+        }
     }
     for (int i = tid; i < 4 * HID; i += nthr) sm[L::WO + i] = (i / HID) < O ? flat[f.Wo + i] : 0.0f;
     for (int i = tid; i < 5 * HID; i += nthr) {
@@ -121,6 +129,32 @@ __device__ void stage_decoder(float* sm, const float* __restrict__ flat, int tid
         sm[L::BIASC + i] = flat[f.bc[i / HID] + i % HID];
     }
     if (tid < 4) sm[L::BO + tid] = tid < O ? flat[f.bo + tid] : 0.0f;
+}
+
+// Grid-feature gradient through the composed matrices: g_c = g_out (Wo Fc_4) + sum_{l<4} g_u_{l+1} G_l, G_l = W_{l+1} Fc_l (the
+// same algebra as the forward), so the product shares its A fragments (the masked g_u) with the main chain.  FC slot l of the
+// backward image holds G_l^T restricted to the 32 input channels that carry gradient.  One thread block builds one slot: W_{l+1}
+// and Fc_l go through shared memory (this runs after every update of a trained decoder, so it must not be latency-bound).
+template <int C, int O>
+__device__ void stage_backward_G(float* img, const float* __restrict__ flat, int l) {
+    using L = DecSmem<C>;
+    __shared__ float sW[HID][HID + 1], sF[HID][HID + 1];
+    const DecFlat f = DecFlat::make(C, O);
+    const float* Wn = flat + f.W[l + 1] + (l == 2 ? EMB : 0);
+    const int ldw = l == 2 ? EMB + HID : HID;
+    for (int i = threadIdx.x; i < HID * HID; i += blockDim.x) {
+        const int r = i / HID, c = i % HID;
+        sW[r][c] = Wn[r * ldw + c];                          // W_{l+1}[o][m]
+        sF[r][c] = flat[f.Fc[l] + r * C + c];                // Fc_l[m][channel], first 32 channels
+    }
+    __syncthreads();
+    stage_matrix(img, L::FC + l * HID * L::SH, HID, HID, threadIdx.x, blockDim.x, [&](int n, int pos) {
+        const int o = perm16(pos), ch = fc_channel_bwd(n);
+        float acc = 0.0f;
+#pragma unroll
+        for (int m = 0; m < HID; ++m) acc = fmaf(sW[o][m], sF[m][ch], acc);
+        return acc;
+    });
 }
 
 // Copy a decoder's pre-split image (built once per weight update by k_build_wimg, same layout as stage_decoder writes) from

@@ -102,18 +102,21 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
             gh[j][2] = fmaf(gout[1][o], w.x, gh[j][2]); gh[j][3] = fmaf(gout[1][o], w.y, gh[j][3]);
         }
     }
-    if (NEED_C) zero_tile(gc);
+    if (NEED_C) {   // g_c starts with the output layer's share g_out (Wo Fc_4); accumulator column 8j+2t+b <-> channel fc_channel_bwd(.)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int ch = fc_channel_bwd(8 * j + 2 * t + b);
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int o = 0; o < NO; ++o) { const float w = sm[L::WOC + o * C + ch]; s0 = fmaf(gout[0][o], w, s0); s1 = fmaf(gout[1][o], w, s1); }
+                gc[j][b] = s0; gc[j][2 + b] = s1;
+            }
+    }
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
         if (STASH) stash_tile(st0, st1, stash::GH + HID * i, gh, t);
-        if (NEED_C) {   // g_c += g_h Fc_i  (only the first 32 input columns carry gradient)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                AFrag<P3> a;
-                afrag_from_c<P3>(a, gh[2 * kk], gh[2 * kk + 1]);
-                kstep_fwd<P3, 4>(gc, a, wmat(sm, L::FC + i * HID * L::SH), L::SH, kk, g, t);   // Fc_i^T [in][out]
-            }
-        }
         apply_mask(gu, gh, masks[i]);
         if (STASH) stash_tile(st0, st1, stash::GU + HID * i, gu, t);
         if (NEED_E && i == 3) {
@@ -129,13 +132,14 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
 #pragma unroll
                     for (int q = 0; q < 4; ++q) gu0[j][q] = gu[j][q];
             }
-        } else {   // g_h_i = g_u W_i
+        } else {   // g_h_i = g_u W_i, and with the same A fragments g_c += g_u G_{i-1} (composed grid-feature path)
             zero_tile(gh);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 AFrag<P3> a;
                 afrag_from_c<P3>(a, gu[2 * kk], gu[2 * kk + 1]);
                 kstep_fwd<P3, 4>(gh, a, wmat(sm, L::w(i)), L::SH, kk, g, t);                // W_i^T
+                if (NEED_C) kstep_fwd<P3, 4>(gc, a, wmat(sm, L::FC + (i - 1) * HID * L::SH), L::SH, kk, g, t);   // G_{i-1}^T [channel][out]
             }
         }
     }

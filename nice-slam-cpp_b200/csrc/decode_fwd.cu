@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(512) k_build_wimg(WimgParams W) {
     const int d = 1 + blockIdx.y / 3, kind = blockIdx.y % 3;
     if (!(((kind == 2 ? W.cmp_mask : W.mask) >> d) & 1)) return;
     if (kind == 0 && d != 3) return;
+    if (kind == 1 && blockIdx.x < 4) {   // the composed G_l^T slots of the backward image: one block each
+        if (d == 1) stage_backward_G<32, 1>(W.bwd[1], W.flat[1], blockIdx.x);
+        else if (d == 2) stage_backward_G<64, 1>(W.bwd[2], W.flat[2], blockIdx.x);
+        else stage_backward_G<32, 4>(W.bwd[3], W.flat[3], blockIdx.x);
+    }
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     if (d == 1) { if (kind == 1) stage_decoder<32, 1, true>(W.bwd[1], W.flat[1], tid, nthr); else stage_decoder_composed<32, 1>(W.cmp[1], W.flat[1], W.comp[1], tid, nthr); }
     else if (d == 2) { if (kind == 1) stage_decoder<64, 1, true>(W.bwd[2], W.flat[2], tid, nthr); else stage_decoder_composed<64, 1>(W.cmp[2], W.flat[2], W.comp[2], tid, nthr); }
