@@ -24,7 +24,8 @@ UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("decode_fwd_tc.cu", []), ("deco
 VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC_TIMING"],
             # occupancy experiments: warps per CTA of the forward / backward decoder kernels
             "f20b20": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=20"], "f16b24": ["-DNSB_BWD_WARPS=24"], "f20b24": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=24"],
-            "f24b24": ["-DNSB_FWD_WARPS=24", "-DNSB_BWD_WARPS=24"], "f16b20": ["-DNSB_BWD_WARPS=20"]}
+            "f24b24": ["-DNSB_FWD_WARPS=24", "-DNSB_BWD_WARPS=24"], "f16b20": ["-DNSB_BWD_WARPS=20"],
+            "emb1": ["-DNSB_EMB_UNROLL=1"], "emb3": ["-DNSB_EMB_UNROLL=3"], "emb6": ["-DNSB_EMB_UNROLL=6"]}
 
 
 def lib_path(variant=""):

@@ -7,7 +7,13 @@
 #include "common.cuh"
 #include "params.h"
 
+#ifndef NSB_EMB_UNROLL
+#define NSB_EMB_UNROLL 2   // k-steps of the embedding loop unrolled together (tools/sweep_variants.sh: 1 / 2 / 3 / 6 measured)
+#endif
+
 namespace nsb {
+
+constexpr int EMB_UNROLL = NSB_EMB_UNROLL;
 
 // Offsets (floats) of one decoder inside its flat parameter vector (layout documented in include/nsb.h).
 struct DecFlat {
@@ -251,7 +257,7 @@ __device__ __forceinline__ void embed_layers(const float* __restrict__ sm, const
     using L = DecSmem<C>;
     init_bias(acc0, sm + L::BIAS + 0 * HID, t);
     init_bias(accS, sm + L::BIAS + 3 * HID, t);
-#pragma unroll 2
+#pragma unroll EMB_UNROLL
     for (int kk = 0; kk < EMBP / 16; ++kk) {
         const int f0 = 16 * kk + 4 * t;
         const float4 B0 = *reinterpret_cast<const float4*>(sm + L::B + f0);

@@ -1,5 +1,5 @@
 # Times the build variants (NSB_VARIANT=<name of build.py VARIANTS>) with the default bench.
-for v in "" f20b20 f16b24 f20b24 f24b24; do NSB_VARIANT=$v python bench.py --no-cpu-baseline --steps 60 2>/dev/null | python -c "
+for v in ${VARIANTS:-"" f20b20 f16b24 f20b24 f24b24}; do NSB_VARIANT=$v python bench.py --no-cpu-baseline --steps 60 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
