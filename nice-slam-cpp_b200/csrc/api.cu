@@ -451,6 +451,7 @@ static int ensure_scratch(nsb_ctx* ctx, size_t n) {
 }
 
 extern "C" int nsb_set_grid(nsb_ctx* ctx, int level, const float* host) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     const size_t n = ctx->nvox[level] * CDIM;
     if (ensure_scratch(ctx, n)) return -1;
@@ -471,14 +472,17 @@ static int get_cl(nsb_ctx* ctx, const float* src, int level, float* host) {
     return 0;
 }
 extern "C" int nsb_get_grid(nsb_ctx* ctx, int level, float* host) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     return get_cl(ctx, ctx->param + ctx->off_grid[level], level, host);
 }
 extern "C" int nsb_get_grid_grad(nsb_ctx* ctx, int level, float* host) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     return get_cl(ctx, ctx->grad + ctx->off_grid[level], level, host);
 }
 extern "C" int nsb_set_decoder(nsb_ctx* ctx, int which, const float* host, int64_t n) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (which < 0 || which > 3 || n != ctx->dec_n[which]) return fail(ctx, "decoder %d: expected %lld floats, got %lld", which, (long long)ctx->dec_n[which], (long long)n);
     CK(cudaMemcpyAsync(ctx->param + ctx->off_dec[which], host, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -494,12 +498,14 @@ static int get_dec(nsb_ctx* ctx, const float* base, int which, float* host, int6
 extern "C" int nsb_get_decoder(nsb_ctx* ctx, int which, float* host, int64_t n) { return get_dec(ctx, ctx->param, which, host, n); }
 extern "C" int nsb_get_decoder_grad(nsb_ctx* ctx, int which, float* host, int64_t n) { return get_dec(ctx, ctx->grad, which, host, n); }
 extern "C" int nsb_set_ttables(nsb_ctx* ctx, const float* t32, const float* t16) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     CK(cudaMemcpyAsync(ctx->t_samples, t32, 32 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->t_surface, t16, 16 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 extern "C" int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     if (!host) { if (ctx->vmask[level]) { cudaFree(ctx->vmask[level]); ctx->vmask[level] = nullptr; } return 0; }
     if (!ctx->vmask[level]) CK(dalloc(&ctx->vmask[level], ctx->nvox[level]));
@@ -510,6 +516,7 @@ extern "C" int nsb_set_voxel_mask(nsb_ctx* ctx, int level, const uint8_t* host) 
 // Mapper::get_mask_from_c2w (Mapper.cpp:42-130): frustum voxel mask of grid `level` for the depth frame in `slot` seen from
 // c2w16 (NULL = the slot's pose).  host_mask_zyx (Z*Y*X bytes) may be NULL; install != 0 makes it the level's Adam mask.
 extern "C" int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int level, uint8_t* host_mask_zyx, int install) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
@@ -557,12 +564,14 @@ extern "C" int nsb_frustum_mask(nsb_ctx* ctx, int slot, const float* c2w16, int 
 }
 
 extern "C" int nsb_set_frame_pose(nsb_ctx* ctx, int slot, const float* c2w16) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 extern "C" int nsb_set_frame(nsb_ctx* ctx, int slot, const float* depth, const float* color, const float* c2w16) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     const size_t hw = (size_t)ctx->cfg.H * ctx->cfg.W;
     CK(cudaMemcpyAsync(ctx->f_depth + hw * slot, depth, hw * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -575,6 +584,7 @@ extern "C" int nsb_set_frame(nsb_ctx* ctx, int slot, const float* depth, const f
 // nsb_host_alloc) host buffers while the compute stream keeps iterating; the next call that samples frames waits for it on the
 // device (event), not on the host.  The caller keeps the buffers alive until nsb_frames_ready or the next synchronising call.
 extern "C" int nsb_set_frame_async(nsb_ctx* ctx, int slot, const float* depth, const float* color, const float* c2w16) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     const size_t hw = (size_t)ctx->cfg.H * ctx->cfg.W;
     CK(cudaMemcpyAsync(ctx->f_depth + hw * slot, depth, hw * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
@@ -592,6 +602,7 @@ extern "C" int nsb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? 
 // grids in the reference's (1,C,Z,Y,X) layout, decoders as the flat vectors of nsb_set_decoder -------------------------------------
 struct CkptHeader { char magic[8]; int32_t abi, c_dim, gdim[4][3]; int64_t dec_n[4]; };
 extern "C" int nsb_save_checkpoint(nsb_ctx* ctx, const char* path) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     FILE* f = fopen(path, "wb");
     if (!f) return fail(ctx, "cannot open %s for writing", path);
     CkptHeader h; memset(&h, 0, sizeof h); memcpy(h.magic, "NSBCKPT1", 8); h.abi = NSB_ABI_VERSION; h.c_dim = CDIM;
@@ -612,6 +623,7 @@ extern "C" int nsb_save_checkpoint(nsb_ctx* ctx, const char* path) {
     return ok ? 0 : fail(ctx, "short write to %s", path);
 }
 extern "C" int nsb_load_checkpoint(nsb_ctx* ctx, const char* path) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     FILE* f = fopen(path, "rb");
     if (!f) return fail(ctx, "cannot open %s", path);
     CkptHeader h;
@@ -881,6 +893,7 @@ static void fill_sample_params(nsb_ctx* ctx, SampleParams& P, int n, int H0, int
 
 extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H0, int H1, int W0, int W1, int n, const int64_t* idx,
                                float* rays_o, float* rays_d, float* gt_depth, float* gt_color, uint8_t* inside, int64_t* idx_out) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
@@ -914,6 +927,7 @@ static int render_prepare_stats(nsb_ctx* ctx, int n, bool have_depth) {
 
 extern "C" int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const float* d_rays_d, const float* d_rays_o, const float* d_gt_depth,
                                         float* d_rgb, float* d_depth, float* d_var, float* d_weights) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     const bool hd = d_gt_depth != nullptr;
@@ -939,6 +953,7 @@ static int upload_rays(nsb_ctx* ctx, int n, const float* rays_d, const float* ra
 
 extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o, const float* gt_depth,
                                     float* rgb, float* depth, float* var, float* weights) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     if (n <= 0) return 0;
     const bool hd = gt_depth != nullptr;
@@ -968,6 +983,7 @@ extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float*
 // rendered in chunks of max_rays.  The batch-global scalars of Renderer.cpp:76,93 (and utils.h:153 in reference mode) are
 // taken over the whole image in a first pass, exactly as one render_batch_ray call over all pixels would.
 extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int stage, int use_gt_depth, float* rgb, float* depth, float* var) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
@@ -1007,6 +1023,7 @@ extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int st
 }
 
 extern "C" int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (n != ctx->last_n || S != ctx->last_S) return fail(ctx, "last render was %d x %d, asked %d x %d", ctx->last_n, ctx->last_S, n, S);
     CK(cudaMemcpyAsync(z, ctx->z, 4 * (size_t)n * S, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1014,6 +1031,7 @@ extern "C" int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z) {
 }
 
 extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts, float* raw) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     const nsb_config& c = ctx->cfg;
     const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
@@ -1047,6 +1065,7 @@ extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts
 
 extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_d, const float* rays_o, const float* gt_depth,
                               const float* g_rgb, const float* g_depth, const float* g_var, int flags, float* d_rays_d, float* d_rays_o) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (n > ctx->cap) return fail(ctx, "n %d exceeds max_rays %d", n, ctx->cap);
     if (stage < 1 || stage > 3) return fail(ctx, "vjp supports stages middle/fine/color");
     const bool hd = gt_depth != nullptr;
@@ -1135,12 +1154,14 @@ static int stage_of_iter(const nsb_config& c, int it, int n_iters) {   // Mapper
 }
 
 extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     return nsb_mapping_begin_ba(ctx, n_frames, slots, n_iters, lr_factor, 0u);
 }
 
 // ba_mask bit f: frame f's pose joins the optimisation as a 7-vector (Mapper.cpp:305-329: every frame of optimize_frame but
 // the oldest one when BA is on); its lr is BA_cam_lr in the colour stage and 0 before (Mapper.cpp:366-368).
 extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (n_frames < 1 || n_frames > MAX_OPT_FRAMES) return fail(ctx, "n_frames %d out of range", n_frames);
     if (n_frames > ctx->cfg.max_frames) return fail(ctx, "n_frames %d exceeds max_frames %d", n_frames, ctx->cfg.max_frames);
@@ -1190,6 +1211,7 @@ extern "C" int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, in
 }
 
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     const nsb_config& c = ctx->cfg;
     if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
     if (wait_uploads(ctx)) return -1;
@@ -1299,6 +1321,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
 // Bundle-adjustment write-back (Mapper.cpp:467-489): est_c2w of every optimised frame <- get_camera_from_tensor(camera_tensor).
 // cam7s_out ([n_frames][7], may be NULL) receives the optimised 7-vectors (frames outside the mask: their initial pose).
 extern "C" int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (!ctx->map_ba_mask) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
     const int nf = ctx->map_frames;
     std::vector<float> cams(8 * (size_t)nf);
@@ -1316,6 +1339,7 @@ extern "C" int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out) {
 }
 // d L / d (q, t) of the optimised frames at the last bundle-adjustment iteration ([n_frames][7]; zeros outside the mask).
 extern "C" int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     std::vector<float> h(8 * (size_t)ctx->map_frames);
     CK(cudaMemcpyAsync(h.data(), ctx->cam_grad_last, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1323,6 +1347,7 @@ extern "C" int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s) {
     return 0;
 }
 extern "C" int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     CK(cudaMemcpyAsync(c2w12, ctx->f_pose + 12 * slot, 12 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1332,6 +1357,7 @@ extern "C" int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12) {
 // Pre-load pixel indices for n_iters iterations ([n_iters][n] int64, host) so that nsb_mapping_iter(idx = NULL) runs
 // with every input already resident in HBM; rows are consumed in order, wrapping around.  NULL clears the pool.
 extern "C" int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (ctx->idx_pool) { cudaFree(ctx->idx_pool); ctx->idx_pool = nullptr; ctx->pool_iters = ctx->pool_n = 0; }
     if (!host_idx) return 0;
     CK(dalloc(&ctx->idx_pool, (size_t)n_iters * n));
@@ -1342,6 +1368,7 @@ extern "C" int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx,
 }
 
 extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses, int* n_inside) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     std::vector<float> h(4 * (size_t)n);
     for (int i = 0; i < n; ++i)
         CK(cudaMemcpyAsync(h.data() + 4 * i, ctx->stats + 4 * ((first + i) % LOSS_RING), 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1354,12 +1381,14 @@ extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses,
 }
 
 extern "C" int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (nsb_mapping_iter_async(ctx, iter, idx)) return -1;
     if (loss) return nsb_mapping_losses(ctx, ctx->map_step - 1, 1, loss, nullptr);
     return 0;
 }
 
 extern "C" int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, float* losses) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (nsb_mapping_begin(ctx, n_frames, slots, n_iters, lr_factor)) return -1;
     for (int it = 0; it < n_iters; ++it) if (nsb_mapping_iter_async(ctx, it, nullptr)) return -1;
     if (losses) { for (int o = 0; o < n_iters; o += LOSS_RING) if (nsb_mapping_losses(ctx, o, std::min(LOSS_RING, n_iters - o), losses + o, nullptr)) return -1; }
@@ -1384,6 +1413,7 @@ static void invert_pose(const float* c2w12, float* w2c12) {
 
 extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const float* cur_c2w16, int n_kf, const float* kf_c2w16, int k_overlap,
                                               const int64_t* idx, int pixels, int n_samples, int* selected, int* n_selected, float* percent_out) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     *n_selected = 0;
     if (n_kf <= 0) return 0;
     if (wait_uploads(ctx)) return -1;
@@ -1425,6 +1455,7 @@ extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const 
 
 // ---- tracking -----------------------------------------------------------------------------------------------------------
 extern "C" int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (slot < 0 || slot >= ctx->cfg.max_frames) return fail(ctx, "bad frame slot %d", slot);
     if (ctx->cfg.tracking_pixels > ctx->cap) return fail(ctx, "tracking_pixels %d exceeds max_rays %d", ctx->cfg.tracking_pixels, ctx->cap);
@@ -1436,6 +1467,7 @@ extern "C" int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7) {
 }
 
 extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, float* cam_grad7) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     const nsb_config& c = ctx->cfg;
     const int n = c.tracking_pixels;
     const int H0 = c.ignore_edge_H, H1 = c.H - c.ignore_edge_H, W0 = c.ignore_edge_W, W1 = c.W - c.ignore_edge_W;   // Tracker.cpp:46
@@ -1503,6 +1535,7 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
 }
 
 extern "C" int nsb_tracking_get_camera(nsb_ctx* ctx, float* cam7) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     CK(cudaMemcpyAsync(cam7, ctx->param + ctx->off_cam, 28, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1517,6 +1550,7 @@ extern "C" int nsb_comm_unique_id(char* id128) {
     return 0;
 }
 extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int world) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (!g_nccl.load()) return fail(ctx, "libnccl.so.2 not found");
     ncclUniqueId id; memcpy(id.internal, id128, 128);
     CK(cudaSetDevice(ctx->device));
@@ -1527,6 +1561,7 @@ extern "C" int nsb_comm_init(nsb_ctx* ctx, const char* id128, int rank, int worl
 }
 // ---- peer-memory mode: CUDA IPC handles of {gradient arena, parameter arena, flag block} ----------------------------------------
 extern "C" int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     cudaIpcMemHandle_t h[3];
     CK(cudaSetDevice(ctx->device));
     CK(cudaIpcGetMemHandle(&h[0], ctx->grad)); CK(cudaIpcGetMemHandle(&h[1], ctx->param)); CK(cudaIpcGetMemHandle(&h[2], ctx->p2p_flags));
@@ -1537,6 +1572,7 @@ extern "C" int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192) {
 // all_handles: [world][192] gathered from every rank's nsb_comm_p2p_export (rank order).  After this call the mapping iteration
 // replaces ncclAllReduce + Adam by k_reduce_adam.  The caller must put a host barrier between the imports and the first iteration.
 extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (!all_handles) { ctx->p2p = false; return 0; }   // back to the NCCL path (e.g. another rank could not open the handles)
     if (world < 2 || world > P2P_MAX_WORLD) return fail(ctx, "peer-memory mode supports 2..%d ranks, got %d", P2P_MAX_WORLD, world);
     if (ctx->comm && (rank != ctx->rank || world != ctx->world)) return fail(ctx, "rank/world differ from nsb_comm_init");
@@ -1557,6 +1593,7 @@ extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank 
 // Grid sampling alone on the rays / z values of the last forward (n rays, S samples): returns the average device time of
 // `reps` launches in ms.  Algorithmic traffic per launch = n * S * 3 lookups * 8 corners * 128 B.
 extern "C" int nsb_bench_gather(nsb_ctx* ctx, int reps, float* ms_out) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     const int n = ctx->last_n, S = ctx->last_S;
     if (n <= 0) return fail(ctx, "no forward has run yet");
     DecodeParams P; fill_decode_params(ctx, P, n, S, nullptr);
@@ -1577,6 +1614,7 @@ extern "C" int nsb_bench_gather(nsb_ctx* ctx, int reps, float* ms_out) {
 // ---- instrumentation ----------------------------------------------------------------------------------------------------
 // Cycle counters of the tcgen05 forward (only filled by the NSB_TC_TIMING build variant): 32 values, reset on read.
 extern "C" int nsb_debug_counters(nsb_ctx* ctx, unsigned long long* out32) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     CK(cudaMemcpyAsync(out32, ctx->dbg, 32 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1587,6 +1625,7 @@ extern "C" int64_t nsb_launch_count(nsb_ctx* ctx, int reset) { const int64_t v =
 extern "C" int nsb_set_profiling(nsb_ctx* ctx, int on) { ctx->profiling = on != 0; ctx->ev_used = 0; return 0; }
 // Sum of the device times of every region timed since nsb_set_profiling(1), per category.
 extern "C" int nsb_get_kernel_ms(nsb_ctx* ctx, float* ms) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < T_N; ++i) ms[i] = 0.f;
     for (size_t k = 0; k < ctx->ev_used; ++k) {

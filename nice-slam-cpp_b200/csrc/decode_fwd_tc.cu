@@ -524,11 +524,12 @@ int compose_floats(int which) { return which == 2 ? tc::comp_total(64) : tc::com
 
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st) {
     const size_t smem = decode_fwd_tc_smem();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned attr_done = 0;      // per device: function attributes are per-device state
+    int dev = 0; cudaGetDevice(&dev);
+    if (!((attr_done >> (dev & 31)) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_decode_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done |= 1u << (dev & 31);
     }
     tc::k_decode_fwd_tc<<<grid, tc::THREADS, smem, st>>>(P);
     return cudaGetLastError();

@@ -400,11 +400,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fwd_tc16(const DecodePara
 
 cudaError_t launch_decode_fwd_tc16(const DecodeParams& P, int grid, cudaStream_t st) {
     const size_t smem = (size_t)tc16::Smem<64>::TOTAL + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned attr_done = 0;      // per device: function attributes are per-device state
+    int dev = 0; cudaGetDevice(&dev);
+    if (!((attr_done >> (dev & 31)) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(tc16::k_decode_fwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done |= 1u << (dev & 31);
     }
     tc16::k_decode_fwd_tc16<<<grid, tc16::THREADS, smem, st>>>(P);
     return cudaGetLastError();

@@ -200,18 +200,16 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
 }
 
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st) {
-    static bool init = false;
-    if (!init) {
+    static unsigned init = 0;           // per device: the task table lives in that device's constant memory
+    int dev = 0; cudaGetDevice(&dev);
+    const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
+    if (!((init >> (dev & 31)) & 1u)) {
         const WGTable T = build_table();
         cudaError_t e = cudaMemcpyToSymbol(c_wg, &T, sizeof(T));
-        if (e != cudaSuccess) return e;
-    }
-    const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
-    if (!init) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        init = true;
+        init |= 1u << (dev & 31);
     }
     if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
     else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);

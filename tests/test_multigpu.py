@@ -74,3 +74,39 @@ def test_two_gpu_mapping_equals_one_gpu(nsb, ba, p2p):
         assert np.abs(o["dec"] - ref["dec"]).max() < 2e-2 * np.abs(ref["dec"] - nsb.synthetic.make_decoders(0, bias_scale=0.05)["color"]).max()
         assert np.abs(o["cams"] - ref["cams"]).max() < 1e-4
     assert np.array_equal(got[0]["middle"], got[1]["middle"]) and np.array_equal(got[0]["dec"], got[1]["dec"])   # replicas stay bit-identical
+
+
+def test_two_contexts_in_one_process(nsb):
+    """One nsb_ctx per GPU, two of them driven alternately from ONE process: every entry point selects its context's device, and
+    per-device state (function attributes, the wgrad task table in constant memory) is initialised on both."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    syn = nsb.synthetic
+    grids = syn.make_grids(0); decs = syn.make_decoders(0, bias_scale=0.05)
+    depths, colors, poses = syn.make_frames(2, 0)
+    engines = []
+    for dev in (0, 1):
+        cfg = nsb.default_config(); cfg.mapping_pixels = 600; cfg.max_rays = 1024; cfg.frustum_feature_selection = 0
+        e = nsb.Engine(cfg, device=dev)
+        e.set_model(grids, decs)
+        for f in range(2):
+            e.set_frame(f, depths[f], colors[f], poses[f])
+        e.seed(5)
+        engines.append(e)
+    for e in engines:
+        e.mapping_begin([0, 1], 60, 1.0)
+    losses = [[], []]
+    for it in (0, 59, 59):                      # interleaved: the current device changes between consecutive calls
+        for k, e in enumerate(engines):
+            losses[k].append(e.mapping_iter(it))
+    idx = syn.mt19937_indices(9, 200, 480 * 640)
+    outs = []
+    for e in engines:
+        ro, rd, gd, gc, ins, _ = e.get_samples(0, 0, 480, 0, 640, 200, idx=idx)
+        outs.append(e.render_batch_ray(rd[ins], ro[ins], "color", gd[ins]))
+    assert np.allclose(losses[0], losses[1], rtol=1e-5), losses
+    assert np.abs(engines[0].get_decoder("color") - engines[1].get_decoder("color")).max() < 1e-5      # both ran the wgrad kernel
+    assert np.abs(engines[0].get_decoder("color") - decs["color"]).max() > 1e-4
+    assert np.allclose(outs[0][1], outs[1][1], rtol=1e-4) and np.allclose(outs[0][0], outs[1][0], rtol=1e-3, atol=1e-4)
+    for e in engines:
+        e.close()
