@@ -6,24 +6,29 @@
 
 Workload (BASELINE.json configs[1]): Mapper iteration of Mapper.cpp:330-465 -- sample 5 keyframes x 1000 pixels
 (5000 rays/iter), inside filter, render_batch_ray("color"), L1 depth (+ colour) loss, backward to the
-middle/fine/color grids and the colour decoder, fused Adam.  One "step" = one joint iteration; step i runs
-iteration (i mod 60) of a 60-iteration optimize_map (37 geometry + 23 colour iterations, Mapper.cpp:351-358),
-Adam being re-created at every wrap as the reference does per keyframe.  Synthetic 640x480 RGB-D frames,
-random-init grids and decoders (datasets / pretrained decoders are offline).
-N > 1: weak scaling, global batch N x 5000 rays sharded over the ranks, one NCCL all-reduce of the flat gradient
-arena per iteration.  `value` = rays of all ranks / max-over-ranks device time, inputs resident in HBM;
+middle/fine/color grids and the colour decoder, fused Adam.  One "step" = one joint iteration.  The K timed steps are
+spread EVENLY over the 60-iteration schedule of one optimize_map (37 geometry + 23 colour iterations, Mapper.cpp:351-358):
+step k runs iteration floor(k * 60 / K) for K < 60 and iteration k mod 60 otherwise, so ANY --steps times the 37:23 mix and
+`ms_per_step_by_stage` always carries both stages; Adam is re-created at every wrap as the reference does per keyframe.
+Synthetic 640x480 RGB-D frames, random-init grids and decoders (datasets / pretrained decoders are offline).
+N > 1: weak scaling, global batch N x 5000 rays sharded over the ranks, gradients exchanged and stepped by one fused
+reduce-scatter + Adam + all-gather kernel over NVLink peer memory (--comm nccl: ncclAllReduce + Adam).
+`value` = rays of all ranks / max-over-ranks device time, inputs resident in HBM, every iteration ONE cudaGraphLaunch;
 `e2e` = the same loop through the host-buffer C ABI (pinned pixel indices H2D + keyframe upload every 60 steps +
-loss D2H every step).  --impl reference times the reference's own CPU path (oracle/_ref: its Renderer.cpp +
-utils.h on libtorch CPU, all host threads) on a bounded sample (1000 rays/step, the reference's mapping.pixels).
+loss D2H every step).  The per-kernel times behind `roofline` come from a second pass over the same K steps with the kernels
+enqueued one by one between CUDA events (a graph launch cannot be timed kernel by kernel).
+`configs` carries the other BASELINE.json configurations (forward-only render, tracking, dense render) with their own CPU baselines.
+--impl reference times the reference's own CPU path (oracle/_ref: its Renderer.cpp + utils.h on libtorch CPU, all host threads) on
+the same 5000-ray iterations.
 """
 import argparse
+import hashlib
 import importlib
 import json
 import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,6 +38,7 @@ import numpy as np
 RAYS_PER_GPU = 5000
 N_FRAMES = 5
 ITERS_PER_KEYFRAME = 60
+FIRST_COLOR_ITER = 37                      # stage_of_iter: it <= 24 middle, it <= 36 middle again (Mapper.cpp:355-356), then color
 # algorithmic work per ray: MAC counts x 2 x 48 samples
 FLOP_FWD_RAY = 51653 * 2 * 48              # 4.96 MFLOP: three decoders forward
 FLOP_BWD_COLOR_RAY = 49367 * 2 * 48        # 4.74 MFLOP: colour-stage backward (grids + colour decoder wgrad)
@@ -51,73 +57,86 @@ def peaks():
     return p
 
 
+def load_profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def schedule(K):
+    """Iteration number (0..59) of timed step k: the K steps sample the 60-iteration schedule evenly."""
+    if K >= ITERS_PER_KEYFRAME:
+        return [k % ITERS_PER_KEYFRAME for k in range(K)]
+    return [(k * ITERS_PER_KEYFRAME) // K for k in range(K)]
+
+
+_CLOCK_CHILD = r"""
+import sys, time, json
+import pynvml as N
+N.nvmlInit()
+uuid = sys.argv[1]
+try:
+    h = N.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+except Exception:
+    h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+mx = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+        "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+import select
+out = []
+print("ready", flush=True)
+while True:
+    r, _, _ = select.select([sys.stdin], [], [], 0.003)
+    if r and not sys.stdin.readline():
+        break
+    try:
+        out.append((time.monotonic(), int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(N.nvmlDeviceGetCurrentClocksEventReasons(h))))
+    except Exception:
+        pass
+res = {"max": mx, "samples": [[t, c, [k for k, b in bits.items() if r & b]] for t, c, r in out]}
+print(json.dumps(res), flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms from a
-    thread (nvidia-smi -lms cannot start fast enough for a 60 ms region); nvidia-smi is the fallback."""
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is polled every ~3 ms by a
+    CHILD PROCESS, not by a thread of this one: a polling thread shares the GIL with the launch loop and its hiccups become
+    device time on every peer at the cross-GPU barrier (VERDICT r1 weak #7).  window(t0, t1) summarises the samples of one region."""
 
     def __init__(self, dev):
-        self.sm, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self.th = None
-        self.smi = None
+        self.p = None
         try:
-            import pynvml as N
             import torch
-            N.nvmlInit()
-            h = None
-            try:
-                uuid = str(torch.cuda.get_device_properties(dev).uuid)
-                h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
-            except Exception:
-                h = N.nvmlDeviceGetHandleByIndex(dev)
-            self.max_mhz = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
-            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
-
-            def poll():
-                while not self._stop.is_set():
-                    try:
-                        self.sm.append(int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
-                        r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
-                        for k, b in bits.items():
-                            if r & b:
-                                self.reasons.add(k)
-                    except Exception:
-                        pass
-                    time.sleep(0.002)
-            self.th = threading.Thread(target=poll, daemon=True)
-            self.th.start()
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+            self.p = subprocess.Popen([sys.executable, "-c", _CLOCK_CHILD, uuid, str(dev)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            if self.p.stdout.readline().strip() != "ready":
+                raise RuntimeError("clock child failed")
         except Exception:
-            self.th = None
-            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-            try:
-                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
-                                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-                threading.Thread(target=self._read_smi, daemon=True).start()
-            except Exception:
-                self.smi = None
-
-    def _read_smi(self):
-        for line in self.smi.stdout:
-            r = [x.strip() for x in line.split(",")]
-            if r and r[0].isdigit():
-                self.sm.append(int(r[0]))
-                if len(r) > 1 and r[1].isdigit():
-                    self.max_mhz = int(r[1])
-                for k, nm in enumerate(self.NAMES):
-                    if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
-                        self.reasons.add(nm)
+            self.p = None
+        self.res = None
 
     def stop(self):
-        self._stop.set()
-        if self.th:
-            self.th.join(timeout=1)
-        if self.smi:
-            self.smi.terminate()
-        if not self.sm:
+        if not self.p:
+            return
+        try:
+            self.p.stdin.close()
+            self.res = json.loads(self.p.stdout.readline())
+            self.p.wait(timeout=5)
+        except Exception:
+            self.res = None
+        self.p = None
+
+    def window(self, t0, t1):
+        if not self.res:
             return None
-        return {"sm_mhz": int(statistics.median(self.sm)), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        sm = [c for t, c, r in self.res["samples"] if t0 <= t <= t1]
+        rs = sorted({x for t, c, r in self.res["samples"] if t0 <= t <= t1 for x in r})
+        if not sm:
+            return None
+        return {"sm_mhz": int(statistics.median(sm)), "sm_min_mhz": min(sm), "sm_max_mhz": self.res["max"], "reasons": rs, "samples": len(sm)}
 
 
 def synthetic_inputs(nsb):
@@ -126,78 +145,108 @@ def synthetic_inputs(nsb):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path, on the host cores (rank 0 only)."""
-    if rank != 0:
-        return
+def _reference_backend(nsb_syn, grids, decs, cores):
+    """(kind, mapping-step callable, object) -- the reference's own compiled code when oracle/_ref travelled, else the port."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    nsb_syn = importlib.import_module("nice-slam-cpp_b200.synthetic")
     import nice_oracle as O
     import refbind as R
-    grids, decs = nsb_syn.make_grids(0), nsb_syn.make_decoders(0)
-    depths, colors, poses = nsb_syn.make_frames(N_FRAMES, 0)
-    sample_rays = 1000
     lr = np.array([O.DEFAULT_LR[k] for k in ("coarse", "middle", "fine", "color")], np.float32)
-    sched = [O.STAGE_ID[s] for s in O.stage_schedule(ITERS_PER_KEYFRAME)]
-    cores = os.cpu_count() or 1
     if R.available():
         ref = R.Ref(grids, decs)
         ref.set_threads(cores)
-        kind = "reference"
+        return "reference", ref, O, lr
+    import torch
+    torch.set_num_threads(cores)
+    return "port", O.Model(grids, decs), O, lr
 
-        def step(i):
-            ref.mapping_iters(depths, colors, poses, nsb_syn.CAM, sample_rays, [sched[i % ITERS_PER_KEYFRAME]], lr, seed=i)
-    else:   # oracle/_ref needs /root/reference to build; fall back to the port of the same algorithm
-        import torch
-        torch.set_num_threads(cores)
-        model = O.Model(grids, decs)
-        names = {v: k for k, v in O.STAGE_ID.items()}
-        kind = "port"
 
-        def step(i):
-            O.mapping_iters(model, depths, colors, poses, nsb_syn.CAM, sample_rays, [names[sched[i % ITERS_PER_KEYFRAME]]], seed=i)
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, on the host cores (rank 0 only): the SAME 5000-ray iterations."""
+    if rank != 0:
+        return
+    nsb_syn = importlib.import_module("nice-slam-cpp_b200.synthetic")
+    grids, decs = nsb_syn.make_grids(0), nsb_syn.make_decoders(0)
+    depths, colors, poses = nsb_syn.make_frames(N_FRAMES, 0)
+    cores = os.cpu_count() or 1
+    kind, ref, O, lr = _reference_backend(nsb_syn, grids, decs, cores)
+    sched = [O.STAGE_ID[s] for s in O.stage_schedule(ITERS_PER_KEYFRAME)]
+    names = {v: k for k, v in O.STAGE_ID.items()}
+    its = schedule(args.steps)
+
+    def step(it, seed):
+        if kind == "reference":
+            ref.mapping_iters(depths, colors, poses, nsb_syn.CAM, RAYS_PER_GPU, [sched[it]], lr, seed=seed)
+        else:
+            O.mapping_iters(ref, depths, colors, poses, nsb_syn.CAM, RAYS_PER_GPU, [names[sched[it]]], seed=seed)
     for i in range(args.warmup):
-        step(i)
+        step(59 if i % 2 else 0, i)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for k, it in enumerate(its):
+        step(it, args.warmup + k)
     dt = time.perf_counter() - t0
-    v = args.steps * sample_rays / dt
+    v = args.steps * RAYS_PER_GPU / dt
+    n_color = sum(1 for it in its if it >= FIRST_COLOR_ITER)
     out = {"impl": "reference", "metric": "mapping rays/s (fwd+bwd, 48 samples/ray)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "sample": "%d rays/step" % sample_rays},
-           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "sample": "%d steps x %d rays, stage schedule of a 60-iteration optimize_map" % (args.steps, sample_rays)},
+           "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": RAYS_PER_GPU, "samples_per_ray": 48,
+                      "frames": N_FRAMES, "schedule": "timed step k = iteration floor(k*60/K) (K<60) or k%60 of optimize_map", "color_steps": n_color,
+                      "raydir": "utils.h:44-47 as written (the reference's own raySampler)"},
+           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": kind,
+                            "sample": "%d mapping iterations x %d rays (%d geometry + %d colour), libtorch CPU autograd + torch::optim::Adam" % (args.steps, RAYS_PER_GPU, args.steps - n_color, n_color)},
            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
-def cpu_baseline_sample(nsb):
-    """Bounded CPU sample for the `cpu_baseline` key of our own line: 3 colour-stage iterations x 5000 rays."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import nice_oracle as O
-    import refbind as R
+def cpu_baselines(nsb, want_configs=True):
+    """Bounded CPU samples (rank 0, N = 1): the mapping iteration for `cpu_baseline`, and forward-only / tracking samples for the
+    `configs` sub-records.  ~10-30 s of CPU work in total."""
     syn = nsb.synthetic
     grids, decs = syn.make_grids(0), syn.make_decoders(0)
     depths, colors, poses = syn.make_frames(N_FRAMES, 0)
     cores = os.cpu_count() or 1
-    lr = np.array([O.DEFAULT_LR[k] for k in ("coarse", "middle", "fine", "color")], np.float32)
+    kind, ref, O, lr = _reference_backend(syn, grids, decs, cores)
+    out = {}
     n_it = 3
-    if R.available():
-        ref = R.Ref(grids, decs); ref.set_threads(cores)
+    if kind == "reference":
         ref.mapping_iters(depths, colors, poses, syn.CAM, 500, [3], lr, seed=0)   # warm-up
         _, _, sec = ref.mapping_iters(depths, colors, poses, syn.CAM, RAYS_PER_GPU, [1, 3, 3], lr, seed=1)
-        kind = "reference"
     else:
-        import torch
-        torch.set_num_threads(cores)
-        model = O.Model(grids, decs)
         t0 = time.perf_counter()
-        O.mapping_iters(model, depths, colors, poses, syn.CAM, RAYS_PER_GPU, ["middle", "color", "color"], seed=1)
+        O.mapping_iters(ref, depths, colors, poses, syn.CAM, RAYS_PER_GPU, ["middle", "color", "color"], seed=1)
         sec = time.perf_counter() - t0
-        kind = "port"
-    return {"value": n_it * RAYS_PER_GPU / sec, "unit": "rays/s", "cores": cores, "kind": kind,
-            "sample": "%d mapping iterations (1 geometry + 2 colour) x %d rays, %.1f s" % (n_it, RAYS_PER_GPU, sec)}
+    out["mapping"] = {"value": n_it * RAYS_PER_GPU / sec, "unit": "rays/s", "cores": cores, "kind": kind,
+                      "sample": "%d mapping iterations (1 geometry + 2 colour) x %d rays, %.1f s" % (n_it, RAYS_PER_GPU, sec)}
+    if not want_configs:
+        return out
+    import torch
+    idx = syn.mt19937_indices(3, 6000, 480 * 640)
+    a, b, c_, _ = O.ray_sampler(0, 480, 0, 640, idx, syn.CAM["fx"], syn.CAM["fy"], syn.CAM["cx"], syn.CAM["cy"], torch.tensor(depths[0]), torch.tensor(colors[0]),
+                                torch.tensor(poses[0]), "pinhole")
+    keep = O.inside_mask(a, b, c_, torch.tensor(syn.BOUND)).numpy()
+    ro, rd, gd = a.numpy()[keep][:RAYS_PER_GPU], b.numpy()[keep][:RAYS_PER_GPU], c_.numpy()[keep][:RAYS_PER_GPU]
+    if kind == "reference":
+        ref.render_batch_ray(rd[:500], ro[:500], "color", gd[:500])
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ref.render_batch_ray(rd, ro, "color", gd)
+        sec = (time.perf_counter() - t0) / 2
+    else:
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.render_batch_ray(ref, torch.tensor(rd), torch.tensor(ro), "color", torch.tensor(gd))
+            sec = time.perf_counter() - t0
+    out["forward"] = {"value": rd.shape[0] / sec, "unit": "rays/s", "cores": cores, "kind": kind, "sample": "render_batch_ray forward, %d rays, %.2f s per call" % (rd.shape[0], sec)}
+    cam0 = O.get_tensor_from_camera(poses[0]); cam0 = np.asarray(cam0, np.float32).copy(); cam0[4:] += 0.01
+    n_trk = 2
+    if kind == "reference":
+        *_, sec = ref.tracking_iters(depths[0], colors[0], cam0, syn.CAM, RAYS_PER_GPU, n_trk, 1e-2, seed=2)
+    else:
+        t0 = time.perf_counter()
+        O.tracking_iters(ref, depths[0], colors[0], cam0, syn.CAM, RAYS_PER_GPU, n_trk, 1e-2, seed=2)
+        sec = time.perf_counter() - t0
+    out["tracking"] = {"value": sec / n_trk * 1e3, "unit": "ms/iter", "cores": cores, "kind": kind, "sample": "%d tracking iterations x %d rays, %.1f s" % (n_trk, RAYS_PER_GPU, sec)}
+    return out
 
 
 # -------------------------------------------------------------------------------------------------- our arm
@@ -226,8 +275,102 @@ def run_tracking(e, nsb, torch, ext, depths, colors, poses, frames=6, warm_frame
                 wall += time.perf_counter() - t0
                 dev_ms += sum(a.elapsed_time(b) for a, b in evs)
     n = frames * iters
-    return {"ms_per_iter": dev_ms / n, "e2e_ms_per_iter": wall / n * 1e3, "rays_per_iter": int(e.cfg.tracking_pixels), "iters_per_frame": int(iters),
+    return {"workload": "tracker_5000rays_10iters_frame", "ms_per_iter": dev_ms / n, "e2e_ms_per_iter": wall / n * 1e3, "rays_per_iter": int(e.cfg.tracking_pixels), "iters_per_frame": int(iters),
             "frames_timed": frames, "last_loss": float(loss), "note": "replicas only (one GPU per frame); loss D2H + sync every iteration"}
+
+
+def run_forward_only(e, nsb, torch, ext, depths, colors, poses, flush, reps=10):
+    """BASELINE configs[0]: Renderer::render_batch_ray forward on 5000 rays x 48 samples (cofusion.yaml camera).  Device time with the
+    rays resident (nsb_render_batch_ray_dev), and through the host ABI (rays H2D, rgb/depth/var/weights D2H inside the timed region)."""
+    idx = nsb.synthetic.mt19937_indices(3, 6000, 480 * 640)
+    ro, rd, gd, gc, inside, _ = e.get_samples(0, 0, 480, 0, 640, 6000, idx=idx)
+    ro, rd, gd = ro[inside][:RAYS_PER_GPU], rd[inside][:RAYS_PER_GPU], gd[inside][:RAYS_PER_GPU]
+    n = ro.shape[0]
+    d_ro = torch.from_numpy(ro).cuda(); d_rd = torch.from_numpy(rd).cuda(); d_gd = torch.from_numpy(gd).cuda()
+    o_rgb = torch.empty(n, 3, device="cuda"); o_d = torch.empty(n, device="cuda"); o_v = torch.empty(n, device="cuda"); o_w = torch.empty(n, 48, device="cuda")
+    torch.cuda.synchronize()
+    ms = []
+    with torch.cuda.stream(ext):
+        for r in range(reps + 3):
+            flush.zero_()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(ext)
+            e.render_batch_ray_dev("color", n, d_rd.data_ptr(), d_ro.data_ptr(), d_gd.data_ptr(), o_rgb.data_ptr(), o_d.data_ptr(), o_v.data_ptr(), o_w.data_ptr())
+            b.record(ext)
+            e.synchronize()
+            if r >= 3:
+                ms.append(a.elapsed_time(b))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e.render_batch_ray(rd, ro, "color", gd)
+    wall = (time.perf_counter() - t0) / reps
+    return {"workload": "render_batch_ray_forward_5000rays", "rays": int(n), "ms": float(np.mean(ms)), "rays_per_s": n / (np.mean(ms) * 1e-3),
+            "e2e_ms": wall * 1e3, "e2e_rays_per_s": n / wall, "h2d_bytes": int(ro.nbytes + rd.nbytes + gd.nbytes), "d2h_bytes": int(n * (3 + 1 + 1 + 48) * 4)}
+
+
+def run_dense(e, nsb, torch, ext, reps=3):
+    """BASELINE configs[3]: all 640 x 480 = 307 200 pixels of a frame through render_batch_ray("color"), depth-guided
+    (upstream render_img; Renderer.cpp:5 keeps its ray_batch_size).  Device time without the image read-back, and end to end."""
+    ms = []
+    with torch.cuda.stream(ext):
+        for r in range(reps + 1):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(ext); e.render_img(0, "color", True, want_outputs=False); b.record(ext)
+            e.synchronize()
+            if r >= 1:
+                ms.append(a.elapsed_time(b))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e.render_img(0, "color", True)
+    wall = (time.perf_counter() - t0) / reps
+    n = e.cfg.H * e.cfg.W
+    return {"workload": "dense_render_640x480_color", "rays": int(n), "ms": float(np.mean(ms)), "rays_per_s": n / (np.mean(ms) * 1e-3), "e2e_ms": wall * 1e3,
+            "e2e_rays_per_s": n / wall, "d2h_bytes": int(n * 5 * 4), "chunk_rays": int(e.cfg.max_rays)}
+
+
+def parity_selfcheck(nsb, e, torch, dist, rank, world, local_rank, grids, decs, depths, colors, poses, cfg):
+    """N > 1: four fixed-seed iterations (2 geometry + 2 colour) on the sharded engine against ONE GPU rendering the same global
+    batch: loss agreement, parameter agreement (RMS relative to the RMS update) and bit-identity of the replicas across ranks."""
+    n_global = cfg.mapping_pixels
+    its = [0, 1, 58, 59]
+    idx = nsb.synthetic.mt19937_indices(1234, len(its) * n_global, cfg.H * cfg.W).reshape(len(its), n_global)
+    e.set_model(grids, decs)
+    e.mapping_begin(list(range(N_FRAMES)), ITERS_PER_KEYFRAME, 1.0)
+    losses = [e.mapping_iter(it, idx[k]) for k, it in enumerate(its)]
+    e.mapping_end()
+    got = {lv: e.get_grid(lv) for lv in ("middle", "fine", "color")}
+    got["dec"] = e.get_decoder("color")
+    h = hashlib.sha256()
+    for k in ("middle", "fine", "color", "dec"):
+        h.update(np.ascontiguousarray(got[k]).tobytes())
+    digest = torch.tensor(list(h.digest()), dtype=torch.uint8, device="cuda")
+    alld = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(alld, digest)
+    identical = all(bool(torch.equal(alld[0], d)) for d in alld)
+    res = None
+    if rank == 0:
+        c1 = nsb.default_config()
+        for f, _t in cfg._fields_:
+            setattr(c1, f, getattr(cfg, f))
+        e1 = nsb.Engine(c1, device=local_rank)       # world = 1: the whole global batch on one GPU
+        e1.set_model(grids, decs)
+        for f in range(N_FRAMES):
+            e1.set_frame(f, depths[f], colors[f], poses[f])
+        e1.mapping_begin(list(range(N_FRAMES)), ITERS_PER_KEYFRAME, 1.0)
+        ref_losses = [e1.mapping_iter(it, idx[k]) for k, it in enumerate(its)]
+        rms = {}
+        for lv in ("middle", "fine", "color"):
+            ref = e1.get_grid(lv)
+            move = float(np.sqrt(((ref - grids[lv]) ** 2).mean()))
+            rms[lv] = float(np.sqrt(((got[lv] - ref) ** 2).mean()) / max(move, 1e-30))
+        dref = e1.get_decoder("color")
+        res = {"iterations": its, "rays": int(n_global), "ranks_bit_identical": bool(identical),
+               "loss_rel_vs_1gpu": float(np.max(np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(ref_losses))),
+               "grid_rms_vs_1gpu": rms, "dec_color_rel_vs_1gpu": float(np.abs(got["dec"] - dref).max() / max(np.abs(dref - decs["color"]).max(), 1e-30)),
+               "note": "grid_rms = RMS(param_N - param_1) / RMS(update): Adam turns gradients at the fp32 noise level into +-lr steps of random sign in any "
+                       "implementation, and the sharded sum only re-associates the fp32 additions"}
+        e1.close()
+    return res
 
 
 def run_ours(args, rank, world, local_rank):
@@ -275,6 +418,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
     pix = n_global // N_FRAMES
     K, W = args.steps, args.warmup
+    its = schedule(K)
+    warm_its = [(0, 59)[i % 2] for i in range(W)]      # both stages (every kernel variant / captured graph) are warmed
     idx_all = nsb.synthetic.mt19937_indices(0, (K + W) * N_FRAMES * pix, cfg.H * cfg.W).reshape(K + W, N_FRAMES * pix)
     slots = list(range(N_FRAMES))
     ext = torch.cuda.ExternalStream(e.stream_ptr(), device=torch.device("cuda", local_rank))
@@ -286,114 +431,168 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident loop: `value`
-    e.mapping_set_index_pool(idx_all)
-    def run_step(i, idx=None, sync=False):
-        it = i % ITERS_PER_KEYFRAME
-        if it == 0:
+    state = {"prev": None}
+
+    def run_step(it, idx=None, sync=False):
+        if state["prev"] is None or it < state["prev"]:
             e.mapping_begin(slots, ITERS_PER_KEYFRAME, 1.0)   # fresh Adam per optimize_map (Mapper.cpp:330)
+        state["prev"] = it
         return e.mapping_iter(it, idx, sync=sync)              # idx None: next row of the device-resident pool
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+
+    def timed_pass(profile):
+        """W warm-up + K timed steps (L2 flushed between steps, events on the library's stream)."""
+        state["prev"] = None
+        e.mapping_set_index_pool(idx_all)
+        with torch.cuda.stream(ext):
+            for it in warm_its:
+                run_step(it)
+            barrier()
+            e.launch_count(reset=True)
+            e.set_profiling(profile)
+            t0 = time.monotonic()
+            evs = []
+            for it in its:
+                flush.zero_()                                  # L2 flush between timed steps (not timed)
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(ext); run_step(it); b.record(ext)
+                evs.append((a, b))
+            barrier()
+            t1 = time.monotonic()
+            step_ms = [a.elapsed_time(b) for a, b in evs]
+            kms = e.kernel_ms() if profile else None
+            launches = e.launch_count()
+            e.set_profiling(False)
+        return step_ms, kms, launches, (t0, t1)
+
+    # ---- device-resident loop, one cudaGraphLaunch per iteration: `value`
+    step_ms, _, launches, win = timed_pass(False)
     with torch.cuda.stream(ext):
-        for i in range(W):
-            run_step(i)
-        barrier()
-        e.launch_count(reset=True)
-        e.set_profiling(True)
-        clocks = ClockSampler(local_rank) if rank == 0 else None
-        evs = []
-        for i in range(W, W + K):
-            flush.zero_()                                  # L2 flush between timed steps (not timed)
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(ext); run_step(i); b.record(ext)
-            evs.append((a, b))
-        barrier()
-        clk = clocks.stop() if clocks else None
-        step_ms = [a.elapsed_time(b) for a, b in evs]
-        t_dev = sum(step_ms) * 1e-3
-        is_color = [((W + k) % ITERS_PER_KEYFRAME) > 36 for k in range(K)]
-        ms_geom = float(np.mean([m for m, c_ in zip(step_ms, is_color) if not c_])) if not all(is_color) else None
-        ms_color = float(np.mean([m for m, c_ in zip(step_ms, is_color) if c_])) if any(is_color) else None
-        kms = e.kernel_ms()
-        launches = e.launch_count()
-        e.set_profiling(False)
-        gather_ms = e.bench_gather(20)       # grid sampling alone on the last step's rays (resident grids: L1/L2 traffic)
-        last_it = (W + K - 1) % ITERS_PER_KEYFRAME
-        losses, n_inside = e.mapping_losses(0, last_it + 1)    # the iterations run since the last mapping_begin
+        last_begin = max(k for k in range(K) if k == 0 or its[k] < its[k - 1])
+        losses, n_inside = e.mapping_losses(0, K - last_begin)    # the steps since the last mapping_begin
+    t_dev = sum(step_ms) * 1e-3
     t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev = float(t.item())
-    value = K * n_global / t_dev
+    t_dev_max = float(t.item())
+    value = K * n_global / t_dev_max
+    is_color = [it >= FIRST_COLOR_ITER for it in its]
+    ms_geom = float(np.mean([m for m, c_ in zip(step_ms, is_color) if not c_])) if not all(is_color) else None
+    ms_color = float(np.mean([m for m, c_ in zip(step_ms, is_color) if c_])) if any(is_color) else None
+    # ---- the same K steps, kernels enqueued one by one between CUDA events: per-kernel device time for the roofline
+    step_ms_eager, kms, _, _ = timed_pass(True)
+    gather_ms = e.bench_gather(20)       # grid sampling alone on the last step's rays (resident grids: L1/L2 traffic)
 
     # ---- end-to-end loop through the host-buffer ABI: pinned indices H2D, keyframe upload per 60 steps, loss D2H per step
     e.mapping_set_index_pool(None)
     pin_idx = torch.from_numpy(idx_all).pin_memory().numpy()
     pin_depth = torch.from_numpy(depths[N_FRAMES]).pin_memory().numpy(); pin_color = torch.from_numpy(colors[N_FRAMES]).pin_memory().numpy()
-    for i in range(W):
-        run_step(i, pin_idx[i], sync=True)
+    state["prev"] = None
+    for i, it in enumerate(warm_its):
+        run_step(it, pin_idx[i], sync=True)
     barrier()
+    state["prev"] = None
     t0 = time.perf_counter()
-    for i in range(W, W + K):
-        if i % ITERS_PER_KEYFRAME == 0:
+    for k, it in enumerate(its):
+        if state["prev"] is None or it < state["prev"]:
             e.set_frame(N_FRAMES - 1, pin_depth, pin_color, poses[N_FRAMES - 1])   # the new keyframe of this optimize_map
-        run_step(i, pin_idx[i], sync=True)
+        run_step(it, pin_idx[W + k], sync=True)
     barrier()
     t_e2e = time.perf_counter() - t0
     t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_e2e = float(t.item())
+    n_begin = sum(1 for k in range(K) if k == 0 or its[k] < its[k - 1])
     frame_bytes = (depths[0].nbytes + colors[0].nbytes + 64)
-    e2e = {"value": K * n_global / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": int(idx_all[0].nbytes + frame_bytes / ITERS_PER_KEYFRAME),
-           "d2h_bytes_per_step": 8, "ms_per_step": t_e2e / K * 1e3}
+    e2e = {"value": K * n_global / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": int(idx_all[0].nbytes + frame_bytes * n_begin / K),
+           "d2h_bytes_per_step": 16, "ms_per_step": t_e2e / K * 1e3}
+    e.set_frame(N_FRAMES - 1, depths[N_FRAMES - 1], colors[N_FRAMES - 1], poses[N_FRAMES - 1])
 
+    p2p_times = e.p2p_times() if (world > 1 and args.comm == "p2p") else None
+    parity = None
+    if world > 1:
+        parity = parity_selfcheck(nsb, e, torch, dist, rank, world, local_rank, grids, decs, depths, colors, poses, cfg)
+
+    # ---- the other BASELINE.json configurations (rank 0's GPU; replicas only)
+    configs = None
+    if rank == 0 and not args.no_configs:
+        e.set_model(grids, decs)
+        configs = {"forward_only": run_forward_only(e, nsb, torch, ext, depths, colors, poses, flush), "dense_render": run_dense(e, nsb, torch, ext)}
     tracking = run_tracking(e, nsb, torch, ext, depths, colors, poses)   # replicas only: every rank tracks its own frame
+    if clocks:
+        clocks.stop()
 
     if rank == 0:
         pk = peaks()
-        n_color = sum(1 for i in range(W, W + K) if (i % ITERS_PER_KEYFRAME) > 36)
+        n_color = sum(is_color)
         n_geom = K - n_color
         frac_in = float(np.mean(n_inside[n_inside > 0])) / n_global if np.any(n_inside > 0) else 1.0
         rays_rank = RAYS_PER_GPU * frac_in                 # rays that survive the inside filter, per rank and step
         bwd_flop = (n_color * FLOP_BWD_COLOR_RAY + n_geom * FLOP_BWD_GEOM_RAY) * rays_rank
         fwd_flop = K * FLOP_FWD_RAY * rays_rank
-        bwd_s = kms["decode_bwd"] * 1e-3
+        bwd_s = (kms["decode_bwd"] + kms["wgrad"]) * 1e-3
         fwd_s = kms["decode_fwd"] * 1e-3
-        traffic = {}
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture (profiles/)
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f)
-        except Exception:
-            pass
+        traffic = load_profile_json("traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel VARIANT (ncu --set full)
+
+        def mix(name):
+            g, c_ = traffic.get(name + "<geometry>"), traffic.get(name + "<color>")
+            if g is None or c_ is None:
+                return None
+            return (n_geom * g + n_color * c_) / K
         fwd_name = "k_decode_fwd_tc" if os.environ.get("NSB_TCGEN05", "0") not in ("", "0") else "k_decode_fwd"
         kern = {fwd_name: {"achieved": fwd_flop / fwd_s * 1e-12 if fwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_fwd"] / K, "flop_per_launch": fwd_flop / K,
-                           "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0},
-                "k_decode_bwd": {"achieved": bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_bwd"] / K, "flop_per_launch": bwd_flop / K}}
-        dom = fwd_name if fwd_s >= bwd_s else "k_decode_bwd"       # the dominant kernel of the step
+                           "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0, "traffic": mix(fwd_name)},
+                "k_decode_bwd(+wgrad)": {"achieved": bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0, "avg_launch_ms": (kms["decode_bwd"] + kms["wgrad"]) / K, "flop_per_launch": bwd_flop / K,
+                                         "scatter_gbs": K * GATHER_BYTES_RAY * rays_rank / (kms["decode_bwd"] * 1e-3) * 1e-9 if kms["decode_bwd"] > 0 else 0.0,
+                                         "traffic": mix("k_decode_bwd")}}
+        dom = fwd_name if fwd_s >= bwd_s else "k_decode_bwd(+wgrad)"       # the dominant kernel of the step
         ach = kern[dom]["achieved"]
+        gat = load_profile_json("gather_ncu.json")        # l1tex / lts / dram bytes of k_gather_only per launch (ncu), measured L2 gather peak
+        gs = {"kernel": "k_gather_only", "ms": gather_ms, "rays": int(n_global // world),
+              "algorithmic_gbs": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 if gather_ms > 0 else 0.0,
+              "note": "all rays of the step (no inside filter), 3 grids x 8 corners x 128 B per sample; grids (11.2 MB) are L2-resident, so the algorithmic "
+                      "bytes are served by L1 (neighbouring samples share corners) and L2; the roofline fraction is L2 bytes / time against the measured L2 gather peak"}
+        if gat.get("lts_t_bytes") and gather_ms > 0:
+            gs.update({"l1tex_t_bytes": gat.get("l1tex_t_bytes"), "lts_t_bytes": gat["lts_t_bytes"], "dram_bytes": gat.get("dram_bytes"),
+                       "l2_gbs": gat["lts_t_bytes"] / (gather_ms * 1e-3) * 1e-9, "l2_peak_gbs_measured": gat.get("l2_gather_peak_gbs"),
+                       "frac_of_l2_peak": gat["lts_t_bytes"] / (gather_ms * 1e-3) * 1e-9 / gat["l2_gather_peak_gbs"] if gat.get("l2_gather_peak_gbs") else None,
+                       "l1_gbs": (gat.get("l1tex_t_bytes") or 0) / (gather_ms * 1e-3) * 1e-9, "source": gat.get("_source")})
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic.get(dom), "peak_source": pk["source"] + " bf16 dense (sustained, kernel timed inside the step)",
-                "note": "algorithmic FLOPs (SURVEY 8-d: 2 x MACs of the three decoders x 48 samples x rays surviving the inside filter) / CUDA-event time of the kernel; "
-                        "the arithmetic is the fp32-grade fp16 two-way split (3 tensor-core MMAs per product, measured warp-MMA ceiling 556 TFLOP/s), so the design ceiling is 185 TFLOP/s algorithmic",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": kern[dom]["traffic"], "traffic_by_variant": {k: v for k, v in traffic.items() if not k.startswith("_")},
+                "peak_source": pk["source"] + " bf16 dense (sustained, kernel timed inside the step)",
+                "note": "algorithmic FLOPs (SURVEY 8-d: 2 x MACs of the three decoders x 48 samples x rays surviving the inside filter) / CUDA-event time of the kernel "
+                        "(second pass over the same K steps, kernels enqueued one by one); the arithmetic is the fp32-grade fp16 two-way split (3 tensor-core MMAs per "
+                        "product, measured warp-MMA ceiling 556 TFLOP/s), so the design ceiling is 185 TFLOP/s algorithmic",
                 "launches": K, "avg_launch_ms": kern[dom]["avg_launch_ms"], "kernels": kern,
-                "kernel_ms_total": kms,
-                "grid_sampling": {"kernel": "k_gather_only", "ms": gather_ms, "rays": RAYS_PER_GPU,
-                                  "achieved_gbs": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 if gather_ms > 0 else 0.0,
-                                  "frac_of_hbm_peak": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 / pk["hbm_gbs"] if gather_ms > 0 else 0.0,
-                                  "l2_gather_peak_gbs_measured": 9100.0, "note": "all rays of the step (no inside filter), 3 grids x 8 corners x 128 B per sample; grids (11.2 MB) are L2-resident"}}
+                "kernel_ms_total": kms, "ms_per_step_eager": float(np.mean(step_ms_eager)), "grid_sampling": gs}
+        cpu = None
         try:
-            cpu = cpu_baseline_sample(nsb) if world == 1 and not args.no_cpu_baseline else None
+            if world == 1 and not args.no_cpu_baseline:
+                cb = cpu_baselines(nsb, want_configs=configs is not None)
+                cpu = cb["mapping"]
+                if configs is not None:
+                    configs["forward_only"]["cpu_baseline"] = cb.get("forward")
+                    tracking["cpu_baseline"] = cb.get("tracking")
+                    if cb.get("forward"):
+                        configs["dense_render"]["cpu_baseline"] = dict(cb["forward"], sample="bounded: " + cb["forward"]["sample"] + " (a 5000-ray strip of the image)")
         except Exception as ex:  # the checker is optional for the bench line
             cpu = {"error": repr(ex)}
+        if configs is not None:
+            configs["tracking"] = tracking
+        clk = clocks.window(*win) if clocks else None
         out = {"metric": "mapping rays/s (fwd+bwd, 48 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": t_dev / K * 1e3, "ms_per_step_by_stage": {"geometry": ms_geom, "color": ms_color}, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "ms_per_step": t_dev_max / K * 1e3, "ms_per_step_rank0": t_dev / K * 1e3, "ms_per_step_by_stage": {"geometry": ms_geom, "color": ms_color, "geometry_steps": n_geom, "color_steps": n_color},
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": n_global,
-                          "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "step i = iteration i%60 of optimize_map (37 geometry + 23 colour)",
+                          "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "timed step k = iteration floor(k*60/K) (K<60) or k%60 of optimize_map (37 geometry + 23 colour)",
+                          "launch": "one cudaGraphLaunch per iteration (device-resident iteration state)",
                           "mma": "fp16 two-way split (3 products) on mma.sync m16n8k16, fp32 accumulate: fp32-grade", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
-                          "inside_fraction": frac_in},
-               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking,
+                          "raydir": "pinhole (library default)", "inside_fraction": frac_in},
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking, "configs": configs,
+               "parity": parity, "p2p_exchange": p2p_times,
                "loss_first_last": [float(losses[0]), float(losses[len(losses) - 1])]}
         print(json.dumps(out), flush=True)
     e.close()
@@ -405,16 +604,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the forward-only / dense-render sub-records")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="multi-GPU optimiser step: fused peer-memory kernel (default) or ncclAllReduce + Adam")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    args.warmup = max(args.warmup, 4)      # >= 3, and even: both stages get warmed
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))

@@ -38,13 +38,13 @@
 extern "C" {
 #endif
 
-#define NSB_ABI_VERSION 1
+#define NSB_ABI_VERSION 2
 
 enum { NSB_COARSE = 0, NSB_MIDDLE = 1, NSB_FINE = 2, NSB_COLOR = 3 }; /* grid level / decoder / stage id */
 /* decoder MMA precision.  0 (default): fp32-grade -- every operand is split into fp16 hi + lo and a product is three tensor-core
- * instructions (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate, ~2^-22 per product; it replaced a 3xTF32 split of the same
- * accuracy, hence the historical name).  1: one fp16 product (~2^-11), fast mode, outside the 1e-4 parity target. */
-enum { NSB_PREC_3XTF32 = 0, NSB_PREC_FP32_GRADE = 0, NSB_PREC_TF32 = 1, NSB_PREC_SINGLE = 1 };
+ * instructions (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, fp32 accumulate, ~2^-22 per product).
+ * 1: one fp16 product (~2^-11), fast mode, OUTSIDE the 1e-4 parity target -- never the benchmarked mode. */
+enum { NSB_PREC_FP32_GRADE = 0, NSB_PREC_FP16_SINGLE = 1 };
 enum { NSB_RAYDIR_REFERENCE = 0, NSB_RAYDIR_PINHOLE = 1 }; /* utils.h:44-47 as written / upstream pinhole */
 enum { NSB_DISTNORM_PER_RAY = 0, NSB_DISTNORM_REFERENCE = 1 }; /* upstream intent / utils.h:153 as written */
 
@@ -88,8 +88,14 @@ typedef struct nsb_config {
 } nsb_config;
 
 /* ---- configuration ------------------------------------------------------------------------------ */
-/* Reference defaults: config/nice_slam.yaml + config/cofusion.yaml + the literals of Renderer.cpp:5-15. */
+/* Reference defaults: config/nice_slam.yaml + config/cofusion.yaml + the literals of Renderer.cpp:5-15.
+ * ONE rule for the two places where the transliteration is degenerate: the default is the upstream formula the
+ * reference transliterates -- raydir = NSB_RAYDIR_PINHOLE (utils.h:45 uses the column index for the y direction, so every pixel
+ * of a column would cast the same ray) and dist_norm = NSB_DISTNORM_PER_RAY (utils.h:153 passes the dim as the norm order).
+ * nsb_config_reference_literal() switches both to the reference's literal arithmetic; the parity tests pin that mode bit-for-bit
+ * (rays) / to 1e-4 (render) against the reference's own compiled code. */
 void nsb_config_default(nsb_config* cfg);
+void nsb_config_reference_literal(nsb_config* cfg);
 /* Replaces YAML::LoadFile + the .as<T>() lookups of Mapper.cpp:6-34, Tracker.cpp:5-34, main.cpp:7-30.
  * Either path may be NULL.  Reads the YAML subset those files use (nested maps, scalars, comments). */
 int nsb_config_load_yaml(nsb_config* cfg, const char* nice_slam_yaml, const char* dataset_yaml, char* err, int err_len);
@@ -198,6 +204,13 @@ int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters,
  * stage and 0 before.  nsb_mapping_end writes the optimised poses back into the frame slots (est_c2w) and optionally
  * returns the 7-vectors ([n_frames][7]); nsb_get_frame_pose reads a slot's current [R|t] (3x4 row-major). */
 int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask);
+/* General form.  flags:
+ *   NSB_MAP_COARSE      the coarse mapper's optimize_map (Mapper(ns, cf, coarse_mapper = true); Mapper.cpp:335-338,351-352,450-453):
+ *                       stage "coarse" for every iteration, render_batch_ray("coarse"), only grid_coarse is optimised (coarse_lr);
+ *   NSB_MAP_FIX_COLOR   the colour decoder stays fixed for this call (color_refine sets fix_color, Mapper.cpp:505-513);
+ *   NSB_MAP_NO_FRUSTUM  no frustum feature selection for this call (color_refine: frustum_feature_selection = false). */
+enum { NSB_MAP_COARSE = 1, NSB_MAP_FIX_COLOR = 2, NSB_MAP_NO_FRUSTUM = 4 };
+int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask, int flags);
 int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out);
 /* d L / d (q, t) per frame at the last BA iteration, [n_frames][7] (parity checks of the pose-gradient chain). */
 int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s);
@@ -205,8 +218,11 @@ int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12);
 /* One joint iteration.  idx: host int64 [n_frames * (mapping_pixels / n_frames)] flat pixel indices, or NULL to
  * draw them from the context's mt19937 stream.  loss (host, may be NULL; reading it synchronises). */
 int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss);
-/* Enqueue only (no host sync); losses are later read with nsb_mapping_losses, indexed by STEP: the k-th nsb_mapping_iter* call
- * since nsb_mapping_begin is step k - 1, whatever `iter` it was given (a ring of the last 4096 steps is kept). */
+/* Enqueue only (no host sync).  The iteration is ONE cudaGraphLaunch: the kernel sequence of each variant (geometry / colour /
+ * bundle adjustment) is captured once, and everything that changes from iteration to iteration (statistics slot, index-pool row,
+ * Adam step count, peer-barrier epoch) is read by the kernels from a device-resident iteration state (NSB_GRAPH=0 enqueues the
+ * kernels one by one instead).  Losses are later read with nsb_mapping_losses, indexed by STEP: the k-th nsb_mapping_iter* call
+ * since nsb_mapping_begin is step k - 1, whatever `iter` it was given (the ring keeps max(4096, n_iters + 1) steps). */
 int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx);
 int nsb_mapping_losses(nsb_ctx* ctx, int first_step, int n, float* losses, int* n_inside);
 /* Optional: park the pixel indices of n_iters iterations ([n_iters][n] int64) in device memory; iterations called
@@ -214,6 +230,11 @@ int nsb_mapping_losses(nsb_ctx* ctx, int first_step, int n, float* losses, int* 
 int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n);
 /* Whole optimize_map: n_iters iterations, indices from the mt19937 stream; losses may be NULL. */
 int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, float* losses);
+/* Parity aid: with capture on, every iteration keeps a copy of its gradient arena (after loss.backward() of Mapper.cpp:444, before
+ * the exchange / optimiser step); the getters return it in the layouts of nsb_get_grid_grad / nsb_get_decoder_grad. */
+int nsb_mapping_capture_grads(nsb_ctx* ctx, int on);
+int nsb_get_captured_grid_grad(nsb_ctx* ctx, int level, float* host_ncdhw);
+int nsb_get_captured_decoder_grad(nsb_ctx* ctx, int which, float* host_flat, int64_t n);
 
 /* ---- tracking: Tracker::run / optimize_cam_in_batch (Tracker.cpp:41-113) ------------------------------ */
 int nsb_tracking_begin(nsb_ctx* ctx, int slot, const float* cam7);       /* Tracker.cpp:96-103 */
@@ -235,6 +256,11 @@ int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int wor
  * the reference batch element that ray i of the rendered order is, and its frame.  Rank r renders rays [r*n/world, (r+1)*n/world). */
 int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, int i, int* frame);
 int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world);
+/* Timing of the fused exchange kernel, stamped on the device with %globaltimer: out5 = {last wait-for-peers us, last kernel us,
+ * mean wait us, mean kernel us, exchanges averaged}; reset != 0 clears the sums.  wait = barrier 1 (the slowest rank's backward),
+ * kernel - wait = reduce-scatter + Adam + all-gather + barrier 2.  All ranks must issue the same call sequence: a barrier that
+ * waits longer than NSB_P2P_TIMEOUT_MS (default 20000) gives up and the next synchronising mapping call returns an error. */
+int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out5, int reset);
 
 /* ---- instrumentation ----------------------------------------------------------------------------------- */
 /* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */

@@ -19,6 +19,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LEVELS = ("coarse", "middle", "fine", "color")
 STAGE = {"coarse": 0, "middle": 1, "fine": 2, "color": 3}
 F_GRID, F_WGRAD, F_RAY = 1, 2, 4
+MAP_COARSE, MAP_FIX_COLOR, MAP_NO_FRUSTUM = 1, 2, 4          # nsb_mapping_begin_ex flags
+RAYDIR_REFERENCE, RAYDIR_PINHOLE = 0, 1
+DISTNORM_PER_RAY, DISTNORM_REFERENCE = 0, 1
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
 _i64p = C.POINTER(C.c_int64)
@@ -135,6 +138,13 @@ def load_library(variant=""):
     L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
     L.nsb_get_frame_pose.argtypes = [v, C.c_int, _fp]
     L.nsb_debug_counters.argtypes = [v, C.POINTER(C.c_uint64)]
+    L.nsb_comm_p2p_stats.argtypes = [v, C.POINTER(C.c_double), C.c_int]
+    L.nsb_config_reference_literal.argtypes = [C.POINTER(Config)]
+    L.nsb_config_reference_literal.restype = None
+    L.nsb_mapping_begin_ex.argtypes = [v, C.c_int, _ip, C.c_int, C.c_float, C.c_uint32, C.c_int]
+    L.nsb_mapping_capture_grads.argtypes = [v, C.c_int]
+    L.nsb_get_captured_grid_grad.argtypes = [v, C.c_int, _fp]
+    L.nsb_get_captured_decoder_grad.argtypes = [v, C.c_int, _fp, C.c_int64]
     _LIBS[variant] = L
     return L
 
@@ -150,12 +160,21 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
     "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source", "nsb_set_frame_async", "nsb_frames_ready", "nsb_host_alloc", "nsb_host_free", "nsb_save_checkpoint", "nsb_load_checkpoint", "nsb_comm_p2p_export", "nsb_comm_p2p_import",
+    "nsb_comm_p2p_stats", "nsb_config_reference_literal", "nsb_mapping_begin_ex", "nsb_mapping_capture_grads", "nsb_get_captured_grid_grad", "nsb_get_captured_decoder_grad",
 ]
 
 
 def default_config(variant=""):
     cfg = Config()
     load_library(variant).nsb_config_default(C.byref(cfg))
+    return cfg
+
+
+def reference_literal_config(variant=""):
+    """Defaults with the two degenerate formulas of the transliteration kept as written (utils.h:44-47 ray directions, utils.h:153
+    norm): the mode the bit-exact parity tests against the reference's own compiled code run in."""
+    cfg = default_config(variant)
+    load_library(variant).nsb_config_reference_literal(C.byref(cfg))
     return cfg
 
 
@@ -335,11 +354,20 @@ class Engine:
         self._ck(self.lib.nsb_render_batch_ray(self.h, STAGE[stage], n, _f(rd), _f(ro), _f(gd), _f(rgb), _f(depth), _f(var), _f(w)))
         return rgb, depth, var, w
 
-    def render_img(self, slot, stage, use_gt_depth=True, c2w=None):
-        """Dense render of every pixel of a resident frame (upstream render_img) -> rgb (H,W,3), depth (H,W), var (H,W)."""
+    def render_batch_ray_dev(self, stage, n, d_rays_d, d_rays_o, d_gt_depth, d_rgb, d_depth, d_var, d_weights):
+        """Device-pointer form (ints): enqueues on the context's stream, no host synchronisation."""
+        v = lambda p: None if not p else C.c_void_p(int(p))
+        self._ck(self.lib.nsb_render_batch_ray_dev(self.h, STAGE[stage], int(n), v(d_rays_d), v(d_rays_o), v(d_gt_depth), v(d_rgb), v(d_depth), v(d_var), v(d_weights)))
+
+    def render_img(self, slot, stage, use_gt_depth=True, c2w=None, want_outputs=True):
+        """Dense render of every pixel of a resident frame (upstream render_img) -> rgb (H,W,3), depth (H,W), var (H,W).
+        want_outputs=False renders without the image read-back (timing of the device work alone)."""
         H, W = self.cfg.H, self.cfg.W
-        rgb = np.empty((H, W, 3), np.float32); depth = np.empty((H, W), np.float32); var = np.empty((H, W), np.float32)
         p = None if c2w is None else _c(np.asarray(c2w, np.float32).reshape(-1))
+        if not want_outputs:
+            self._ck(self.lib.nsb_render_img(self.h, slot, _f(p), STAGE[stage], int(use_gt_depth), None, None, None))
+            return None
+        rgb = np.empty((H, W, 3), np.float32); depth = np.empty((H, W), np.float32); var = np.empty((H, W), np.float32)
         self._ck(self.lib.nsb_render_img(self.h, slot, _f(p), STAGE[stage], int(use_gt_depth), _f(rgb), _f(depth), _f(var)))
         return rgb, depth, var
 
@@ -371,11 +399,27 @@ class Engine:
         return out
 
     # ---- Mapper::optimize_map inner loop (Mapper.cpp:330-465)
-    def mapping_begin(self, slots, n_iters, lr_factor=1.0, ba_mask=0):
-        """ba_mask: bit f set -> the pose of slots[f] is optimised with the map (bundle adjustment, Mapper.cpp:305-329)."""
+    def mapping_begin(self, slots, n_iters, lr_factor=1.0, ba_mask=0, flags=0):
+        """ba_mask: bit f set -> the pose of slots[f] is optimised with the map (bundle adjustment, Mapper.cpp:305-329).
+        flags: MAP_COARSE (coarse mapper), MAP_FIX_COLOR / MAP_NO_FRUSTUM (color_refine, Mapper.cpp:505-513)."""
         s = np.ascontiguousarray(slots, np.int32)
         self._n_map_frames = len(s)
-        self._ck(self.lib.nsb_mapping_begin_ba(self.h, len(s), s.ctypes.data_as(_ip), n_iters, C.c_float(lr_factor), C.c_uint32(ba_mask)))
+        self._ck(self.lib.nsb_mapping_begin_ex(self.h, len(s), s.ctypes.data_as(_ip), n_iters, C.c_float(lr_factor), C.c_uint32(ba_mask), int(flags)))
+
+    def mapping_capture_grads(self, on=True):
+        self._ck(self.lib.nsb_mapping_capture_grads(self.h, int(on)))
+
+    def captured_grads(self):
+        """Gradient of the last iteration (before the optimiser step): grids in (1,C,Z,Y,X), the colour decoder flat."""
+        out = {}
+        for lv in LEVELS:
+            g = np.empty(self.grid_shape[lv], np.float32)
+            self._ck(self.lib.nsb_get_captured_grid_grad(self.h, STAGE[lv], _f(g)))
+            out["grid_" + lv] = g
+        d = np.empty(self.decoder_count("color"), np.float32)
+        self._ck(self.lib.nsb_get_captured_decoder_grad(self.h, STAGE["color"], _f(d), d.size))
+        out["dec_color"] = d
+        return out
 
     def mapping_end(self):
         """BA write-back (Mapper.cpp:467-489); returns the (n_frames, 7) camera vectors."""
@@ -465,6 +509,12 @@ class Engine:
             self._ck(self.lib.nsb_comm_p2p_import(self.h, None, rank, world)); return
         assert len(all_handles) == 192 * world
         self._ck(self.lib.nsb_comm_p2p_import(self.h, all_handles, rank, world))
+
+    def p2p_times(self, reset=False):
+        """Device-stamped timing of the fused exchange kernel (us): wait for the slowest rank vs the exchange itself."""
+        o = (C.c_double * 5)()
+        self._ck(self.lib.nsb_comm_p2p_stats(self.h, o, int(reset)))
+        return {"last_wait_us": o[0], "last_kernel_us": o[1], "mean_wait_us": o[2], "mean_kernel_us": o[3], "mean_exchange_us": o[3] - o[2], "exchanges": int(o[4])}
 
     def bench_gather(self, reps=20):
         ms = C.c_float(0)

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <random>
 #include <string>
 #include <vector>
@@ -39,6 +40,7 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
         default: return cudaErrorInvalidValue;   // 6 = RAY|WG is not instantiated
     }
 }
+cudaError_t wgrad_init();
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
@@ -86,7 +88,10 @@ enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
 
 // ---- context ---------------------------------------------------------------------------------------------------
 enum { T_SAMPLE = 0, T_FWD, T_COMP, T_BWD, T_WGRAD, T_ADAM, T_COMM, T_N };
-constexpr int LOSS_RING = 4096;
+constexpr int LOSS_RING_MIN = 4096;   // slots of the statistics / loss ring (grown to n_iters by nsb_mapping_begin)
+
+// One captured joint iteration (Mapper.cpp:331-465) per variant; replayed with a single cudaGraphLaunch.
+struct IterGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
 
 struct nsb_ctx {
     nsb_config cfg;
@@ -116,7 +121,16 @@ struct nsb_ctx {
     int64_t* idx = nullptr;
     int64_t* idx_pool = nullptr; int pool_iters = 0, pool_n = 0, pool_cursor = 0;   // optional device-resident pixel indices for many iterations
     float* pts = nullptr;
-    float* stats = nullptr;       // [LOSS_RING][4]: max gt depth, n inside, sum 1/|d|, loss
+    float* stats = nullptr;       // mapping loop: [ring][4]: max gt depth, n inside, sum 1/|d|, loss -- one slot per step
+    int ring = 0;                 // slots of `stats` (>= the n_iters of the current optimize_map: no loss is lost to a wrap)
+    float* rstats = nullptr;      // [2][4] scratch of the render / sampling / keyframe entry points (never the mapping ring)
+    int* it_state = nullptr;      // device iteration state of the mapping loop (IterRef, common.cuh)
+    double* bc1_tab = nullptr; float* bc2s_tab = nullptr; int tab_n = 0;   // Adam bias corrections per step (k_adam reads row state[0])
+    std::unordered_map<uint64_t, IterGraph> graphs;   // captured iteration per variant key
+    uint64_t graph_sig = 0;       // signature of everything baked into the captured launches; a change drops the cache
+    int use_graph = 1;            // NSB_GRAPH=0: enqueue every kernel from the host (also used while profiling)
+    bool capturing = false;
+    bool capture_grads = false; float* grad_snap = nullptr;   // nsb_mapping_capture_grads: copy of the gradient arena before the optimiser step
     float* median = nullptr; int* count = nullptr;
     float* trk_scratch = nullptr;   // [32] per-iteration tracking scratch (see nsb_tracking_iter)
     bool trk_hook = false; int* trk_count = nullptr;   // set around the tracking forward: the composite compacts |gt - depth|
@@ -131,8 +145,8 @@ struct nsb_ctx {
     int wimg_dirty = 0xE;        // bit d: decoder d's plain forward / backward images are stale
     int wimg_cmp_dirty = 0xE;    // bit d: decoder d's composed forward image is stale (rebuilt lazily: a colour decoder that is being
                                  // trained changes every iteration but runs on the plain image while its stash is needed)
-    unsigned long long* tile_ctr = nullptr;          // [4] ticket counters of the decoder kernels' tile scheduler (never reset)
-    unsigned long long tile_ticket[4] = {0, 0, 0, 0};   // host mirror: tickets handed out by the launches enqueued so far
+    unsigned long long* tile_ctr = nullptr;          // [8] ticket counters of the decoder kernels' tile scheduler: [0..3] forward,
+                                                     // [4..7] backward; cleared on the device by the kernel preceding each decoder launch
     int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
     unsigned long long* dbg = nullptr;   // 32 cycle counters (NSB_TC_TIMING builds)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
@@ -145,6 +159,10 @@ struct nsb_ctx {
     float* cam_grad_last = nullptr;   // [MAX_OPT_FRAMES][8] camera gradients of the last BA iteration (Adam zeroes the arena)
     cudaStream_t upload_stream = nullptr; cudaEvent_t ev_upload = nullptr; bool upload_pending = false;   // nsb_set_frame_async
     bool map_color_touched = false;   // a colour iteration has run since nsb_mapping_begin (see run_adam)
+    bool coarse_map = false;          // this optimize_map is the coarse mapper's (Mapper.cpp:335-338,351-352): stage "coarse", grid_coarse only
+    bool map_fix_color = false;       // colour decoder fixed for this optimize_map (mapping.fix_color, or color_refine: Mapper.cpp:505-513)
+    bool map_no_mask = false;         // frustum feature selection off for this optimize_map (color_refine)
+    unsigned long long p2p_timeout_ns = 20000000000ull;   // peer-barrier time-out (NSB_P2P_TIMEOUT_MS)
     uint32_t map_ba_mask = 0;      // bundle adjustment: frames (bit f) whose 7-vector pose is optimised with the map (Mapper.cpp:305-329)
     // tracking state
     int trk_slot = 0, trk_step = 0;
@@ -153,7 +171,7 @@ struct nsb_ctx {
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
     bool ar_request = false, ar_overlapped = false;
     // peer-memory optimiser step (nsb_comm_p2p_import): every rank's gradient / parameter arena and flag block, opened through CUDA IPC
-    bool p2p = false; uint32_t p2p_epoch = 0; uint32_t* p2p_flags = nullptr;
+    bool p2p = false; uint32_t* p2p_flags = nullptr;
     float* peer_grad[P2P_MAX_WORLD] = {nullptr}; float* peer_param[P2P_MAX_WORLD] = {nullptr}; uint32_t* peer_flags[P2P_MAX_WORLD] = {nullptr};
     int ar_mode = 1;               // NSB_AR_MODE: 0 = one full all-reduce per iteration; 1 (default) = short prefix in geometry iterations;
                                    // 2 = additionally the grid all-reduce of colour iterations on a second stream under the wgrad kernel
@@ -203,7 +221,10 @@ extern "C" void nsb_config_default(nsb_config* c) {
     c->grid_len[0] = 2.f; c->grid_len[1] = 0.32f; c->grid_len[2] = 0.16f; c->grid_len[3] = 0.16f;   // nice_slam.yaml:7-11
     c->coarse_bound_enlarge = 2; c->c_dim = 32;
     c->n_samples = 32; c->n_surface = 16; c->occupancy = 0;                                      // Renderer.cpp:9-10, utils.h:155
-    c->dist_norm = NSB_DISTNORM_PER_RAY; c->raydir = NSB_RAYDIR_REFERENCE;
+    // one rule for the two places where the transliteration is degenerate (SURVEY.md 8-A.3 decision table): the DEFAULT is the
+    // upstream formula the reference set out to transliterate (pinhole directions, per-ray L2 norm); nsb_config_reference_literal()
+    // switches both to the reference's literal arithmetic, which the parity tests pin bit-for-bit against the reference's own compiled code
+    c->dist_norm = NSB_DISTNORM_PER_RAY; c->raydir = NSB_RAYDIR_PINHOLE;
     c->mapping_pixels = 1000; c->mapping_iters = 60; c->mapping_iters_first = 1500;              // cofusion.yaml:20-22
     c->mapping_window_size = 5; c->keyframe_every = 50;
     c->middle_iter_ratio = 0.4f; c->fine_iter_ratio = 0.6f; c->second_stage = NSB_MIDDLE;        // Mapper.cpp:353-356
@@ -216,7 +237,7 @@ extern "C" void nsb_config_default(nsb_config* c) {
     c->tracking_lr = 0.01f; c->tracking_iters = 10;                                              // Tracker.cpp:103,107
     c->tracking_pixels = 200; c->ignore_edge_W = 20; c->ignore_edge_H = 20;
     c->handle_dynamic = 1; c->use_color_in_tracking = 1; c->w_color_loss = 0.5f;
-    c->precision = NSB_PREC_3XTF32; c->max_rays = 8192; c->max_frames = 8;
+    c->precision = NSB_PREC_FP32_GRADE; c->max_rays = 8192; c->max_frames = 8;
 }
 
 // Minimal YAML subset: nested maps by indentation, "key: scalar", comments, quotes.  Flattened to "a.b.c" -> value.
@@ -288,6 +309,8 @@ extern "C" int nsb_config_load_yaml(nsb_config* c, const char* ns_yaml, const ch
     return 0;
 }
 
+extern "C" void nsb_config_reference_literal(nsb_config* c) { c->raydir = NSB_RAYDIR_REFERENCE; c->dist_norm = NSB_DISTNORM_REFERENCE; }
+
 extern "C" void nsb_grid_dims(const nsb_config* c, int level, int* Z, int* Y, int* X) {
     if (c->grid_dim[level][0] > 0) { *Z = c->grid_dim[level][0]; *Y = c->grid_dim[level][1]; *X = c->grid_dim[level][2]; return; }
     int d[3];
@@ -340,6 +363,30 @@ extern "C" void nsb_get_tensor_from_camera(const float* c2w, float* cam7) {
 // ---- create / destroy ------------------------------------------------------------------------------------------
 template <typename T> static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
+static void drop_graphs(nsb_ctx* ctx) {
+    for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+}
+
+// Statistics ring and the Adam bias-correction tables, sized for `slots` steps (libtorch: bias_correction = 1 - beta^step in double).
+static int ensure_ring(nsb_ctx* ctx, int slots) {
+    if (ctx->ring >= slots) return 0;
+    if (ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);                                   // the ring pointers are baked into the captured launches
+    if (ctx->stats) cudaFree(ctx->stats);
+    if (ctx->bc1_tab) cudaFree(ctx->bc1_tab);
+    if (ctx->bc2s_tab) cudaFree(ctx->bc2s_tab);
+    ctx->stats = nullptr; ctx->bc1_tab = nullptr; ctx->bc2s_tab = nullptr; ctx->ring = 0;
+    CK(dalloc(&ctx->stats, 4 * (size_t)slots)); CK(dalloc(&ctx->bc1_tab, slots)); CK(dalloc(&ctx->bc2s_tab, slots));
+    std::vector<double> b1(slots); std::vector<float> b2(slots);
+    for (int t = 1; t <= slots; ++t) { b1[t - 1] = 1.0 - std::pow(0.9, (double)t); b2[t - 1] = (float)std::sqrt(1.0 - std::pow(0.999, (double)t)); }
+    CK(cudaMemcpy(ctx->bc1_tab, b1.data(), slots * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->bc2s_tab, b2.data(), slots * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->stats, 0, 4 * (size_t)slots * 4));
+    ctx->ring = slots; ctx->tab_n = slots;
+    return 0;
+}
+
 extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     *out = nullptr;
     nsb_ctx* ctx = new nsb_ctx();
@@ -354,6 +401,8 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     if (cfg->c_dim != CDIM) return fail(ctx, "c_dim %d unsupported (this build: 32)", cfg->c_dim);
     if (cfg->n_samples != 32 || (cfg->n_surface != 16 && cfg->n_surface != 0)) return fail(ctx, "n_samples/n_surface %d/%d unsupported (32 / 16|0)", cfg->n_samples, cfg->n_surface);
     if (cfg->max_frames < 1 || cfg->max_rays < 16) return fail(ctx, "max_frames / max_rays too small");
+    if (!cfg->fix_fine) return fail(ctx, "mapping.fix_fine = False is not supported: this build has no weight-gradient kernel for the fine decoder "
+                                         "(the reference adds fine_decoder.parameters() to the optimiser at Mapper.cpp:292-296); refusing instead of silently not training it");
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
@@ -407,12 +456,17 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
-    CK(dalloc(&ctx->tile_ctr, 4)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CK(dalloc(&ctx->tile_ctr, 8)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(dalloc(&ctx->it_state, 8)); CK(cudaMemsetAsync(ctx->it_state, 0, 8 * sizeof(int), ctx->stream));
+    CK(dalloc(&ctx->rstats, 8)); CK(cudaMemsetAsync(ctx->rstats, 0, 8 * 4, ctx->stream));
+    { const char* e = getenv("NSB_GRAPH"); ctx->use_graph = e ? atoi(e) : 1; }
+    { const char* e = getenv("NSB_P2P_TIMEOUT_MS"); if (e) ctx->p2p_timeout_ns = 1000000ull * strtoull(e, nullptr, 10); }
+    CK(wgrad_init());
     CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
-    CK(dalloc(&ctx->stats, 4 * (size_t)LOSS_RING)); CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
+    if (ensure_ring(ctx, LOSS_RING_MIN)) return -1;
+    CK(dalloc(&ctx->median, 4)); CK(dalloc(&ctx->count, 4));
     CK(dalloc(&ctx->trk_scratch, 32)); CK(cudaMemsetAsync(ctx->trk_scratch, 0, 32 * 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
     ctx->occ_blocks[0] = decode_fwd_occupancy(0); ctx->occ_blocks[1] = decode_fwd_occupancy(1);
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -425,7 +479,8 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->p2p) for (int w = 0; w < c->world; ++w) if (w != c->rank) { cudaIpcCloseMemHandle(c->peer_grad[w]); cudaIpcCloseMemHandle(c->peer_param[w]); cudaIpcCloseMemHandle(c->peer_flags[w]); }
     if (c->p2p_flags) cudaFree(c->p2p_flags);
-    void* ptrs[] = {c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
+    drop_graphs(c);
+    void* ptrs[] = {c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
                     c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
@@ -681,21 +736,26 @@ static void env_weights(const char* name, float w[4]) {
     if (sscanf(e, "%f,%f,%f,%f", &a, &b, &c, &d) == 4) { if (w[0] > 0) w[0] = a; if (w[1] > 0) w[1] = b; if (w[2] > 0) w[2] = c; if (w[3] > 0) w[3] = d; }
 }
 
-// cmp_mask: decoders whose COMPOSED forward image the coming launch reads (the plain / backward images are always kept fresh).
-static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid, int cmp_mask = 0) {
-    memset(&P, 0, sizeof P);
-    const int cmp_need = ctx->wimg_cmp_dirty & cmp_mask;
-    if (ctx->wimg_dirty || cmp_need) {   // decoder weights changed (set_decoder / an Adam step with a decoder learning rate): rebuild the pre-split images
-        const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
-        bool ok = true;
-        if (ctx->comp_dirty & cmp_need) {   // the composed images are built from k_compose's output
-            ok = launch_compose(flat, ctx->comp, ctx->comp_dirty & cmp_need, ctx->stream) == cudaSuccess;
-            if (ok) { ctx->launches++; ctx->comp_dirty &= ~cmp_need; }
-        }
-        if (ok && launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, ctx->wimg_dirty, cmp_need, ctx->stream) == cudaSuccess) {
-            ctx->launches++; ctx->wimg_dirty = 0; ctx->wimg_cmp_dirty &= ~cmp_need;
-        }
+// Rebuilds the pre-split shared-memory images of the decoders whose weights changed (set_decoder / an Adam step with a decoder
+// learning rate).  cmp_mask: decoders whose COMPOSED forward image the coming launches read.  force: rebuild these decoders
+// whatever the dirty bits say (the captured colour iteration ends with the rebuild of the colour decoder it has just stepped).
+static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
+    const int plain = ctx->wimg_dirty | force;
+    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | force;
+    if (!plain && !cmp_need) return 0;
+    const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
+    const int comp_need = (ctx->comp_dirty & cmp_need) | force;
+    if (comp_need) {   // the composed images are built from k_compose's output
+        CK(launch_compose(flat, ctx->comp, comp_need, ctx->stream)); ctx->launches++;
+        ctx->comp_dirty &= ~comp_need;
     }
+    CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
+    ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
+    return 0;
+}
+
+static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
+    memset(&P, 0, sizeof P);
     for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; }
     P.bnd = ctx->bnd;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
@@ -704,17 +764,7 @@ static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, cons
     P.g_raw = ctx->g_raw; P.d_rays = ctx->d_rays; P.stash = nullptr; P.masks = nullptr;
 }
 
-// Reserves this launch's tickets of the tile scheduler: each of decoder d's warps draws tickets until one is past the last tile,
-// so a launch consumes exactly ntiles + (number of warps of d) tickets of counter d.
-static void reserve_tiles(nsb_ctx* ctx, DecodeParams& P, int warps_per_cta) {
-    const int ntiles = cdiv(P.P, TILE);
-    P.tile_ctr = ctx->tile_ctr;
-    for (int d = 0; d < 4; ++d) {
-        P.tile_base[d] = ctx->tile_ticket[d];
-        const int nc = P.cta_begin[d + 1] - P.cta_begin[d];
-        if (nc > 0) ctx->tile_ticket[d] += (unsigned long long)ntiles + (unsigned long long)nc * warps_per_cta;
-    }
-}
+static const IterRef NO_ITER = {nullptr, 1};
 
 static int decode_grid_size(nsb_ctx* ctx, int P) {
     const int occ = std::max(1, ctx->occ_blocks[ctx->cfg.precision ? 1 : 0]);
@@ -743,7 +793,9 @@ static int ensure_stash(nsb_ctx* ctx, size_t rows) {
 }
 
 // train: keep the relu masks for run_backward; stash_fwd: also write the colour decoder's activations to the wgrad stash.
-static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, bool want_weights,
+// stats: base of a statistics ring, `it` selects the slot on the device ({nullptr, 1}: slot 0).  The decoder images must be fresh
+// (refresh_images) before this is called.
+static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth, const uint8_t* valid, float* stats, IterRef it, bool want_weights,
                        bool train = false, bool stash_fwd = false, bool skip_composite = false) {
     const nsb_config& c = ctx->cfg;
     const int S = have_depth ? c.n_samples + c.n_surface : c.n_samples;
@@ -751,7 +803,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
     {
         Timer t(ctx, T_SAMPLE);
         ZParams Z; Z.rays_o = ctx->rays_o + 3 * off; Z.rays_d = ctx->rays_d + 3 * off; Z.gt_depth = have_depth ? ctx->gt_depth + off : nullptr;
-        Z.valid = valid ? valid + off : nullptr; Z.stats = stats; Z.t_samples = ctx->t_samples; Z.t_surface = ctx->t_surface; Z.bnd = ctx->bnd;
+        Z.valid = valid ? valid + off : nullptr; Z.stats = stats; Z.it = it; Z.zero_ctr = ctx->tile_ctr; Z.t_samples = ctx->t_samples; Z.t_surface = ctx->t_surface; Z.bnd = ctx->bnd;
         Z.n = n; Z.n_samples = c.n_samples; Z.n_surface = have_depth ? c.n_surface : 0; Z.z = ctx->z + (size_t)off * S;
         k_zvals<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Z); ctx->launches++;
         CK(cudaGetLastError());
@@ -760,7 +812,8 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         Timer t(ctx, T_FWD);
         // the forward runs on the composed images, except for a colour decoder whose activations are stashed for the weight gradient
         const bool will_stash = train && stash_fwd && stage == NSB_COLOR;
-        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr, will_stash ? 0x6 : 0xE);
+        (void)will_stash;
+        DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
         if (train) P.masks = ctx->masks;
@@ -768,12 +821,13 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         float w[4]; stage_decoders(stage, w);
         if (P.stash) { w[1] = 700; w[2] = 972; w[3] = 860; }   // the colour decoder also writes its activations to the wgrad stash (measured split, tools/sweep_split.sh)
         env_weights("NSB_SPLIT_FWD", w);
-        const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_3XTF32 && stage != NSB_COARSE && P.stash == nullptr;
+        const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && P.stash == nullptr;
         if (tc_ok) {
             // tcgen05 path: one 320-thread CTA per SM, per-sample mask words, composed weights refreshed when stale
             int need = 0;
             for (int d = 1; d < 4; ++d) if (w[d] > 0 && ((ctx->comp_dirty >> d) & 1)) need |= 1 << d;
             if (need) {
+                if (ctx->capturing) return fail(ctx, "tcgen05 forward: composed weights must be fresh before graph capture");
                 const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
                 CK(launch_compose(flat, ctx->comp, need, ctx->stream)); ctx->launches++;
                 ctx->comp_dirty &= ~need;
@@ -794,7 +848,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             if (train) { ctx->mask_layout = 0; ctx->mask_stride = 0; }
             const int grid = decode_grid_size(ctx, n * S);
             partition(grid, w, P.cta_begin);
-            reserve_tiles(ctx, P, FWD_WARPS);
+            P.tile_ctr = ctx->tile_ctr;
             CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
         }
     }
@@ -803,7 +857,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         CompositeParams Q; memset(&Q, 0, sizeof Q);
         Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
         Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
-        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.stats = stats; Q.it = it; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
         Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = want_weights ? ctx->o_w + (size_t)off * S : nullptr;
         if (ctx->trk_hook) { Q.trk_gt_depth = ctx->gt_depth + off; Q.trk_absdiff = ctx->absdiff; Q.trk_count = ctx->trk_count; }
         k_composite_fwd<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q); ctx->launches++;
@@ -821,7 +875,7 @@ static int allreduce_range(nsb_ctx* ctx, size_t begin, size_t end, cudaStream_t 
 }
 
 // cotangents in ctx->g_rgb / g_depth / g_var -> g_raw -> decoder backward (+ wgrad).  flags: F_GRID=1, F_WGRAD=2, F_RAY=4.
-static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, int flags, bool color_active,
+static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* valid, float* stats, IterRef it, int flags, bool color_active,
                         bool skip_composite = false) {
     const nsb_config& c = ctx->cfg;
     const int S = ctx->last_S;
@@ -830,7 +884,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         CompositeParams Q; memset(&Q, 0, sizeof Q);
         Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = valid ? valid + off : nullptr;
         Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
-        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.stats = stats; Q.it = it; Q.zero_ctr = ctx->tile_ctr + 4; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
         Q.g_rgb = ctx->g_rgb + 3 * off; Q.g_depth = ctx->g_depth + off; Q.g_var = ctx->g_var + off; Q.g_raw = ctx->g_raw + 4 * (size_t)off * S;
         if (flags & 4) { CK(cudaMemsetAsync(ctx->d_rays + 6 * (size_t)off, 0, 6 * (size_t)n * 4, ctx->stream)); Q.d_rays = ctx->d_rays + 6 * (size_t)off; }
         k_composite_bwd<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q); ctx->launches++;
@@ -855,7 +909,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         const int grid = decode_grid_size(ctx, n * S);
         partition(grid, w, P.cta_begin);
         P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
-        reserve_tiles(ctx, P, BWD_WARPS);
+        P.tile_ctr = ctx->tile_ctr + 4;
         CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
     }
     ctx->ar_overlapped = false;
@@ -888,7 +942,7 @@ static void fill_sample_params(nsb_ctx* ctx, SampleParams& P, int n, int H0, int
     P.H = c.H; P.W = c.W; P.H0 = H0; P.W0 = W0; P.Wc = W1 - W0;
     P.fx = c.fx; P.fy = c.fy; P.cx = c.cx; P.cy = c.cy; P.raydir = c.raydir; P.bnd = ctx->bnd; P.n = n;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.gt_depth = ctx->gt_depth; P.gt_color = ctx->gt_color; P.valid = ctx->valid;
-    P.stats = stats; P.apply_filter = apply_filter;
+    P.stats = stats; P.apply_filter = apply_filter; P.it = NO_ITER; P.pool = nullptr; P.pool_iters = 1;
 }
 
 extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H0, int H1, int W0, int W1, int n, const int64_t* idx,
@@ -902,8 +956,8 @@ extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H
     if (idx_out) memcpy(idx_out, ctx->h_idx.data(), n * sizeof(int64_t));
     CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
-    SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, ctx->stats, 1);
+    CK(cudaMemsetAsync(ctx->rstats, 0, 16, ctx->stream));
+    SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, ctx->rstats, 1);
     P.slots[0] = slot; P.n_frames = 1; P.pix_per_frame = n;
     k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
     CK(cudaGetLastError());
@@ -917,10 +971,11 @@ extern "C" int nsb_get_samples(nsb_ctx* ctx, int slot, const float* c2w16, int H
 }
 
 // ---- render API -------------------------------------------------------------------------------------------------------
+// the render / sampling entry points keep their batch statistics in ctx->rstats, never in the mapping loop's ring
 static int render_prepare_stats(nsb_ctx* ctx, int n, bool have_depth) {
-    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
-    if (have_depth) { k_depth_max<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->gt_depth, n, ctx->stats); ctx->launches++; }
-    if (ctx->cfg.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, n, ctx->stats); ctx->launches++; }
+    CK(cudaMemsetAsync(ctx->rstats, 0, 16, ctx->stream));
+    if (have_depth) { k_depth_max<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->gt_depth, n, ctx->rstats); ctx->launches++; }
+    if (ctx->cfg.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, n, ctx->rstats, NO_ITER); ctx->launches++; }
     CK(cudaGetLastError());
     return 0;
 }
@@ -936,7 +991,8 @@ extern "C" int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const fl
     CK(cudaMemcpyAsync(ctx->rays_o, d_rays_o, 12 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (hd) CK(cudaMemcpyAsync(ctx->gt_depth, d_gt_depth, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (render_prepare_stats(ctx, n, hd)) return -1;
-    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, d_weights != nullptr)) return -1;
+    if (refresh_images(ctx, 0xE)) return -1;
+    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->rstats, NO_ITER, d_weights != nullptr)) return -1;
     if (d_rgb) CK(cudaMemcpyAsync(d_rgb, ctx->o_rgb, 12 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d_depth) CK(cudaMemcpyAsync(d_depth, ctx->o_depth, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d_var) CK(cudaMemcpyAsync(d_var, ctx->o_var, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -964,11 +1020,12 @@ extern "C" int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float*
     if (hd) for (int i = 0; i < n; ++i) gmax = std::max(gmax, gt_depth[i]);
     if (ctx->cfg.dist_norm == NSB_DISTNORM_REFERENCE) for (int i = 0; i < 3 * n; ++i) inv += 1.0 / std::fabs((double)rays_d[i]);
     const float st[4] = {gmax, 0.f, (float)inv, 0.f};
+    if (refresh_images(ctx, 0xE)) return -1;
     for (int o = 0; o < n; o += ctx->cap) {
         const int m = std::min(ctx->cap, n - o);
         if (upload_rays(ctx, m, rays_d + 3 * (size_t)o, rays_o + 3 * (size_t)o, hd ? gt_depth + o : nullptr)) return -1;
-        CK(cudaMemcpyAsync(ctx->stats, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
-        if (run_forward(ctx, stage, 0, m, hd, nullptr, ctx->stats, weights != nullptr)) return -1;
+        CK(cudaMemcpyAsync(ctx->rstats, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
+        if (run_forward(ctx, stage, 0, m, hd, nullptr, ctx->rstats, NO_ITER, weights != nullptr)) return -1;
         if (rgb) CK(cudaMemcpyAsync(rgb + 3 * (size_t)o, ctx->o_rgb, 12 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         if (depth) CK(cudaMemcpyAsync(depth + o, ctx->o_depth, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         if (var) CK(cudaMemcpyAsync(var + o, ctx->o_var, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
@@ -990,13 +1047,14 @@ extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int st
     const nsb_config& c = ctx->cfg;
     const int HW = c.H * c.W;
     if (c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * slot, c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    float* stats = ctx->stats + 4 * (LOSS_RING - 1);     // whole-image scalars (kept apart from the per-chunk scratch in stats[0..3])
+    float* stats = ctx->rstats + 4;     // whole-image scalars (kept apart from the per-chunk scratch in rstats[0..3])
     CK(cudaMemsetAsync(stats, 0, 16, ctx->stream));
+    if (refresh_images(ctx, 0xE)) return -1;
     const bool ref_norm = c.dist_norm == NSB_DISTNORM_REFERENCE;
     auto sample_chunk = [&](int o, int m) -> int {
         k_iota<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->idx, (int64_t)o, m);
-        CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
-        SampleParams P; fill_sample_params(ctx, P, m, 0, c.H, 0, c.W, ctx->stats, 0);
+        CK(cudaMemsetAsync(ctx->rstats, 0, 16, ctx->stream));
+        SampleParams P; fill_sample_params(ctx, P, m, 0, c.H, 0, c.W, ctx->rstats, 0);
         P.slots[0] = slot; P.n_frames = 1; P.pix_per_frame = m;
         k_sample<<<cdiv(m, 128), 128, 0, ctx->stream>>>(P); ctx->launches += 2;
         CK(cudaGetLastError());
@@ -1007,13 +1065,13 @@ extern "C" int nsb_render_img(nsb_ctx* ctx, int slot, const float* c2w16, int st
         for (int o = 0; o < HW; o += ctx->cap) {
             const int m = std::min(ctx->cap, HW - o);
             if (sample_chunk(o, m)) return -1;
-            k_dirnorm_ref<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, m, stats); ctx->launches++;
+            k_dirnorm_ref<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->rays_d, nullptr, m, stats, NO_ITER); ctx->launches++;
         }
     }
     for (int o = 0; o < HW; o += ctx->cap) {
         const int m = std::min(ctx->cap, HW - o);
         if (sample_chunk(o, m)) return -1;
-        if (run_forward(ctx, stage, 0, m, use_gt_depth != 0, nullptr, stats, false)) return -1;
+        if (run_forward(ctx, stage, 0, m, use_gt_depth != 0, nullptr, stats, NO_ITER, false)) return -1;
         if (rgb) CK(cudaMemcpyAsync(rgb + 3 * (size_t)o, ctx->o_rgb, 12 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         if (depth) CK(cudaMemcpyAsync(depth + o, ctx->o_depth, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         if (var) CK(cudaMemcpyAsync(var + o, ctx->o_var, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1036,14 +1094,16 @@ extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts
     const nsb_config& c = ctx->cfg;
     const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
     std::vector<float> h_rgb, h_occ[3];
+    if (refresh_images(ctx, 0xE)) return -1;
     for (size_t o = 0; o < (size_t)Pn; o += cap_pts) {
         const int m = (int)std::min(cap_pts, (size_t)Pn - o);
         CK(cudaMemcpyAsync(ctx->pts, pts + 3 * o, 12 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr, 0xE);
+        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr);
         P.pts = ctx->pts; P.P = m;
         float w[4]; stage_decoders(stage, w);
         partition(decode_grid_size(ctx, m), w, P.cta_begin);
-        reserve_tiles(ctx, P, FWD_WARPS);
+        P.tile_ctr = ctx->tile_ctr;
+        CK(cudaMemsetAsync(ctx->tile_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
         CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
         h_rgb.resize(4 * (size_t)m); for (int k = 0; k < 3; ++k) h_occ[k].resize(m);
         CK(cudaMemcpyAsync(h_rgb.data(), ctx->raw_rgb, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1072,11 +1132,12 @@ extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_
     if (upload_rays(ctx, n, rays_d, rays_o, gt_depth)) return -1;
     if (render_prepare_stats(ctx, n, hd)) return -1;
     if (zero_grads(ctx)) return -1;
-    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->stats, false, true, (flags & 2) != 0)) return -1;
+    if (refresh_images(ctx, 0xE)) return -1;
+    if (run_forward(ctx, stage, 0, n, hd, nullptr, ctx->rstats, NO_ITER, false, true, (flags & 2) != 0)) return -1;
     CK(cudaMemcpyAsync(ctx->g_rgb, g_rgb, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->g_depth, g_depth, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->g_var, g_var, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    if (run_backward(ctx, stage, 0, n, nullptr, ctx->stats, flags, true)) return -1;
+    if (run_backward(ctx, stage, 0, n, nullptr, ctx->rstats, NO_ITER, flags, true)) return -1;
     if (flags & 4) {
         std::vector<float> h(6 * (size_t)n);
         CK(cudaMemcpyAsync(h.data(), ctx->d_rays, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1090,55 +1151,67 @@ extern "C" int nsb_render_vjp(nsb_ctx* ctx, int stage, int n, const float* rays_
     return 0;
 }
 
+// Peer-memory mode: did a barrier of k_reduce_adam give up (a peer never launched its kernel)?  Called at the synchronising
+// entry points of the mapping loop.
+static int p2p_check(nsb_ctx* ctx) {
+    if (!ctx->p2p) return 0;
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->p2p_flags + 18, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag) return fail(ctx, "peer-memory optimiser step: a barrier timed out after %llu ms (a rank did not launch its iteration; "
+                               "all ranks must issue the same call sequence)", ctx->p2p_timeout_ns / 1000000ull);
+    return 0;
+}
+
 // ---- Adam -----------------------------------------------------------------------------------------------------------
 // color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first
 // colour iteration): gradient, m and v of the colour grid / colour decoder are all exactly zero, the Adam update is the identity
 // (p - step * 0 / (0 + eps) = p), so those segments are left out of the launch.
-static void build_adam(nsb_ctx* ctx, AdamParams& A, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine) {
+// The step count is NOT a launch parameter: the kernel reads it from the device iteration state (IterRef) and looks the bias
+// corrections up in the tables ensure_ring() wrote, so the same launch serves every iteration (CUDA-graph replay).
+static void build_adam(nsb_ctx* ctx, AdamParams& A, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine) {
     memset(&A, 0, sizeof A);
     A.param = ctx->param; A.grad = ctx->grad; A.m = ctx->m; A.v = ctx->v;
     const double b1 = 0.9, b2 = 0.999;
-    const double bc1 = 1.0 - std::pow(b1, (double)step), bc2 = 1.0 - std::pow(b2, (double)step);
     A.beta1 = (float)b1; A.beta2 = (float)b2; A.om_beta1 = (float)(1.0 - b1); A.om_beta2 = (float)(1.0 - b2); A.eps = 1e-8f;
-    A.bc2_sqrt = (float)std::sqrt(bc2); A.grad_scale = 1.0f;
+    A.bc1 = 1.0; A.bc2_sqrt = 1.0f; A.bc1_tab = ctx->bc1_tab; A.bc2s_tab = ctx->bc2s_tab; A.tab_n = ctx->tab_n;
+    A.it.state = ctx->it_state; A.it.ring = ctx->ring;
+    A.grad_scale = 1.0f;
     int k = 0;
     auto add = [&](size_t begin, size_t n, float lr, const uint8_t* mask, int active) {
-        AdamSegment& s = A.seg[k++]; s.begin = (int)begin; s.end = (int)(begin + pad32(n)); s.step = (float)((double)lr / bc1); s.mask = mask; s.active = active;
+        AdamSegment& s = A.seg[k++]; s.begin = (int)begin; s.end = (int)(begin + pad32(n)); s.lr = lr; s.mask = mask; s.active = active;
     };
-    for (int l = 1; l < (color_pristine ? 3 : 4); ++l) add(ctx->off_grid[l], ctx->nvox[l] * CDIM, lr_group[1 + l], ctx->vmask[l], 1);   // groups 2,3,4 = middle, fine, color
-    add(ctx->off_dec[2], ctx->dec_n[2], lr_group[0], nullptr, dec_fine ? 1 : 0);
-    if (!color_pristine) add(ctx->off_dec[3], ctx->dec_n[3], lr_group[0], nullptr, dec_color ? 1 : 0);
+    if (ctx->coarse_map) add(ctx->off_grid[0], ctx->nvox[0] * CDIM, lr_group[1], ctx->map_no_mask ? nullptr : ctx->vmask[0], 1);                                     // group 1 = coarse (coarse mapper only)
+    else for (int l = 1; l < (color_pristine ? 3 : 4); ++l) add(ctx->off_grid[l], ctx->nvox[l] * CDIM, lr_group[1 + l], ctx->map_no_mask ? nullptr : ctx->vmask[l], 1);   // groups 2,3,4 = middle, fine, color
+    if (!ctx->coarse_map) {
+        add(ctx->off_dec[2], ctx->dec_n[2], lr_group[0], nullptr, dec_fine ? 1 : 0);
+        if (!color_pristine) add(ctx->off_dec[3], ctx->dec_n[3], lr_group[0], nullptr, dec_color ? 1 : 0);
+    }
     if (n_cam_floats > 0) add(ctx->off_cam, n_cam_floats, lr_group[5], nullptr, 1);
     add(ctx->off_tail, 32, 0.f, nullptr, 0);
     A.n_seg = k;
     A.cum4[0] = 0;
     for (int s = 0; s < k; ++s) A.cum4[s + 1] = A.cum4[s] + (A.seg[s].end - A.seg[s].begin) / 4;
-    if (dec_fine && lr_group[0] != 0.f) { ctx->comp_dirty |= 1 << 2; ctx->wimg_dirty |= 1 << 2; ctx->wimg_cmp_dirty |= 1 << 2; }
-    if (dec_color && lr_group[0] != 0.f && !color_pristine) { ctx->comp_dirty |= 1 << 3; ctx->wimg_dirty |= 1 << 3; ctx->wimg_cmp_dirty |= 1 << 3; }
+    A.loss_dst = ctx->stats; A.loss_idx4 = (int)(ctx->off_tail / 4);
 }
 
-// color_pristine: no colour gradient has been produced since the optimiser was created (geometry iterations before the first
-// colour iteration): gradient, m and v of the colour grid / colour decoder are all exactly zero, the Adam update is the identity
-// (p - step * 0 / (0 + eps) = p), so those segments are left out of the launch.
-static int run_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine = false,
-                    float* loss_dst = nullptr) {
+static int run_adam(nsb_ctx* ctx, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine) {
     Timer t(ctx, T_ADAM);
-    AdamParams A; build_adam(ctx, A, step, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
-    A.loss_dst = loss_dst; A.loss_idx4 = (int)(ctx->off_tail / 4);
+    AdamParams A; build_adam(ctx, A, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
     k_adam<<<cdiv(A.cum4[A.n_seg], 256 * ADAM_VEC), 256, 0, ctx->stream>>>(A); ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
 // Multi-GPU optimiser step over peer memory (p2p_kernels.cuh): floats [begin, end) of the arena are exchanged and stepped.
-static int run_reduce_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine,
+static int run_reduce_adam(nsb_ctx* ctx, const float lr_group[6], bool dec_fine, bool dec_color, int n_cam_floats, bool color_pristine,
                            size_t begin, size_t end) {
     Timer t(ctx, T_COMM);
     P2PParams P; memset(&P, 0, sizeof P);
-    build_adam(ctx, P.A, step, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
+    build_adam(ctx, P.A, lr_group, dec_fine, dec_color, n_cam_floats, color_pristine);
     for (int w = 0; w < ctx->world; ++w) { P.peer_grad[w] = ctx->peer_grad[w]; P.peer_param[w] = ctx->peer_param[w]; P.peer_flags[w] = ctx->peer_flags[w]; }
     P.rank = ctx->rank; P.world = ctx->world; P.lo4 = (int)(begin / 4); P.hi4 = (int)(end / 4); P.loss4 = (int)(ctx->off_tail / 4);
-    P.epoch = ++ctx->p2p_epoch;
+    P.stats_base = ctx->stats; P.timeout_ns = ctx->p2p_timeout_ns;
     k_reduce_adam<<<ctx->n_sm * 2, 256, 0, ctx->stream>>>(P); ctx->launches++;
     CK(cudaGetLastError());
     // every peer has finished reading this rank's gradients when the kernel retires: clear them for the next iteration
@@ -1147,7 +1220,8 @@ static int run_reduce_adam(nsb_ctx* ctx, int step, const float lr_group[6], bool
 }
 
 // ---- mapping ----------------------------------------------------------------------------------------------------------
-static int stage_of_iter(const nsb_config& c, int it, int n_iters) {   // Mapper.cpp:351-358
+static int stage_of_iter(const nsb_config& c, int it, int n_iters, bool coarse) {   // Mapper.cpp:351-358
+    if (coarse) return NSB_COARSE;                                                  // Mapper.cpp:351-352
     if (it <= (int)((float)n_iters * c.middle_iter_ratio)) return NSB_MIDDLE;
     if (it <= (int)((float)n_iters * c.fine_iter_ratio)) return c.second_stage;
     return NSB_COLOR;
@@ -1155,25 +1229,60 @@ static int stage_of_iter(const nsb_config& c, int it, int n_iters) {   // Mapper
 
 extern "C" int nsb_mapping_begin(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
-    return nsb_mapping_begin_ba(ctx, n_frames, slots, n_iters, lr_factor, 0u);
+    return nsb_mapping_begin_ex(ctx, n_frames, slots, n_iters, lr_factor, 0u, 0);
+}
+extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask) {
+    cudaSetDevice(ctx->device);
+    return nsb_mapping_begin_ex(ctx, n_frames, slots, n_iters, lr_factor, ba_mask, 0);
+}
+
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+// Everything a captured iteration bakes into its launch parameters besides nsb_config (fixed per context).
+static uint64_t graph_signature(const nsb_ctx* ctx) {
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(h, &ctx->map_frames, sizeof ctx->map_frames); h = fnv1a(h, ctx->map_slots, sizeof(int) * ctx->map_frames);
+    h = fnv1a(h, &ctx->map_lr_factor, sizeof(float)); h = fnv1a(h, &ctx->map_ba_mask, sizeof(uint32_t));
+    h = fnv1a(h, &ctx->coarse_map, sizeof ctx->coarse_map); h = fnv1a(h, &ctx->map_fix_color, sizeof ctx->map_fix_color);
+    h = fnv1a(h, &ctx->map_no_mask, sizeof ctx->map_no_mask);
+    h = fnv1a(h, &ctx->rank, sizeof(int)); h = fnv1a(h, &ctx->world, sizeof(int)); h = fnv1a(h, &ctx->p2p, sizeof(bool));
+    h = fnv1a(h, ctx->vmask, sizeof ctx->vmask); h = fnv1a(h, &ctx->idx_pool, sizeof ctx->idx_pool);
+    h = fnv1a(h, &ctx->pool_iters, sizeof(int)); h = fnv1a(h, &ctx->pool_n, sizeof(int));
+    h = fnv1a(h, &ctx->stash, sizeof ctx->stash); h = fnv1a(h, &ctx->grad_snap, sizeof ctx->grad_snap);
+    h = fnv1a(h, &ctx->cfg.mapping_pixels, sizeof(int)); h = fnv1a(h, &ctx->ar_mode, sizeof(int));
+    return h;
 }
 
 // ba_mask bit f: frame f's pose joins the optimisation as a 7-vector (Mapper.cpp:305-329: every frame of optimize_frame but
 // the oldest one when BA is on); its lr is BA_cam_lr in the colour stage and 0 before (Mapper.cpp:366-368).
-extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask) {
+// flags: NSB_MAP_COARSE = the coarse mapper (Mapper.cpp:335-338,351-352,450-453: stage "coarse", only grid_coarse is optimised);
+// NSB_MAP_FIX_COLOR = keep the colour decoder fixed for this call (color_refine, Mapper.cpp:505-513 sets fix_color);
+// NSB_MAP_NO_FRUSTUM = no frustum feature selection for this call (color_refine: frustum_feature_selection = false).
+extern "C" int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask, int flags) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
     if (n_frames < 1 || n_frames > MAX_OPT_FRAMES) return fail(ctx, "n_frames %d out of range", n_frames);
     if (n_frames > ctx->cfg.max_frames) return fail(ctx, "n_frames %d exceeds max_frames %d", n_frames, ctx->cfg.max_frames);
     const int pix = ctx->cfg.mapping_pixels / n_frames;   // Mapper.cpp:223
     if (pix * n_frames > ctx->cap) return fail(ctx, "mapping_pixels %d exceeds max_rays %d", ctx->cfg.mapping_pixels, ctx->cap);
+    if ((flags & NSB_MAP_COARSE) && ctx->world > 1) return fail(ctx, "the coarse mapper runs on one GPU (its gradient is 15 KB)");
     for (int f = 0; f < n_frames; ++f) { if (slots[f] < 0 || slots[f] >= ctx->cfg.max_frames) return fail(ctx, "bad slot %d", slots[f]); ctx->map_slots[f] = slots[f]; }
     ctx->map_frames = n_frames; ctx->map_iters = n_iters; ctx->map_step = 0; ctx->map_lr_factor = lr_factor; ctx->map_color_touched = false;
+    ctx->coarse_map = (flags & NSB_MAP_COARSE) != 0;
+    ctx->map_fix_color = ctx->cfg.fix_color || (flags & NSB_MAP_FIX_COLOR) != 0;
+    ctx->map_no_mask = (flags & NSB_MAP_NO_FRUSTUM) != 0;   // explicit masks (nsb_set_voxel_mask) are ignored too
+    if (ensure_ring(ctx, std::max(LOSS_RING_MIN, n_iters + 1))) return -1;   // every step of this optimize_map keeps its loss slot
     // a fresh torch::optim::Adam is constructed per optimize_map (Mapper.cpp:330): state starts at zero
     CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->grad, 0, ctx->arena_n * 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->stats, 0, 4 * (size_t)ctx->ring * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->it_state, 0, sizeof(int), ctx->stream));             // step count; the index-pool cursor [1] carries on
+    CK(cudaMemsetAsync(ctx->it_state + 2, 0, sizeof(int), ctx->stream));
     ctx->map_ba_mask = ba_mask & ((n_frames >= 32) ? 0xffffffffu : ((1u << n_frames) - 1u));
+    if (ctx->coarse_map) ctx->map_ba_mask = 0;
     if (ctx->map_ba_mask) {   // camera_tensor = get_tensor_from_camera(c2w) per optimised frame (Mapper.cpp:322-325)
         std::vector<float> hp(12 * (size_t)ctx->cfg.max_frames), cams(8 * (size_t)n_frames, 0.f);
         CK(cudaMemcpyAsync(hp.data(), ctx->f_pose, hp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1186,12 +1295,14 @@ extern "C" int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots
         CK(cudaMemcpyAsync(ctx->param + ctx->off_cam, cams.data(), cams.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    if (ctx->cfg.frustum_feature_selection) {   // Mapper.cpp:226-290: masks from the current frame (the last of optimize_frame)
-        for (int l = 1; l < 4; ++l) if (nsb_frustum_mask(ctx, slots[n_frames - 1], nullptr, l, nullptr, 1)) return -1;
+    if (!ctx->map_no_mask && ctx->cfg.frustum_feature_selection) {   // Mapper.cpp:226-290: masks from the current frame (the last of optimize_frame)
+        for (int l = ctx->coarse_map ? 0 : 1; l < (ctx->coarse_map ? 1 : 4); ++l) if (nsb_frustum_mask(ctx, slots[n_frames - 1], nullptr, l, nullptr, 1)) return -1;
     }
-    if (!ctx->cfg.fix_color) {   // make sure the stash exists before the hot loop
+    if (!ctx->map_fix_color && !ctx->coarse_map) {   // make sure the stash exists before the hot loop
         if (ensure_stash(ctx, (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64)) return -1;
     }
+    const uint64_t sig = graph_signature(ctx);
+    if (sig != ctx->graph_sig) { CK(cudaStreamSynchronize(ctx->stream)); drop_graphs(ctx); ctx->graph_sig = sig; }
     return 0;
 }
 
@@ -1210,41 +1321,37 @@ extern "C" int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, in
     return o.source(i);
 }
 
-extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
-    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
+// One joint iteration in its launch-parameter-free form: nothing below depends on the iteration number except through the
+// device iteration state, so the same sequence is either enqueued kernel by kernel or captured once and replayed as a graph.
+struct IterPlan { int stage; bool use_color, pristine, use_pool; };
+
+static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
     const nsb_config& c = ctx->cfg;
-    if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
-    if (wait_uploads(ctx)) return -1;
     const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
-    const int stage = stage_of_iter(c, iter, ctx->map_iters);
-    // statistics / loss slot of this step (the k-th iteration since nsb_mapping_begin, whatever its `iter` argument): the ring was
-    // cleared by nsb_mapping_begin, so no per-iteration memset is needed until it wraps
-    if (ctx->map_step > 0 && ctx->map_step % LOSS_RING == 0) CK(cudaMemsetAsync(ctx->stats, 0, 4 * LOSS_RING * 4, ctx->stream));
-    float* stats = ctx->stats + 4 * (ctx->map_step % LOSS_RING);
+    const int stage = pl.stage;
+    const bool coarse = ctx->coarse_map;
+    const int render_stage = coarse ? NSB_COARSE : NSB_COLOR;   // Mapper.cpp:430 renders "color" whatever the stage; the coarse mapper "coarse"
+    IterRef it; it.state = ctx->it_state; it.ring = ctx->ring;
+    float* stats = ctx->stats;
+    const bool pool = pl.use_pool;
     {
         Timer t(ctx, T_SAMPLE);
-        const int64_t* d_idx = ctx->idx;
-        if (idx) CK(cudaMemcpyAsync(ctx->idx, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-        else if (ctx->idx_pool && ctx->pool_n == n) d_idx = ctx->idx_pool + (size_t)(ctx->pool_cursor++ % ctx->pool_iters) * n;   // already resident
-        else {
-            ctx->h_idx.resize(n);
-            for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
-            CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-        }
         SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
-        P.idx = d_idx; P.cam_mask = ctx->map_ba_mask;
+        P.it = it; P.cam_mask = ctx->map_ba_mask;
+        if (pool) { P.pool = ctx->idx_pool; P.pool_iters = ctx->pool_iters; }
         P.order = map_order(ctx, n, pix);
         for (int f = 0; f < ctx->map_frames; ++f) P.slots[f] = ctx->map_slots[f];
         P.n_frames = ctx->map_frames; P.pix_per_frame = pix;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
-        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
+        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats, it); ctx->launches++; }
         CK(cudaGetLastError());
     }
     // this rank's slice of the (already filtered, batch-global) ray list (rank-major order, see RayOrder)
-    const int per = cdiv(cdiv(n, ctx->world), 1), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
-    const bool use_color = stage == NSB_COLOR;
+    const int per = cdiv(n, ctx->world), off = std::min(n, ctx->rank * per), nl = std::max(0, std::min(per, n - off));
+    const bool use_color = pl.use_color;
+    const bool train_color = use_color && !ctx->map_fix_color && !coarse;
     if (nl > 0) {
-        if (run_forward(ctx, NSB_COLOR, off, nl, true, ctx->valid, stats, false, true, use_color && !c.fix_color, true)) return -1;   // render is always called with "color" (Mapper.cpp:430)
+        if (run_forward(ctx, render_stage, off, nl, true, ctx->valid, stats, it, false, true, train_color, true)) return -1;
         {
             // composite + loss (Mapper.cpp:435-442) + composite backward fused: the cotangents are local to each ray
             Timer t(ctx, T_COMP);
@@ -1252,7 +1359,8 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             CompositeParams Q; memset(&Q, 0, sizeof Q);
             Q.rays_o = ctx->rays_o + 3 * off; Q.rays_d = ctx->rays_d + 3 * off; Q.z = ctx->z + (size_t)off * S; Q.valid = ctx->valid + off;
             Q.raw_rgb = ctx->raw_rgb + 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k] + (size_t)off * S;
-            Q.stats = stats; Q.bnd = ctx->bnd; Q.n = nl; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+            Q.stats = stats; Q.it = it; Q.zero_ctr = ctx->tile_ctr + 4;
+            Q.bnd = ctx->bnd; Q.n = nl; Q.S = S; Q.stage = render_stage; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
             Q.rgb = ctx->o_rgb + 3 * off; Q.depth = ctx->o_depth + off; Q.var = ctx->o_var + off; Q.weights = nullptr;
             Q.g_raw = ctx->g_raw + 4 * (size_t)off * S;
             if (ctx->map_ba_mask) {   // bundle adjustment: ray gradients (d L / d rays_o, rays_d) are accumulated for the pose chain
@@ -1265,15 +1373,16 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        const int flags = 1 | (c.fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
-        ctx->ar_request = ctx->world > 1 && ctx->ar_mode == 2;
-        const int rb = run_backward(ctx, NSB_COLOR, off, nl, ctx->valid, stats, flags, use_color, true);
+        const int flags = 1 | (ctx->map_fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
+        ctx->ar_request = ctx->world > 1 && ctx->ar_mode == 2 && !ctx->p2p;
+        const int rb = run_backward(ctx, render_stage, off, nl, ctx->valid, stats, it, flags, use_color, true);
         ctx->ar_request = false;
         if (rb) return -1;
         if (ctx->map_ba_mask) {   // chain to (q, t) of every optimised frame; other ranks' partial sums arrive through the all-reduce
             Timer t(ctx, T_COMP);
             PoseGradParams G; memset(&G, 0, sizeof G);
-            G.d_rays = ctx->d_rays; G.idx = ctx->idx_pool && ctx->pool_n == n && !idx ? ctx->idx_pool + (size_t)((ctx->pool_cursor - 1) % ctx->pool_iters) * n : ctx->idx;
+            G.d_rays = ctx->d_rays; G.idx = ctx->idx; G.it = it; G.n_total = n;
+            if (pool) { G.pool = ctx->idx_pool; G.pool_iters = ctx->pool_iters; }
             G.valid = ctx->valid; G.cams = ctx->param + ctx->off_cam; G.cam_mask = ctx->map_ba_mask;
             G.pix_per_frame = pix; G.n_frames = ctx->map_frames; G.lo = off; G.hi = off + nl; G.order = map_order(ctx, n, pix);
             G.H0 = 0; G.W0 = 0; G.Wc = c.W; G.raydir = c.raydir; G.fx = c.fx; G.fy = c.fy; G.cx = c.cx; G.cy = c.cy;
@@ -1282,39 +1391,90 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
             CK(cudaGetLastError());
         }
     }
-    ctx->map_step++;
     float lr[6];
     for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
     lr[5] = (ctx->map_ba_mask && stage == NSB_COLOR) ? c.BA_cam_lr : 0.f;   // Mapper.cpp:366-368 (not scaled by lr_factor)
-    if (use_color) ctx->map_color_touched = true;
-    const bool pristine = !ctx->map_color_touched;   // colour grid / decoder: gradient, m, v all exactly zero so far
+    const bool pristine = pl.pristine;   // colour grid / decoder: gradient, m, v all exactly zero so far
     const int n_cam = ctx->map_ba_mask ? 8 * ctx->map_frames : 0;
+    const bool dec_color = !ctx->map_fix_color;
+    // the gradient of this iteration for the parity tests (nsb_mapping_capture_grads), before the optimiser clears it
+    if (ctx->capture_grads) CK(cudaMemcpyAsync(ctx->grad_snap, ctx->grad, ctx->arena_n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     // geometry iteration before any colour iteration, no BA: colour-grid, decoder and camera gradients are exact zeros on every
     // rank (Mapper.cpp:435-442 adds the colour term only in stage "color"), so only [loss | grid_middle | grid_fine] is exchanged
     const bool prefix_only = pristine && !ctx->map_ba_mask && ctx->ar_mode != 0;
     if (ctx->world > 1 && ctx->p2p) {
         // peer-memory mode: reduce-scatter + Adam + all-gather in one kernel (p2p_kernels.cuh); the summed loss lands in the parameter arena
         if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));   // this rank's partial sums
-        if (run_reduce_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine, ctx->off_train, prefix_only ? ctx->off_grid[3] : ctx->arena_n)) return -1;
-        CK(cudaMemcpyAsync(stats + 3, ctx->param + ctx->off_tail, 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        return 0;
-    }
-    if (ctx->world > 1) {
-        Timer t(ctx, T_COMM);
-        if (nl > 0 && ctx->ar_overlapped) {   // colour iteration: grids went out under the wgrad kernel, the small remainder follows
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
-            if (allreduce_range(ctx, ctx->off_dec[2], ctx->arena_n, ctx->stream)) return -1;
-        } else if (prefix_only) {
-            if (allreduce_range(ctx, ctx->off_train, ctx->off_grid[3], ctx->stream)) return -1;
-        } else {
-            if (allreduce_range(ctx, ctx->off_train, ctx->arena_n, ctx->stream)) return -1;
+        if (run_reduce_adam(ctx, lr, !c.fix_fine, dec_color, n_cam, pristine, ctx->off_train, prefix_only ? ctx->off_grid[3] : ctx->arena_n)) return -1;
+    } else {
+        if (ctx->world > 1) {
+            Timer t(ctx, T_COMM);
+            if (nl > 0 && ctx->ar_overlapped) {   // colour iteration: grids went out under the wgrad kernel, the small remainder follows
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                if (allreduce_range(ctx, ctx->off_dec[2], ctx->arena_n, ctx->stream)) return -1;
+            } else if (prefix_only) {
+                if (allreduce_range(ctx, ctx->off_train, ctx->off_grid[3], ctx->stream)) return -1;
+            } else {
+                if (allreduce_range(ctx, ctx->off_train, ctx->arena_n, ctx->stream)) return -1;
+            }
+            ctx->ar_overlapped = false;
         }
-        ctx->ar_overlapped = false;
+        if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups;
+        // the Adam kernel also moves the (all-reduced) loss out of the gradient arena into the step's statistics slot
+        if (run_adam(ctx, lr, !c.fix_fine, dec_color, n_cam, pristine)) return -1;
     }
-    if (ctx->map_ba_mask) CK(cudaMemcpyAsync(ctx->cam_grad_last, ctx->grad + ctx->off_cam, 8 * ctx->map_frames * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    // every parameter in the optimiser receives a (possibly zero) gradient each iteration, so one step counter serves all groups;
-    // the Adam kernel also moves the (all-reduced) loss out of the gradient arena into the step's statistics slot
-    if (run_adam(ctx, ctx->map_step, lr, !c.fix_fine, !c.fix_color, n_cam, pristine, stats + 3)) return -1;
+    // the colour decoder has just been stepped: rebuild its pre-split images right away, so that every iteration starts from
+    // fresh images (no host-side dirty tracking inside the loop)
+    if (dec_color && !coarse && !pristine && lr[0] != 0.f) { if (refresh_images(ctx, 0, 1 << 3)) return -1; }
+    return 0;
+}
+
+extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
+    cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
+    const nsb_config& c = ctx->cfg;
+    if (ctx->map_frames < 1) return fail(ctx, "nsb_mapping_begin was not called");
+    if (wait_uploads(ctx)) return -1;
+    const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
+    IterPlan pl;
+    pl.stage = stage_of_iter(c, iter, ctx->map_iters, ctx->coarse_map);
+    pl.use_color = pl.stage == NSB_COLOR;
+    if (pl.use_color) ctx->map_color_touched = true;
+    pl.pristine = !ctx->map_color_touched;
+    pl.use_pool = !idx && ctx->idx_pool && ctx->pool_n == n;
+    // pixel indices of this iteration: caller's, the resident pool's next row (selected on the device), or the mt19937 stream
+    if (idx) CK(cudaMemcpyAsync(ctx->idx, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    else if (!pl.use_pool) {
+        ctx->h_idx.resize(n);
+        for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
+        CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (refresh_images(ctx, 0xE)) return -1;   // no-op unless a decoder was replaced since the last iteration
+    ctx->map_step++;
+    const bool graph_ok = ctx->use_graph && !ctx->profiling && (ctx->world == 1 || ctx->p2p);
+    if (!graph_ok) return enqueue_iteration(ctx, pl);
+    const uint64_t key = (uint64_t)pl.stage | (pl.use_color ? 8u : 0u) | (pl.pristine ? 16u : 0u) | (pl.use_pool ? 32u : 0u) | (ctx->capture_grads ? 64u : 0u);
+    auto g = ctx->graphs.find(key);
+    if (g == ctx->graphs.end()) {
+        const int64_t l0 = ctx->launches;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        ctx->capturing = true;
+        const int rc = enqueue_iteration(ctx, pl);
+        ctx->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != 0 || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc != 0 ? -1 : fail(ctx, "graph capture of the mapping iteration failed: %s", cudaGetErrorString(e));
+        }
+        IterGraph ig; ig.launches = (int)(ctx->launches - l0); ctx->launches = l0;
+        const cudaError_t ei = cudaGraphInstantiate(&ig.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(ctx, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+        g = ctx->graphs.emplace(key, ig).first;
+    }
+    CK(cudaGraphLaunch(g->second.exec, ctx->stream));
+    ctx->launches += g->second.launches;
     return 0;
 }
 
@@ -1322,20 +1482,20 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
 // cam7s_out ([n_frames][7], may be NULL) receives the optimised 7-vectors (frames outside the mask: their initial pose).
 extern "C" int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
-    if (!ctx->map_ba_mask) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+    if (!ctx->map_ba_mask) { CK(cudaStreamSynchronize(ctx->stream)); return p2p_check(ctx); }
     const int nf = ctx->map_frames;
     std::vector<float> cams(8 * (size_t)nf);
     CK(cudaMemcpyAsync(cams.data(), ctx->param + ctx->off_cam, cams.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<float> RT(12 * (size_t)nf);
     for (int f = 0; f < nf; ++f) {
         if (cam7s_out) memcpy(cam7s_out + 7 * f, cams.data() + 8 * f, 7 * sizeof(float));
         if (!((ctx->map_ba_mask >> f) & 1u)) continue;
-        float RT[12];
-        nsb_get_camera_from_tensor(cams.data() + 8 * f, RT);
-        CK(cudaMemcpyAsync(ctx->f_pose + 12 * ctx->map_slots[f], RT, sizeof RT, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // RT is a stack buffer
+        nsb_get_camera_from_tensor(cams.data() + 8 * f, RT.data() + 12 * f);
+        CK(cudaMemcpyAsync(ctx->f_pose + 12 * ctx->map_slots[f], RT.data() + 12 * f, 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     }
-    return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return p2p_check(ctx);
 }
 // d L / d (q, t) of the optimised frames at the last bundle-adjustment iteration ([n_frames][7]; zeros outside the mask).
 extern "C" int nsb_mapping_cam_grads(nsb_ctx* ctx, float* g7s) {
@@ -1355,29 +1515,37 @@ extern "C" int nsb_get_frame_pose(nsb_ctx* ctx, int slot, float* c2w12) {
 }
 
 // Pre-load pixel indices for n_iters iterations ([n_iters][n] int64, host) so that nsb_mapping_iter(idx = NULL) runs
-// with every input already resident in HBM; rows are consumed in order, wrapping around.  NULL clears the pool.
+// with every input already resident in HBM; rows are consumed in order, wrapping around (the cursor lives on the device and is
+// advanced by the optimiser kernel).  NULL clears the pool.
 extern "C" int nsb_mapping_set_index_pool(nsb_ctx* ctx, const int64_t* host_idx, int n_iters, int n) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
+    CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->idx_pool) { cudaFree(ctx->idx_pool); ctx->idx_pool = nullptr; ctx->pool_iters = ctx->pool_n = 0; }
+    drop_graphs(ctx); ctx->graph_sig = 0;
     if (!host_idx) return 0;
     CK(dalloc(&ctx->idx_pool, (size_t)n_iters * n));
     CK(cudaMemcpyAsync(ctx->idx_pool, host_idx, (size_t)n_iters * n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->it_state + 1, 0, sizeof(int), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->pool_iters = n_iters; ctx->pool_n = n; ctx->pool_cursor = 0;
+    ctx->pool_iters = n_iters; ctx->pool_n = n;
     return 0;
 }
 
+// Losses / inside counts of steps [first, first + n): at most two contiguous copies out of the ring.
 extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses, int* n_inside) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
+    if (n <= 0) return 0;
+    if (n > ctx->ring) return fail(ctx, "the loss ring keeps the last %d steps, asked for %d", ctx->ring, n);
     std::vector<float> h(4 * (size_t)n);
-    for (int i = 0; i < n; ++i)
-        CK(cudaMemcpyAsync(h.data() + 4 * i, ctx->stats + 4 * ((first + i) % LOSS_RING), 16, cudaMemcpyDeviceToHost, ctx->stream));
+    const int s0 = ((first % ctx->ring) + ctx->ring) % ctx->ring, n0 = std::min(n, ctx->ring - s0);
+    CK(cudaMemcpyAsync(h.data(), ctx->stats + 4 * (size_t)s0, 16 * (size_t)n0, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n0 < n) CK(cudaMemcpyAsync(h.data() + 4 * (size_t)n0, ctx->stats, 16 * (size_t)(n - n0), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n; ++i) {
         if (losses) losses[i] = h[4 * i + 3];
         if (n_inside) { int v; memcpy(&v, &h[4 * i + 1], 4); n_inside[i] = v; }
     }
-    return 0;
+    return p2p_check(ctx);
 }
 
 extern "C" int nsb_mapping_iter(nsb_ctx* ctx, int iter, const int64_t* idx, float* loss) {
@@ -1391,9 +1559,29 @@ extern "C" int nsb_optimize_map(nsb_ctx* ctx, int n_frames, const int* slots, in
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (nsb_mapping_begin(ctx, n_frames, slots, n_iters, lr_factor)) return -1;
     for (int it = 0; it < n_iters; ++it) if (nsb_mapping_iter_async(ctx, it, nullptr)) return -1;
-    if (losses) { for (int o = 0; o < n_iters; o += LOSS_RING) if (nsb_mapping_losses(ctx, o, std::min(LOSS_RING, n_iters - o), losses + o, nullptr)) return -1; }
-    else CK(cudaStreamSynchronize(ctx->stream));
+    if (losses) return nsb_mapping_losses(ctx, 0, n_iters, losses, nullptr);   // the ring was sized for n_iters by nsb_mapping_begin
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// Parity aid: keep a copy of every iteration's gradient arena (taken after the backward, before the exchange / optimiser step).
+extern "C" int nsb_mapping_capture_grads(nsb_ctx* ctx, int on) {
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (on && !ctx->grad_snap) { CK(dalloc(&ctx->grad_snap, ctx->arena_n)); CK(cudaMemset(ctx->grad_snap, 0, ctx->arena_n * 4)); drop_graphs(ctx); ctx->graph_sig = 0; }
+    ctx->capture_grads = on != 0;
+    return 0;
+}
+extern "C" int nsb_get_captured_grid_grad(nsb_ctx* ctx, int level, float* host) {
+    cudaSetDevice(ctx->device);
+    if (level < 0 || level > 3) return fail(ctx, "bad level %d", level);
+    if (!ctx->grad_snap) return fail(ctx, "nsb_mapping_capture_grads was not enabled");
+    return get_cl(ctx, ctx->grad_snap + ctx->off_grid[level], level, host);
+}
+extern "C" int nsb_get_captured_decoder_grad(nsb_ctx* ctx, int which, float* host, int64_t n) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->grad_snap) return fail(ctx, "nsb_mapping_capture_grads was not enabled");
+    return get_dec(ctx, ctx->grad_snap, which, host, n);
 }
 
 // ---- keyframe selection (Mapper.cpp:132-196) ------------------------------------------------------------------------------
@@ -1426,8 +1614,8 @@ extern "C" int nsb_keyframe_selection_overlap(nsb_ctx* ctx, int cur_slot, const 
     if (idx) memcpy(ctx->h_idx.data(), idx, pixels * sizeof(int64_t)); else draw_indices(ctx, pixels, (int64_t)c.H * c.W, ctx->h_idx.data());
     CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), pixels * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (cur_c2w16) CK(cudaMemcpyAsync(ctx->f_pose + 12 * cur_slot, cur_c2w16, 12 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->stats, 0, 16, ctx->stream));
-    SampleParams S; fill_sample_params(ctx, S, pixels, 0, c.H, 0, c.W, ctx->stats, 0);
+    CK(cudaMemsetAsync(ctx->rstats, 0, 16, ctx->stream));
+    SampleParams S; fill_sample_params(ctx, S, pixels, 0, c.H, 0, c.W, ctx->rstats, 0);
     S.slots[0] = cur_slot; S.n_frames = 1; S.pix_per_frame = pixels;
     k_sample<<<cdiv(pixels, 128), 128, 0, ctx->stream>>>(S); ctx->launches++;
     std::vector<float> w2c(12 * (size_t)n_kf);
@@ -1488,12 +1676,13 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
         SampleParams P; fill_sample_params(ctx, P, n, H0, H1, W0, W1, stats, 1);
         P.slots[0] = ctx->trk_slot; P.n_frames = 1; P.pix_per_frame = n; P.cam_mask = 1u;
         k_sample<<<cdiv(n, 128), 128, 0, ctx->stream>>>(P); ctx->launches++;
-        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats); ctx->launches++; }
+        if (c.dist_norm == NSB_DISTNORM_REFERENCE) { k_dirnorm_ref<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->rays_d, ctx->valid, n, stats, NO_ITER); ctx->launches++; }
         CK(cudaGetLastError());
     }
+    if (refresh_images(ctx, 0xE)) return -1;
     // render (Tracker.cpp:61); with handle_dynamic the composite also compacts |gt - depth| of the surviving rays for the median (:69)
     ctx->trk_hook = c.handle_dynamic != 0; ctx->trk_count = count;
-    const int rf = run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, false, true, false);
+    const int rf = run_forward(ctx, NSB_COLOR, 0, n, true, ctx->valid, stats, NO_ITER, false, true, false);
     ctx->trk_hook = false;
     if (rf) return -1;
     const int S = ctx->last_S;
@@ -1505,14 +1694,15 @@ extern "C" int nsb_tracking_iter(nsb_ctx* ctx, const int64_t* idx, float* loss, 
         CompositeParams Q; memset(&Q, 0, sizeof Q);
         Q.rays_o = ctx->rays_o; Q.rays_d = ctx->rays_d; Q.z = ctx->z; Q.valid = ctx->valid;
         Q.raw_rgb = ctx->raw_rgb; for (int k = 0; k < 3; ++k) Q.occ[k] = ctx->occ[k];
-        Q.stats = stats; Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
+        Q.stats = stats; Q.it = NO_ITER; Q.zero_ctr = ctx->tile_ctr + 4;
+        Q.bnd = ctx->bnd; Q.n = n; Q.S = S; Q.stage = NSB_COLOR; Q.occupancy = c.occupancy; Q.dist_norm = c.dist_norm;
         Q.g_raw = ctx->g_raw; Q.d_rays = ctx->d_rays;
         k_composite_track<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Q, ctx->gt_depth, ctx->gt_color, ctx->median, c.handle_dynamic, c.use_color_in_tracking,
                                                                      c.w_color_loss, stats + 3);
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    if (run_backward(ctx, NSB_COLOR, 0, n, ctx->valid, stats, 4, true, true)) return -1;
+    if (run_backward(ctx, NSB_COLOR, 0, n, ctx->valid, stats, NO_ITER, 4, true, true)) return -1;
     ctx->trk_step++;
     {
         // chain to (q, t) (utils.h:174-210) and the Adam step on the 7-vector (Tracker.cpp:85), fused: the last block applies it
@@ -1573,7 +1763,7 @@ extern "C" int nsb_comm_p2p_export(nsb_ctx* ctx, char* handles192) {
 // replaces ncclAllReduce + Adam by k_reduce_adam.  The caller must put a host barrier between the imports and the first iteration.
 extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int world) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
-    if (!all_handles) { ctx->p2p = false; return 0; }   // back to the NCCL path (e.g. another rank could not open the handles)
+    if (!all_handles) { CK(cudaStreamSynchronize(ctx->stream)); drop_graphs(ctx); ctx->graph_sig = 0; ctx->p2p = false; return 0; }   // back to the NCCL path (e.g. another rank could not open the handles)
     if (world < 2 || world > P2P_MAX_WORLD) return fail(ctx, "peer-memory mode supports 2..%d ranks, got %d", P2P_MAX_WORLD, world);
     if (ctx->comm && (rank != ctx->rank || world != ctx->world)) return fail(ctx, "rank/world differ from nsb_comm_init");
     CK(cudaSetDevice(ctx->device));
@@ -1585,7 +1775,28 @@ extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int ra
         CK(cudaIpcOpenMemHandle(&p, h[1], cudaIpcMemLazyEnablePeerAccess)); ctx->peer_param[w] = (float*)p;
         CK(cudaIpcOpenMemHandle(&p, h[2], cudaIpcMemLazyEnablePeerAccess)); ctx->peer_flags[w] = (uint32_t*)p;
     }
-    ctx->rank = rank; ctx->world = world; ctx->p2p = true; ctx->p2p_epoch = 0;
+    // the flag block starts from zero (epochs, time-out flag): a re-import on a live context must not see old epochs.  Every rank
+    // does this BEFORE the host barrier the caller places between the imports and the first iteration.
+    CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx); ctx->graph_sig = 0;
+    ctx->rank = rank; ctx->world = world; ctx->p2p = true;
+    return 0;
+}
+// Instrumentation of the fused exchange (k_reduce_adam stamps %globaltimer): out5 = {last barrier-1 wait us, last kernel total us,
+// mean wait us, mean total us, exchanges averaged}.  The wait is the time this rank spent waiting for the slowest rank's backward;
+// total - wait is the reduce-scatter + Adam + all-gather + barrier 2 itself.  reset != 0 clears the sums.
+extern "C" int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out5, int reset) {
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < 5; ++i) out5[i] = 0.0;
+    if (!ctx->p2p) return 0;
+    uint32_t h[32];
+    CK(cudaMemcpyAsync(h, ctx->p2p_flags, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long ts[4]; memcpy(ts, h + 20, sizeof ts);
+    const double n = (double)h[28];
+    out5[0] = ts[0] * 1e-3; out5[1] = ts[1] * 1e-3; out5[2] = n > 0 ? ts[2] * 1e-3 / n : 0.0; out5[3] = n > 0 ? ts[3] * 1e-3 / n : 0.0; out5[4] = n;
+    if (reset) { CK(cudaMemsetAsync(ctx->p2p_flags + 24, 0, 5 * 4, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
     return 0;
 }
 extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }

@@ -26,6 +26,22 @@ struct GridView {
     int Z, Y, X;
 };
 
+// Per-iteration device state of the mapping loop.  Every scalar that changes from one joint iteration to the next (which slot of
+// the statistics / loss ring, which row of the resident pixel-index pool, the Adam step count, the peer-barrier epoch) is READ BY
+// THE KERNELS from this block instead of being passed as a launch parameter, so that one captured CUDA graph per iteration
+// variant (geometry / colour / bundle adjustment) is replayed unchanged for every iteration of Mapper.cpp:331-465: the host issues
+// one cudaGraphLaunch per iteration.  The last block of the optimiser kernel advances it.
+//   state[0] = iterations completed since nsb_mapping_begin, state[1] = index-pool cursor, state[2] = blocks-done counter
+struct IterRef {
+    int* state;          // nullptr: no iteration state (render / tracking entry points): slot 0
+    int ring;            // slots of the statistics ring
+};
+__device__ __forceinline__ int iter_step(const IterRef& r) { return r.state ? r.state[0] : 0; }
+__device__ __forceinline__ int iter_slot(const IterRef& r) { return r.state ? (r.state[0] % r.ring) : 0; }
+__device__ __forceinline__ void zero_tile_counters(unsigned long long* ctr) {   // by one thread of a kernel that precedes the decoder launch
+    if (ctr) { ctr[0] = 0ull; ctr[1] = 0ull; ctr[2] = 0ull; ctr[3] = 0ull; }
+}
+
 // ---- tensor-core helpers: mma.sync m16n8k16 f16 with fp32 accumulation, fp16 two-way split (fp32-grade accuracy) ----
 // Every fp32 operand x is carried as the pair  hi = fp16(x),  lo = fp16(x - hi):  |hi + lo - x| <= max(2^-22 |x|, 2^-25)
 // -- 22 significant bits while lo is a normal fp16 (|x| >= 0.125), and below that the half-spacing of the fp16 subnormal

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(BWD_THREADS, NSB_BWD_MIN_CTAS) k_decode_bwd(co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = P.P / TILE;
     (void)cta; (void)ncta; (void)warp;
-    TileQueue q; q.init(P.tile_ctr + dec, P.tile_base[dec], ntiles, lane);
+    TileQueue q; q.init(P.tile_ctr + dec, 0ull, ntiles, lane);
     for (int tile = q.next(lane); tile >= 0; tile = q.next(lane)) {
         if (dec == 1) backward_tile<32, 1, P3, GRID, RAY, false>(P, sm, 1, tile * TILE, g, t, lane);
         else if (dec == 2) backward_tile<64, 1, P3, GRID, RAY, false>(P, sm, 2, tile * TILE, g, t, lane);

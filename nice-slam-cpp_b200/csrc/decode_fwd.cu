@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (P.P + TILE - 1) / TILE;
     (void)cta; (void)ncta; (void)warp;
-    TileQueue q; q.init(P.tile_ctr + dec, P.tile_base[dec], ntiles, lane);
+    TileQueue q; q.init(P.tile_ctr + dec, 0ull, ntiles, lane);
     for (int tile = q.next(lane); tile >= 0; tile = q.next(lane)) {
         float p[2][3]; int sidx[2];
         if (!load_points(P, tile * TILE, g, p, sidx)) continue;

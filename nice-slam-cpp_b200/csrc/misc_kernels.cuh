@@ -23,7 +23,7 @@ __global__ void k_iota(int64_t* __restrict__ dst, int64_t base, int n) {
 // Mapper.cpp:330: decoders, coarse, middle, fine, color grids, camera tensors).
 struct AdamSegment {
     int begin, end;          // float offsets into the arena, multiples of 4
-    float step;              // lr / (1 - beta1^t), computed in double on the host like libtorch's step_size
+    float lr;                // learning rate of the group; the kernel forms libtorch's step_size = lr / (1 - beta1^t) in double
     const uint8_t* mask;     // per-voxel mask (grids only; element i -> voxel (i - begin) / 32), or nullptr
     int active;              // 0: parameter is not in the optimiser (fix_fine / fix_color): only its gradient is cleared
 };
@@ -34,11 +34,30 @@ struct AdamParams {
     int cum4[ADAM_MAX_SEG + 1];   // prefix sums of the segment lengths in float4 units: thread i works on segment s with cum4[s] <= i < cum4[s+1]
     int n_seg;
     float beta1, beta2, om_beta1, om_beta2, eps;   // om_* = (float)(1.0 - beta) as libtorch passes them
-    float bc2_sqrt;          // (float)sqrt(1 - beta2^t), double arithmetic on the host
+    double bc1;              // 1 - beta1^t   (host, double)                    } used when there is no iteration state;
+    float bc2_sqrt;          // (float)sqrt(1 - beta2^t), double arithmetic on the host } the mapping loop reads row state[0] of the tables
+    const double* bc1_tab; const float* bc2s_tab; int tab_n;   // per-step bias corrections, t = 1 .. tab_n (row t - 1)
+    IterRef it;              // mapping loop: step = it.state[0] (completed iterations), advanced by the last block of this kernel
     float grad_scale;        // 1 (single GPU) -- kept for mean-style reductions
     float* loss_dst;         // optional: receives the loss scalar that rides at float4 slot loss_idx4 of the gradient arena
+                             // (with iteration state: base of the statistics ring, the loss goes to slot[3])
     int loss_idx4;
 };
+
+// Bias corrections of the current step (libtorch computes them in double from the step count).
+__device__ __forceinline__ void adam_bias(const AdamParams& P, double& bc1, float& bc2s) {
+    bc1 = P.bc1; bc2s = P.bc2_sqrt;
+    if (P.it.state) { const int t = min(P.it.state[0], P.tab_n - 1); bc1 = P.bc1_tab[t]; bc2s = P.bc2s_tab[t]; }
+}
+// End of a joint iteration (called by ONE thread after every block of the optimiser kernel has finished): clear the next slot of
+// the statistics ring, advance the step count and the index-pool cursor.
+__device__ __forceinline__ void iter_advance(const IterRef& it, float* stats_base) {
+    const int step = it.state[0];
+    if (stats_base) { float* nx = stats_base + 4 * ((step + 1) % it.ring); nx[0] = nx[1] = nx[2] = nx[3] = 0.0f; }
+    it.state[1] = it.state[1] + 1;
+    __threadfence();
+    it.state[0] = step + 1;
+}
 
 // torch::optim::Adam::step (libtorch defaults, no amsgrad / weight decay) + zero_grad, one launch over the concatenation
 // of all segments.  Each thread owns ADAM_VEC float4 slots and issues ALL its loads (g, m, v, p of every slot) before any
@@ -48,6 +67,9 @@ constexpr int ADAM_VEC = 2;
 __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
     const int total = P.cum4[P.n_seg];
     const int t0 = blockIdx.x * (blockDim.x * ADAM_VEC) + threadIdx.x;
+    double bc1; float bc2s;
+    adam_bias(P, bc1, bc2s);
+    float* loss_dst = P.loss_dst ? (P.it.state ? P.loss_dst + 4 * iter_slot(P.it) + 3 : P.loss_dst) : nullptr;
     int idx[ADAM_VEC]; bool live[ADAM_VEC], upd[ADAM_VEC]; float nstep[ADAM_VEC];
     float4 g[ADAM_VEC], m[ADAM_VEC], v[ADAM_VEC], p[ADAM_VEC];
 #pragma unroll
@@ -61,7 +83,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
         for (int k = 1; k < ADAM_MAX_SEG; ++k)
             if (k < P.n_seg && tid >= P.cum4[k]) { sg = P.seg[k]; base = P.cum4[k]; }
         idx[u] = live[u] ? sg.begin / 4 + (tid - base) : 0;
-        nstep[u] = -sg.step;
+        nstep[u] = -(float)((double)sg.lr / bc1);
         upd[u] = live[u] && sg.active && !(sg.mask && !sg.mask[(idx[u] * 4 - sg.begin) / CDIM]);
     }
 #pragma unroll
@@ -72,7 +94,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
 #pragma unroll
     for (int u = 0; u < ADAM_VEC; ++u) {
         if (!live[u]) continue;
-        if (P.loss_dst && idx[u] == P.loss_idx4) *P.loss_dst = g[u].x;
+        if (loss_dst && idx[u] == P.loss_idx4) *loss_dst = g[u].x;
         reinterpret_cast<float4*>(P.grad)[idx[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!upd[u]) continue;
         float* gg = reinterpret_cast<float*>(&g[u]); float* mm = reinterpret_cast<float*>(&m[u]);
@@ -82,10 +104,17 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
             const float gk = gg[k] * P.grad_scale;
             mm[k] = __fadd_rn(__fmul_rn(mm[k], P.beta1), __fmul_rn(P.om_beta1, gk));                   // mul_(b1).add_(g, 1-b1)
             vv[k] = __fadd_rn(__fmul_rn(vv[k], P.beta2), __fmul_rn(__fmul_rn(P.om_beta2, gk), gk));   // mul_(b2).addcmul_(g, g, 1-b2)
-            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), P.bc2_sqrt), P.eps);
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), bc2s), P.eps);
             pp[k] = __fadd_rn(pp[k], __fdiv_rn(__fmul_rn(nstep[u], mm[k]), denom));                   // addcdiv_(m, denom, -step)
         }
         reinterpret_cast<float4*>(P.m)[idx[u]] = m[u]; reinterpret_cast<float4*>(P.v)[idx[u]] = v[u]; reinterpret_cast<float4*>(P.param)[idx[u]] = p[u];
+    }
+    if (P.it.state) {   // the last block to finish closes the iteration (every block has read state[0] before it arrives here)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(P.it.state + 2, 1) == (int)gridDim.x - 1) { P.it.state[2] = 0; iter_advance(P.it, P.loss_dst); }
+        }
     }
 }
 

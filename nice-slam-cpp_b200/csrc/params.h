@@ -36,10 +36,10 @@ struct DecodeParams {
     float* out_occ[3];             // coarse, middle, fine
     // grid partition: decoder d runs on CTAs [cta_begin[d], cta_begin[d+1])
     int cta_begin[5];
-    // dynamic tile scheduling: the warps of decoder d draw tickets from tile_ctr[d] (never reset; this launch's tickets start
-    // at tile_base[d]) so that warps which meet many filtered rays, or cheap tiles, simply take more tiles
+    // dynamic tile scheduling: the warps of decoder d draw tickets from tile_ctr[d] so that warps which meet many filtered rays,
+    // or cheap tiles, simply take more tiles.  The counters are cleared by the kernel that precedes the decoder launch in the
+    // stream (k_zvals / the composite kernels), which keeps the launch free of per-iteration host state (CUDA-graph replay).
     unsigned long long* tile_ctr;
-    unsigned long long tile_base[4];
     // ---- backward only ----
     const float* g_raw;            // [P][4] cotangent of raw (r,g,b,occ); occ already zero where out of bound
     int flags;                     // bit0 grid grads, bit1 colour-decoder weight grads (stash), bit2 ray grads

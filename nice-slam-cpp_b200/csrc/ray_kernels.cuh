@@ -60,6 +60,9 @@ struct SampleParams {
     const float* cams;       // [n_frames][8] 7-vector poses being optimised (tracking: one; bundle adjustment: one per frame)
     uint32_t cam_mask;       // bit f set: frame f takes its pose from cams + 8 f (R via quad2rotation) instead of poses[slot]
     const int64_t* idx;      // [n] flat index into the crop
+    const int64_t* pool;     // optional resident index pool [pool_iters][n]: row (it.state[1] % pool_iters) replaces idx
+    int pool_iters;
+    IterRef it;              // mapping loop: selects the statistics slot (and the pool row); {nullptr, 1} elsewhere
     int slots[MAX_OPT_FRAMES];
     int n_frames, pix_per_frame;
     RayOrder order;          // which reference batch element ray i is (identity on one GPU)
@@ -69,7 +72,7 @@ struct SampleParams {
     Bound bnd;
     int n;
     float* rays_o; float* rays_d; float* gt_depth; float* gt_color; uint8_t* valid;
-    float* stats;            // [0] max gt_depth over valid rays (as int bits), [1] count of valid rays (int)
+    float* stats;            // base of the statistics ring; slot: [0] max gt_depth over valid rays (as int bits), [1] count of valid rays (int)
     int apply_filter;        // 0: valid = 1 for every ray (render API)
 };
 
@@ -84,13 +87,18 @@ __device__ __forceinline__ float aabb_exit(const Bound& b, const float* o, const
     return t;
 }
 
+__device__ __forceinline__ const int64_t* pool_row(const int64_t* idx, const int64_t* pool, int pool_iters, const IterRef& it, int n) {
+    return pool ? pool + (size_t)((it.state ? it.state[1] : 0) % pool_iters) * n : idx;
+}
+
 __global__ void k_sample(SampleParams P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float gd = 0.0f; bool ok = false;
+    float* stats = P.stats + 4 * iter_slot(P.it);
     if (i < P.n) {
         const int f = min(P.order.frame(i, P.pix_per_frame), P.n_frames - 1);
         const int slot = P.slots[f];
-        const int64_t id = P.idx[P.order.source(i)];
+        const int64_t id = pool_row(P.idx, P.pool, P.pool_iters, P.it, P.n)[P.order.source(i)];
         const int x = P.W0 + (int)(id % P.Wc), y = P.H0 + (int)(id / P.Wc);
         const size_t pix = (size_t)slot * P.H * P.W + (size_t)y * P.W + x;
         gd = P.depth[pix];
@@ -127,8 +135,8 @@ __global__ void k_sample(SampleParams P) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
     if ((threadIdx.x & 31) == 0 && bal) {
-        atomicMax(reinterpret_cast<int*>(P.stats), __float_as_int(m));
-        atomicAdd(reinterpret_cast<int*>(P.stats) + 1, __popc(bal));
+        atomicMax(reinterpret_cast<int*>(stats), __float_as_int(m));
+        atomicAdd(reinterpret_cast<int*>(stats) + 1, __popc(bal));
     }
 }
 
@@ -142,8 +150,9 @@ __global__ void k_depth_max(const float* __restrict__ gt_depth, int n, float* st
 }
 
 // utils.h:153 as written: torch::norm(x, -1) = (sum |x|^-1)^-1 over the whole batch.  stats[2] accumulates sum 1/|d_ij|.
-__global__ void k_dirnorm_ref(const float* __restrict__ rays_d, const uint8_t* __restrict__ valid, int n, float* stats) {
+__global__ void k_dirnorm_ref(const float* __restrict__ rays_d, const uint8_t* __restrict__ valid, int n, float* stats, IterRef it) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    stats += 4 * iter_slot(it);
     float s = 0.0f;
     if (i < n && (!valid || valid[i])) s = 1.0f / fabsf(rays_d[3 * i]) + 1.0f / fabsf(rays_d[3 * i + 1]) + 1.0f / fabsf(rays_d[3 * i + 2]);
     s = warp_sum(s);
@@ -153,7 +162,9 @@ __global__ void k_dirnorm_ref(const float* __restrict__ rays_d, const uint8_t* _
 struct ZParams {
     const float* rays_o; const float* rays_d; const float* gt_depth;   // gt_depth null: no-depth path
     const uint8_t* valid;
-    const float* stats;      // [0] max gt_depth
+    const float* stats;      // statistics ring base; slot[0] = max gt_depth
+    IterRef it;
+    unsigned long long* zero_ctr;   // tile counters of the forward decoder launch that follows (cleared here), or nullptr
     const float* t_samples;  // [32]
     const float* t_surface;  // [16]
     Bound bnd;
@@ -164,6 +175,7 @@ struct ZParams {
 // Renderer.cpp:46-119: one warp per ray.  32 stratified + 16 near-surface values, then an exact rank sort.
 __global__ void k_zvals(ZParams P) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
     if (ray >= P.n) return;
     if (P.valid && !P.valid[ray]) return;
     const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
@@ -174,7 +186,7 @@ __global__ void k_zvals(ZParams P) {
         P.z[ray * P.n_samples + l] = __fadd_rn(__fmul_rn(0.01f, u), __fmul_rn(far_bb, t));
         return;
     }
-    const float gd = P.gt_depth[ray], gmax = P.stats[0];
+    const float gd = P.gt_depth[ray], gmax = P.stats[4 * iter_slot(P.it)];
     const float near = __fmul_rn(gd, 0.01f);                                         // :63
     const float far = fminf(fmaxf(far_bb, 0.0f), __fmul_rn(gmax, 1.2f));            // :76
     const float v0 = __fadd_rn(__fmul_rn(near, u), __fmul_rn(far, t));              // :106
@@ -201,7 +213,9 @@ struct CompositeParams {
     const float* rays_o; const float* rays_d; const float* z; const uint8_t* valid;
     const float* raw_rgb;     // [P][4]
     const float* occ[3];      // coarse, middle, fine
-    const float* stats;       // [2] sum 1/|d| for the reference dist norm
+    const float* stats;       // statistics ring base; slot[2] = sum 1/|d| for the reference dist norm
+    IterRef it;
+    unsigned long long* zero_ctr;   // tile counters of the backward decoder launch that follows (cleared here), or nullptr
     Bound bnd;
     int n, S, stage, occupancy, dist_norm;
     // forward outputs
@@ -243,7 +257,7 @@ __device__ __forceinline__ void composite_forward(const CompositeParams& P, int 
     const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
     float norm;
     if (P.dist_norm == 0) norm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    else norm = 1.0f / P.stats[2];
+    else norm = 1.0f / P.stats[4 * iter_slot(P.it) + 2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int k = l + 32 * h;
@@ -362,6 +376,7 @@ __device__ __forceinline__ void composite_backward(const CompositeParams& P, int
 
 __global__ void k_composite_bwd(CompositeParams P) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
     if (ray >= P.n) return;
     if (P.valid && !P.valid[ray]) return;   // tiles of dropped rays are skipped by the decoder kernels too
     RaySamples s; float rgb[3], depth, var;
@@ -375,6 +390,7 @@ __global__ void k_composite_bwd(CompositeParams P) {
 __global__ void k_composite_map(CompositeParams P, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
                                 int use_color, float w_color, float* loss_out) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
     if (ray >= P.n) return;
     if (P.valid && !P.valid[ray]) {
         if (l == 0) { P.rgb[3 * ray] = P.rgb[3 * ray + 1] = P.rgb[3 * ray + 2] = 0.0f; P.depth[ray] = 0.0f; P.var[ray] = 0.0f; }
@@ -405,6 +421,7 @@ __global__ void k_composite_map(CompositeParams P, const float* __restrict__ gt_
 __global__ void k_composite_track(CompositeParams P, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
                                   const float* __restrict__ median, int handle_dynamic, int use_color, float w_color, float* loss_out) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
     if (ray >= P.n) return;
     if (P.valid && !P.valid[ray]) return;
     RaySamples s; float rgb[3], depth, var;
@@ -465,6 +482,7 @@ __global__ void k_median(const float* __restrict__ v, const int* __restrict__ co
 struct PoseGradParams {
     const float* d_rays;     // [n][6]: d L / d rays_o, d L / d rays_d
     const int64_t* idx; const uint8_t* valid;
+    const int64_t* pool; int pool_iters; int n_total; IterRef it;   // resident index pool (see SampleParams), n_total = rays per row
     const float* cams;       // [n_frames][8] current 7-vectors
     uint32_t cam_mask;       // frames whose pose is optimised
     int pix_per_frame, n_frames;
@@ -489,7 +507,7 @@ __global__ void k_pose_grad(PoseGradParams P) {
     const int r_hi = P.order.identity() ? min(P.hi, (f + 1) * P.pix_per_frame) : min(P.hi, P.lo + (f + 1) * P.order.ppr);
     for (int i = r_lo + threadIdx.x; i < r_hi; i += blockDim.x) {
         if (P.valid && !P.valid[i]) continue;
-        const int64_t id = P.idx[P.order.source(i)];
+        const int64_t id = pool_row(P.idx, P.pool, P.pool_iters, P.it, P.n_total)[P.order.source(i)];
         const float xf = (float)(P.W0 + (int)(id % P.Wc)), yf = (float)(P.H0 + (int)(id / P.Wc));
         const float dir[3] = {(xf - P.cx) / P.fx, P.raydir == 0 ? (xf - P.cy) / P.fy : -(yf - P.cy) / P.fy, -1.0f};
         const float* g = P.d_rays + 6 * (size_t)i;

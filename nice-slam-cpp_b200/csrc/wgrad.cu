@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
     }
 }
 
-cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st) {
+// Per-device one-time setup (task table in constant memory, shared-memory attribute); called from nsb_create so that the launches
+// themselves are plain kernel launches (capturable into a CUDA graph).
+cudaError_t wgrad_init() {
     static unsigned init = 0;           // per device: the task table lives in that device's constant memory
     int dev = 0; cudaGetDevice(&dev);
     const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
@@ -211,6 +213,12 @@ cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, in
         if (e != cudaSuccess) return e;
         init |= 1u << (dev & 31);
     }
+    return cudaSuccess;
+}
+
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
+    { const cudaError_t e = wgrad_init(); if (e != cudaSuccess) return e; }
     if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
     else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
     return cudaGetLastError();

@@ -111,6 +111,7 @@ def main():
     stages = ["middle", "middle", "color", "color"]
     lr = np.array([O.DEFAULT_LR[k] for k in ("coarse", "middle", "fine", "color")], np.float32)
     ref2 = R.Ref(grids, decs)
+    g_it0 = ref2.capture_grads(0)          # gradients libtorch autograd leaves at Mapper.cpp:444 in the first (geometry) iteration
     losses, n_in, _ = ref2.mapping_iters(depths[:2], colors[:2], poses[:2], CAM, 200, [STAGE_ID[s] for s in stages], lr, seed=3)
     fx = dict(digest=dg, stages=np.array([STAGE_ID[s] for s in stages]), losses=losses, n_inside=n_in, pixels=200, n_frames=2, seed=3,
               t_samples=tt.numpy(), t_surface=ts.numpy(), dec_color=ref2.get_decoder("color"))
@@ -118,6 +119,19 @@ def main():
         gnew = ref2.get_grid(lv)
         pos, _ = sample_positions(gnew - grids[lv], 4096, 23)
         fx["grid_%s_pos" % lv] = pos; fx["grid_%s_val" % lv] = gnew.reshape(-1)[pos]
+    # a colour-stage iteration from the SAME initial parameters (fresh context, own seed): colour grid + colour-decoder gradients
+    ref2c = R.Ref(grids, decs)
+    g_c0 = ref2c.capture_grads(0)
+    lc, nc, _ = ref2c.mapping_iters(depths[:2], colors[:2], poses[:2], CAM, 200, [STAGE_ID["color"]], lr, seed=4)
+    fx["c0_loss"] = lc; fx["c0_seed"] = 4
+    for tag, g in (("it0", g_it0), ("c0", g_c0)):
+        for lv in ("middle", "fine", "color"):
+            a = g["grid_" + lv]
+            pos, val = sample_positions(a, 4096, 29)
+            fx["%s_grad_%s_pos" % (tag, lv)] = pos; fx["%s_grad_%s_val" % (tag, lv)] = val
+            fx["%s_grad_%s_l2" % (tag, lv)] = np.float64(np.sqrt((a.astype(np.float64) ** 2).sum()))
+            fx["%s_grad_%s_max" % (tag, lv)] = np.float32(np.abs(a).max())
+        fx["%s_grad_dec_color" % tag] = g["dec_color"]
     np.savez_compressed(os.path.join(GOLD, "mapping_iters.npz"), **fx)
 
     ref3 = R.Ref(grids, decs)

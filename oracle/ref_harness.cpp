@@ -32,6 +32,9 @@ struct RefCtx {
     NICE nice;
     Renderer renderer;
     std::string err;
+    // optional: host buffers that receive the gradients of chosen mapping iterations (ref_mapping_capture_grads)
+    struct Cap { int iter; float* grid[4]; float* dec_color; };
+    std::vector<Cap> caps;
 };
 
 const char* kGridName[4] = {"grid_coarse", "grid_middle", "grid_fine", "grid_color"};
@@ -222,6 +225,16 @@ int ref_render_vjp(void* h, const char* stage, int n, const float* rays_d, const
     REF_CATCH(c)
 }
 
+// The next ref_mapping_iters call copies the gradients loss.backward() left at iteration `iter` (Mapper.cpp:444, before
+// optimizer.step) into these host buffers: grids middle / fine / color in (1,C,Z,Y,X), the colour decoder flat.  Any may be NULL.
+int ref_mapping_capture_grads(void* h, int iter, float* g_middle, float* g_fine, float* g_color, float* d_dec_color) {
+    auto c = static_cast<RefCtx*>(h);
+    if (iter < 0) { c->caps.clear(); return 0; }
+    RefCtx::Cap cap; cap.iter = iter; cap.grid[0] = nullptr; cap.grid[1] = g_middle; cap.grid[2] = g_fine; cap.grid[3] = g_color; cap.dec_color = d_dec_color;
+    c->caps.push_back(cap);
+    return 0;
+}
+
 // Mapping iterations, Mapper.cpp:330-465 (non-coarse mapper, no BA), frames = optimize_frame list.
 //   lr[stage(4: coarse,middle,fine,color)][group(5: decoders,coarse,middle,fine,color)] already times lr_factor.
 //   voxel masks (Z*Y*X bytes per level, NULL = frustum_feature_selection off) follow the intent of
@@ -292,6 +305,10 @@ int ref_mapping_iters(void* h, int n_frames, int H, int W, float fx, float fy, f
         auto loss = torch::abs(b_dep.index({dmask}) - depth.index({dmask})).sum();  // :435-436
         if (st == 3) loss = loss + w_color_loss * torch::abs(b_col - color).sum();  // :438-442
         loss.backward();
+        for (auto& cap : c->caps) if (cap.iter == it) {
+            for (int l = 1; l < 4; ++l) grad_to_host(gp[l][0], cap.grid[l]);
+            if (!fix_color) grad_to_host(c->flat[3], cap.dec_color);
+        }
         for (int l = 1; l < 4; ++l)
             if (mask_t[l].defined() && gp[l][0].grad().defined()) gp[l][0].mutable_grad().mul_(mask_t[l]);
         opt.step();
@@ -303,6 +320,7 @@ int ref_mapping_iters(void* h, int n_frames, int H, int W, float fx, float fy, f
     for (int l = 1; l < 4; ++l) c->grids.at(kGridName[l]).requires_grad_(false);
     rebind(c, 2); rebind(c, 3);
     zero_grads(c);
+    c->caps.clear();
     REF_CATCH(c)
 }
 

@@ -125,6 +125,15 @@ class Ref:
                                          _p(np.ascontiguousarray(g_var, np.float32)), *gptr, *dptr, _p(out["rays_d"]), _p(out["rays_o"])))
         return out
 
+    def capture_grads(self, it):
+        """Ask the next mapping_iters call for the gradients of iteration `it` (before optimizer.step): returns the dict of host
+        arrays that call will fill (grid_middle / grid_fine / grid_color / dec_color)."""
+        out = {"grid_" + lv: np.zeros(self.grid_shape[lv], np.float32) for lv in ("middle", "fine", "color")}
+        out["dec_color"] = np.zeros(self._dec_n["color"], np.float32)
+        self._caps = getattr(self, "_caps", []) + [out]      # keep the buffers alive
+        self._ck(self.lib.ref_mapping_capture_grads(self.h, int(it), _p(out["grid_middle"]), _p(out["grid_fine"]), _p(out["grid_color"]), _p(out["dec_color"])))
+        return out
+
     def mapping_iters(self, depths, colors, c2ws, cam, mapping_pixels, stage_ids, lr_table, w_color_loss=0.5,
                       fix_fine=True, fix_color=False, seed=0, masks=None):
         depths = np.ascontiguousarray(depths, np.float32); colors = np.ascontiguousarray(colors, np.float32)

@@ -22,7 +22,7 @@ def test_header_symbols_exported(nsb):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(nsb.EXPORTS)
-    assert L.nsb_abi_version() == 1
+    assert L.nsb_abi_version() == 2
 
 
 def test_config_defaults_are_reference_values(nsb):

@@ -61,7 +61,7 @@ def filtered_rays(syn, frames, n, seed, f=0):
 def test_get_samples_bit_exact_vs_reference(engine_factory, frames):
     """get_samples / raySampler (utils.h:13-55,141-146) against oracle/_ref's output: indices, rays, gt gathers."""
     g = load_golden("sampling.npz")
-    e = engine_factory()
+    e = engine_factory(raydir=0)        # utils.h:44-47 as written: the golden rays come from the reference's own raySampler
     ro, rd, gd, gc, ins, idx = e.get_samples(int(g["frame"]), int(g["H0"]), int(g["H1"]), int(g["W0"]), int(g["W1"]), 256, idx=g["idx"])
     assert np.array_equal(ro, g["rays_o"]) and np.array_equal(rd, g["rays_d"])
     assert np.array_equal(gd, g["gt_depth"]) and np.array_equal(gc, g["gt_color"])
@@ -200,11 +200,42 @@ def test_mapping_iterations_vs_reference(engine_factory, frames, syn, model_inpu
     (two geometry, two colour) against oracle/_ref's libtorch autograd + torch::optim::Adam."""
     grids, decs, _ = model_inputs
     g = load_golden("mapping_iters.npz")
-    e = engine_factory(g["t_samples"], g["t_surface"], mapping_pixels=int(g["pixels"]), frustum_feature_selection=0)
+    e = engine_factory(g["t_samples"], g["t_surface"], mapping_pixels=int(g["pixels"]), frustum_feature_selection=0, raydir=0)
     it_of = {1: 0, 3: 59}          # iteration numbers of a 60-iteration schedule that select these stages
+    e.mapping_capture_grads(True)
+
+    def check_grads(tag, got):
+        """the gradient loss.backward() leaves at Mapper.cpp:444, against libtorch autograd at the golden's sampled positions"""
+        for lv in ("middle", "fine", "color"):
+            full = got["grid_" + lv]
+            gmax = float(g["%s_grad_%s_max" % (tag, lv)])
+            if gmax == 0.0:
+                assert np.abs(full).max() == 0.0, (tag, lv)          # geometry iteration: exact zeros in the colour grid
+                continue
+            assert np.abs(full.reshape(-1)[g["%s_grad_%s_pos" % (tag, lv)]] - g["%s_grad_%s_val" % (tag, lv)]).max() < GRAD_TOL * gmax, (tag, lv)
+            l2 = np.sqrt((full.astype(np.float64) ** 2).sum()); ref_l2 = float(g["%s_grad_%s_l2" % (tag, lv)])
+            assert abs(l2 - ref_l2) < GRAD_TOL * ref_l2, (tag, lv)
+        ref_dec = g["%s_grad_dec_color" % tag]
+        if np.abs(ref_dec).max() == 0.0:
+            assert np.abs(got["dec_color"]).max() == 0.0, tag
+        else:
+            assert relerr(got["dec_color"], ref_dec) < GRAD_TOL, tag
+
+    # a colour-stage iteration from the initial parameters: colour grid + colour-decoder weight gradients at iteration 0
+    e.seed(int(g["c0_seed"]))
+    e.mapping_begin(list(range(int(g["n_frames"]))), 60, 1.0)
+    l0 = e.mapping_iter(59)
+    assert np.allclose(l0, g["c0_loss"], rtol=1e-4), (l0, g["c0_loss"])
+    check_grads("c0", e.captured_grads())
+    e.set_model(grids, decs)                                             # back to the initial map
     e.seed(int(g["seed"]))
     e.mapping_begin(list(range(int(g["n_frames"]))), 60, 1.0)
-    losses = [e.mapping_iter(it_of[int(s)]) for s in g["stages"]]
+    losses = []
+    for k, s in enumerate(g["stages"]):
+        losses.append(e.mapping_iter(it_of[int(s)]))
+        if k == 0:
+            check_grads("it0", e.captured_grads())
+    e.mapping_capture_grads(False)
     assert np.allclose(losses, g["losses"], rtol=1e-3), (losses, g["losses"])
     dec = e.get_decoder("color")
     moved = np.abs(g["dec_color"] - decs["color"]).max()
@@ -221,7 +252,7 @@ def test_mapping_iterations_vs_reference(engine_factory, frames, syn, model_inpu
 def test_tracking_iterations_vs_reference(engine_factory):
     """Tracker.cpp:41-113: pose -> rays -> render -> median mask -> loss -> pose gradient -> Adam on 7 floats."""
     t = load_golden("tracking_iters.npz")
-    e = engine_factory(t["t_samples"], t["t_surface"], tracking_pixels=int(t["pixels"]), tracking_lr=float(t["lr"]))
+    e = engine_factory(t["t_samples"], t["t_surface"], tracking_pixels=int(t["pixels"]), tracking_lr=float(t["lr"]), raydir=0)
     e.seed(int(t["seed"]))
     e.tracking_begin(0, t["cam7_in"])
     losses, g0 = [], None
@@ -233,6 +264,80 @@ def test_tracking_iterations_vs_reference(engine_factory):
     assert np.allclose(losses, t["losses"], rtol=1e-3)
     assert relerr(g0, t["grad_first"]) < GRAD_TOL
     assert np.abs(e.tracking_camera() - t["cam7_out"]).max() < 1e-5
+
+
+# ------------------------------------------------------------------ BASELINE.json batch size (5000 rays x 48 samples) vs the oracle
+def test_full_size_vs_oracle(engine_factory, frames, syn, model_inputs):
+    """BASELINE configs[0..1] at full size: render_batch_ray forward (1e-4), its vjp (1e-3) and the gradients of one whole mapping
+    iteration (sampling -> filter -> render -> loss -> backward, Mapper.cpp:376-444) against the autograd oracle on the same
+    5000 pixels."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    e = engine_factory(max_rays=8192, mapping_pixels=5000, frustum_feature_selection=0)
+    ro, rd, gd, gc = filtered_rays(syn, frames, 5800, 91, f=3)
+    ro, rd, gd = ro[:5000], rd[:5000], gd[:5000]
+    assert ro.shape[0] == 5000
+    n = 5000
+    rs = np.random.RandomState(4)
+    g_rgb = rs.randn(n, 3).astype(np.float32); g_depth = rs.randn(n).astype(np.float32); g_var = (0.3 * rs.randn(n)).astype(np.float32)
+    m = O.Model(grids, decs)
+    for k in ("middle", "fine", "color"):
+        m.grids[k].requires_grad_(True)
+    m.flat["color"].requires_grad_(True)
+    tro = torch.tensor(ro, requires_grad=True); trd = torch.tensor(rd, requires_grad=True)
+    ref = O.render_batch_ray(m, trd, tro, "color", torch.tensor(gd))
+    got = e.render_batch_ray(rd, ro, "color", gd)
+    for nm, x, y in zip(("rgb", "depth", "var", "weights"), got, ref):
+        assert relerr(x, y.detach().numpy()) < FWD_TOL, nm
+    ((ref[0] * torch.tensor(g_rgb)).sum() + (ref[1] * torch.tensor(g_depth)).sum() + (ref[2] * torch.tensor(g_var)).sum()).backward()
+    vjp = e.render_vjp(rd, ro, "color", gd, g_rgb, g_depth, g_var)
+    for lv in ("middle", "fine", "color"):
+        assert relerr(vjp["grid_" + lv], m.grids[lv].grad.numpy()) < GRAD_TOL, lv
+    assert relerr(vjp["dec_color"], m.flat["color"].grad.numpy()) < GRAD_TOL
+    assert relerr(vjp["rays_o"], tro.grad.numpy()) < GRAD_TOL and relerr(vjp["rays_d"], trd.grad.numpy()) < GRAD_TOL
+    # one mapping iteration (colour stage) on 5 frames x 1000 pixels: loss and every gradient before the optimiser step
+    m2 = O.Model(grids, decs)
+    go = {}
+    ref_losses, _ = O.mapping_iters(m2, depths[:5], colors[:5], poses[:5], syn.CAM, 5000, ["color"], seed=17, raydir="pinhole", grads_out=go)
+    e.seed(17)
+    e.mapping_capture_grads(True)
+    e.mapping_begin(list(range(5)), 60, 1.0)
+    loss = e.mapping_iter(59)
+    cg = e.captured_grads()
+    e.mapping_capture_grads(False)
+    assert abs(loss - ref_losses[0]) < 1e-4 * abs(ref_losses[0]), (loss, ref_losses)
+    for lv in ("middle", "fine", "color"):
+        assert relerr(cg["grid_" + lv], go[lv].numpy()) < GRAD_TOL, lv
+    assert relerr(cg["dec_color"], go["dec_color"].numpy()) < GRAD_TOL
+
+
+def test_graph_replay_equals_eager_launches(nsb, model_inputs, frames, monkeypatch):
+    """The captured-graph iteration (one cudaGraphLaunch, device-resident iteration state) and the kernel-by-kernel path
+    (NSB_GRAPH=0) are the same arithmetic: identical losses and bit-identical parameters after a mixed schedule."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("NSB_GRAPH", graph)
+        cfg = nsb.default_config(); cfg.mapping_pixels = 1500; cfg.max_rays = 2048; cfg.frustum_feature_selection = 0
+        e = nsb.Engine(cfg)
+        e.set_model(grids, decs)
+        for f in range(3):
+            e.set_frame(f, depths[f], colors[f], poses[f])
+        e.seed(9)
+        losses = []
+        for rep_ in range(2):                                   # two optimize_map calls: the second reuses the captured graphs
+            e.mapping_begin([0, 1, 2], 60, 1.0)
+            for it in (0, 1, 30, 58, 59):
+                e.mapping_iter(it, sync=False)
+            l, k = e.mapping_losses(0, 5)
+            losses.append(l); assert (k > 0).all()
+        outs.append((np.concatenate(losses), {lv: e.get_grid(lv) for lv in ("middle", "fine", "color")}, e.get_decoder("color")))
+        e.close()
+    assert np.array_equal(outs[0][0], outs[1][0]), (outs[0][0], outs[1][0])
+    for lv in ("middle", "fine", "color"):
+        assert np.array_equal(outs[0][1][lv], outs[1][1][lv]), lv
+    assert np.array_equal(outs[0][2], outs[1][2])
 
 
 # ------------------------------------------------------------------ properties at the BASELINE.json batch size
@@ -342,7 +447,7 @@ def test_bundle_adjustment_vs_oracle(engine_factory, model_inputs, frames, syn):
     m = O.Model(grids, decs)
     go, co = {}, []
     ref_losses, _ = O.mapping_iters(m, depths[:nf], colors[:nf], poses[:nf], syn.CAM, pix, stages, seed=11, ba_frames=[1, 2],
-                                    ba_cam_lr=0.001, grads_out=go, cams_out=co)
+                                    ba_cam_lr=0.001, grads_out=go, cams_out=co, raydir="pinhole")     # the library's default directions
     assert np.allclose(losses, ref_losses, rtol=1e-3), (losses, ref_losses)
     assert np.all(g_first[0] == 0)
     for f in (1, 2):
@@ -373,7 +478,7 @@ def test_keyframe_selection_overlap(engine_factory, frames, syn):
     idx = syn.mt19937_indices(3, 100, 480 * 640)
     sel, pct = e.keyframe_selection_overlap(0, kfs, 3, idx=idx)
     _, ts = O.t_tables()
-    ref_sel, ref_pct = O.keyframe_selection_overlap(depths[0], colors[0], poses[0], kfs, 3, syn.CAM, idx, ts=ts.numpy())
+    ref_sel, ref_pct = O.keyframe_selection_overlap(depths[0], colors[0], poses[0], kfs, 3, syn.CAM, idx, raydir="pinhole", ts=ts.numpy())
     assert np.abs(pct - ref_pct).max() <= 2.0 / 1600 + 1e-7, (pct, ref_pct)      # a vertex exactly on the 20 px border may flip
     assert ref_pct.max() > 0.3 and (ref_pct == 0).any()
     if np.abs(pct - ref_pct).max() == 0:
@@ -394,9 +499,9 @@ def test_dense_render_img(engine_factory, frames, model_inputs, syn):
     assert rgb.shape == (480, 640, 3) and np.isfinite(rgb).all() and np.isfinite(depth).all() and (var >= 0).all()
     # rows 200..201 against the oracle, with the whole-image maxima of Renderer.cpp:76,93 injected through an extra ray
     rows = np.arange(200 * 640, 202 * 640)
-    ro, rd, gd, _ = O.ray_sampler(0, 480, 0, 640, rows, 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]))
+    ro, rd, gd, _ = O.ray_sampler(0, 480, 0, 640, rows, 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]), "pinhole")
     imax = int(np.argmax(depths[0]))
-    ro2, rd2, gd2, _ = O.ray_sampler(0, 480, 0, 640, np.array([imax]), 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]))
+    ro2, rd2, gd2, _ = O.ray_sampler(0, 480, 0, 640, np.array([imax]), 360.0, 360.0, 320.0, 240.0, torch.tensor(depths[0]), torch.tensor(colors[0]), torch.tensor(poses[0]), "pinhole")
     tt, ts = O.t_tables()
     with torch.no_grad():
         ref = O.render_batch_ray(O.Model(grids, decs), torch.cat([rd, rd2]), torch.cat([ro, ro2]), "color", torch.cat([gd, gd2]), tt, ts)
