@@ -283,8 +283,9 @@ def run_forward_only(e, nsb, torch, ext, depths, colors, poses, flush, reps=10):
     """BASELINE configs[0]: Renderer::render_batch_ray forward on 5000 rays x 48 samples (cofusion.yaml camera).  Device time with the
     rays resident (nsb_render_batch_ray_dev), and through the host ABI (rays H2D, rgb/depth/var/weights D2H inside the timed region)."""
     idx = nsb.synthetic.mt19937_indices(3, 6000, 480 * 640)
-    ro, rd, gd, gc, inside, _ = e.get_samples(0, 0, 480, 0, 640, 6000, idx=idx)
-    ro, rd, gd = ro[inside][:RAYS_PER_GPU], rd[inside][:RAYS_PER_GPU], gd[inside][:RAYS_PER_GPU]
+    parts = [e.get_samples(0, 0, 480, 0, 640, 3000, idx=idx[h * 3000:(h + 1) * 3000]) for h in range(2)]
+    inside = np.concatenate([p[4] for p in parts])
+    ro, rd, gd = (np.concatenate([p[k] for p in parts])[inside][:RAYS_PER_GPU] for k in (0, 1, 2))
     n = ro.shape[0]
     d_ro = torch.from_numpy(ro).cuda(); d_rd = torch.from_numpy(rd).cuda(); d_gd = torch.from_numpy(gd).cuda()
     o_rgb = torch.empty(n, 3, device="cuda"); o_d = torch.empty(n, device="cuda"); o_v = torch.empty(n, device="cuda"); o_w = torch.empty(n, 48, device="cuda")

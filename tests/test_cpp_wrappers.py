@@ -60,7 +60,7 @@ def test_wrappers_match_ctypes_and_oracle(nsb, syn, model_inputs, frames, tmp_pa
     got = e.render_batch_ray(rd, ro, "color", gd)
     assert np.array_equal(got[1], out["depth"]) and np.array_equal(got[0].reshape(-1), out["rgb"])
     # Mapper::optimize_map (3 iterations on the current frame) vs the oracle's Mapper.cpp:330-465 restatement
-    l_or, _ = O.mapping_iters(O.Model(grids, decs), depths[:1], colors[:1], poses[:1], syn.CAM, 400, O.stage_schedule(3), seed=3, tt=tt, ts=ts)
+    l_or, _ = O.mapping_iters(O.Model(grids, decs), depths[:1], colors[:1], poses[:1], syn.CAM, 400, O.stage_schedule(3), seed=3, tt=tt, ts=ts, raydir="pinhole")
     assert np.allclose(out["map_losses"], l_or, rtol=1e-3)
     assert np.abs(out["grid_middle"] - grids["middle"].reshape(-1)).max() > 0.05      # the dict got the optimised grid back
     assert len(out["trk_losses"]) == 2 and np.all(np.isfinite(out["cam"])) and abs(np.linalg.norm(out["cam"][:4]) - 1) < 1e-2
