@@ -237,6 +237,15 @@ def cpu_baselines(nsb, want_configs=True):
             O.render_batch_ray(ref, torch.tensor(rd), torch.tensor(ro), "color", torch.tensor(gd))
             sec = time.perf_counter() - t0
     out["forward"] = {"value": rd.shape[0] / sec, "unit": "rays/s", "cores": cores, "kind": kind, "sample": "render_batch_ray forward, %d rays, %.2f s per call" % (rd.shape[0], sec)}
+    pts = np.random.RandomState(0).uniform(syn.BOUND[:, 0], syn.BOUND[:, 1], (200000, 3)).astype(np.float32)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        ref.eval_points(pts, "color")
+    else:
+        with torch.no_grad():
+            ref.eval_points(torch.tensor(pts), "color")
+    sec = time.perf_counter() - t0
+    out["eval_points"] = {"value": pts.shape[0] / sec, "unit": "points/s", "cores": cores, "kind": kind, "sample": "bounded: Renderer::eval_points on 200 000 of the 256^3 lattice points, %.2f s" % sec}
     cam0 = O.get_tensor_from_camera(poses[0]); cam0 = np.asarray(cam0, np.float32).copy(); cam0[4:] += 0.01
     n_trk = 2
     if kind == "reference":
@@ -327,6 +336,18 @@ def run_dense(e, nsb, torch, ext, reps=3):
     n = e.cfg.H * e.cfg.W
     return {"workload": "dense_render_640x480_color", "rays": int(n), "ms": float(np.mean(ms)), "rays_per_s": n / (np.mean(ms) * 1e-3), "e2e_ms": wall * 1e3,
             "e2e_rays_per_s": n / wall, "d2h_bytes": int(n * 5 * 4), "chunk_rays": int(e.cfg.max_rays)}
+
+
+def run_lattice(e, res=256):
+    """SURVEY 8-f row 3 / nice_slam.yaml meshing.resolution: eval_points("color") over a res^3 lattice generated on the device, the
+    stage assembly and the bound mask applied in-kernel; wall time includes the read-back of the occupancy channel."""
+    e.eval_lattice("color", 32, 32, 32)
+    t0 = time.perf_counter()
+    occ = e.eval_lattice("color", res, res, res)
+    wall = time.perf_counter() - t0
+    n = res ** 3
+    return {"workload": "eval_points_lattice_%d^3_color" % res, "points": int(n), "e2e_ms": wall * 1e3, "points_per_s": n / wall, "d2h_bytes": int(n * 4),
+            "inside_fraction": float((occ != 100.0).mean())}
 
 
 def parity_selfcheck(nsb, e, torch, dist, rank, world, local_rank, grids, decs, depths, colors, poses, cfg):
@@ -520,7 +541,8 @@ def run_ours(args, rank, world, local_rank):
     configs = None
     if rank == 0 and not args.no_configs:
         e.set_model(grids, decs)
-        configs = {"forward_only": run_forward_only(e, nsb, torch, ext, depths, colors, poses, flush), "dense_render": run_dense(e, nsb, torch, ext)}
+        configs = {"forward_only": run_forward_only(e, nsb, torch, ext, depths, colors, poses, flush), "dense_render": run_dense(e, nsb, torch, ext),
+                   "mesh_lattice": run_lattice(e)}
     tracking = run_tracking(e, nsb, torch, ext, depths, colors, poses)   # replicas only: every rank tracks its own frame
     if clocks:
         clocks.stop()
@@ -575,6 +597,7 @@ def run_ours(args, rank, world, local_rank):
                 cpu = cb["mapping"]
                 if configs is not None:
                     configs["forward_only"]["cpu_baseline"] = cb.get("forward")
+                    configs["mesh_lattice"]["cpu_baseline"] = cb.get("eval_points")
                     tracking["cpu_baseline"] = cb.get("tracking")
                     if cb.get("forward"):
                         configs["dense_render"]["cpu_baseline"] = dict(cb["forward"], sample="bounded: " + cb["forward"]["sample"] + " (a 5000-ray strip of the image)")

@@ -85,6 +85,7 @@ typedef struct nsb_config {
     int precision;                   /* NSB_PREC_* */
     int max_rays;                    /* capacity of the per-call ray batch */
     int max_frames;                  /* resident frame slots (keyframes + current) */
+    int color_refine;                /* mapping.color_refine (nice_slam.yaml:86): the last frame is mapped once more with the settings of Mapper.cpp:505-513 */
 } nsb_config;
 
 /* ---- configuration ------------------------------------------------------------------------------ */
@@ -168,8 +169,14 @@ int nsb_render_batch_ray(nsb_ctx* ctx, int stage, int n, const float* rays_d, co
                          const float* gt_depth, float* rgb, float* depth, float* var, float* weights);
 int nsb_render_batch_ray_dev(nsb_ctx* ctx, int stage, int n, const float* d_rays_d, const float* d_rays_o,
                              const float* d_gt_depth, float* d_rgb, float* d_depth, float* d_var, float* d_weights);
-/* Renderer::eval_points (Renderer.h:12, Renderer.cpp:19-42): raw (P,4) for P points. */
+/* Renderer::eval_points (Renderer.h:12, Renderer.cpp:19-42): raw (P,4) for P points.  The stage assembly (NICE.cpp:16-51) and the
+ * out-of-bound occupancy 100 (Renderer.cpp:26-36) are applied on the device; host form: one synchronisation at the end. */
 int nsb_eval_points(nsb_ctx* ctx, int stage, int P, const float* pts, float* raw);
+int nsb_eval_points_dev(nsb_ctx* ctx, int stage, int P, const float* d_pts, float* d_raw);
+/* eval_points over a regular nx x ny x nz lattice between lo3 and hi3 (NULL: the scene bound) -- the mesh-extraction query of
+ * nice_slam.yaml meshing.resolution.  The points are generated on the device; outputs are host arrays, either may be NULL:
+ * raw4 (n,4), occ (n) = channel 3.  Point order q = (j*nx + i)*nz + k <-> (x_i, y_j, z_k) (numpy.meshgrid(x,y,z).ravel()). */
+int nsb_eval_lattice(nsb_ctx* ctx, int stage, int nx, int ny, int nz, const float* lo3, const float* hi3, float* raw4, float* occ);
 /* Dense render of all H*W pixels of the frame in `slot` seen from c2w16 (NULL: the slot's pose) -- upstream's
  * Renderer::render_img, of which the reference keeps only ray_batch_size (Renderer.cpp:5); equals ONE render_batch_ray over
  * the H*W rays in row-major pixel order.  use_gt_depth != 0: depth-guided with the frame's depth image (48 samples/ray);
@@ -208,8 +215,13 @@ int nsb_mapping_begin_ba(nsb_ctx* ctx, int n_frames, const int* slots, int n_ite
  *   NSB_MAP_COARSE      the coarse mapper's optimize_map (Mapper(ns, cf, coarse_mapper = true); Mapper.cpp:335-338,351-352,450-453):
  *                       stage "coarse" for every iteration, render_batch_ray("coarse"), only grid_coarse is optimised (coarse_lr);
  *   NSB_MAP_FIX_COLOR   the colour decoder stays fixed for this call (color_refine sets fix_color, Mapper.cpp:505-513);
- *   NSB_MAP_NO_FRUSTUM  no frustum feature selection for this call (color_refine: frustum_feature_selection = false). */
-enum { NSB_MAP_COARSE = 1, NSB_MAP_FIX_COLOR = 2, NSB_MAP_NO_FRUSTUM = 4 };
+ *   NSB_MAP_NO_FRUSTUM  no frustum feature selection for this call (color_refine: frustum_feature_selection = false);
+ *   NSB_MAP_ZERO_RATIOS middle_iter_ratio = fine_iter_ratio = 0 for this call (color_refine, Mapper.cpp:508-509);
+ *   NSB_MAP_COLOR_REFINE = the three color_refine settings of Mapper.cpp:505-513 together.
+ * The coarse mapper follows upstream's intent: the transliteration renders "color" at Mapper.cpp:430 whatever the stage, which
+ * never touches grid_coarse, so its coarse mapper would optimise nothing; here the coarse mapper renders stage "coarse" without
+ * depth guidance (upstream: gt_depth = None) and back-propagates the depth loss into grid_coarse. */
+enum { NSB_MAP_COARSE = 1, NSB_MAP_FIX_COLOR = 2, NSB_MAP_NO_FRUSTUM = 4, NSB_MAP_ZERO_RATIOS = 8, NSB_MAP_COLOR_REFINE = 2 | 4 | 8 };
 int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask, int flags);
 int nsb_mapping_end(nsb_ctx* ctx, float* cam7s_out);
 /* d L / d (q, t) per frame at the last BA iteration, [n_frames][7] (parity checks of the pose-gradient chain). */

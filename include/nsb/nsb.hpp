@@ -203,7 +203,7 @@ struct KeyFrame { Tensor est_c2w, gt_c2w, color, depth; int idx = 0; int slot = 
 // ---- include/Mapper.h -----------------------------------------------------------------------------------------------------
 class Mapper {
   public:
-    Mapper(EnginePtr engine, bool coarse_mapper = false) : e_(std::move(engine)), coarse_mapper_(coarse_mapper) {}
+    Mapper(EnginePtr engine, bool coarse_mapper = false) : e_(std::move(engine)), coarse_mapper_(coarse_mapper) { mapping_window_size_ = e_->cfg().mapping_window_size; }
     // Mapper.cpp:132-196 (member form): indices into keyframes() of the k_overlap keyframes that see most of the current view.
     void keyframe_selection_overlap(Tensor gt_color, Tensor gt_depth, Tensor c2w, const std::vector<KeyFrame>& keyframe_vector, int k_overlap,
                                     std::vector<int>& selected_kf) {
@@ -216,14 +216,13 @@ class Mapper {
     void optimize_map(int num_joint_iters, Dict& c, Tensor cur_gt_color, Tensor cur_gt_depth, Tensor gt_cur_c2w, Tensor& cur_c2w, NICE& decoders,
                       float lr_factor = 1.f, std::vector<float>* losses = nullptr) {
         (void)gt_cur_c2w; (void)decoders;
-        if (coarse_mapper_) throw std::runtime_error("coarse mapper: not on the accelerated path (SURVEY.md 8-f)");
         e_->sync_grids_to_device(c);
         const int cur_slot = e_->cfg().max_frames - 1;
         float m[16] = {0}; m[15] = 1.f; std::memcpy(m, cur_c2w.data(), sizeof(float) * std::min<int64_t>(16, cur_c2w.numel()));
         e_->check(nsb_set_frame(e_->ctx(), cur_slot, cur_gt_depth.data(), cur_gt_color.data(), m));
         // optimize_frame (Mapper.cpp:200-216): overlap-selected keyframes, the latest keyframe, then the current frame (-1)
         std::vector<int> optimize_frame;
-        if (!keyframes_.empty()) select_overlap(cur_slot, keyframes_, e_->cfg().mapping_window_size - 2, optimize_frame);
+        if (!keyframes_.empty()) select_overlap(cur_slot, keyframes_, mapping_window_size_ - 2, optimize_frame);
         int oldest_frame = -1;
         if (!keyframes_.empty()) {
             optimize_frame.push_back((int)keyframes_.size() - 1);
@@ -239,9 +238,11 @@ class Mapper {
             if (BA && fr != oldest_frame) ba_mask |= 1u << f;          // Mapper.cpp:305-329 (the current frame always joins)
         }
         std::vector<float> l((size_t)num_joint_iters);
-        e_->check(nsb_mapping_begin_ba(e_->ctx(), (int)slots.size(), slots.data(), num_joint_iters, lr_factor, ba_mask));
+        // coarse mapper: stage "coarse", only grid_coarse (Mapper.cpp:335-338,351-352); color_refine: Mapper.cpp:505-513
+        const int flags = (coarse_mapper_ ? NSB_MAP_COARSE : 0) | (refine_ ? NSB_MAP_COLOR_REFINE : 0);
+        e_->check(nsb_mapping_begin_ex(e_->ctx(), (int)slots.size(), slots.data(), num_joint_iters, lr_factor, coarse_mapper_ ? 0u : ba_mask, flags));
         for (int it = 0; it < num_joint_iters; ++it) e_->check(nsb_mapping_iter_async(e_->ctx(), it, nullptr));
-        for (int o = 0; o < num_joint_iters; o += 4096) e_->check(nsb_mapping_losses(e_->ctx(), o, std::min(4096, num_joint_iters - o), l.data() + o, nullptr));
+        e_->check(nsb_mapping_losses(e_->ctx(), 0, num_joint_iters, l.data(), nullptr));   // the loss ring holds every step of this call
         e_->check(nsb_mapping_end(e_->ctx(), nullptr));
         if (losses) *losses = l;
         if (ba_mask) {                                               // Mapper.cpp:467-489: est_c2w / cur_c2w <- optimised cameras
@@ -258,14 +259,29 @@ class Mapper {
     // Mapper.cpp:493-552.  The transliteration hard-codes `init = true` (:495); the intent (upstream) is the first frame only.
     void run(NICE& decoders, Dict& c, std::vector<Tensor>& estimate_c2w_vec, Tensor gt_color_t, Tensor gt_depth_t, Tensor gt_c2w_t, int idx, int n_imgs) {
         const bool first = keyframes_.empty() && idx == 0;
-        const int iters = first ? e_->cfg().mapping_iters_first : e_->cfg().mapping_iters;
+        int iters = first ? e_->cfg().mapping_iters_first : e_->cfg().mapping_iters;
         const float lrf = first ? e_->cfg().lr_first_factor : e_->cfg().lr_factor;
+        int outer_joint_iters = 1;
+        if (!first && idx == n_imgs - 1 && e_->cfg().color_refine && !coarse_mapper_) {                 // Mapper.cpp:505-513: the final refinement pass
+            outer_joint_iters = 5;
+            mapping_window_size_ *= 2;
+            refine_ = true;            // middle_iter_ratio = fine_iter_ratio = 0, fix_color = true, frustum_feature_selection = false
+            iters *= 5;
+        }
         Tensor cur = estimate_c2w_vec[(size_t)idx];
-        BA = keyframes_.size() > 4 && e_->cfg().BA && !coarse_mapper_;                                  // Mapper.cpp:530
-        optimize_map(iters, c, gt_color_t, gt_depth_t, gt_c2w_t, cur, decoders, lrf);
-        if (BA) estimate_c2w_vec[(size_t)idx] = cur;                                                    // Mapper.cpp:533-534
-        if ((idx % e_->cfg().keyframe_every == 0 || idx == n_imgs - 2) && (int)keyframes_.size() < e_->cfg().max_frames - 1) {
+        iters = iters / outer_joint_iters;                                                               // Mapper.cpp:526
+        for (int outer = 0; outer < outer_joint_iters; ++outer) {
+            BA = keyframes_.size() > 4 && e_->cfg().BA && !coarse_mapper_;                              // Mapper.cpp:530
+            optimize_map(iters, c, gt_color_t, gt_depth_t, gt_c2w_t, cur, decoders, lrf);
+            if (BA) estimate_c2w_vec[(size_t)idx] = cur;                                                // Mapper.cpp:533-534
+        }
+        if (idx % e_->cfg().keyframe_every == 0 || idx == n_imgs - 2) {
             for (const KeyFrame& k : keyframes_) if (k.idx == idx) return;                              // Mapper.cpp:539
+            // the reference's keyframe_vector is unbounded; here every keyframe occupies a resident device slot (the last slot is
+            // the current frame's): say so instead of silently dropping keyframes (size max_frames from n_imgs / keyframe_every + 2)
+            if ((int)keyframes_.size() >= e_->cfg().max_frames - 1)
+                throw std::runtime_error("Mapper::run: the " + std::to_string(e_->cfg().max_frames) + " resident frame slots are exhausted at frame " + std::to_string(idx) +
+                                         "; create the engine with max_frames >= n_imgs / keyframe_every + 3");
             KeyFrame kf; kf.idx = idx; kf.gt_c2w = gt_c2w_t; kf.est_c2w = cur; kf.color = gt_color_t; kf.depth = gt_depth_t; kf.slot = (int)keyframes_.size();
             float m[16] = {0}; m[15] = 1.f; std::memcpy(m, cur.data(), sizeof(float) * std::min<int64_t>(16, cur.numel()));
             e_->check(nsb_set_frame(e_->ctx(), kf.slot, gt_depth_t.data(), gt_color_t.data(), m));
@@ -288,6 +304,8 @@ class Mapper {
     }
     EnginePtr e_;
     bool coarse_mapper_;
+    bool refine_ = false;              // color_refine has been switched on by run() (Mapper.cpp:505-513)
+    int mapping_window_size_ = 0;      // mapping.mapping_window_size, doubled by color_refine (Mapper.cpp:507)
     std::vector<KeyFrame> keyframes_;
 };
 

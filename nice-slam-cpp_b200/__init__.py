@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LEVELS = ("coarse", "middle", "fine", "color")
 STAGE = {"coarse": 0, "middle": 1, "fine": 2, "color": 3}
 F_GRID, F_WGRAD, F_RAY = 1, 2, 4
-MAP_COARSE, MAP_FIX_COLOR, MAP_NO_FRUSTUM = 1, 2, 4          # nsb_mapping_begin_ex flags
+MAP_COARSE, MAP_FIX_COLOR, MAP_NO_FRUSTUM, MAP_ZERO_RATIOS, MAP_COLOR_REFINE = 1, 2, 4, 8, 14          # nsb_mapping_begin_ex flags
 RAYDIR_REFERENCE, RAYDIR_PINHOLE = 0, 1
 DISTNORM_PER_RAY, DISTNORM_REFERENCE = 0, 1
 _fp = C.POINTER(C.c_float)
@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("tracking_lr", C.c_float), ("tracking_iters", C.c_int), ("tracking_pixels", C.c_int),
         ("ignore_edge_W", C.c_int), ("ignore_edge_H", C.c_int), ("handle_dynamic", C.c_int),
         ("use_color_in_tracking", C.c_int), ("w_color_loss", C.c_float),
-        ("precision", C.c_int), ("max_rays", C.c_int), ("max_frames", C.c_int),
+        ("precision", C.c_int), ("max_rays", C.c_int), ("max_frames", C.c_int), ("color_refine", C.c_int),
     ]
 
 
@@ -138,6 +138,8 @@ def load_library(variant=""):
     L.nsb_keyframe_selection_overlap.argtypes = [v, C.c_int, _fp, C.c_int, _fp, C.c_int, _i64p, C.c_int, C.c_int, _ip, _ip, _fp]
     L.nsb_get_frame_pose.argtypes = [v, C.c_int, _fp]
     L.nsb_debug_counters.argtypes = [v, C.POINTER(C.c_uint64)]
+    L.nsb_eval_points_dev.argtypes = [v, C.c_int, C.c_int, v, v]
+    L.nsb_eval_lattice.argtypes = [v, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
     L.nsb_comm_p2p_stats.argtypes = [v, C.POINTER(C.c_double), C.c_int]
     L.nsb_config_reference_literal.argtypes = [C.POINTER(Config)]
     L.nsb_config_reference_literal.restype = None
@@ -160,7 +162,7 @@ EXPORTS = [  # every symbol include/nsb.h declares (checked by tests/test_abi.py
     "nsb_tracking_get_camera", "nsb_comm_unique_id", "nsb_comm_init", "nsb_comm_rank_world", "nsb_launch_count",
     "nsb_set_profiling", "nsb_get_kernel_ms", "nsb_debug_counters", "nsb_bench_gather",
     "nsb_mapping_begin_ba", "nsb_mapping_end", "nsb_get_frame_pose", "nsb_mapping_cam_grads", "nsb_keyframe_selection_overlap", "nsb_render_img", "nsb_ray_order_source", "nsb_set_frame_async", "nsb_frames_ready", "nsb_host_alloc", "nsb_host_free", "nsb_save_checkpoint", "nsb_load_checkpoint", "nsb_comm_p2p_export", "nsb_comm_p2p_import",
-    "nsb_comm_p2p_stats", "nsb_config_reference_literal", "nsb_mapping_begin_ex", "nsb_mapping_capture_grads", "nsb_get_captured_grid_grad", "nsb_get_captured_decoder_grad",
+    "nsb_eval_points_dev", "nsb_eval_lattice", "nsb_comm_p2p_stats", "nsb_config_reference_literal", "nsb_mapping_begin_ex", "nsb_mapping_capture_grads", "nsb_get_captured_grid_grad", "nsb_get_captured_decoder_grad",
 ]
 
 
@@ -382,6 +384,16 @@ class Engine:
         p = _c(pts); raw = np.empty((p.shape[0], 4), np.float32)
         self._ck(self.lib.nsb_eval_points(self.h, STAGE[stage], p.shape[0], _f(p), _f(raw)))
         return raw
+
+    def eval_lattice(self, stage, nx, ny, nz, lo=None, hi=None, want_raw=False):
+        """eval_points over a regular lattice generated on the device (mesh-extraction query) -> occupancy (ny, nx, nz)
+        [numpy.meshgrid(x, y, z) order], and raw (ny, nx, nz, 4) when want_raw."""
+        n = nx * ny * nz
+        occ = np.empty(n, np.float32); raw = np.empty((n, 4), np.float32) if want_raw else None
+        l = None if lo is None else _c(lo); h = None if hi is None else _c(hi)
+        self._ck(self.lib.nsb_eval_lattice(self.h, STAGE[stage], nx, ny, nz, _f(l), _f(h), _f(raw), _f(occ)))
+        occ = occ.reshape(ny, nx, nz)
+        return (occ, raw.reshape(ny, nx, nz, 4)) if want_raw else occ
 
     # ---- loss.backward() through render_batch_ray
     def render_vjp(self, rays_d, rays_o, stage, gt_depth, g_rgb, g_depth, g_var, flags=F_GRID | F_WGRAD | F_RAY):

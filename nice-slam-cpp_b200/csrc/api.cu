@@ -44,6 +44,7 @@ cudaError_t wgrad_init();
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
+cudaError_t launch_coarse_bwd(const DecodeParams& P, int precision, int grid, cudaStream_t st);
 cudaError_t launch_build_wimg(const float* const flat[4], const float* const comp[4], float* const img_fwd[4], float* const img_bwd[4], float* const img_cmp[4],
                               int mask, int cmp_mask, cudaStream_t st);
 size_t wimg_floats(int which);
@@ -162,6 +163,7 @@ struct nsb_ctx {
     bool coarse_map = false;          // this optimize_map is the coarse mapper's (Mapper.cpp:335-338,351-352): stage "coarse", grid_coarse only
     bool map_fix_color = false;       // colour decoder fixed for this optimize_map (mapping.fix_color, or color_refine: Mapper.cpp:505-513)
     bool map_no_mask = false;         // frustum feature selection off for this optimize_map (color_refine)
+    bool map_zero_ratios = false;     // middle_iter_ratio = fine_iter_ratio = 0 for this optimize_map (color_refine)
     unsigned long long p2p_timeout_ns = 20000000000ull;   // peer-barrier time-out (NSB_P2P_TIMEOUT_MS)
     uint32_t map_ba_mask = 0;      // bundle adjustment: frames (bit f) whose 7-vector pose is optimised with the map (Mapper.cpp:305-329)
     // tracking state
@@ -237,7 +239,7 @@ extern "C" void nsb_config_default(nsb_config* c) {
     c->tracking_lr = 0.01f; c->tracking_iters = 10;                                              // Tracker.cpp:103,107
     c->tracking_pixels = 200; c->ignore_edge_W = 20; c->ignore_edge_H = 20;
     c->handle_dynamic = 1; c->use_color_in_tracking = 1; c->w_color_loss = 0.5f;
-    c->precision = NSB_PREC_FP32_GRADE; c->max_rays = 8192; c->max_frames = 8;
+    c->precision = NSB_PREC_FP32_GRADE; c->max_rays = 8192; c->max_frames = 8; c->color_refine = 1;                         // nice_slam.yaml:86
 }
 
 // Minimal YAML subset: nested maps by indentation, "key: scalar", comments, quotes.  Flattened to "a.b.c" -> value.
@@ -294,7 +296,7 @@ extern "C" int nsb_config_load_yaml(nsb_config* c, const char* ns_yaml, const ch
         F(*m, "mapping.lr_factor", c->lr_factor); F(*m, "mapping.lr_first_factor", c->lr_first_factor);
         Bo(*m, "mapping.fix_fine", c->fix_fine); Bo(*m, "mapping.fix_color", c->fix_color);
         Bo(*m, "mapping.frustum_feature_selection", c->frustum_feature_selection); Bo(*m, "mapping.BA", c->BA);
-        F(*m, "mapping.BA_cam_lr", c->BA_cam_lr);
+        F(*m, "mapping.BA_cam_lr", c->BA_cam_lr); Bo(*m, "mapping.color_refine", c->color_refine);
         const char* st[4] = {"coarse", "middle", "fine", "color"};
         const char* gr[5] = {"decoders_lr", "coarse_lr", "middle_lr", "fine_lr", "color_lr"};
         for (int s = 0; s < 4; ++s) for (int g = 0; g < 5; ++g) {
@@ -904,7 +906,13 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         if (stage == NSB_MIDDLE) w[1] = 480 + ge;
         else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
         else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); if (wg && !ge) { w[1] = 460; w[2] = 500; w[3] = 1250; } }   // measured (tools/sweep_split.sh)
-        else return fail(ctx, "backward through the coarse stage is not implemented");
+        else {   // coarse stage (the coarse mapper): MLP_no_xyz data gradient -> grid_coarse; no embedding, so no ray gradient path here
+            if (flags & 4) return fail(ctx, "ray gradients through the coarse stage are not supported (the coarse mapper runs without bundle adjustment, Mapper.cpp:530)");
+            if (ctx->mask_layout != 0) return fail(ctx, "coarse backward needs the warp-MMA forward's mask layout");
+            P.tile_ctr = nullptr;
+            CK(launch_coarse_bwd(P, c.precision, std::max(1, std::min(ctx->n_sm * 4, cdiv(cdiv(n * S, TILE), 8))), ctx->stream)); ctx->launches++;
+            return 0;
+        }
         env_weights("NSB_SPLIT_BWD", w);
         const int grid = decode_grid_size(ctx, n * S);
         partition(grid, w, P.cta_begin);
@@ -1088,38 +1096,74 @@ extern "C" int nsb_get_last_zvals(nsb_ctx* ctx, int n, int S, float* z) {
     return 0;
 }
 
+// Decoders + stage assembly + bound mask for m points already in ctx->pts: raw (m,4) to d_raw4 and / or the occupancy channel to
+// d_occ (device pointers, either may be null).  Everything stays on the device; no synchronisation.
+static int eval_chunk(nsb_ctx* ctx, int stage, int m, float* d_raw4, float* d_occ) {
+    const nsb_config& c = ctx->cfg;
+    DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr);
+    P.pts = ctx->pts; P.P = m;
+    float w[4]; stage_decoders(stage, w);
+    partition(decode_grid_size(ctx, m), w, P.cta_begin);
+    P.tile_ctr = ctx->tile_ctr;
+    CK(cudaMemsetAsync(ctx->tile_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+    k_assemble_raw<<<cdiv(m, 256), 256, 0, ctx->stream>>>(ctx->pts, ctx->raw_rgb, ctx->occ[0], ctx->occ[1], ctx->occ[2], stage, ctx->bnd, m, d_raw4, d_occ);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Renderer::eval_points (Renderer.cpp:19-42), host buffers: chunks of the context's point capacity, one synchronisation at the end.
 extern "C" int nsb_eval_points(nsb_ctx* ctx, int stage, int Pn, const float* pts, float* raw) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
     const nsb_config& c = ctx->cfg;
     const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
-    std::vector<float> h_rgb, h_occ[3];
     if (refresh_images(ctx, 0xE)) return -1;
     for (size_t o = 0; o < (size_t)Pn; o += cap_pts) {
         const int m = (int)std::min(cap_pts, (size_t)Pn - o);
         CK(cudaMemcpyAsync(ctx->pts, pts + 3 * o, 12 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        DecodeParams P; fill_decode_params(ctx, P, 0, 16, nullptr);
-        P.pts = ctx->pts; P.P = m;
-        float w[4]; stage_decoders(stage, w);
-        partition(decode_grid_size(ctx, m), w, P.cta_begin);
-        P.tile_ctr = ctx->tile_ctr;
-        CK(cudaMemsetAsync(ctx->tile_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        CK(launch_decode_fwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
-        h_rgb.resize(4 * (size_t)m); for (int k = 0; k < 3; ++k) h_occ[k].resize(m);
-        CK(cudaMemcpyAsync(h_rgb.data(), ctx->raw_rgb, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(h_occ[k].data(), ctx->occ[k], 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (int i = 0; i < m; ++i) {   // NICE.cpp:16-51 assembly + the bound mask of Renderer.cpp:26-36
-            const float* p = pts + 3 * (o + i);
-            float* r = raw + 4 * (o + i);
-            r[0] = r[1] = r[2] = 0.f;
-            if (stage == NSB_COLOR) { r[0] = h_rgb[4 * i]; r[1] = h_rgb[4 * i + 1]; r[2] = h_rgb[4 * i + 2]; }
-            float occ = stage == NSB_COARSE ? h_occ[0][i] : stage == NSB_MIDDLE ? h_occ[1][i] : h_occ[2][i] + h_occ[1][i];
-            bool in = true;
-            for (int a = 0; a < 3; ++a) in = in && p[a] < c.bound[a][1] && p[a] > c.bound[a][0];
-            r[3] = in ? occ : 100.f;
-        }
+        if (eval_chunk(ctx, stage, m, ctx->g_raw, nullptr)) return -1;           // g_raw doubles as the (m,4) staging buffer
+        CK(cudaMemcpyAsync(raw + 4 * o, ctx->g_raw, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// Device-pointer form: d_pts (P,3) -> d_raw (P,4), enqueued on the context's stream, no host synchronisation.
+extern "C" int nsb_eval_points_dev(nsb_ctx* ctx, int stage, int Pn, const float* d_pts, float* d_raw) {
+    cudaSetDevice(ctx->device);
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    const nsb_config& c = ctx->cfg;
+    const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
+    if (refresh_images(ctx, 0xE)) return -1;
+    for (size_t o = 0; o < (size_t)Pn; o += cap_pts) {
+        const int m = (int)std::min(cap_pts, (size_t)Pn - o);
+        CK(cudaMemcpyAsync(ctx->pts, d_pts + 3 * o, 12 * (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (eval_chunk(ctx, stage, m, d_raw + 4 * o, nullptr)) return -1;
+    }
+    return 0;
+}
+// Mesh-extraction query (nice_slam.yaml meshing: eval_points over a regular lattice): the nx*ny*nz lattice points between lo and hi
+// are generated on the device, evaluated chunk by chunk and masked by the bound; the outputs are HOST arrays (either may be NULL):
+// raw4 (n,4) and / or occ (n) = the occupancy channel, point order q = (j*nx + i)*nz + k (numpy.meshgrid(x,y,z) ravelled).
+extern "C" int nsb_eval_lattice(nsb_ctx* ctx, int stage, int nx, int ny, int nz, const float* lo3, const float* hi3, float* raw4, float* occ) {
+    cudaSetDevice(ctx->device);
+    if (stage < 0 || stage > 3) return fail(ctx, "bad stage %d", stage);
+    if (nx < 1 || ny < 1 || nz < 1) return fail(ctx, "bad lattice %d x %d x %d", nx, ny, nz);
+    const nsb_config& c = ctx->cfg;
+    const size_t cap_pts = (size_t)ctx->cap * (c.n_samples + c.n_surface);
+    const long long total = (long long)nx * ny * nz;
+    LatticeParams L; L.nx = nx; L.ny = ny; L.nz = nz;
+    for (int a = 0; a < 3; ++a) { L.lo[a] = lo3 ? lo3[a] : c.bound[a][0]; L.hi[a] = hi3 ? hi3[a] : c.bound[a][1]; }
+    if (refresh_images(ctx, 0xE)) return -1;
+    for (long long o = 0; o < total; o += (long long)cap_pts) {
+        const int m = (int)std::min<long long>((long long)cap_pts, total - o);
+        k_lattice_points<<<cdiv(m, 256), 256, 0, ctx->stream>>>(L, o, m, ctx->pts); ctx->launches++;
+        if (eval_chunk(ctx, stage, m, raw4 ? ctx->g_raw : nullptr, occ ? ctx->o_w : nullptr)) return -1;      // o_w: (cap, S) scratch
+        if (raw4) CK(cudaMemcpyAsync(raw4 + 4 * o, ctx->g_raw, 16 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (occ) CK(cudaMemcpyAsync(occ + o, ctx->o_w, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1220,10 +1264,12 @@ static int run_reduce_adam(nsb_ctx* ctx, const float lr_group[6], bool dec_fine,
 }
 
 // ---- mapping ----------------------------------------------------------------------------------------------------------
-static int stage_of_iter(const nsb_config& c, int it, int n_iters, bool coarse) {   // Mapper.cpp:351-358
-    if (coarse) return NSB_COARSE;                                                  // Mapper.cpp:351-352
-    if (it <= (int)((float)n_iters * c.middle_iter_ratio)) return NSB_MIDDLE;
-    if (it <= (int)((float)n_iters * c.fine_iter_ratio)) return c.second_stage;
+static int stage_of_iter(const nsb_ctx* ctx, int it, int n_iters) {   // Mapper.cpp:351-358
+    const nsb_config& c = ctx->cfg;
+    if (ctx->coarse_map) return NSB_COARSE;                                         // Mapper.cpp:351-352
+    const float mr = ctx->map_zero_ratios ? 0.f : c.middle_iter_ratio, fr = ctx->map_zero_ratios ? 0.f : c.fine_iter_ratio;   // color_refine: Mapper.cpp:508-509
+    if (it <= (int)((float)n_iters * mr)) return NSB_MIDDLE;
+    if (it <= (int)((float)n_iters * fr)) return c.second_stage;
     return NSB_COLOR;
 }
 
@@ -1260,7 +1306,8 @@ static uint64_t graph_signature(const nsb_ctx* ctx) {
 // the oldest one when BA is on); its lr is BA_cam_lr in the colour stage and 0 before (Mapper.cpp:366-368).
 // flags: NSB_MAP_COARSE = the coarse mapper (Mapper.cpp:335-338,351-352,450-453: stage "coarse", only grid_coarse is optimised);
 // NSB_MAP_FIX_COLOR = keep the colour decoder fixed for this call (color_refine, Mapper.cpp:505-513 sets fix_color);
-// NSB_MAP_NO_FRUSTUM = no frustum feature selection for this call (color_refine: frustum_feature_selection = false).
+// NSB_MAP_NO_FRUSTUM = no frustum feature selection for this call (color_refine: frustum_feature_selection = false);
+// NSB_MAP_ZERO_RATIOS = middle_iter_ratio = fine_iter_ratio = 0 for this call (color_refine, Mapper.cpp:508-509).
 extern "C" int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots, int n_iters, float lr_factor, uint32_t ba_mask, int flags) {
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (wait_uploads(ctx)) return -1;
@@ -1274,6 +1321,7 @@ extern "C" int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots
     ctx->coarse_map = (flags & NSB_MAP_COARSE) != 0;
     ctx->map_fix_color = ctx->cfg.fix_color || (flags & NSB_MAP_FIX_COLOR) != 0;
     ctx->map_no_mask = (flags & NSB_MAP_NO_FRUSTUM) != 0;   // explicit masks (nsb_set_voxel_mask) are ignored too
+    ctx->map_zero_ratios = (flags & NSB_MAP_ZERO_RATIOS) != 0;
     if (ensure_ring(ctx, std::max(LOSS_RING_MIN, n_iters + 1))) return -1;   // every step of this optimize_map keeps its loss slot
     // a fresh torch::optim::Adam is constructed per optimize_map (Mapper.cpp:330): state starts at zero
     CK(cudaMemsetAsync(ctx->m, 0, ctx->arena_n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->v, 0, ctx->arena_n * 4, ctx->stream));
@@ -1351,7 +1399,8 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
     const bool use_color = pl.use_color;
     const bool train_color = use_color && !ctx->map_fix_color && !coarse;
     if (nl > 0) {
-        if (run_forward(ctx, render_stage, off, nl, true, ctx->valid, stats, it, false, true, train_color, true)) return -1;
+        // the coarse mapper renders without depth guidance (upstream passes gt_depth = None for it: 32 stratified samples)
+        if (run_forward(ctx, render_stage, off, nl, !coarse, ctx->valid, stats, it, false, true, train_color, true)) return -1;
         {
             // composite + loss (Mapper.cpp:435-442) + composite backward fused: the cotangents are local to each ray
             Timer t(ctx, T_COMP);
@@ -1373,7 +1422,7 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        const int flags = 1 | (ctx->map_fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0);
+        const int flags = coarse ? 1 : (1 | (ctx->map_fix_color ? 0 : 2) | (ctx->map_ba_mask ? 4 : 0));
         ctx->ar_request = ctx->world > 1 && ctx->ar_mode == 2 && !ctx->p2p;
         const int rb = run_backward(ctx, render_stage, off, nl, ctx->valid, stats, it, flags, use_color, true);
         ctx->ar_request = false;
@@ -1437,7 +1486,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     if (wait_uploads(ctx)) return -1;
     const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
     IterPlan pl;
-    pl.stage = stage_of_iter(c, iter, ctx->map_iters, ctx->coarse_map);
+    pl.stage = stage_of_iter(ctx, iter, ctx->map_iters);
     pl.use_color = pl.stage == NSB_COLOR;
     if (pl.use_color) ctx->map_color_touched = true;
     pl.pristine = !ctx->map_color_touched;

@@ -466,7 +466,7 @@ __device__ inline void stage_coarse(float* sm, const float* __restrict__ flat, i
     if (tid == 0) sm[L::BO] = flat[f.bo];
 }
 template <bool P3>
-__device__ __forceinline__ void coarse_forward(const float* __restrict__ sm, const float (&c)[2][8], int g, int t, float (&out)[2]) {
+__device__ __forceinline__ void coarse_forward(const float* __restrict__ sm, const float (&c)[2][8], int g, int t, float (&out)[2], uint32_t (&masks)[5]) {
     using L = CoarseSmem;
     float acc[4][4], h[4][4];
     const int wofs[5] = {L::W0, L::W1, L::W2, L::W3H, L::W4};
@@ -489,7 +489,7 @@ __device__ __forceinline__ void coarse_forward(const float* __restrict__ sm, con
                 kstep_fwd<P3, 4>(acc, a, wmat(sm, wofs[i]), L::SH, kk, g, t);
             }
         }
-        relu_mask(h, acc);
+        masks[i] = relu_mask(h, acc);
     }
     float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
@@ -500,6 +500,61 @@ __device__ __forceinline__ void coarse_forward(const float* __restrict__ sm, con
     }
     out[0] = quad_sum(s0) + sm[L::BO];
     out[1] = quad_sum(s1) + sm[L::BO];
+}
+
+// Backward image of the coarse decoder: the transposed matrices (rows = input feature, contraction over the output features,
+// whose operand comes from accumulator fragments -> perm16); the two matrices that multiply the grid feature (W0, the c columns
+// of the skip layer) have their rows in the scatter order of fc_channel_bwd.  Same slots as CoarseSmem.
+__device__ inline void stage_coarse_bwd(float* sm, const float* __restrict__ flat, int tid, int nthr) {
+    using L = CoarseSmem;
+    const CoarseFlat f = CoarseFlat::make();
+    stage_matrix(sm, L::W0, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[0] + perm16(pos) * CDIM + fc_channel_bwd(n)]; });
+    stage_matrix(sm, L::W1, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[1] + perm16(pos) * HID + n]; });
+    stage_matrix(sm, L::W2, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[2] + perm16(pos) * HID + n]; });
+    stage_matrix(sm, L::W3C, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[3] + perm16(pos) * (CDIM + HID) + fc_channel_bwd(n)]; });
+    stage_matrix(sm, L::W3H, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[3] + perm16(pos) * (CDIM + HID) + CDIM + n]; });
+    stage_matrix(sm, L::W4, HID, HID, tid, nthr, [&](int n, int pos) { return flat[f.W[4] + perm16(pos) * HID + n]; });
+    for (int i = tid; i < HID; i += nthr) sm[L::WO + i] = flat[f.Wo + i];
+}
+
+// Data gradient of MLP_no_xyz (MLP.cpp:165-181) for one tile: gout[r] = cotangent of the occupancy of rows g / g+8, masks = relu
+// patterns of the training forward; returns gcf[r][8] = d L / d c for the thread's channels 4t..4t+3, 16+4t..16+4t+3.
+template <bool P3>
+__device__ __forceinline__ void coarse_backward(const float* __restrict__ sm, int g, int t, const float (&gout)[2], const uint32_t (&masks)[5],
+                                                float (&gcf)[2][8]) {
+    using L = CoarseSmem;
+    float gh[4][4], gu[4][4], gc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 w = *reinterpret_cast<const float2*>(sm + L::WO + 8 * j + 2 * t);
+        gh[j][0] = gout[0] * w.x; gh[j][1] = gout[0] * w.y; gh[j][2] = gout[1] * w.x; gh[j][3] = gout[1] * w.y;
+        gc[j][0] = gc[j][1] = gc[j][2] = gc[j][3] = 0.0f;
+    }
+    const int wofs[5] = {L::W0, L::W1, L::W2, L::W3H, L::W4};
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gu[j][q] = ((masks[i] >> (4 * j + q)) & 1u) ? gh[j][q] : 0.0f;
+        if (i > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            AFrag<P3> a;
+            afrag_from_c<P3>(a, gu[2 * kk], gu[2 * kk + 1]);
+            if (i > 0) kstep_fwd<P3, 4>(gh, a, wmat(sm, wofs[i]), L::SH, kk, g, t);          // g_h = g_u W_i (hidden columns)
+            if (i == 3) kstep_fwd<P3, 4>(gc, a, wmat(sm, L::W3C), L::SH, kk, g, t);          // skip layer: the c columns
+            if (i == 0) kstep_fwd<P3, 4>(gc, a, wmat(sm, L::W0), L::SH, kk, g, t);           // first layer acts on c itself
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gcf[0][2 * j] = gc[j][0]; gcf[0][2 * j + 1] = gc[j][1];
+        gcf[1][2 * j] = gc[j][2]; gcf[1][2 * j + 1] = gc[j][3];
+    }
 }
 
 }  // namespace nsb

@@ -1,6 +1,7 @@
 // Forward decoder kernel: one launch evaluates every decoder the stage needs; the grid is partitioned between
 // the decoders (each CTA keeps ONE decoder's weights resident in shared memory and walks that decoder's tiles).
 #include "decode.cuh"
+#include "decode_bwd.cuh"
 #include "params.h"
 
 namespace nsb {
@@ -65,10 +66,11 @@ __global__ void __launch_bounds__(FWD_THREADS, NSB_FWD_MIN_CTAS) k_decode_fwd(co
         float p[2][3]; int sidx[2];
         if (!load_points(P, tile * TILE, g, p, sidx)) continue;
         if (dec == 0) {
-            float c[2][8], out[2];
+            float c[2][8], out[2]; uint32_t masks[5];
             gather8(P.grid[0], P.bnd, p[0], t, c[0]);
             gather8(P.grid[0], P.bnd, p[1], t, c[1]);
-            coarse_forward<P3>(sm, c, g, t, out);
+            coarse_forward<P3>(sm, c, g, t, out, masks);
+            if (TRAIN) save_masks(P, 1, tile, ntiles, lane, masks);     // the coarse mapper runs no other decoder: slot of decoder 1
             if (t == 0) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) if (sidx[r] < P.P) P.out_occ[0][sidx[r]] = out[r];
@@ -142,6 +144,39 @@ __global__ void __launch_bounds__(256) k_gather_only(const DecodeParams P, float
         acc[0] = quad_sum(acc[0]); acc[1] = quad_sum(acc[1]);
         if (t == 0) { out[sidx[0]] = acc[0]; out[sidx[1]] = acc[1]; }
     }
+}
+
+// Backward of the coarse stage (the coarse mapper, Mapper.cpp:335-338,351-352: only grid_coarse is optimised): data gradient of
+// MLP_no_xyz from the saved relu masks, scattered into the coarse grid's gradient with the same quad-wide vector reductions as the
+// other levels.  Warp = 16-sample tile, static striding (the launch is small: 32 samples per ray, one decoder).
+template <bool P3>
+__global__ void __launch_bounds__(256) k_coarse_bwd(const DecodeParams P) {
+    extern __shared__ __align__(128) float sm[];
+    stage_coarse_bwd(sm, P.dec_flat[0], threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5, ntiles = P.P / TILE;
+    for (int tile = warp; tile < ntiles; tile += nwarps) {
+        float p[2][3]; int sidx[2];
+        const uint32_t* mb = P.masks + (size_t)tile * 96 + lane;
+        const uint32_t m0 = mb[0], m1 = mb[32], m2 = mb[64];
+        if (!load_points(P, tile * TILE, g, p, sidx)) continue;
+        const float gout[2] = {P.g_raw[4 * (size_t)sidx[0] + 3], P.g_raw[4 * (size_t)sidx[1] + 3]};
+        if (!__any_sync(0xffffffffu, gout[0] != 0.0f || gout[1] != 0.0f)) continue;
+        const uint32_t masks[5] = {m0 & 0xffffu, m0 >> 16, m1 & 0xffffu, m1 >> 16, m2};
+        float gcf[2][8], gp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        coarse_backward<P3>(sm, g, t, gout, masks, gcf);
+        grid_backward<true, false>(P.grid[0], P.bnd, p, gcf, t, gp);
+    }
+}
+cudaError_t launch_coarse_bwd(const DecodeParams& P, int precision, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(float) * CoarseSmem::TOTAL;
+    cudaError_t e = precision == 0 ? cudaFuncSetAttribute(k_coarse_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(k_coarse_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (precision == 0) k_coarse_bwd<true><<<grid, 256, smem, st>>>(P);
+    else k_coarse_bwd<false><<<grid, 256, smem, st>>>(P);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st) {

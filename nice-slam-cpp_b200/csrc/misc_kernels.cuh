@@ -118,6 +118,43 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
     }
 }
 
+// Renderer::eval_points epilogue on the device (Renderer.cpp:26-36 + the stage assembly of NICE.cpp:16-51): raw = (r, g, b, occ)
+// with the stage's occupancy sum, and occupancy 100 for points that are not strictly inside the bound.
+__global__ void k_assemble_raw(const float* __restrict__ pts, const float* __restrict__ raw_rgb, const float* __restrict__ occ0,
+                               const float* __restrict__ occ1, const float* __restrict__ occ2, int stage, Bound bnd, int n,
+                               float* __restrict__ raw4, float* __restrict__ occ_only) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (stage == 3) { const float4 c = *reinterpret_cast<const float4*>(raw_rgb + 4 * (size_t)i); r.x = c.x; r.y = c.y; r.z = c.z; }
+    const float occ = stage == 0 ? occ0[i] : stage == 1 ? occ1[i] : __fadd_rn(occ2[i], occ1[i]);
+    const bool in = px < bnd.hi[0] && px > bnd.lo[0] && py < bnd.hi[1] && py > bnd.lo[1] && pz < bnd.hi[2] && pz > bnd.lo[2];
+    r.w = in ? occ : 100.0f;
+    if (raw4) *reinterpret_cast<float4*>(raw4 + 4 * (size_t)i) = r;
+    if (occ_only) occ_only[i] = r.w;
+}
+
+// Points of a regular lattice, generated on the device (mesh extraction queries, nice_slam.yaml meshing.resolution): point index
+// q = (j * nx + i) * nz + k  <->  (x_i, y_j, z_k), the ravel order of numpy.meshgrid(x, y, z) that upstream's mesher uses;
+// axis values are torch/numpy linspace(lo, hi, n) in fp32 (symmetric formula).
+struct LatticeParams { int nx, ny, nz; float lo[3], hi[3]; };
+__device__ __forceinline__ float lattice_axis(float lo, float hi, int n, int i) {
+    if (n <= 1) return lo;
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(n - 1));
+    return i < n / 2 ? __fadd_rn(lo, __fmul_rn(step, (float)i)) : __fsub_rn(hi, __fmul_rn(step, (float)(n - 1 - i)));
+}
+__global__ void k_lattice_points(LatticeParams L, long long first, int n, float* __restrict__ pts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long q = first + t;
+    const int k = (int)(q % L.nz); const long long r = q / L.nz;
+    const int i = (int)(r % L.nx), j = (int)(r / L.nx);
+    pts[3 * (size_t)t] = lattice_axis(L.lo[0], L.hi[0], L.nx, i);
+    pts[3 * (size_t)t + 1] = lattice_axis(L.lo[1], L.hi[1], L.ny, j);
+    pts[3 * (size_t)t + 2] = lattice_axis(L.lo[2], L.hi[2], L.nz, k);
+}
+
 __global__ void k_fill(float* p, float v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -54,6 +54,19 @@ int main(int argc, char** argv) {
         mapper.optimize_map(3, c, color_t, depth_t, c2w_t, c2w_t, decoders, 1.f, &losses);
         wr(d + "out_map_losses.bin", losses.data(), losses.size());
         wr(d + "out_grid_middle.bin", c.at("grid_middle").data(), (size_t)c.at("grid_middle").numel());
+        // the coarse mapper (Mapper(ns, cf, coarse_mapper = true), Mapper.cpp:335-338,351-352): two iterations move grid_coarse only
+        {
+            const size_t ncoarse = (size_t)c.at("grid_coarse").numel(), nmid = (size_t)c.at("grid_middle").numel();
+            std::vector<float> coarse0(c.at("grid_coarse").data(), c.at("grid_coarse").data() + ncoarse), mid0(c.at("grid_middle").data(), c.at("grid_middle").data() + nmid);
+            nsb::Mapper coarse_mapper(engine, true);
+            std::vector<float> cl;
+            coarse_mapper.optimize_map(2, c, color_t, depth_t, c2w_t, c2w_t, decoders, 1.f, &cl);
+            float dc = 0.f, dm = 0.f;
+            for (size_t i = 0; i < ncoarse; ++i) dc = std::max(dc, std::fabs(c.at("grid_coarse").data()[i] - coarse0[i]));
+            for (size_t i = 0; i < nmid; ++i) dm = std::max(dm, std::fabs(c.at("grid_middle").data()[i] - mid0[i]));
+            const float cm[4] = {cl[0], cl[1], dc, dm};
+            wr(d + "out_coarse_mapper.bin", cm, 4);
+        }
         // tracking: Tracker::run (2 iterations)
         nsb::Tracker tracker(engine, c);
         engine->check(nsb_seed(engine->ctx(), 5));

@@ -63,6 +63,8 @@ def test_wrappers_match_ctypes_and_oracle(nsb, syn, model_inputs, frames, tmp_pa
     l_or, _ = O.mapping_iters(O.Model(grids, decs), depths[:1], colors[:1], poses[:1], syn.CAM, 400, O.stage_schedule(3), seed=3, tt=tt, ts=ts, raydir="pinhole")
     assert np.allclose(out["map_losses"], l_or, rtol=1e-3)
     assert np.abs(out["grid_middle"] - grids["middle"].reshape(-1)).max() > 0.05      # the dict got the optimised grid back
+    cm = np.fromfile(os.path.join(d, "out_coarse_mapper.bin"), np.float32)       # coarse mapper: finite losses, grid_coarse moved, grid_middle untouched
+    assert np.all(np.isfinite(cm[:2])) and cm[:2].min() > 0 and 1e-4 < cm[2] < 0.05 and cm[3] == 0.0, cm
     assert len(out["trk_losses"]) == 2 and np.all(np.isfinite(out["cam"])) and abs(np.linalg.norm(out["cam"][:4]) - 1) < 1e-2
     # Mapper::run over 7 frames with keyframe_every = 1: seven keyframes, BA from the sixth frame on (keyframes > 4), and the
     # bundle-adjusted current pose is written back into estimate_c2w (Mapper.cpp:530-534)

@@ -481,6 +481,95 @@ def test_bundle_adjustment_vs_oracle(engine_factory, model_inputs, frames, syn):
     assert np.abs(e.get_frame_pose(0) - poses[0][:3]).max() == 0
 
 
+def test_coarse_mapper_vs_oracle(engine_factory, model_inputs, frames, syn, nsb):
+    """The coarse mapper (Mapper(ns, cf, coarse_mapper=true); Mapper.cpp:335-338,351-352,450-453, upstream's intent: stage "coarse"
+    rendered without depth guidance, only grid_coarse in the optimiser): losses, the coarse-grid gradient of the first iteration
+    (backward through MLP_no_xyz, k_coarse_bwd) and the optimised grid against the autograd oracle; every other parameter untouched."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    nf, pix = 2, 800
+    e = engine_factory(mapping_pixels=pix, frustum_feature_selection=0)
+    e.seed(23)
+    e.mapping_capture_grads(True)
+    e.mapping_begin(list(range(nf)), 60, 1.0, flags=nsb.MAP_COARSE)
+    losses, g0 = [], None
+    for it in (0, 30, 59):
+        losses.append(e.mapping_iter(it))
+        if g0 is None:
+            g0 = e.captured_grads()
+    e.mapping_capture_grads(False)
+    m = O.Model(grids, decs)
+    go = {}
+    ref_losses, _ = O.mapping_iters(m, depths[:nf], colors[:nf], poses[:nf], syn.CAM, pix, ["coarse"] * 3, seed=23, raydir="pinhole", grads_out=go, coarse_mapper=True)
+    assert np.allclose(losses, ref_losses, rtol=1e-3), (losses, ref_losses)
+    assert relerr(g0["grid_coarse"], go["coarse"].numpy()) < GRAD_TOL
+    for lv in ("middle", "fine", "color"):
+        assert np.abs(g0["grid_" + lv]).max() == 0.0 and np.array_equal(e.get_grid(lv), grids[lv]), lv
+    ref = m.grids["coarse"].numpy(); got = e.get_grid("coarse")
+    move = np.sqrt(((ref - grids["coarse"]) ** 2).mean())
+    assert move > 0 and np.sqrt(((got - ref) ** 2).mean()) < 5e-2 * move
+    assert np.array_equal(e.get_decoder("color"), decs["color"])
+
+
+def test_color_refine_settings(engine_factory, model_inputs, frames, syn, nsb):
+    """color_refine (Mapper.cpp:505-513): middle_iter_ratio = fine_iter_ratio = 0 (iteration 0 is still "middle": it <= int(n * 0)),
+    fix_color = true (the colour decoder stays fixed), frustum_feature_selection = false (installed masks are ignored)."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    nf, pix = 2, 600
+    e = engine_factory(mapping_pixels=pix, frustum_feature_selection=1)
+    for lv in ("middle", "fine", "color"):
+        e.set_voxel_mask(lv, np.zeros(grids[lv].shape[2:], np.uint8))        # would freeze every voxel if it were honoured
+    e.seed(31)
+    e.mapping_begin(list(range(nf)), 60, 1.0, flags=nsb.MAP_COLOR_REFINE)
+    losses = [e.mapping_iter(it) for it in (0, 1, 2)]
+    m = O.Model(grids, decs)
+    ref_losses, _ = O.mapping_iters(m, depths[:nf], colors[:nf], poses[:nf], syn.CAM, pix, ["middle", "color", "color"], seed=31, raydir="pinhole", fix_color=True)
+    assert np.allclose(losses, ref_losses, rtol=1e-3), (losses, ref_losses)
+    assert np.array_equal(e.get_decoder("color"), decs["color"])
+    for lv in ("middle", "fine", "color"):
+        assert np.abs(e.get_grid(lv) - grids[lv]).max() > 0, lv
+    for lv in ("middle", "fine", "color"):
+        e.set_voxel_mask(lv, None)
+
+
+def test_eval_lattice_and_device_eval_points(engine_factory, model_inputs, syn):
+    """eval_points over a mesh lattice generated on the device (stage assembly + bound mask in-kernel) against
+    the oracle's Renderer::eval_points on the same numpy.meshgrid points, incl. lattice points outside the bound (occupancy 100);
+    the device-pointer form agrees bit for bit with the host form."""
+    grids, decs, _ = model_inputs
+    e = engine_factory(max_rays=2048)
+    model = O.Model(grids, decs)
+    lo = np.array([-5.0, -1.6, -3.2], np.float32); hi = np.array([4.0, 2.1, 2.9], np.float32)     # slightly larger than the bound
+    nx, ny, nz = 21, 13, 17
+    occ, raw = e.eval_lattice("color", nx, ny, nz, lo, hi, want_raw=True)
+    x = np.linspace(lo[0], hi[0], nx, dtype=np.float32); y = np.linspace(lo[1], hi[1], ny, dtype=np.float32); z = np.linspace(lo[2], hi[2], nz, dtype=np.float32)
+    xx, yy, zz = np.meshgrid(x, y, z)
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], 1).astype(np.float32)
+    with torch.no_grad():
+        ref = model.eval_points(torch.tensor(pts), "color").numpy()
+    out_ref = ref[:, 3] == 100.0
+    got = raw.reshape(-1, 4)
+    assert 0.05 < out_ref.mean() < 0.9
+    edge = np.zeros(len(pts), bool)                      # lattice points within an ulp of a bound face may fall on either side
+    bnd = np.asarray(O.BOUND, np.float32)
+    for a in range(3):
+        edge |= (np.abs(pts[:, a] - bnd[a, 0]) < 1e-5) | (np.abs(pts[:, a] - bnd[a, 1]) < 1e-5)
+    assert np.array_equal((got[:, 3] == 100.0)[~edge], out_ref[~edge])
+    ok = ~out_ref & ~edge
+    assert np.abs(got[ok] - ref[ok]).max() < 1e-4 * max(1.0, np.abs(ref[ok]).max())
+    assert np.array_equal(occ.reshape(-1), got[:, 3])
+    raw_h = e.eval_points(pts, "color")
+    d_pts = torch.tensor(pts).cuda(); d_raw = torch.empty(len(pts), 4, device="cuda")
+    torch.cuda.synchronize()
+    e._ck(e.lib.nsb_eval_points_dev(e.h, 3, len(pts), d_pts.data_ptr(), d_raw.data_ptr()))
+    e.synchronize()
+    assert np.array_equal(d_raw.cpu().numpy(), raw_h)
+    assert np.abs(raw_h[ok] - ref[ok]).max() < 1e-4 * max(1.0, np.abs(ref[ok]).max())
+    occ_c = e.eval_lattice("coarse", 9, 7, 5)            # default box = the scene bound: the faces themselves are out of bound
+    assert occ_c.shape == (7, 9, 5) and (occ_c[0] == 100.0).all() and np.isfinite(occ_c).all()
+
+
 def test_keyframe_selection_overlap(engine_factory, frames, syn):
     """Mapper.cpp:132-196: fraction of the current frame's 100 x 16 depth-guided vertices that each keyframe sees, and the
     resulting ranking, against the numpy restatement on the same pixel indices."""
