@@ -94,7 +94,7 @@ class Engine {
         for (int l = 0; l < 4; ++l) if (c.contains(grid_key(l)) && c.dirty(grid_key(l))) { check(nsb_set_grid(ctx_, l, c.at(grid_key(l)).data())); c.mark_clean(grid_key(l)); }
     }
     void sync_grids_to_host(Dict& c) {
-        for (int l = 1; l < 4; ++l) if (c.contains(grid_key(l))) { Tensor t = c.at(grid_key(l)); check(nsb_get_grid(ctx_, l, t.data())); }
+        for (int l = 0; l < 4; ++l) if (c.contains(grid_key(l))) { Tensor t = c.at(grid_key(l)); check(nsb_get_grid(ctx_, l, t.data())); }   // incl. grid_coarse (coarse mapper, Mapper.cpp:450-453)
     }
 
   private:

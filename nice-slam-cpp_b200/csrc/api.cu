@@ -41,6 +41,11 @@ inline cudaError_t launch_decode_bwd(const DecodeParams& P, int precision, int g
     }
 }
 cudaError_t wgrad_init();
+size_t wgrad_fused_img_bytes();
+int wgrad_fused_scratch_floats();
+cudaError_t wgrad_fused_init();
+cudaError_t launch_build_wgimg(const float* flat, uint8_t* img, cudaStream_t st);
+cudaError_t launch_wgrad_fused(const DecodeParams& P, const uint8_t* img, const float* flat, float* dflat, float* scratch, int n_sm, cudaStream_t st);
 cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
@@ -135,7 +140,9 @@ struct nsb_ctx {
     float* median = nullptr; int* count = nullptr;
     float* trk_scratch = nullptr;   // [32] per-iteration tracking scratch (see nsb_tracking_iter)
     bool trk_hook = false; int* trk_count = nullptr;   // set around the tracking forward: the composite compacts |gt - depth|
-    float* stash = nullptr; size_t stash_rows = 0;
+    float* stash = nullptr; size_t stash_rows = 0;   // (round-1 weight-gradient stash: unused by the fused kernel, kept for NSB_WGRAD_STASH=1 experiments)
+    uint8_t* wg_img = nullptr; float* wg_scratch = nullptr;   // fused weight-gradient kernel: plane image of the colour decoder, M_i scratch
+    int wg_stash = 0;
     uint32_t* masks = nullptr;   // relu masks of the last training forward
     int mask_layout = 0, mask_stride = 0;
     float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
@@ -463,7 +470,10 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->rstats, 8)); CK(cudaMemsetAsync(ctx->rstats, 0, 8 * 4, ctx->stream));
     { const char* e = getenv("NSB_GRAPH"); ctx->use_graph = e ? atoi(e) : 1; }
     { const char* e = getenv("NSB_P2P_TIMEOUT_MS"); if (e) ctx->p2p_timeout_ns = 1000000ull * strtoull(e, nullptr, 10); }
-    CK(wgrad_init());
+    CK(wgrad_init()); CK(wgrad_fused_init());
+    CK(cudaMalloc((void**)&ctx->wg_img, wgrad_fused_img_bytes()));
+    CK(dalloc(&ctx->wg_scratch, (size_t)wgrad_fused_scratch_floats())); CK(cudaMemsetAsync(ctx->wg_scratch, 0, wgrad_fused_scratch_floats() * 4, ctx->stream));
+    { const char* e = getenv("NSB_WGRAD_STASH"); ctx->wg_stash = e ? atoi(e) : 0; }
     CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     if (ensure_ring(ctx, LOSS_RING_MIN)) return -1;
@@ -482,7 +492,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->p2p) for (int w = 0; w < c->world; ++w) if (w != c->rank) { cudaIpcCloseMemHandle(c->peer_grad[w]); cudaIpcCloseMemHandle(c->peer_param[w]); cudaIpcCloseMemHandle(c->peer_flags[w]); }
     if (c->p2p_flags) cudaFree(c->p2p_flags);
     drop_graphs(c);
-    void* ptrs[] = {c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
+    void* ptrs[] = {c->wg_img, c->wg_scratch, c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
                     c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
@@ -752,6 +762,7 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
         ctx->comp_dirty &= ~comp_need;
     }
     CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
+    if (plain & 8) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (fused weight gradient)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
 }
@@ -819,7 +830,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
         if (train) P.masks = ctx->masks;
-        if (train && stash_fwd && stage == NSB_COLOR) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
+        if (train && stash_fwd && stage == NSB_COLOR && ctx->wg_stash) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
         float w[4]; stage_decoders(stage, w);
         if (P.stash) { w[1] = 700; w[2] = 972; w[3] = 860; }   // the colour decoder also writes its activations to the wgrad stash (measured split, tools/sweep_split.sh)
         env_weights("NSB_SPLIT_FWD", w);
@@ -893,19 +904,22 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         CK(cudaGetLastError());
     }
     const bool wg = (flags & 2) && stage == NSB_COLOR && color_active;
-    if (wg && ctx->stash_rows < (size_t)n * S) return fail(ctx, "wgrad stash missing: the forward must run with stash_fwd");
+    const bool wg_stash = wg && ctx->wg_stash;      // round-1 path (stash + split-K k_wgrad), NSB_WGRAD_STASH=1 only
+    if (wg_stash && ctx->stash_rows < (size_t)n * S) return fail(ctx, "wgrad stash missing: the forward must run with stash_fwd");
+    DecodeParams Pw; memset(&Pw, 0, sizeof Pw);
     {
         Timer t(ctx, T_BWD);
         DecodeParams P; fill_decode_params(ctx, P, n, S, valid ? valid + off : nullptr);
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S; P.g_raw += 4 * (size_t)off * S; P.d_rays += 6 * (size_t)off;
         P.stash = ctx->stash; P.masks = ctx->masks; P.mask_layout = ctx->mask_layout; P.mask_stride = ctx->mask_stride;
-        P.flags = (flags & 1) | (wg ? 2 : 0) | (flags & 4);
-        if (P.flags == 0) return 0;
+        P.flags = (flags & 1) | (wg_stash ? 2 : 0) | (flags & 4);
+        Pw = P;
+        if (P.flags == 0 && !wg) return 0;
         float w[4] = {0, 0, 0, 0};
         const float ge = (flags & 4) ? 288.f : 0.f;
         if (stage == NSB_MIDDLE) w[1] = 480 + ge;
         else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
-        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg ? 288.f + 300.f : ge); if (wg && !ge) { w[1] = 460; w[2] = 500; w[3] = 1250; } }   // measured (tools/sweep_split.sh)
+        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg_stash ? 288.f + 300.f : ge); if (wg_stash && !ge) { w[1] = 460; w[2] = 500; w[3] = 1250; } }   // measured (tools/sweep_split.sh)
         else {   // coarse stage (the coarse mapper): MLP_no_xyz data gradient -> grid_coarse; no embedding, so no ray gradient path here
             if (flags & 4) return fail(ctx, "ray gradients through the coarse stage are not supported (the coarse mapper runs without bundle adjustment, Mapper.cpp:530)");
             if (ctx->mask_layout != 0) return fail(ctx, "coarse backward needs the warp-MMA forward's mask layout");
@@ -918,7 +932,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         partition(grid, w, P.cta_begin);
         P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
         P.tile_ctr = ctx->tile_ctr + 4;
-        CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        if (P.flags != 0) { CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++; }
     }
     ctx->ar_overlapped = false;
     if (wg && ctx->ar_request && ctx->world > 1) {
@@ -930,9 +944,15 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         CK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
         ctx->ar_overlapped = true;
     }
-    if (wg) {
+    if (wg_stash) {
         Timer t(ctx, T_WGRAD);
         CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->grad + ctx->off_dec[3], c.precision, ctx->n_sm, ctx->stream)); ctx->launches++;
+    } else if (wg) {
+        // colour-decoder weight gradient without a stash: recomputed per tile, contracted through shared memory (wgrad_fused.cu)
+        Timer t(ctx, T_WGRAD);
+        if (ctx->mask_layout != 0) return fail(ctx, "the fused weight-gradient kernel needs the warp-MMA forward's relu-mask layout (NSB_TCGEN05 must be 0)");
+        if (c.precision != NSB_PREC_FP32_GRADE) return fail(ctx, "the fused weight-gradient kernel is fp32-grade only");
+        CK(launch_wgrad_fused(Pw, ctx->wg_img, ctx->param + ctx->off_dec[3], ctx->grad + ctx->off_dec[3], ctx->wg_scratch, ctx->n_sm, ctx->stream)); ctx->launches += 2;
     }
     return 0;
 }
@@ -1346,7 +1366,7 @@ extern "C" int nsb_mapping_begin_ex(nsb_ctx* ctx, int n_frames, const int* slots
     if (!ctx->map_no_mask && ctx->cfg.frustum_feature_selection) {   // Mapper.cpp:226-290: masks from the current frame (the last of optimize_frame)
         for (int l = ctx->coarse_map ? 0 : 1; l < (ctx->coarse_map ? 1 : 4); ++l) if (nsb_frustum_mask(ctx, slots[n_frames - 1], nullptr, l, nullptr, 1)) return -1;
     }
-    if (!ctx->map_fix_color && !ctx->coarse_map) {   // make sure the stash exists before the hot loop
+    if (!ctx->map_fix_color && !ctx->coarse_map && ctx->wg_stash) {   // make sure the stash exists before the hot loop
         if (ensure_stash(ctx, (size_t)cdiv(pix * n_frames, ctx->world) * (ctx->cfg.n_samples + ctx->cfg.n_surface) + 64)) return -1;
     }
     const uint64_t sig = graph_signature(ctx);
