@@ -140,7 +140,7 @@ struct nsb_ctx {
     float* median = nullptr; int* count = nullptr;
     float* trk_scratch = nullptr;   // [32] per-iteration tracking scratch (see nsb_tracking_iter)
     bool trk_hook = false; int* trk_count = nullptr;   // set around the tracking forward: the composite compacts |gt - depth|
-    float* stash = nullptr; size_t stash_rows = 0;   // (round-1 weight-gradient stash: unused by the fused kernel, kept for NSB_WGRAD_STASH=1 experiments)
+    float* stash = nullptr; size_t stash_rows = 0;   // weight-gradient stash of the split-K k_wgrad path (wg_stash = 1)
     uint8_t* wg_img = nullptr; float* wg_scratch = nullptr;   // fused weight-gradient kernel: plane image of the colour decoder, M_i scratch
     int wg_stash = 0;
     uint32_t* masks = nullptr;   // relu masks of the last training forward
@@ -473,7 +473,10 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(wgrad_init()); CK(wgrad_fused_init());
     CK(cudaMalloc((void**)&ctx->wg_img, wgrad_fused_img_bytes()));
     CK(dalloc(&ctx->wg_scratch, (size_t)wgrad_fused_scratch_floats())); CK(cudaMemsetAsync(ctx->wg_scratch, 0, wgrad_fused_scratch_floats() * 4, ctx->stream));
-    { const char* e = getenv("NSB_WGRAD_STASH"); ctx->wg_stash = e ? atoi(e) : 0; }
+    // colour-decoder weight gradient: 1 (default) = activation stash + split-K k_wgrad (fastest measured: 0.19 ms + ~0.07 ms of stash
+    // writes per colour iteration at 5000 rays, but 1.2 GB of HBM traffic); 0 = k_wgrad_fused, no stash (13 MB of HBM traffic, 0.43 ms:
+    // the recomputation costs more issue slots than the traffic it removes costs bandwidth -- DESIGN.md section 4)
+    { const char* e = getenv("NSB_WGRAD_STASH"); ctx->wg_stash = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->p2p_flags, 32)); CK(cudaMemsetAsync(ctx->p2p_flags, 0, 32 * 4, ctx->stream));
     CK(dalloc(&ctx->cam_grad_last, 8 * MAX_OPT_FRAMES)); CK(cudaMemsetAsync(ctx->cam_grad_last, 0, 8 * MAX_OPT_FRAMES * 4, ctx->stream));
     if (ensure_ring(ctx, LOSS_RING_MIN)) return -1;
@@ -904,7 +907,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         CK(cudaGetLastError());
     }
     const bool wg = (flags & 2) && stage == NSB_COLOR && color_active;
-    const bool wg_stash = wg && ctx->wg_stash;      // round-1 path (stash + split-K k_wgrad), NSB_WGRAD_STASH=1 only
+    const bool wg_stash = wg && ctx->wg_stash;      // stash + split-K k_wgrad; otherwise the stash-free fused kernel
     if (wg_stash && ctx->stash_rows < (size_t)n * S) return fail(ctx, "wgrad stash missing: the forward must run with stash_fwd");
     DecodeParams Pw; memset(&Pw, 0, sizeof Pw);
     {

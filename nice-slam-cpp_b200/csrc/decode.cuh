@@ -291,17 +291,19 @@ __device__ __forceinline__ void add_cterm(const float* __restrict__ sm, int l, c
     for (int kk = 0; kk < C / 16; ++kk) kstep_fwd<P3, 4>(h, ca[kk], wmat(sm, L::FC + l * L::FCS), L::SC, kk, g, t);
 }
 
+// h = relu(acc) and the 16-bit pattern of the active units (bit 4j+q), two instructions per value: FMNMX for the relu and one
+// funnel shift that collects the SIGN bit (the pattern is the complement of the sign bits; a pre-activation of exactly +0 counts
+// as active, which only matters for the sub-gradient at the kink).
 __device__ __forceinline__ uint32_t relu_mask(float (&h)[4][4], const float (&acc)[4][4]) {
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 3; j >= 0; --j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool pos = acc[j][q] > 0.0f;
-            m |= (pos ? 1u : 0u) << (4 * j + q);
-            h[j][q] = pos ? acc[j][q] : 0.0f;
+        for (int q = 3; q >= 0; --q) {
+            m = __funnelshift_l(__float_as_uint(acc[j][q]), m, 1);
+            h[j][q] = fmaxf(acc[j][q], 0.0f);
         }
-    return m;
+    return ~m & 0xffffu;
 }
 
 // C-layout tile (rows g / g+8, features 8j+2t, 8j+2t+1) -> 32 floats of two stash rows

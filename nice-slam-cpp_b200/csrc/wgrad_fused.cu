@@ -25,7 +25,10 @@
 namespace nsb {
 namespace wgf {
 
-constexpr int NW = 16;                        // warps per CTA = tiles per round
+constexpr int NW = 16;                        // warps per CTA
+constexpr int GW = 8;                         // warps per GROUP = tiles per round: the CTA runs two independent groups (own staging
+                                              // buffers, own named barriers) that drift out of phase, so that one group's barrier
+                                              // waits are filled with the other group's work
 constexpr int THREADS = NW * 32;
 constexpr int RS32 = 80, RS96 = 208;          // row strides (bytes) of the K = 32 / K = 96 planes: 2K + 16 -> conflict-free ldmatrix
 constexpr int PL32 = 32 * RS32, PL96 = 32 * RS96;
@@ -92,12 +95,21 @@ __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
 __device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(THREADS) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(THREADS) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GW * 32) : "memory"); }
 
-// acc[j] += A(kk) . W[8j..8j+7][k-step kk]^T  (forward orientation: rows of the plane = outputs, k contiguous), fp32-grade
-__device__ __forceinline__ void kstep_w(float (&acc)[4][4], const AFrag<true>& a, uint32_t mat, int plane, int rs, int kk, int lane) {
-    const uint32_t base = mat + ((lane >> 4) & 1) * plane + (lane & 7) * rs + (16 * kk + ((lane >> 3) & 1) * 8) * 2;
+// Per-lane byte offsets of the ldmatrix row addresses, computed once per thread: forward (rows of the plane = outputs, k contiguous)
+// and transposed (contraction over the ROWS of the same plane) orientation, for the K = 32 and K = 96 planes.
+struct LaneOff { uint32_t f32, f96, t32, t96; };
+__device__ __forceinline__ LaneOff lane_offsets(int lane) {
+    LaneOff o;
+    const uint32_t hl = (lane >> 4) & 1, kh = (lane >> 3) & 1, r = lane & 7;
+    o.f32 = hl * PL32 + r * RS32 + kh * 16; o.f96 = hl * PL96 + r * RS96 + kh * 16;
+    o.t32 = hl * PL32 + (kh * 8 + r) * RS32; o.t96 = hl * PL96 + (kh * 8 + r) * RS96;
+    return o;
+}
+// acc[j] += A(kk) . W[8j..8j+7][k-step kk]^T, fp32-grade; `base` = matrix + the thread's forward lane offset
+__device__ __forceinline__ void kstep_w(float (&acc)[4][4], const AFrag<true>& a, uint32_t base, int rs, int kk) {
+    base += 32 * kk;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t b[4];
@@ -107,10 +119,10 @@ __device__ __forceinline__ void kstep_w(float (&acc)[4][4], const AFrag<true>& a
         mma_f16(acc[j], a.hi, b[0], b[1]);
     }
 }
-// acc[j] += A(kk) . W[16kk..16kk+15][8(j0+j)..]  (backward orientation: contraction over the ROWS of the same plane, transposed load)
+// acc[j] += A(kk) . W[16kk..16kk+15][8(j0+j)..]  (transposed load); `base` = matrix + the thread's transposed lane offset
 template <bool P3>
-__device__ __forceinline__ void kstep_wt(float (&acc)[4][4], const AFrag<P3>& a, uint32_t mat, int plane, int rs, int kk, int j0, int lane) {
-    const uint32_t base = mat + ((lane >> 4) & 1) * plane + (16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7)) * rs + 16 * j0;
+__device__ __forceinline__ void kstep_wt(float (&acc)[4][4], const AFrag<P3>& a, uint32_t base, int rs, int kk, int j0) {
+    base += 16 * kk * rs + 16 * j0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t b[4];
@@ -144,31 +156,36 @@ __device__ __forceinline__ void stage_g(uint8_t* gt, int col0, const float (&gu)
 }
 
 // One (m-tile, n-tile) block of the round: d = sum over the active tiles of  G[:, mcol..mcol+15]^T . X[:, 8 nt..8 nt+7]
-__device__ __forceinline__ void consume(uint32_t smG, uint32_t smX, const volatile int* active, int mcol, int nt, int lane, float (&d)[4]) {
+// ga / xb: G / X staging base + the thread's ldmatrix lane offset (consume_offsets); tiles [t0, t0 + NT) of the round, `act` = bit mask
+// of the live tiles.  Two independent accumulation chains (X_hi and X_lo products) keep the tensor pipe busy.
+template <int NT>
+__device__ __forceinline__ void consume(uint32_t ga, uint32_t xb, uint32_t act, int t0, int mcol, int nt, float (&d)[4]) {
+    float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     d[0] = d[1] = d[2] = d[3] = 0.0f;
-    const int mat = lane >> 3, r = lane & 7;
-    const uint32_t aoff = ((mat >> 1) * 8 + r) * GS + 2 * (mcol + (mat & 1) * 8);
-    const uint32_t boff = (mat >> 1) * X_PLANE + ((mat & 1) * 8 + r) * RS32 + 16 * nt;
-#pragma unroll 4
-    for (int tile = 0; tile < NW; ++tile) {
-        if (!active[tile]) continue;
-        uint32_t a[4], b[4];
-        ldsm4t(smG + tile * G_TILE + aoff, a);
-        ldsm4t(smX + tile * X_TILE + boff, b);
-        mma_f16(d, a, b[0], b[1]);
-        mma_f16(d, a, b[2], b[3]);
+    ga += t0 * G_TILE + 2 * mcol; xb += t0 * X_TILE + 16 * nt;
+#pragma unroll
+    for (int tile = 0; tile < NT; ++tile) {
+        if ((act >> (t0 + tile)) & 1u) {
+            uint32_t a[4], b[4];
+            ldsm4t(ga + tile * G_TILE, a);
+            ldsm4t(xb + tile * X_TILE, b);
+            mma_f16(d, a, b[0], b[1]);
+            mma_f16(e, a, b[2], b[3]);
+        }
     }
+    d[0] += e[0]; d[1] += e[1]; d[2] += e[2]; d[3] += e[3];
 }
 // column sums of an m-tile of G over the round (bias gradients): B = ones
-__device__ __forceinline__ void consume_ones(uint32_t smG, const volatile int* active, int mcol, int lane, float (&d)[4]) {
+__device__ __forceinline__ void consume_ones(uint32_t ga, uint32_t act, int mcol, float (&d)[4]) {
     d[0] = d[1] = d[2] = d[3] = 0.0f;
-    const int mat = lane >> 3, r = lane & 7;
-    const uint32_t aoff = ((mat >> 1) * 8 + r) * GS + 2 * (mcol + (mat & 1) * 8);
-    for (int tile = 0; tile < NW; ++tile) {
-        if (!active[tile]) continue;
-        uint32_t a[4];
-        ldsm4t(smG + tile * G_TILE + aoff, a);
-        mma_f16(d, a, 0x3C003C00u, 0x3C003C00u);
+    ga += 2 * mcol;
+#pragma unroll
+    for (int tile = 0; tile < GW; ++tile) {
+        if ((act >> tile) & 1u) {
+            uint32_t a[4];
+            ldsm4t(ga + tile * G_TILE, a);
+            mma_f16(d, a, 0x3C003C00u, 0x3C003C00u);
+        }
     }
 }
 __device__ __forceinline__ void red2(float* p, float a, float b) { asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory"); }
@@ -198,7 +215,11 @@ struct Params {
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
     extern __shared__ __align__(128) uint8_t sm[];
     const DecodeParams& P = Q.D;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x;
+    int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    // the thread-invariant indices and ldmatrix offsets below are made opaque to the compiler: at 128 registers it would otherwise
+    // REMATERIALISE them from threadIdx at every use (measured: ~45 M of 133 M executed instructions were such recomputations)
+    asm volatile("" : "+r"(warp), "+r"(lane), "+r"(g), "+r"(t));
     {
         const uint4* src = reinterpret_cast<const uint4*>(Q.img);
         uint4* dst = reinterpret_cast<uint4*>(sm + S_IMG);
@@ -207,21 +228,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
     __syncthreads();
     const uint32_t sb = smem_u32(sm);
     const float* fs = reinterpret_cast<const float*>(sm + S_IMG + I_F32);
-    volatile int* active = reinterpret_cast<volatile int*>(sm + S_FLAG);
+    int grp = warp >> 3, wl = warp & 7;           // group of the warp, warp within the group
+    asm volatile("" : "+r"(grp), "+r"(wl));
+    volatile int* active = reinterpret_cast<volatile int*>(sm + S_FLAG) + GW * grp;
     uint8_t* gt = sm + S_G + warp * G_TILE;
     uint8_t* xt = sm + S_X + warp * X_TILE;
     const DecFlat f = DecFlat::make(32, 4);
     const int ntiles = P.P / TILE;
-    const int nrounds = (ntiles + NW - 1) / NW;
+    const int nrounds = (ntiles + GW - 1) / GW;
+    const int bar1 = 1 + 2 * grp, bar2 = 2 + 2 * grp;
+    LaneOff lo = lane_offsets(lane);
+    const uint32_t img = sb + S_IMG;
+    lo.f32 += img; lo.f96 += img; lo.t32 += img; lo.t96 += img;
+    // ldmatrix lane offsets of the consumer side: G rows (samples) x feature columns, X planes
+    uint32_t ga = sb + S_G + grp * GW * G_TILE + (((lane >> 4) & 1) * 8 + (lane & 7)) * GS + ((lane >> 3) & 1) * 16;
+    uint32_t xb = sb + S_X + grp * GW * X_TILE + ((lane >> 4) & 1) * X_PLANE + (((lane >> 3) & 1) * 8 + (lane & 7)) * RS32;
+    // own G tile, non-transposed A fragments (Q phases): rows (lane>>3 & 1)*8 + r, columns (lane>>4)*8
+    uint32_t gown = sb + S_G + warp * G_TILE + (((lane >> 3) & 1) * 8 + (lane & 7)) * GS + ((lane >> 4) & 1) * 16;
+    asm volatile("" : "+r"(lo.f32), "+r"(lo.f96), "+r"(lo.t32), "+r"(lo.t96), "+r"(ga), "+r"(xb), "+r"(gown));
 
-    for (int round = blockIdx.x; round < nrounds; round += gridDim.x) {
-        const int tile = round * NW + warp;
+    for (int round = 2 * blockIdx.x + grp; round < nrounds; round += 2 * gridDim.x) {
+        const int tile = round * GW + wl;
         // ------------------------------------------------------------------ inputs of the tile
         bool live = tile < ntiles;
         const int base = tile * TILE, s0 = base + 2 * g, s1 = s0 + 1;
         float p[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-        float gout[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-        uint32_t masks[5] = {0u, 0u, 0u, 0u, 0u};
+        AFrag<true> ca[2];
+        float acc[4][4], accS[4][4], h[4][4];
         if (live) {
             const int ray = base / P.S;
             const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
@@ -231,77 +264,76 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
             const float4 gr0 = *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)s0), gr1 = *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)s1);
             const uint32_t* mb = P.masks + ((size_t)2 * ntiles + tile) * 96 + lane;      // decoder 3's slot of the packed relu masks
             const uint32_t m0 = mb[0], m1 = mb[32], m2 = mb[64];
-            masks[0] = m0 & 0xffffu; masks[1] = m0 >> 16; masks[2] = m1 & 0xffffu; masks[3] = m1 >> 16; masks[4] = m2;
-            gout[0][0] = gr0.x; gout[0][1] = gr0.y; gout[0][2] = gr0.z; gout[1][0] = gr1.x; gout[1][1] = gr1.y; gout[1][2] = gr1.z;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], zz[r]));
             const bool any = gr0.x != 0.f || gr0.y != 0.f || gr0.z != 0.f || gr1.x != 0.f || gr1.y != 0.f || gr1.z != 0.f;
             live = ok && __any_sync(0xffffffffu, any);          // nothing flows into this tile: it contributes exact zeros
-        }
-        if (lane == 0) active[warp] = live ? 1 : 0;
-        AFrag<true> ca[2];
-        float acc[4][4], accS[4][4], h[4][4];
-        if (live) {
-            // ---------------------------------------------------------------- P1: the gu chain, parked in the G tile
-            float gh[4][4], gu[4][4];
+            if (live) {
+                const uint32_t masks[5] = {m0 & 0xffffu, m0 >> 16, m1 & 0xffffu, m1 >> 16, m2};
+                const float gout[2][3] = {{gr0.x, gr0.y, gr0.z}, {gr1.x, gr1.y, gr1.z}};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int o = 0; o < 3; ++o) {
-                    const float2 w = *reinterpret_cast<const float2*>(fs + F_Wo + o * HID + 8 * j + 2 * t);
-                    gh[j][0] = fmaf(gout[0][o], w.x, gh[j][0]); gh[j][1] = fmaf(gout[0][o], w.y, gh[j][1]);
-                    gh[j][2] = fmaf(gout[1][o], w.x, gh[j][2]); gh[j][3] = fmaf(gout[1][o], w.y, gh[j][3]);
-                }
-            }
+                    for (int a = 0; a < 3; ++a) p[r][a] = __fadd_rn(o[a], __fmul_rn(d[a], zz[r]));
+                // ------------------------------------------------------------ P1: the gu chain, parked in the G tile
+                float gh[4][4], gu[4][4];
 #pragma unroll
-            for (int i = 4; i >= 0; --i) {
+                for (int j = 0; j < 4; ++j) {
+                    gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) gu[j][q] = ((masks[i] >> (4 * j + q)) & 1u) ? gh[j][q] : 0.0f;
-                stage_g(gt, 32 * i, gu, g, t);
-                if (i > 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        AFrag<true> a;
-                        afrag_from_c<true>(a, gu[2 * kk], gu[2 * kk + 1]);
-                        kstep_wt<true>(gh, a, sb + S_IMG + I_WH + (i - 1) * 2 * PL32, PL32, RS32, kk, 0, lane);       // g_h = gu_i W_i
+                    for (int o3 = 0; o3 < 3; ++o3) {
+                        const float2 w = *reinterpret_cast<const float2*>(fs + F_Wo + o3 * HID + 8 * j + 2 * t);
+                        gh[j][0] = fmaf(gout[0][o3], w.x, gh[j][0]); gh[j][1] = fmaf(gout[0][o3], w.y, gh[j][1]);
+                        gh[j][2] = fmaf(gout[1][o3], w.x, gh[j][2]); gh[j][3] = fmaf(gout[1][o3], w.y, gh[j][3]);
                     }
                 }
-            }
-            if (t == 0) {   // g_out and the position (hi, lo) rows of the "GP" m-tile
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    __half* row = reinterpret_cast<__half*>(gt + (g + 8 * r) * GS);
+                for (int i = 4; i >= 0; --i) {
 #pragma unroll
-                    for (int o = 0; o < 3; ++o) {
-                        row[C_GOUT + o] = __float2half_rn(gout[r][o] * GSCALE);
-                        const __half ph = __float2half_rn(p[r][o]);
-                        row[C_P + o] = ph; row[C_P + 3 + o] = __float2half_rn(p[r][o] - __half2float(ph));
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) gu[j][q] = ((masks[i] >> (4 * j + q)) & 1u) ? gh[j][q] : 0.0f;
+                    stage_g(gt, 32 * i, gu, g, t);
+                    if (i > 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) gh[j][0] = gh[j][1] = gh[j][2] = gh[j][3] = 0.0f;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            AFrag<true> a;
+                            afrag_from_c<true>(a, gu[2 * kk], gu[2 * kk + 1]);
+                            kstep_wt<true>(gh, a, lo.t32 + I_WH + (i - 1) * 2 * PL32, RS32, kk, 0);       // g_h = gu_i W_i
+                        }
                     }
-#pragma unroll
-                    for (int o = 3; o < 8; ++o) row[C_GOUT + o] = __float2half_rn(0.0f);
-                    row[C_P + 6] = row[C_P + 7] = __float2half_rn(0.0f);
-#pragma unroll
-                    for (int o = 8; o < 16; ++o) row[C_P + o] = __float2half_rn(0.0f);
                 }
-            }
-            // ---------------------------------------------------------------- grid feature of the two samples (gather layout: channels 8t..8t+7)
-            float c[2][8];
-            gather8(P.grid[3], P.bnd, p[0], t, c[0]);
-            gather8(P.grid[3], P.bnd, p[1], t, c[1]);
+                if (t == 0) {   // g_out and the position (hi, lo) rows of the "GP" m-tile
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-                ca[kk].set(c[0][4 * kk], c[0][4 * kk + 1], c[0][4 * kk + 2], c[0][4 * kk + 3], c[1][4 * kk], c[1][4 * kk + 1], c[1][4 * kk + 2], c[1][4 * kk + 3]);
-            init_bias(acc, fs + F_b + 0 * HID, t);
-            init_bias(accS, fs + F_b + 3 * HID, t);
+                    for (int r = 0; r < 2; ++r) {
+                        __half* row = reinterpret_cast<__half*>(gt + (g + 8 * r) * GS);
+#pragma unroll
+                        for (int o3 = 0; o3 < 3; ++o3) {
+                            row[C_GOUT + o3] = __float2half_rn(gout[r][o3] * GSCALE);
+                            const __half ph = __float2half_rn(p[r][o3]);
+                            row[C_P + o3] = ph; row[C_P + 3 + o3] = __float2half_rn(p[r][o3] - __half2float(ph));
+                        }
+#pragma unroll
+                        for (int o3 = 3; o3 < 8; ++o3) row[C_GOUT + o3] = __float2half_rn(0.0f);
+                        row[C_P + 6] = row[C_P + 7] = __float2half_rn(0.0f);
+#pragma unroll
+                        for (int o3 = 8; o3 < 16; ++o3) row[C_P + o3] = __float2half_rn(0.0f);
+                    }
+                }
+                // ------------------------------------------------------------ grid feature of the two samples (gather layout: channels 8t..8t+7)
+                float c[2][8];
+                gather8(P.grid[3], P.bnd, p[0], t, c[0]);
+                gather8(P.grid[3], P.bnd, p[1], t, c[1]);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                    ca[kk].set(c[0][4 * kk], c[0][4 * kk + 1], c[0][4 * kk + 2], c[0][4 * kk + 3], c[1][4 * kk], c[1][4 * kk + 1], c[1][4 * kk + 2], c[1][4 * kk + 3]);
+                init_bias(acc, fs + F_b + 0 * HID, t);
+                init_bias(accS, fs + F_b + 3 * HID, t);
+            }
         }
+        if (lane == 0) active[wl] = live ? 1 : 0;
         __syncwarp();
+        uint32_t act = 0;
 
         // ==================================================================== E phases: embedding chunks, dW0 / dW3 (embedding columns)
 #pragma unroll 1
@@ -328,21 +360,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
                     *reinterpret_cast<uint2*>(xt + (g + 8) * RS32 + 2 * (16 * kq + 4 * t)) = make_uint2(a.hi[1], a.hi[3]);
                     *reinterpret_cast<uint2*>(xt + X_PLANE + g * RS32 + 2 * (16 * kq + 4 * t)) = make_uint2(a.lo[0], a.lo[2]);
                     *reinterpret_cast<uint2*>(xt + X_PLANE + (g + 8) * RS32 + 2 * (16 * kq + 4 * t)) = make_uint2(a.lo[1], a.lo[3]);
-                    kstep_w(acc, a, sb + S_IMG + I_W0, PL96, RS96, kk, lane);
-                    kstep_w(accS, a, sb + S_IMG + I_W3E, PL96, RS96, kk, lane);
+                    kstep_w(acc, a, lo.f96 + I_W0, RS96, kk);
+                    kstep_w(accS, a, lo.f96 + I_W3E, RS96, kk);
                 }
             }
-            bar_sync(1);
-            {   // 16 blocks: m-tiles {gu0 lo, gu0 hi half, gu3 ...} x 4 n-tiles
-                const int mi = warp >> 2, nt = warp & 3;
+            bar_sync(bar1);
+            if (k == 0) act = __ballot_sync(0xffffffffu, active[lane & 7] != 0) & 0xffu;
+#pragma unroll 1
+            for (int blk = wl; blk < 16; blk += GW) {   // 16 blocks: m-tiles {gu0 rows 0-15, gu0 rows 16-31, gu3 ...} x 4 n-tiles
+                const int mi = blk >> 2, nt = blk & 3;
                 const int mcol = (mi < 2 ? 0 : 96) + 16 * (mi & 1);
                 float d[4];
-                consume(sb + S_G, sb + S_X, active, mcol, nt, lane, d);
+                consume<GW>(ga, xb, act, 0, mcol, nt, d);
                 const int ncol = EMB - 32 * k;                     // features 93..95 are padding
                 if (mi < 2) flush_block(Q.dflat + f.W[0] + 32 * k, EMB, 16 * (mi & 1), HID, 8 * nt, ncol, d, GINV, g, t);
                 else flush_block(Q.dflat + f.W[3] + 32 * k, EMB + HID, 16 * (mi & 1), HID, 8 * nt, ncol, d, GINV, g, t);
             }
-            bar_sync(2);
+            bar_sync(bar2);
         }
         // ==================================================================== layers 0..4: h_{i+1}, then dW_{i+1} (or dWo for h_5)
 #pragma unroll 1
@@ -359,64 +393,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
                     for (int kk = 0; kk < 2; ++kk) {
                         AFrag<true> a;
                         afrag_from_c<true>(a, h[2 * kk], h[2 * kk + 1]);
-                        kstep_w(acc, a, sb + S_IMG + I_WH + (i - 1) * 2 * PL32, PL32, RS32, kk, lane);
+                        kstep_w(acc, a, lo.f32 + I_WH + (i - 1) * 2 * PL32, RS32, kk);
                     }
                 }
                 relu_mask(h, acc);
                 add_bias(h, fs + F_bc + i * HID, t);
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) kstep_w(h, ca[kk], sb + S_IMG + I_FC + i * 2 * PL32, PL32, RS32, kk, lane);     // + Fc_i c
+                for (int kk = 0; kk < 2; ++kk) kstep_w(h, ca[kk], lo.f32 + I_FC + i * 2 * PL32, RS32, kk);     // + Fc_i c
                 stage_x(xt, h, g, t);
             }
-            bar_sync(1);
-            if (i < 4) {
-                if (warp < 8) {   // gu_{i+1} (2 m-tiles) x h_{i+1} (4 n-tiles)
-                    const int mi = warp >> 2, nt = warp & 3;
-                    float d[4];
-                    consume(sb + S_G, sb + S_X, active, 32 * (i + 1) + 16 * mi, nt, lane, d);
-                    if (i == 2) flush_block(Q.dflat + f.W[3] + EMB, EMB + HID, 16 * mi, HID, 8 * nt, HID, d, GINV, g, t);
-                    else flush_block(Q.dflat + f.W[i + 1], HID, 16 * mi, HID, 8 * nt, HID, d, GINV, g, t);
-                } else if (i == 0) {   // bias gradients db_i = sum gu_i, dbo = sum g_out: 11 m-tiles over warps 8..15
-                    for (int mt = warp - 8; mt < 11; mt += 8) {
-                        float d[4];
-                        consume_ones(sb + S_G, active, 16 * mt, lane, d);
-                        if (t == 0) {
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const int col = 16 * mt + g + 8 * hh;          // G column
-                                if (col < 160) atomicAdd(Q.dflat + f.b[col >> 5] + (col & 31), d[2 * hh] * GINV);
-                                else if (col < C_GOUT + 3) atomicAdd(Q.dflat + f.bo + (col - C_GOUT), d[2 * hh] * GINV);
-                            }
-                        }
-                    }
-                }
-            } else if (warp < 4) {   // g_out x h_5 -> dWo
+            bar_sync(bar1);
+            if (i < 4) {   // gu_{i+1} (2 m-tiles) x h_{i+1} (4 n-tiles): one block per warp of the group
+                const int mi = wl >> 2, nt = wl & 3;
                 float d[4];
-                consume(sb + S_G, sb + S_X, active, C_GOUT, warp, lane, d);
-                flush_block(Q.dflat + f.Wo, HID, 0, 3, 8 * warp, HID, d, GINV, g, t);
+                consume<GW>(ga, xb, act, 0, 32 * (i + 1) + 16 * mi, nt, d);
+                const int woff = i == 0 ? f.W[1] : i == 1 ? f.W[2] : i == 2 ? f.W[3] + EMB : f.W[4];
+                flush_block(Q.dflat + woff, i == 2 ? EMB + HID : HID, 16 * mi, HID, 8 * nt, HID, d, GINV, g, t);
+            } else {       // g_out x h_5 -> dWo: 4 n-tiles, each split over two warps (tiles 0-3 / 4-7)
+                const int half = wl >> 2, nt = wl & 3;
+                float d[4];
+                consume<GW / 2>(ga, xb, act, 4 * half, C_GOUT, nt, d);
+                flush_block(Q.dflat + f.Wo, HID, 0, 3, 8 * nt, HID, d, GINV, g, t);
             }
-            bar_sync(2);
+            bar_sync(bar2);
         }
-        // ==================================================================== C phase: M_i = sum gu_{i+1}^T c, Mo = sum g_out^T c
+        // ==================================================================== C phase: M_i = sum gu_{i+1}^T c, Mo = sum g_out^T c, bias sums
         if (live) {   // the split grid feature is still in the A fragments: (hi[0], hi[2]) of k-step kk = channels 8t + 4kk .. + 3 of row g
             *reinterpret_cast<uint4*>(xt + g * RS32 + 16 * t) = make_uint4(ca[0].hi[0], ca[0].hi[2], ca[1].hi[0], ca[1].hi[2]);
             *reinterpret_cast<uint4*>(xt + (g + 8) * RS32 + 16 * t) = make_uint4(ca[0].hi[1], ca[0].hi[3], ca[1].hi[1], ca[1].hi[3]);
             *reinterpret_cast<uint4*>(xt + X_PLANE + g * RS32 + 16 * t) = make_uint4(ca[0].lo[0], ca[0].lo[2], ca[1].lo[0], ca[1].lo[2]);
             *reinterpret_cast<uint4*>(xt + X_PLANE + (g + 8) * RS32 + 16 * t) = make_uint4(ca[0].lo[1], ca[0].lo[3], ca[1].lo[1], ca[1].lo[3]);
         }
-        bar_sync(1);
-        for (int blk = warp; blk < 36; blk += NW) {   // 8 m-tiles of gu_1..gu_4 + the g_out m-tile, x 4 n-tiles
-            const int mt = blk >> 2, nt = blk & 3;
+        bar_sync(bar1);
+#pragma unroll 1
+        for (int blk = wl; blk < 47; blk += GW) {   // 8 m-tiles of gu_1..gu_4 + the g_out m-tile, x 4 n-tiles; then the 11 bias column sums
             float d[4];
-            if (mt < 8) {
-                consume(sb + S_G, sb + S_X, active, 32 + 16 * mt, nt, lane, d);
-                flush_block(Q.scratch + SCR_M + (mt >> 1) * HID * HID, HID, 16 * (mt & 1), HID, 8 * nt, HID, d, GINV, g, t);
-            } else {
-                consume(sb + S_G, sb + S_X, active, C_GOUT, nt, lane, d);
-                flush_block(Q.scratch + SCR_MO, HID, 0, 3, 8 * nt, HID, d, GINV, g, t);
+            if (blk < 36) {
+                const int mt = blk >> 2, nt = blk & 3;
+                if (mt < 8) {
+                    consume<GW>(ga, xb, act, 0, 32 + 16 * mt, nt, d);
+                    flush_block(Q.scratch + SCR_M + (mt >> 1) * HID * HID, HID, 16 * (mt & 1), HID, 8 * nt, HID, d, GINV, g, t);
+                } else {
+                    consume<GW>(ga, xb, act, 0, C_GOUT, nt, d);
+                    flush_block(Q.scratch + SCR_MO, HID, 0, 3, 8 * nt, HID, d, GINV, g, t);
+                }
+            } else {   // db_i = sum gu_i, dbo = sum g_out
+                const int mt = blk - 36;
+                consume_ones(ga, act, 16 * mt, d);
+                if (t == 0) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int col = 16 * mt + g + 8 * hh;
+                        const int li = col >> 5;
+                        const int boff = li == 0 ? f.b[0] : li == 1 ? f.b[1] : li == 2 ? f.b[2] : li == 3 ? f.b[3] : f.b[4];
+                        if (col < 160) atomicAdd(Q.dflat + boff + (col & 31), d[2 * hh] * GINV);
+                        else if (col < C_GOUT + 3) atomicAdd(Q.dflat + f.bo + (col - C_GOUT), d[2 * hh] * GINV);
+                    }
+                }
             }
         }
-        bar_sync(2);
+        bar_sync(bar2);
         // ==================================================================== Q phases: q = g_e cos(pB) per 32-feature chunk, dB = p^T q
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
@@ -424,22 +460,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
                 float ge[4][4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) ge[j][0] = ge[j][1] = ge[j][2] = ge[j][3] = 0.0f;
-                const int mat = lane >> 3, r8 = lane & 7;
 #pragma unroll
                 for (int src = 0; src < 2; ++src) {       // g_e = gu_0 W0 + gu_3 W3e; the A fragments come back from the G tile (single fp16)
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
                         AFrag<false> a;
-                        const int col = (src ? 96 : 0) + 16 * kk + (mat >> 1) * 8;
-                        ldsm4(sb + S_G + warp * G_TILE + ((mat & 1) * 8 + r8) * GS + 2 * col, a.hi);
-                        kstep_wt<false>(ge, a, sb + S_IMG + (src ? I_W3E : I_W0), PL96, RS96, kk, 4 * k, lane);
+                        ldsm4(gown + 2 * ((src ? 96 : 0) + 16 * kk), a.hi);
+                        kstep_wt<false>(ge, a, lo.t96 + (src ? I_W3E : I_W0), RS96, kk, 4 * k);
                     }
                 }
-                // image column 32k + 8j + 2t + b holds feature 32k + 16 (j >> 1) + 4t + 2 (j & 1) + b
-                float q[4][4];
+                // image column 32k + 8j + 2t + b holds feature 32k + 16 (j >> 1) + 4t + 2 (j & 1) + b; staged at natural feature columns
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int f0 = 32 * k + 16 * (j >> 1) + 4 * t + 2 * (j & 1);
+                    const int col = 16 * (j >> 1) + 4 * t + 2 * (j & 1), f0 = 32 * k + col;
                     const float2 B0 = *reinterpret_cast<const float2*>(fs + F_B + f0);
                     const float2 B1 = *reinterpret_cast<const float2*>(fs + F_B + EMBP + f0);
                     const float2 B2 = *reinterpret_cast<const float2*>(fs + F_B + 2 * EMBP + f0);
@@ -448,31 +481,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_fused(const Params Q) {
                     ff_sincos(fmaf(p[0][2], B2.y, fmaf(p[0][1], B1.y, p[0][0] * B0.y)), sn, c01);
                     ff_sincos(fmaf(p[1][2], B2.x, fmaf(p[1][1], B1.x, p[1][0] * B0.x)), sn, c10);
                     ff_sincos(fmaf(p[1][2], B2.y, fmaf(p[1][1], B1.y, p[1][0] * B0.y)), sn, c11);
-                    q[j][0] = ge[j][0] * c00 * GINV; q[j][1] = ge[j][1] * c01 * GINV; q[j][2] = ge[j][2] * c10 * GINV; q[j][3] = ge[j][3] * c11 * GINV;
-                }
-                // stage at natural feature columns: tile j covers features 16 (j >> 1) + 4t + 2 (j & 1), +1 of the chunk
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = 16 * (j >> 1) + 4 * t + 2 * (j & 1);
-                    uint32_t hi, lo;
-                    split_f16(q[j][0], q[j][1], hi, lo);
-                    *reinterpret_cast<uint32_t*>(xt + g * RS32 + 2 * col) = hi; *reinterpret_cast<uint32_t*>(xt + X_PLANE + g * RS32 + 2 * col) = lo;
-                    split_f16(q[j][2], q[j][3], hi, lo);
-                    *reinterpret_cast<uint32_t*>(xt + (g + 8) * RS32 + 2 * col) = hi; *reinterpret_cast<uint32_t*>(xt + X_PLANE + (g + 8) * RS32 + 2 * col) = lo;
+                    uint32_t hi, lw;
+                    split_f16(ge[j][0] * c00 * GINV, ge[j][1] * c01 * GINV, hi, lw);
+                    *reinterpret_cast<uint32_t*>(xt + g * RS32 + 2 * col) = hi; *reinterpret_cast<uint32_t*>(xt + X_PLANE + g * RS32 + 2 * col) = lw;
+                    split_f16(ge[j][2] * c10 * GINV, ge[j][3] * c11 * GINV, hi, lw);
+                    *reinterpret_cast<uint32_t*>(xt + (g + 8) * RS32 + 2 * col) = hi; *reinterpret_cast<uint32_t*>(xt + X_PLANE + (g + 8) * RS32 + 2 * col) = lw;
                 }
             }
-            bar_sync(1);
-            if (warp < 4) {   // rows 0..2 = p_hi^T q, rows 3..5 = p_lo^T q of the position m-tile
+            bar_sync(bar1);
+            {   // rows 0..2 = p_hi^T q, rows 3..5 = p_lo^T q of the position m-tile: 4 n-tiles, each split over two warps
+                const int half = wl >> 2, nt = wl & 3;
                 float d[4];
-                consume(sb + S_G, sb + S_X, active, C_P, warp, lane, d);
-                const int c0 = 32 * k + 8 * warp + 2 * t;
+                consume<GW / 2>(ga, xb, act, 4 * half, C_P, nt, d);
+                const int c0 = 32 * k + 8 * nt + 2 * t;
                 if (g < 6) {
                     float* dst = Q.dflat + f.B + (g % 3) * EMB + c0;
                     if (c0 < EMB) atomicAdd(dst, d[0]);
                     if (c0 + 1 < EMB) atomicAdd(dst + 1, d[1]);
                 }
             }
-            bar_sync(2);
+            bar_sync(bar2);
         }
     }
 }
@@ -521,8 +549,8 @@ cudaError_t launch_build_wgimg(const float* flat, uint8_t* img, cudaStream_t st)
 // P: the backward's decode parameters (rays, z, valid, g_raw, masks of the training forward; P.P samples, multiple of 16).
 cudaError_t launch_wgrad_fused(const DecodeParams& P, const uint8_t* img, const float* flat, float* dflat, float* scratch, int n_sm, cudaStream_t st) {
     wgf::Params Q; Q.D = P; Q.img = img; Q.dflat = dflat; Q.scratch = scratch;
-    const int nrounds = (P.P / TILE + wgf::NW - 1) / wgf::NW;
-    const int grid = nrounds < n_sm ? (nrounds > 0 ? nrounds : 1) : n_sm;
+    const int nrounds = (P.P / TILE + wgf::GW - 1) / wgf::GW;
+    const int grid = (nrounds + 1) / 2 < n_sm ? ((nrounds + 1) / 2 > 0 ? (nrounds + 1) / 2 : 1) : n_sm;
     wgf::k_wgrad_fused<<<grid, wgf::THREADS, wgf::SMEM_BYTES, st>>>(Q);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -194,6 +194,38 @@ def test_render_vjp_middle_and_fine_stage(engine_factory, frames, syn, model_inp
         assert relerr(got["rays_o"], tro.grad.numpy()) < GRAD_TOL and relerr(got["rays_d"], trd.grad.numpy()) < GRAD_TOL
 
 
+def test_stash_free_weight_gradient_kernel(nsb, model_inputs, frames, monkeypatch):
+    """NSB_WGRAD_STASH=0: the colour-decoder weight gradient from k_wgrad_fused (per-tile recomputation, operands exchanged through
+    shared memory, no HBM stash) against oracle/_ref's libtorch autograd -- the same golden vectors as the default (stash) path:
+    the vjp golden and the whole-iteration gradient golden -- and against the default path itself."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    g = load_golden("render_vjp.npz"); gm = load_golden("mapping_iters.npz")
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NSB_WGRAD_STASH", mode)
+        cfg = nsb.default_config(); cfg.max_rays = 8192; cfg.mapping_pixels = int(gm["pixels"]); cfg.frustum_feature_selection = 0; cfg.raydir = 0
+        e = nsb.Engine(cfg)
+        e.set_model(grids, decs); e.set_ttables(g["t_samples"], g["t_surface"])
+        for f in range(2):
+            e.set_frame(f, depths[f], colors[f], poses[f])
+        got = e.render_vjp(g["rays_d"], g["rays_o"], "color", g["gt_depth"], g["g_rgb"], g["g_depth"], g["g_var"])
+        assert relerr(got["dec_color"], g["d_dec_color"]) < GRAD_TOL, mode
+        only = e.render_vjp(g["rays_d"], g["rays_o"], "color", g["gt_depth"], g["g_rgb"], g["g_depth"], g["g_var"], flags=nsb.F_WGRAD)
+        assert relerr(only["dec_color"], got["dec_color"]) < 1e-5, mode
+        e.mapping_capture_grads(True)
+        e.seed(int(gm["c0_seed"]))
+        e.mapping_begin(list(range(int(gm["n_frames"]))), 60, 1.0)
+        loss = e.mapping_iter(59)
+        cg = e.captured_grads()
+        assert np.allclose(loss, gm["c0_loss"], rtol=1e-4)
+        assert relerr(cg["dec_color"], gm["c0_grad_dec_color"]) < GRAD_TOL, mode
+        res[mode] = (got["dec_color"], cg["dec_color"], e.get_decoder("color"))
+        e.close()
+    assert relerr(res["0"][0], res["1"][0]) < 3e-4 and relerr(res["0"][1], res["1"][1]) < 3e-4      # G operand is single fp16 in the fused kernel
+    assert np.abs(res["0"][2] - decs["color"]).max() > 1e-4                                             # the decoder was stepped
+
+
 # --------------------------------------------------------------------------------- mapping / tracking loops
 def test_mapping_iterations_vs_reference(engine_factory, frames, syn, model_inputs):
     """Mapper.cpp:330-465: sampling stream, inside filter, render, loss, backward, fused Adam -- four iterations
