@@ -46,7 +46,7 @@ size_t decode_fwd_smem();
 
 template <bool P3>
 static cudaError_t launch_one(const DecodeParams& P, int grid, cudaStream_t st) {
-    const size_t smem = decode_fwd_smem();
+    const size_t smem = decode_fwd_smem() + sizeof(float) * BWD_WARPS * SCAT_FLOATS;
     cudaError_t e = cudaFuncSetAttribute(k_decode_bwd<P3, NSB_G, NSB_R, NSB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_decode_bwd<P3, NSB_G, NSB_R, NSB_W><<<grid, BWD_THREADS, smem, st>>>(P);

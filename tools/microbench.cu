@@ -104,6 +104,59 @@ __global__ void k_red2(float* buf, uint32_t nlines, int iters) {
         }
     }
 }
+
+// Does legacy HMMA work overlap with FP32 ALU work?  MODE 0: every warp issues 8 independent HMMAs + NALU independent FFMAs per
+// step; MODE 1: even warps only HMMAs (16 per step), odd warps only FFMAs (2 NALU per step); MODE 2: FFMAs only; MODE 3: HMMAs only.
+template <int MODE, int NALU>
+__global__ void k_mma_alu(float* out, int iters) {
+    float d[8][4], f[16];
+    for (int i = 0; i < 8; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+    for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 0.001f + i;
+    uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 7, b1 = a0 * 5;
+    const bool odd = (threadIdx.x >> 7) & 1;   // warps 4..7, 12..15: every scheduler (warp % 4) gets two warps of each kind
+    const float m = 1.0001f, c = 0.5f;
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0 || MODE == 3 || (MODE == 1 && !odd)) {
+#pragma unroll
+            for (int rep = 0; rep < (MODE == 1 ? 2 : 1); ++rep)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+        if (MODE == 0 || MODE == 2 || (MODE == 1 && odd)) {
+#pragma unroll
+            for (int rep = 0; rep < (MODE == 1 ? 2 : 1) * NALU / 16; ++rep)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(m), "f"(c));
+        }
+    }
+    float s = 0; for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    for (int i = 0; i < 16; ++i) s += f[i];
+    if (s == 12345.f) out[0] = s;
+}
+template <int MODE, int NALU>
+static void run_mma_alu(float* out, int sms, int clk, const char* name, cudaEvent_t e0, cudaEvent_t e1) {
+    const int iters = 4000, warps = 16; float ms;
+    k_mma_alu<MODE, NALU><<<sms, warps * 32>>>(out, 50);
+    cudaEventRecord(e0); k_mma_alu<MODE, NALU><<<sms, warps * 32>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf(", \"%s_clk_per_step\": %.1f", name, ms * 1e-3 * clk * 1e6 / iters);   // SM clocks per loop step (16 warps)
+}
+
+// whole-line reductions: one warp instruction adds 32 consecutive floats (lane = channel) of a random 128-byte line
+__global__ void k_red_line(float* buf, uint32_t nlines, int iters) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    uint32_t s = warp * 2654435761u + 777u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            const uint32_t line = (s >> 8) % nlines;
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(buf + line * 32 + lane), "f"(1.0f) : "memory");
+        }
+    }
+}
 template <int MODE, bool SAME>
 static void run_red2(float* buf, uint32_t nlines, int sms, const char* name, cudaEvent_t e0, cudaEvent_t e1) {
     const int grid = sms * 8, iters = 50; float ms;
@@ -166,6 +219,20 @@ int main() {
     run_red2<1, false>((float*)buf, nlines, p.multiProcessorCount, "red_mode1_gbs", e0, e1);
     run_red2<0, true>((float*)buf, nlines, p.multiProcessorCount, "red_mode0_sameline_gbs", e0, e1);
     run_red2<1, true>((float*)buf, nlines, p.multiProcessorCount, "red_mode1_sameline_gbs", e0, e1);
+
+    {
+        const int grid = p.multiProcessorCount * 8, iters = 200;
+        k_red_line<<<grid, 256>>>((float*)buf, nlines, 5);
+        cudaEventRecord(e0); k_red_line<<<grid, 256>>>((float*)buf, nlines, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf(", \"red_line_f32_gbs\": %.0f", 128.0 * 8 * iters * (double)grid * 8 / ms * 1e-6);
+    }
+    run_mma_alu<3, 64>(out, p.multiProcessorCount, clk / 1000, "hmma8_only", e0, e1);
+    run_mma_alu<2, 64>(out, p.multiProcessorCount, clk / 1000, "ffma64_only", e0, e1);
+    run_mma_alu<0, 64>(out, p.multiProcessorCount, clk / 1000, "hmma8_ffma64_same_warp", e0, e1);
+    run_mma_alu<1, 64>(out, p.multiProcessorCount, clk / 1000, "hmma16_ffma128_alternate_warps", e0, e1);
+    run_mma_alu<0, 128>(out, p.multiProcessorCount, clk / 1000, "hmma8_ffma128_same_warp", e0, e1);
+    run_mma_alu<2, 128>(out, p.multiProcessorCount, clk / 1000, "ffma128_only", e0, e1);
     printf(", \"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
