@@ -55,6 +55,9 @@ cudaError_t launch_build_wimg(const float* const flat[4], const float* const com
 size_t wimg_floats(int which);
 cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_decode_fwd_tc16(const DecodeParams& P, int grid, cudaStream_t st);
+cudaError_t launch_decode_fwd_t5(const DecodeParams& P, int grid, cudaStream_t st);
+size_t t5_img_bytes(int which);
+cudaError_t launch_build_t5img(const float* const flat[4], const float* const comp[4], uint8_t* const img[4], int mask, cudaStream_t st);
 cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
 int compose_floats(int which);
 }  // namespace nsb
@@ -146,6 +149,7 @@ struct nsb_ctx {
     uint32_t* masks = nullptr;   // relu masks of the last training forward
     int mask_layout = 0, mask_stride = 0;
     float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
+    uint8_t* wimg_t5[4] = {nullptr, nullptr, nullptr, nullptr};   // images of the tcgen05 forward (NSB_TCGEN05=3), rebuilt with the composed images
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
     float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
     float* wimg_bwd[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -461,7 +465,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
-    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); }
+    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_t5[d], t5_img_bytes(d))); }
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
@@ -498,7 +502,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->wg_img, c->wg_scratch, c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -765,6 +769,7 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
         ctx->comp_dirty &= ~comp_need;
     }
     CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
+    if (ctx->use_tc == 3 && cmp_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, cmp_need, ctx->stream)); ctx->launches++; }
     if (plain & 8) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (fused weight gradient)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
@@ -772,7 +777,7 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
 
 static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
     memset(&P, 0, sizeof P);
-    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; }
+    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; P.wimg_t5[d] = ctx->wimg_t5[d]; }
     P.bnd = ctx->bnd;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
     P.S = S; P.P = n * S;
@@ -853,9 +858,11 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             P.mask_layout = 1; P.mask_stride = n * S;
             if (train) { ctx->mask_layout = 1; ctx->mask_stride = n * S; }
             float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
-            if (ctx->use_tc == 2) {   // kind::f16 kernel: three 128-sample tiles per CTA
+            if (ctx->use_tc >= 2) {   // kind::f16 kernels: three 128-sample tiles per CTA (3 = every A operand in tensor memory)
                 partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 384))), wt, P.cta_begin);
-                CK(launch_decode_fwd_tc16(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+                if (ctx->use_tc == 3) CK(launch_decode_fwd_t5(P, P.cta_begin[4], ctx->stream));
+                else CK(launch_decode_fwd_tc16(P, P.cta_begin[4], ctx->stream));
+                ctx->launches++;
             } else {
                 partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 256))), wt, P.cta_begin);
                 CK(launch_decode_fwd_tc(P, P.cta_begin[4], ctx->stream)); ctx->launches++;

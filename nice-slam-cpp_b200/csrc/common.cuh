@@ -58,12 +58,15 @@ __device__ __forceinline__ uint32_t pack_f16(float lo_half, float hi_half) {
     const __half2 v = __floats2half2_rn(lo_half, hi_half);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
-// (x0, x1) -> hi = f16x2(x0, x1), lo = f16x2(x0 - hi0, x1 - hi1)
+// (x0, x1) -> hi = f16x2(x0, x1), lo = f16x2(x0 - hi0, x1 - hi1): four instructions per pair.  The residual uses sm_100's
+// mixed-precision add (add.f32.f16 -> FHADD, which reads one half of the packed register directly), so the fp16 -> fp32 unpack of
+// the older form (two more instructions per pair) disappears; the result is bit-identical (x - hi is exact in fp32 either way).
 __device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(x0, x1);
-    const float2 hf = __half22float2(h);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = pack_f16(x0 - hf.x, x1 - hf.y);
+    float r0, r1;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    asm("{\n\t.reg .b16 l, h, nl, nh;\n\tmov.b32 {l, h}, %2;\n\tneg.f16 nl, l;\n\tneg.f16 nh, h;\n\t"
+        "add.rn.f32.f16 %0, nl, %3;\n\tadd.rn.f32.f16 %1, nh, %4;\n\t}" : "=f"(r0), "=f"(r1) : "r"(hi), "f"(x0), "f"(x1));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(

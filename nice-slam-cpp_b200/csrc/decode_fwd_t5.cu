@@ -1,0 +1,425 @@
+// Forward decoder kernel on the 5th-generation tensor cores, third generation: tcgen05.mma kind::f16 with EVERY A operand in
+// TENSOR MEMORY (grid features, Fourier features, hidden activations), weights (B operands) resident in shared memory, fp32
+// accumulators in tensor memory.  Same fp32-grade product as the warp-MMA path,
+//     D += a_lo.b_hi + a_hi.b_lo + a_hi.b_hi,   x = hi + lo,  hi = fp16(x), lo = fp16(x - hi).
+//
+// Why this exists (measured, tools/microbench, profiles/r2_microbench.json): on sm_100a a legacy warp-level HMMA does not overlap
+// with FP32/ALU work of the same SM sub-partition -- 8 HMMA + 64 FFMA per warp take 411 clk where either alone takes 280 / 265, and
+// HMMA-only warps next to FFMA-only warps take the SUM (555 clk).  k_decode_fwd is therefore pinned at T(HMMA) + T(ALU); only
+// the asynchronous tcgen05 pipe runs the products underneath the per-value work (sines, fp16 splits, relu, gather).
+//
+// One CTA per SM keeps ONE decoder's weights resident and runs NG = 3 tiles of 128 samples concurrently:
+//   warps 4g..4g+3 (tile group g)   one thread per sample = one TMEM lane.  Quad-cooperative trilinear gather (a quad fetches a voxel
+//                                   line in one wavefront) handed to the owner lane through a per-warp scratch; Fourier features;
+//                                   per-layer epilogues (tcgen05.ld, bias, relu, mask, fp16 split).  Operands go back to tensor
+//                                   memory with tcgen05.st as packed f16x2 words: no swizzled shared-memory stores, no bank
+//                                   conflicts, no async-proxy fence.
+//   warps 12..14                    one elected lane per group issues the tcgen05.mma stream and commits to an mbarrier
+// Tensor-memory columns of a group (64 + C + 40 of the 512):  acc0 | accS | c (hi 16 | lo 16 per 32 channels) | x (hi 16 | lo 16) | ones.
+// Biases are products too: a constant operand (1, 1, 0, ..) times a tile holding (hi(b'), lo(b'), 0, ..) per output adds b' to the
+// accumulator inside the tensor pipe, so the epilogue is relu + sign-bit mask + split only.
+// Algebra (k_compose): a_{i+1} = W_{i+1} relu(a_i) + G_i c + b'_{i+1}, G_i = W_{i+1} Fc_i.  c stays in its columns for the whole
+// tile and its term joins each layer's product, so a layer's accumulator is rewritten in place (acc0 serves layers 0, 1, 2, 4;
+// accS collects the skip layer) -- 64 accumulator columns per tile instead of the 160 of decode_fwd_tc16.cu.
+// Replaces NICE::forward / MLP::forward (NICE.cpp:16-51, MLP.cpp:76-102); selected with NSB_TCGEN05=3 when no wgrad stash is needed.
+#include "decode.cuh"
+#include "params.h"
+
+namespace nsb {
+namespace t5 {
+
+constexpr int TM = 128;                        // samples per tile (UMMA M)
+constexpr int NG = 3;                          // tile groups per CTA
+constexpr int GTHREADS = 128;                  // compute threads per group: one per sample
+constexpr int CTHREADS = NG * GTHREADS;
+constexpr int THREADS = CTHREADS + 32 * NG;    // + one issuer warp per group
+constexpr int ACC0 = 0, ACCS = 32, CCOL = 64;  // tensor-memory columns inside a group
+__host__ __device__ constexpr int xcol(int C) { return CCOL + C; }
+__host__ __device__ constexpr int onecol(int C) { return CCOL + C + 32; }   // constant A operand (1, 1, 0, ...) of the bias products: 8 columns
+__host__ __device__ constexpr int gcols(int C) { return CCOL + C + 40; }
+constexpr int SCR_ROW = 36;                    // floats per row of the gather scratch (conflict-free 16-byte stores and loads)
+
+// composed weights (global, per decoder), layout of k_compose: G[4][32][C] | bp[5][32] | woc[4][C] | boc[4]
+__host__ __device__ constexpr int comp_bp(int C) { return 4 * HID * C; }
+__host__ __device__ constexpr int comp_woc(int C) { return comp_bp(C) + 5 * HID; }
+__host__ __device__ constexpr int comp_boc(int C) { return comp_woc(C) + 4 * C; }
+
+template <int C>
+struct Smem {   // bytes; every UMMA tile starts on a multiple of 1024 B, rows are 128 B = [hi 32 halves | lo 32 halves]
+    static constexpr int WE = 0;                                   // 3 chunks x [64 rows]: rows 0-31 W0, 32-63 W3 (embedding columns)
+    static constexpr int WH = WE + 3 * 64 * 128;                   // 4 x [32 rows]: W1, W2, W3 (hidden columns), W4
+    static constexpr int G = WH + 4 * 32 * 128;                    // 4 x (C/32) x [32 rows]: G_i restricted to channel chunk cc at (i * C/32 + cc)
+    static constexpr int BT = G + 4 * (C / 32) * 32 * 128;         // bias tile [64 rows]: k16 step 0 = b'_0 (rows 0-31) | b'_3 (rows 32-63), steps 1, 2, 3 = b'_1, b'_2, b'_4
+    static constexpr int BM = BT + 64 * 128;                       // Fourier matrix [3][96] fp32
+    static constexpr int BP = BM + 3 * EMBP * 4;                   // b'[5][32]
+    static constexpr int WO = BP + 5 * HID * 4;                    // Wo[4][32]
+    static constexpr int WOC = WO + 4 * HID * 4;                   // (Wo Fc_4)[4][C]
+    static constexpr int BOC = WOC + 4 * C * 4;                    // const[4]
+    static constexpr int IMG = BOC + 16;                           // everything above is the decoder's image, prebuilt in global memory (k_build_t5img)
+    static constexpr int SCR = IMG;                                // gather scratch: one [32][SCR_ROW] fp32 block per compute warp
+    static constexpr int BAR = SCR + (CTHREADS / 32) * 32 * SCR_ROW * 4;   // mbarriers: full[NG], done[NG]
+    static constexpr int TMEMPTR = BAR + 2 * NG * 8;
+    static constexpr int TOTAL = TMEMPTR + 16;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // try_wait sleeps in hardware until the phase flips or a time limit
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major SWIZZLE_128B, SBO 1024 B, version 1
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {   // kind::f16: A, B = F16 (format 0), D = F32, both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                   "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                   "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+                   "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 fp32 values of this thread's row -> 32 tensor-memory columns: 16 packed f16x2 words of hi parts, then 16 of lo parts
+__device__ __forceinline__ void store_operand(uint32_t taddr, const float (&v)[32]) {
+    uint32_t w[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split_f16(v[2 * i], v[2 * i + 1], w[i], w[16 + i]);
+    tmem_st32(taddr, w);
+}
+
+// byte offset of the 16-byte chunk `c` (0..3 hi, 4..7 lo) of row r inside a SWIZZLE_128B tile
+__device__ __forceinline__ int chunk_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
+// one element of a weight tile: row r, logical input index k (0..31) -> hi at half k, lo at half 32 + k
+__device__ __forceinline__ void put_w(uint8_t* tile, int r, int k, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    *reinterpret_cast<__half*>(tile + chunk_off(r, k >> 3) + (k & 7) * 2) = h;
+    *reinterpret_cast<__half*>(tile + chunk_off(r, 4 + (k >> 3)) + (k & 7) * 2) = l;
+}
+
+template <int C, int O>
+__device__ void stage(uint8_t* sm, const float* __restrict__ flat, const float* __restrict__ comp, int tid, int nthr) {
+    using L = Smem<C>;
+    const DecFlat f = DecFlat::make(C, O);
+    for (int idx = tid; idx < 3 * 64 * 32; idx += nthr) {
+        const int j = idx / 2048, r = (idx / 32) % 64, k = idx % 32, ft = 32 * j + k;
+        float v = 0.0f;
+        if (ft < EMB) v = r < 32 ? flat[f.W[0] + r * EMB + ft] : flat[f.W[3] + (r - 32) * (EMB + HID) + ft];
+        put_w(sm + L::WE + j * 8192, r, k, v);
+    }
+    for (int idx = tid; idx < 4 * 32 * 32; idx += nthr) {
+        const int l = idx / 1024, o = (idx / 32) % 32, k = idx % 32;   // l = 0..3 <-> layers 1..4
+        const float v = l == 2 ? flat[f.W[3] + o * (EMB + HID) + EMB + k] : flat[f.W[l + 1] + o * HID + k];
+        put_w(sm + L::WH + l * 4096, o, k, v);
+    }
+    for (int idx = tid; idx < 4 * (C / 32) * 32 * 32; idx += nthr) {
+        const int tile = idx / 1024, i = tile / (C / 32), cc = tile % (C / 32), o = (idx / 32) % 32, k = idx % 32;
+        put_w(sm + L::G + tile * 4096, o, k, comp[(i * HID + o) * C + 32 * cc + k]);
+    }
+    for (int idx = tid; idx < 64 * 64; idx += nthr) {               // bias tile: half 16 s of row r = hi(b), half 16 s + 1 = lo(b), rest 0
+        const int r = idx / 64, hpos = idx % 64, st = hpos / 16, kk = hpos % 16;
+        float b = 0.0f;
+        if (st == 0) b = comp[comp_bp(C) + (r < 32 ? 0 : 3) * HID + (r & 31)];
+        else if (r < 32) b = comp[comp_bp(C) + (st == 3 ? 4 : st) * HID + r];
+        const __half h = __float2half_rn(b);
+        const __half l = __float2half_rn(b - __half2float(h));
+        *reinterpret_cast<__half*>(sm + L::BT + chunk_off(r, hpos >> 3) + (hpos & 7) * 2) = kk == 0 ? h : kk == 1 ? l : __float2half_rn(0.0f);
+    }
+    float* bm = reinterpret_cast<float*>(sm + L::BM);
+    for (int i = tid; i < 3 * EMBP; i += nthr) { const int d = i / EMBP, c = i % EMBP; bm[i] = c < EMB ? flat[f.B + d * EMB + c] : 0.0f; }
+    float* bp = reinterpret_cast<float*>(sm + L::BP);
+    for (int i = tid; i < 5 * HID; i += nthr) bp[i] = comp[comp_bp(C) + i];
+    float* wo = reinterpret_cast<float*>(sm + L::WO);
+    for (int i = tid; i < 4 * HID; i += nthr) wo[i] = (i / HID) < O ? flat[f.Wo + i] : 0.0f;
+    float* woc = reinterpret_cast<float*>(sm + L::WOC);
+    for (int i = tid; i < 4 * C; i += nthr) woc[i] = comp[comp_woc(C) + i];
+    float* boc = reinterpret_cast<float*>(sm + L::BOC);
+    if (tid < 4) boc[tid] = comp[comp_boc(C) + tid];
+}
+
+// fp32-grade product over one 32-input block, A at tensor-memory column `a` (hi 16 columns | lo 16 columns, 8 columns per k16
+// step), B a shared-memory tile (descriptor units of 16 B: +2 = one k16 step, +4 = the lo half of the 128-byte row)
+__device__ __forceinline__ void issue3(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, bool zero_first) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mma_ts(d, a + 16 + 8 * k, b + 2 * k, idesc, (zero_first && k == 0) ? 0u : 1u);   // a_lo . b_hi (small terms first)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mma_ts(d, a + 8 * k, b + 4 + 2 * k, idesc, 1u);                                 // a_hi . b_lo
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mma_ts(d, a + 8 * k, b + 2 * k, idesc, 1u);                                     // a_hi . b_hi
+}
+
+template <int C, int O>
+__device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta, int ncta) {
+    using L = Smem<C>;
+    constexpr int GCOLS = gcols(C), XCOL = xcol(C);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (P.P + TM - 1) / TM;
+    const uint32_t bar0 = smem_u32(sm + L::BAR);
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::TMEMPTR);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm + L::TMEMPTR)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NG; ++s) { mbar_init(bar0 + 8 * s, GTHREADS); mbar_init(bar0 + 8 * NG + 8 * s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    {   // the decoder's image (pre-split weight tiles, bias tile, small fp32 tables) was built once per weight update: 16-byte copies
+        const uint4* src = reinterpret_cast<const uint4*>(P.wimg_t5[dec]);
+        uint4* dst = reinterpret_cast<uint4*>(sm);
+        for (int i = tid; i < L::IMG / 16; i += THREADS) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    constexpr int NO = O == 4 ? 3 : 1;
+
+    if (warp < NG * 4) {
+        // ------------------------------------------------------------------ compute threads: one per sample (= TMEM lane)
+        const int grp = warp >> 2, wq = warp & 3, row = (wq << 5) | lane, q = lane >> 2, t = lane & 3;
+        const uint32_t tm = tmem + grp * GCOLS + ((uint32_t)(wq * 32) << 16);
+        const uint32_t full = bar0 + 8 * grp, done = bar0 + 8 * NG + 8 * grp;
+        const float* bm = reinterpret_cast<const float*>(sm + L::BM);
+        const float* bp = reinterpret_cast<const float*>(sm + L::BP);
+        const float* wo = reinterpret_cast<const float*>(sm + L::WO);
+        const float* woc = reinterpret_cast<const float*>(sm + L::WOC);
+        const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
+        float* scr = reinterpret_cast<float*>(sm + L::SCR) + warp * 32 * SCR_ROW;
+        uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
+        {   // constant A operand of the bias products: k = 0, 1 -> 1.0 (packed f16x2 0x3C003C00), k = 2..15 -> 0
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"r"(tm + onecol(C)), "r"(0x3C003C00u), "r"(0u) : "memory");
+            tmem_st_wait();
+        }
+        for (int tile = cta * NG + grp; tile < ntiles; tile += ncta * NG) {
+            const int s = tile * TM + row;
+            bool active = s < P.P;
+            float p[3] = {0.f, 0.f, 0.f};
+            if (active) {
+                if (P.pts) { p[0] = P.pts[3 * (size_t)s]; p[1] = P.pts[3 * (size_t)s + 1]; p[2] = P.pts[3 * (size_t)s + 2]; }
+                else {
+                    const int ray = s / P.S;
+                    const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
+                    const float z = P.z[s];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(P.rays_o[3 * ray + a], __fmul_rn(P.rays_d[3 * ray + a], z));   // Renderer.cpp:121
+                    if (!ok) { active = false; p[0] = p[1] = p[2] = 0.0f; }      // sin(0 . B) = 0: an inactive row contributes exact zeros
+                }
+            }
+            // ---- grid features.  Quad-cooperative gather: in pass r the quad q of this warp serves sample 8r + q of the warp and
+            // leaves its 8 channels in the scratch row of that sample; the owner lane then reads its whole row, adds the
+            // grid-feature part of the output layer and moves the row to tensor memory as the A operand of every G_i c product.
+            float outc[NO];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) outc[o] = boc[o];
+#pragma unroll
+            for (int cc = 0; cc < C / 32; ++cc) {
+                const GridView& G = P.grid[cc == 0 ? dec : 1];          // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int j = 8 * r + q;
+                    float pj[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) pj[a] = __shfl_sync(0xffffffffu, p[a], j);
+                    const bool act = __shfl_sync(0xffffffffu, active ? 1 : 0, j) != 0;
+                    float c8[8];
+                    if (act) gather8(G, P.bnd, pj, t, c8);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) c8[i] = 0.0f;
+                    }
+                    *reinterpret_cast<float4*>(scr + j * SCR_ROW + 8 * t) = make_float4(c8[0], c8[1], c8[2], c8[3]);
+                    *reinterpret_cast<float4*>(scr + j * SCR_ROW + 8 * t + 4) = make_float4(c8[4], c8[5], c8[6], c8[7]);
+                }
+                __syncwarp();
+                float c[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(scr + lane * SCR_ROW + 4 * i);
+                    c[4 * i] = v4.x; c[4 * i + 1] = v4.y; c[4 * i + 2] = v4.z; c[4 * i + 3] = v4.w;
+                }
+                __syncwarp();                                           // the scratch is rewritten by the next chunk / tile
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    float acc = outc[o];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(woc + o * C + 32 * cc + 4 * i);
+                        acc = fmaf(c[4 * i], w4.x, acc); acc = fmaf(c[4 * i + 1], w4.y, acc); acc = fmaf(c[4 * i + 2], w4.z, acc); acc = fmaf(c[4 * i + 3], w4.w, acc);
+                    }
+                    outc[o] = acc;
+                }
+                store_operand(tm + CCOL + 32 * cc, c);                  // the previous tile's last product has been waited for (layer 4)
+            }
+            // ---- Fourier features, 32 per handshake, this thread's own sample
+#pragma unroll 1
+            for (int j = 0; j < 3; ++j) {
+                float e[32];
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const int ft = 32 * j + 4 * k4;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bm + ft), b1 = *reinterpret_cast<const float4*>(bm + EMBP + ft), b2 = *reinterpret_cast<const float4*>(bm + 2 * EMBP + ft);
+                    e[4 * k4] = ff_sin(fmaf(p[2], b2.x, fmaf(p[1], b1.x, p[0] * b0.x)));
+                    e[4 * k4 + 1] = ff_sin(fmaf(p[2], b2.y, fmaf(p[1], b1.y, p[0] * b0.y)));
+                    e[4 * k4 + 2] = ff_sin(fmaf(p[2], b2.z, fmaf(p[1], b1.z, p[0] * b0.z)));
+                    e[4 * k4 + 3] = ff_sin(fmaf(p[2], b2.w, fmaf(p[1], b1.w, p[0] * b0.w)));   // padded columns of B are 0 -> sin(0) = 0
+                }
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_f16(e[2 * i], e[2 * i + 1], w[i], w[16 + i]);
+                if (j > 0) { mbar_wait(done, (step - 1) & 1); fence_after(); }     // the previous chunk's products have consumed x
+                tmem_st32(tm + XCOL, w);
+                tmem_st_wait();
+                fence_before();
+                mbar_arrive(full);
+                ++step;
+            }
+            // ---- five layers: read the accumulator, bias + relu (+ mask), hand u_i back as the next A operand
+#pragma unroll 1
+            for (int i = 0; i < 5; ++i) {
+                mbar_wait(done, (step - 1) & 1);
+                fence_after();
+                float v[32];
+                tmem_ld32(tm + (i == 3 ? ACCS : ACC0), v);
+                tmem_ld_wait();
+                uint32_t m = 0;
+#pragma unroll
+                for (int k = 31; k >= 0; --k) {
+                    m = __funnelshift_l(__float_as_uint(v[k]), m, 1);      // collects the sign bits: bit k of ~m <-> unit k active
+                    v[k] = fmaxf(v[k], 0.0f);
+                }
+                if (P.masks && active) P.masks[((size_t)(dec - 1) * 5 + i) * P.mask_stride + s] = ~m;
+                if (i < 4) {
+                    store_operand(tm + XCOL, v);
+                    tmem_st_wait();
+                    fence_before();
+                    mbar_arrive(full);
+                    ++step;
+                } else {
+                    float out[NO];
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        float acc = outc[o];
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wo + o * HID + 4 * k4);
+                            acc = fmaf(v[4 * k4], w4.x, acc); acc = fmaf(v[4 * k4 + 1], w4.y, acc); acc = fmaf(v[4 * k4 + 2], w4.z, acc); acc = fmaf(v[4 * k4 + 3], w4.w, acc);
+                        }
+                        out[o] = acc;
+                    }
+                    if (active) {
+                        if (O == 4) *reinterpret_cast<float4*>(P.out_rgb + 4 * (size_t)s) = make_float4(out[0], out[NO > 1 ? 1 : 0], out[NO > 2 ? 2 : 0], 0.0f);
+                        else P.out_occ[dec][s] = out[0];
+                    }
+                }
+            }
+            fence_before();       // the accumulator reads above are ordered before the next tile's first arrive
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer of one tile group
+        const int grp = warp - NG * 4;
+        const uint32_t tm = tmem + grp * GCOLS;
+        const uint32_t full = bar0 + 8 * grp, done = bar0 + 8 * NG + 8 * grp;
+        const uint32_t sbase = smem_u32(sm);
+        constexpr uint32_t I32 = make_idesc(128, 32), I64 = make_idesc(128, 64);
+        constexpr int NC = C / 32;
+        uint32_t step = 0;
+        for (int tile = cta * NG + grp; tile < ntiles; tile += ncta * NG) {
+            for (int j = 0; j < 3; ++j) {           // [acc0 | accS] (+)= e_j [W0 ; W3E]_j^T ; the skip layer's grid-feature term rides on the first chunk
+                mbar_wait(full, step & 1); fence_after();
+                issue3(tm + ACC0, tm + XCOL, make_desc(sbase + L::WE + j * 8192), I64, j == 0);
+                if (j == 0) mma_ts(tm + ACC0, tm + onecol(C), make_desc(sbase + L::BT), I64, 1u);                       // + b'_0 | b'_3
+                if (j == 0)
+                    for (int cc = 0; cc < NC; ++cc) issue3(tm + ACCS, tm + CCOL + 32 * cc, make_desc(sbase + L::G + (2 * NC + cc) * 4096), I32, false);
+                mma_commit(done); ++step;
+            }
+            for (int l = 0; l < 4; ++l) {           // layer l+1: acc = u_l W_{l+1}^T + c G_l^T  (layer 3 accumulates into accS, whose c term is in)
+                mbar_wait(full, step & 1); fence_after();
+                const uint32_t d = tm + (l == 2 ? ACCS : ACC0);
+                issue3(d, tm + XCOL, make_desc(sbase + L::WH + l * 4096), I32, l != 2);
+                if (l != 2) mma_ts(d, tm + onecol(C), make_desc(sbase + L::BT) + 2 * (l == 3 ? 3 : l + 1), I32, 1u);    // + b'_{l+1}
+                if (l != 2)
+                    for (int cc = 0; cc < NC; ++cc) issue3(d, tm + CCOL + 32 * cc, make_desc(sbase + L::G + (l * NC + cc) * 4096), I32, false);
+                mma_commit(done); ++step;
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_decode_fwd_t5(const DecodeParams P) {
+    extern __shared__ __align__(1024) uint8_t sm[];                 // used in place (shared state space known to the compiler: LDS, not generic loads)
+    if (smem_u32(sm) & 1023u) __trap();                             // SWIZZLE_128B tiles need 1024-byte alignment
+    int dec = 1;
+#pragma unroll
+    for (int d = 2; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
+    const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
+    if (dec == 1) run_decoder<32, 1>(P, sm, 1, cta, ncta);
+    else if (dec == 2) run_decoder<64, 1>(P, sm, 2, cta, ncta);
+    else run_decoder<32, 4>(P, sm, 3, cta, ncta);
+}
+
+// Builds the shared-memory image of decoder d (blockIdx.y = d - 1) in global memory; run after k_compose whenever the weights change.
+struct T5ImgParams { const float* flat[4]; const float* comp[4]; uint8_t* img[4]; int mask; };
+__global__ void __launch_bounds__(512) k_build_t5img(T5ImgParams W) {
+    const int d = 1 + blockIdx.y;
+    if (!((W.mask >> d) & 1)) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (d == 1) stage<32, 1>(W.img[1], W.flat[1], W.comp[1], tid, nthr);
+    else if (d == 2) stage<64, 1>(W.img[2], W.flat[2], W.comp[2], tid, nthr);
+    else stage<32, 4>(W.img[3], W.flat[3], W.comp[3], tid, nthr);
+}
+
+}  // namespace t5
+
+size_t t5_img_bytes(int which) { return which == 2 ? t5::Smem<64>::IMG : t5::Smem<32>::IMG; }
+cudaError_t launch_build_t5img(const float* const flat[4], const float* const comp[4], uint8_t* const img[4], int mask, cudaStream_t st) {
+    t5::T5ImgParams W;
+    for (int d = 0; d < 4; ++d) { W.flat[d] = flat[d]; W.comp[d] = comp[d]; W.img[d] = img[d]; }
+    W.mask = mask;
+    t5::k_build_t5img<<<dim3(8, 3), 512, 0, st>>>(W);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_fwd_t5(const DecodeParams& P, int grid, cudaStream_t st) {
+    const size_t smem = (size_t)t5::Smem<64>::TOTAL;
+    static unsigned attr_done = 0;      // per device: function attributes are per-device state
+    int dev = 0; cudaGetDevice(&dev);
+    if (!((attr_done >> (dev & 31)) & 1u)) {
+        cudaError_t e = cudaFuncSetAttribute(t5::k_decode_fwd_t5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done |= 1u << (dev & 31);
+    }
+    t5::k_decode_fwd_t5<<<grid, t5::THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace nsb
