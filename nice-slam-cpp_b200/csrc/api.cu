@@ -860,7 +860,12 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
             if (ctx->use_tc >= 2) {   // kind::f16 kernels: three 128-sample tiles per CTA (3 = every A operand in tensor memory)
                 partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 384))), wt, P.cta_begin);
-                if (ctx->use_tc == 3) CK(launch_decode_fwd_t5(P, P.cta_begin[4], ctx->stream));
+                if (ctx->use_tc == 3) {   // four tile groups per CTA (three for the fine decoder), tiles drawn from the ticket counters
+                    float w5[4] = {0, w[1] > 0 ? 700.f : 0.f, w[2] > 0 ? 1300.f : 0.f, w[3] > 0 ? 760.f : 0.f}; env_weights("NSB_SPLIT_FWD_T5", w5);
+                    partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 512))), w5, P.cta_begin);
+                    P.tile_ctr = ctx->tile_ctr;
+                    CK(launch_decode_fwd_t5(P, P.cta_begin[4], ctx->stream));
+                }
                 else CK(launch_decode_fwd_tc16(P, P.cta_begin[4], ctx->stream));
                 ctx->launches++;
             } else {

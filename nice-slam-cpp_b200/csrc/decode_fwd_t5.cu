@@ -8,16 +8,20 @@
 // HMMA-only warps next to FFMA-only warps take the SUM (555 clk).  k_decode_fwd is therefore pinned at T(HMMA) + T(ALU); only
 // the asynchronous tcgen05 pipe runs the products underneath the per-value work (sines, fp16 splits, relu, gather).
 //
-// One CTA per SM keeps ONE decoder's weights resident and runs NG = 3 tiles of 128 samples concurrently:
+// One CTA per SM keeps ONE decoder's weights resident and runs FOUR tiles of 128 samples concurrently (three for the fine decoder, whose
+// 64 grid channels need 160 of the 512 tensor-memory columns per tile):
 //   warps 4g..4g+3 (tile group g)   one thread per sample = one TMEM lane.  Quad-cooperative trilinear gather (a quad fetches a voxel
 //                                   line in one wavefront) handed to the owner lane through a per-warp scratch; Fourier features;
 //                                   per-layer epilogues (tcgen05.ld, bias, relu, mask, fp16 split).  Operands go back to tensor
 //                                   memory with tcgen05.st as packed f16x2 words: no swizzled shared-memory stores, no bank
 //                                   conflicts, no async-proxy fence.
-//   warps 12..14                    one elected lane per group issues the tcgen05.mma stream and commits to an mbarrier
-// Tensor-memory columns of a group (64 + C + 40 of the 512):  acc0 | accS | c (hi 16 | lo 16 per 32 channels) | x (hi 16 | lo 16) | ones.
-// Biases are products too: a constant operand (1, 1, 0, ..) times a tile holding (hi(b'), lo(b'), 0, ..) per output adds b' to the
-// accumulator inside the tensor pipe, so the epilogue is relu + sign-bit mask + split only.
+//   warps 16..19                    one elected lane per group issues the tcgen05.mma stream and commits to an mbarrier
+// The four issuer warps give registers back (setmaxnreg.dec 32) and the sixteen compute warps take them (setmaxnreg.inc 120).
+// Tensor-memory columns of a group (64 + C + 32 of the 512):  acc0 | accS | c (hi 16 | lo 16 per 32 channels) | x (hi 16 | lo 16).
+// Biases are products too: a constant shared-memory operand (1, 1, 0, ..) times a tile holding (hi(b'), lo(b'), 0, ..) per output
+// adds b' to the accumulator inside the tensor pipe, so the epilogue is relu + sign-bit mask + split only.
+// The decoder's image (weight / bias / ones tiles, small tables; built once per weight update) arrives by ONE-dimensional bulk TMA
+// (cp.async.bulk -> mbarrier complete_tx) while the first tile's gather is already running; tiles are drawn from a ticket counter.
 // Algebra (k_compose): a_{i+1} = W_{i+1} relu(a_i) + G_i c + b'_{i+1}, G_i = W_{i+1} Fc_i.  c stays in its columns for the whole
 // tile and its term joins each layer's product, so a layer's accumulator is rewritten in place (acc0 serves layers 0, 1, 2, 4;
 // accS collects the skip layer) -- 64 accumulator columns per tile instead of the 160 of decode_fwd_tc16.cu.
@@ -29,14 +33,16 @@ namespace nsb {
 namespace t5 {
 
 constexpr int TM = 128;                        // samples per tile (UMMA M)
-constexpr int NG = 3;                          // tile groups per CTA
+constexpr int NG = 4;                          // tile groups per CTA (the fine decoder uses three of them)
 constexpr int GTHREADS = 128;                  // compute threads per group: one per sample
 constexpr int CTHREADS = NG * GTHREADS;
 constexpr int THREADS = CTHREADS + 32 * NG;    // + one issuer warp per group
 constexpr int ACC0 = 0, ACCS = 32, CCOL = 64;  // tensor-memory columns inside a group
 __host__ __device__ constexpr int xcol(int C) { return CCOL + C; }
-__host__ __device__ constexpr int onecol(int C) { return CCOL + C + 32; }   // constant A operand (1, 1, 0, ...) of the bias products: 8 columns
-__host__ __device__ constexpr int gcols(int C) { return CCOL + C + 40; }
+__host__ __device__ constexpr int gcols(int C) { return CCOL + C + 32; }
+__host__ __device__ constexpr int ngroups(int C) { return 512 / gcols(C) < NG ? 512 / gcols(C) : NG; }
+// setmaxnreg moves registers inside the CTA's own launch allocation (640 threads x 96 = 61440): 512 x 112 + 128 x 32 = 61440
+constexpr int REGS_COMPUTE = 112, REGS_ISSUE = 32;
 constexpr int SCR_ROW = 36;                    // floats per row of the gather scratch (conflict-free 16-byte stores and loads)
 
 // composed weights (global, per decoder), layout of k_compose: G[4][32][C] | bp[5][32] | woc[4][C] | boc[4]
@@ -50,16 +56,18 @@ struct Smem {   // bytes; every UMMA tile starts on a multiple of 1024 B, rows a
     static constexpr int WH = WE + 3 * 64 * 128;                   // 4 x [32 rows]: W1, W2, W3 (hidden columns), W4
     static constexpr int G = WH + 4 * 32 * 128;                    // 4 x (C/32) x [32 rows]: G_i restricted to channel chunk cc at (i * C/32 + cc)
     static constexpr int BT = G + 4 * (C / 32) * 32 * 128;         // bias tile [64 rows]: k16 step 0 = b'_0 (rows 0-31) | b'_3 (rows 32-63), steps 1, 2, 3 = b'_1, b'_2, b'_4
-    static constexpr int BM = BT + 64 * 128;                       // Fourier matrix [3][96] fp32
+    static constexpr int ONE = BT + 64 * 128;                      // constant A operand of the bias products [128 rows]: halves 0, 1 = 1.0, rest 0
+    static constexpr int BM = ONE + 128 * 128;                     // Fourier matrix [3][96] fp32
     static constexpr int BP = BM + 3 * EMBP * 4;                   // b'[5][32]
     static constexpr int WO = BP + 5 * HID * 4;                    // Wo[4][32]
     static constexpr int WOC = WO + 4 * HID * 4;                   // (Wo Fc_4)[4][C]
     static constexpr int BOC = WOC + 4 * C * 4;                    // const[4]
     static constexpr int IMG = BOC + 16;                           // everything above is the decoder's image, prebuilt in global memory (k_build_t5img)
     static constexpr int SCR = IMG;                                // gather scratch: one [32][SCR_ROW] fp32 block per compute warp
-    static constexpr int BAR = SCR + (CTHREADS / 32) * 32 * SCR_ROW * 4;   // mbarriers: full[NG], done[NG]
-    static constexpr int TMEMPTR = BAR + 2 * NG * 8;
-    static constexpr int TOTAL = TMEMPTR + 16;
+    static constexpr int BAR = SCR + (CTHREADS / 32) * 32 * SCR_ROW * 4;   // mbarriers: full[NG], done[NG], image
+    static constexpr int TMEMPTR = BAR + (2 * NG + 1) * 8;
+    static constexpr int TICKET = TMEMPTR + 8;                     // [NG][2] tile drawn by a group's row 0 for its next round
+    static constexpr int TOTAL = TICKET + NG * 8;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +90,12 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GTHREADS + 32) : "memory"); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -150,6 +164,10 @@ __device__ void stage(uint8_t* sm, const float* __restrict__ flat, const float* 
         const __half l = __float2half_rn(b - __half2float(h));
         *reinterpret_cast<__half*>(sm + L::BT + chunk_off(r, hpos >> 3) + (hpos & 7) * 2) = kk == 0 ? h : kk == 1 ? l : __float2half_rn(0.0f);
     }
+    for (int idx = tid; idx < 128 * 32; idx += nthr) {              // ones operand: first word of every row = (1.0h, 1.0h)
+        const int r = idx / 32, wd = idx % 32;
+        *reinterpret_cast<uint32_t*>(sm + L::ONE + chunk_off(r, wd >> 2) + (wd & 3) * 4) = wd == 0 ? 0x3C003C00u : 0u;
+    }
     float* bm = reinterpret_cast<float*>(sm + L::BM);
     for (int i = tid; i < 3 * EMBP; i += nthr) { const int d = i / EMBP, c = i % EMBP; bm[i] = c < EMB ? flat[f.B + d * EMB + c] : 0.0f; }
     float* bp = reinterpret_cast<float*>(sm + L::BP);
@@ -174,27 +192,32 @@ __device__ __forceinline__ void issue3(uint32_t d, uint32_t a, uint64_t b, uint3
 }
 
 template <int C, int O>
-__device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta, int ncta) {
+__device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
     using L = Smem<C>;
-    constexpr int GCOLS = gcols(C), XCOL = xcol(C);
+    constexpr int GCOLS = gcols(C), XCOL = xcol(C), NGC = ngroups(C);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (P.P + TM - 1) / TM;
-    const uint32_t bar0 = smem_u32(sm + L::BAR);
+    const uint32_t bar0 = smem_u32(sm + L::BAR), bar_img = bar0 + 16 * NG;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::TMEMPTR);
+    volatile int* ticket = reinterpret_cast<volatile int*>(sm + L::TICKET);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm + L::TMEMPTR)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int s = 0; s < NG; ++s) { mbar_init(bar0 + 8 * s, GTHREADS); mbar_init(bar0 + 8 * NG + 8 * s, 1); }
+        mbar_init(bar_img, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
+        // the decoder's image: one-dimensional bulk TMA copies, completion counted in bytes on bar_img
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)L::IMG) : "memory");
+        const uint8_t* src = P.wimg_t5[dec];
+        for (int off = 0; off < L::IMG; off += 16384) {
+            const uint32_t n = (uint32_t)(L::IMG - off < 16384 ? L::IMG - off : 16384);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sm + off)), "l"(src + off), "r"(n), "r"(bar_img) : "memory");
+        }
     }
-    {   // the decoder's image (pre-split weight tiles, bias tile, small fp32 tables) was built once per weight update: 16-byte copies
-        const uint4* src = reinterpret_cast<const uint4*>(P.wimg_t5[dec]);
-        uint4* dst = reinterpret_cast<uint4*>(sm);
-        for (int i = tid; i < L::IMG / 16; i += THREADS) dst[i] = __ldg(src + i);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if ((tid & 127) == 0 && (warp >> 2) < NGC) ticket[2 * (warp >> 2)] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // first tile of every group
     fence_before();
     __syncthreads();
     fence_after();
@@ -203,21 +226,20 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
 
     if (warp < NG * 4) {
         // ------------------------------------------------------------------ compute threads: one per sample (= TMEM lane)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
         const int grp = warp >> 2, wq = warp & 3, row = (wq << 5) | lane, q = lane >> 2, t = lane & 3;
+        if (grp < NGC) {
         const uint32_t tm = tmem + grp * GCOLS + ((uint32_t)(wq * 32) << 16);
         const uint32_t full = bar0 + 8 * grp, done = bar0 + 8 * NG + 8 * grp;
         const float* bm = reinterpret_cast<const float*>(sm + L::BM);
-        const float* bp = reinterpret_cast<const float*>(sm + L::BP);
         const float* wo = reinterpret_cast<const float*>(sm + L::WO);
         const float* woc = reinterpret_cast<const float*>(sm + L::WOC);
         const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
         float* scr = reinterpret_cast<float*>(sm + L::SCR) + warp * 32 * SCR_ROW;
         uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
-        {   // constant A operand of the bias products: k = 0, 1 -> 1.0 (packed f16x2 0x3C003C00), k = 2..15 -> 0
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"r"(tm + onecol(C)), "r"(0x3C003C00u), "r"(0u) : "memory");
-            tmem_st_wait();
-        }
-        for (int tile = cta * NG + grp; tile < ntiles; tile += ncta * NG) {
+        bool image_ready = false;
+        for (int round = 0, tile = ticket[2 * grp]; tile < ntiles; ++round) {
+            if (row == 0) ticket[2 * grp + ((round + 1) & 1)] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // next round's tile, read after the group barrier
             const int s = tile * TM + row;
             bool active = s < P.P;
             float p[3] = {0.f, 0.f, 0.f};
@@ -236,8 +258,6 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
             // leaves its 8 channels in the scratch row of that sample; the owner lane then reads its whole row, adds the
             // grid-feature part of the output layer and moves the row to tensor memory as the A operand of every G_i c product.
             float outc[NO];
-#pragma unroll
-            for (int o = 0; o < NO; ++o) outc[o] = boc[o];
 #pragma unroll
             for (int cc = 0; cc < C / 32; ++cc) {
                 const GridView& G = P.grid[cc == 0 ? dec : 1];          // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
@@ -265,6 +285,11 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
                     c[4 * i] = v4.x; c[4 * i + 1] = v4.y; c[4 * i + 2] = v4.z; c[4 * i + 3] = v4.w;
                 }
                 __syncwarp();                                           // the scratch is rewritten by the next chunk / tile
+                if (!image_ready) { mbar_wait(bar_img, 0); image_ready = true; }   // the first gather ran under the image's TMA copy
+                if (cc == 0) {
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) outc[o] = boc[o];
+                }
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
                     float acc = outc[o];
@@ -300,7 +325,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
                 mbar_arrive(full);
                 ++step;
             }
-            // ---- five layers: read the accumulator, bias + relu (+ mask), hand u_i back as the next A operand
+            // ---- five layers: read the accumulator (bias is already in), relu (+ mask), hand u_i back as the next A operand
 #pragma unroll 1
             for (int i = 0; i < 5; ++i) {
                 mbar_wait(done, (step - 1) & 1);
@@ -340,34 +365,48 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec, int cta
                 }
             }
             fence_before();       // the accumulator reads above are ordered before the next tile's first arrive
+            group_sync(grp);      // row 0's ticket for the next round is visible to the group and its issuer
+            tile = ticket[2 * grp + ((round + 1) & 1)];
         }
-    } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer of one tile group
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer of one tile group (lane 0 issues)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ISSUE));
         const int grp = warp - NG * 4;
+        if (grp < NGC) {
         const uint32_t tm = tmem + grp * GCOLS;
         const uint32_t full = bar0 + 8 * grp, done = bar0 + 8 * NG + 8 * grp;
-        const uint32_t sbase = smem_u32(sm);
         constexpr uint32_t I32 = make_idesc(128, 32), I64 = make_idesc(128, 64);
         constexpr int NC = C / 32;
+        // every shared-memory descriptor is the image's base descriptor plus a byte offset >> 4 (few live registers: the issuer
+        // runs on 32 registers per thread)
+        const uint64_t dbase = make_desc(smem_u32(sm));
         uint32_t step = 0;
-        for (int tile = cta * NG + grp; tile < ntiles; tile += ncta * NG) {
-            for (int j = 0; j < 3; ++j) {           // [acc0 | accS] (+)= e_j [W0 ; W3E]_j^T ; the skip layer's grid-feature term rides on the first chunk
-                mbar_wait(full, step & 1); fence_after();
-                issue3(tm + ACC0, tm + XCOL, make_desc(sbase + L::WE + j * 8192), I64, j == 0);
-                if (j == 0) mma_ts(tm + ACC0, tm + onecol(C), make_desc(sbase + L::BT), I64, 1u);                       // + b'_0 | b'_3
-                if (j == 0)
-                    for (int cc = 0; cc < NC; ++cc) issue3(tm + ACCS, tm + CCOL + 32 * cc, make_desc(sbase + L::G + (2 * NC + cc) * 4096), I32, false);
-                mma_commit(done); ++step;
-            }
-            for (int l = 0; l < 4; ++l) {           // layer l+1: acc = u_l W_{l+1}^T + c G_l^T  (layer 3 accumulates into accS, whose c term is in)
-                mbar_wait(full, step & 1); fence_after();
-                const uint32_t d = tm + (l == 2 ? ACCS : ACC0);
-                issue3(d, tm + XCOL, make_desc(sbase + L::WH + l * 4096), I32, l != 2);
-                if (l != 2) mma_ts(d, tm + onecol(C), make_desc(sbase + L::BT) + 2 * (l == 3 ? 3 : l + 1), I32, 1u);    // + b'_{l+1}
-                if (l != 2)
-                    for (int cc = 0; cc < NC; ++cc) issue3(d, tm + CCOL + 32 * cc, make_desc(sbase + L::G + (l * NC + cc) * 4096), I32, false);
-                mma_commit(done); ++step;
-            }
+        mbar_wait(bar_img, 0);
+        for (int round = 0, tile = ticket[2 * grp]; tile < ntiles; ++round) {
+            if (lane == 0) {
+#pragma unroll 1
+                for (int j = 0; j < 3; ++j) {           // [acc0 | accS] (+)= e_j [W0 ; W3E]_j^T
+                    mbar_wait(full, step & 1); fence_after();
+                    issue3(tm + ACC0, tm + XCOL, dbase + (uint64_t)((L::WE + j * 8192) >> 4), I64, j == 0);
+                    if (j == 0) mma_ss(tm + ACC0, dbase + (L::ONE >> 4), dbase + (L::BT >> 4), I64, 1u);                 // + b'_0 | b'_3
+                    mma_commit(done); ++step;
+                }
+#pragma unroll 1
+                for (int l = 0; l < 4; ++l) {           // layer l+1: acc = u_l W_{l+1}^T + c G_l^T + b'  (layer 3 accumulates into accS)
+                    mbar_wait(full, step & 1); fence_after();
+                    const uint32_t d = tm + (l == 2 ? ACCS : ACC0);
+                    issue3(d, tm + XCOL, dbase + (uint64_t)((L::WH + l * 4096) >> 4), I32, l != 2);
+                    if (l != 2) mma_ss(d, dbase + (L::ONE >> 4), dbase + (uint64_t)((L::BT >> 4) + 2 * (l == 3 ? 3 : l + 1)), I32, 1u);   // + b'_{l+1}
+#pragma unroll 1
+                    for (int cc = 0; cc < NC; ++cc) issue3(d, tm + CCOL + 32 * cc, dbase + (uint64_t)((L::G + (l * NC + cc) * 4096) >> 4), I32, false);
+                    mma_commit(done); ++step;
+                }
+            } else step += 7;
+            __syncwarp();
+            group_sync(grp);
+            tile = ticket[2 * grp + ((round + 1) & 1)];
+        }
         }
     }
     fence_before();
@@ -381,10 +420,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fwd_t5(const DecodeParams
     int dec = 1;
 #pragma unroll
     for (int d = 2; d < 4; ++d) if ((int)blockIdx.x >= P.cta_begin[d]) dec = d;
-    const int cta = blockIdx.x - P.cta_begin[dec], ncta = P.cta_begin[dec + 1] - P.cta_begin[dec];
-    if (dec == 1) run_decoder<32, 1>(P, sm, 1, cta, ncta);
-    else if (dec == 2) run_decoder<64, 1>(P, sm, 2, cta, ncta);
-    else run_decoder<32, 4>(P, sm, 3, cta, ncta);
+    if (dec == 1) run_decoder<32, 1>(P, sm, 1);
+    else if (dec == 2) run_decoder<64, 1>(P, sm, 2);
+    else run_decoder<32, 4>(P, sm, 3);
 }
 
 // Builds the shared-memory image of decoder d (blockIdx.y = d - 1) in global memory; run after k_compose whenever the weights change.
