@@ -63,11 +63,12 @@ struct Smem {   // bytes; every UMMA tile starts on a multiple of 1024 B, rows a
     static constexpr int WOC = WO + 4 * HID * 4;                   // (Wo Fc_4)[4][C]
     static constexpr int BOC = WOC + 4 * C * 4;                    // const[4]
     static constexpr int IMG = BOC + 16;                           // everything above is the decoder's image, prebuilt in global memory (k_build_t5img)
-    static constexpr int SCR = IMG;                                // gather scratch: one [32][SCR_ROW] fp32 block per compute warp
-    static constexpr int BAR = SCR + (CTHREADS / 32) * 32 * SCR_ROW * 4;   // mbarriers: full[NG], done[NG], image
+    static constexpr int SCR = IMG;                                // gather scratch: C/32 blocks of [32][SCR_ROW] fp32 per active compute warp
+    static constexpr int SCRW = (C / 32) * 32 * SCR_ROW * 4;       // bytes per warp
+    static constexpr int BAR = SCR + ngroups(C) * 4 * SCRW;        // mbarriers: full[NG], done[NG], image
     static constexpr int TMEMPTR = BAR + (2 * NG + 1) * 8;
-    static constexpr int TICKET = TMEMPTR + 8;                     // [NG][2] tile drawn by a group's row 0 for its next round
-    static constexpr int TOTAL = TICKET + NG * 8;
+    static constexpr int TICKET = TMEMPTR + 8;                     // [NG][3] ring of tiles drawn by a group's row 0 (current, next, the one after)
+    static constexpr int TOTAL = TICKET + NG * 16;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -217,7 +218,10 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                          ::"r"(smem_u32(sm + off)), "l"(src + off), "r"(n), "r"(bar_img) : "memory");
         }
     }
-    if ((tid & 127) == 0 && (warp >> 2) < NGC) ticket[2 * (warp >> 2)] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // first tile of every group
+    if ((tid & 127) == 0 && (warp >> 2) < NGC) {                    // the first two tiles of every group
+        ticket[4 * (warp >> 2)] = (int)atomicAdd(P.tile_ctr + dec, 1ull);
+        ticket[4 * (warp >> 2) + 1] = (int)atomicAdd(P.tile_ctr + dec, 1ull);
+    }
     fence_before();
     __syncthreads();
     fence_after();
@@ -235,60 +239,68 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         const float* wo = reinterpret_cast<const float*>(sm + L::WO);
         const float* woc = reinterpret_cast<const float*>(sm + L::WOC);
         const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
-        float* scr = reinterpret_cast<float*>(sm + L::SCR) + warp * 32 * SCR_ROW;
-        uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
-        bool image_ready = false;
-        for (int round = 0, tile = ticket[2 * grp]; tile < ntiles; ++round) {
-            if (row == 0) ticket[2 * grp + ((round + 1) & 1)] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // next round's tile, read after the group barrier
+        float* scr = reinterpret_cast<float*>(sm + L::SCR + warp * L::SCRW);
+        // position of this thread's sample in tile `tile` (zero, and inactive, past the end or on a filtered ray)
+        auto load_point = [&](int tile, float (&pp)[3]) -> bool {
             const int s = tile * TM + row;
-            bool active = s < P.P;
-            float p[3] = {0.f, 0.f, 0.f};
-            if (active) {
-                if (P.pts) { p[0] = P.pts[3 * (size_t)s]; p[1] = P.pts[3 * (size_t)s + 1]; p[2] = P.pts[3 * (size_t)s + 2]; }
-                else {
-                    const int ray = s / P.S;
-                    const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
-                    const float z = P.z[s];
+            pp[0] = pp[1] = pp[2] = 0.0f;
+            if (tile >= ntiles || s >= P.P) return false;
+            if (P.pts) { pp[0] = P.pts[3 * (size_t)s]; pp[1] = P.pts[3 * (size_t)s + 1]; pp[2] = P.pts[3 * (size_t)s + 2]; return true; }
+            const int ray = s / P.S;
+            const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
+            const float z = P.z[s];
+            if (!ok) return false;                                       // sin(0 . B) = 0: an inactive row contributes exact zeros
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(P.rays_o[3 * ray + a], __fmul_rn(P.rays_d[3 * ray + a], z));   // Renderer.cpp:121
-                    if (!ok) { active = false; p[0] = p[1] = p[2] = 0.0f; }      // sin(0 . B) = 0: an inactive row contributes exact zeros
-                }
+            for (int a = 0; a < 3; ++a) pp[a] = __fadd_rn(P.rays_o[3 * ray + a], __fmul_rn(P.rays_d[3 * ray + a], z));   // Renderer.cpp:121
+            return true;
+        };
+        // Quad-cooperative gather, pass r of channel chunk cc: the quad q of this warp serves sample 8r + q of the warp and leaves
+        // its 8 channels in the scratch row of that sample (a quad fetches a voxel's 128-byte line in one wavefront).
+        auto gather_pass = [&](const float (&pp)[3], bool act_lane, int cc, int r) {
+            const GridView& G = P.grid[cc == 0 ? dec : 1];              // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
+            const int j = 8 * r + q;
+            float pj[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) pj[a] = __shfl_sync(0xffffffffu, pp[a], j);
+            const bool act = __shfl_sync(0xffffffffu, act_lane ? 1 : 0, j) != 0;
+            float c8[8];
+            if (act) gather8(G, P.bnd, pj, t, c8);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c8[i] = 0.0f;
             }
-            // ---- grid features.  Quad-cooperative gather: in pass r the quad q of this warp serves sample 8r + q of the warp and
-            // leaves its 8 channels in the scratch row of that sample; the owner lane then reads its whole row, adds the
-            // grid-feature part of the output layer and moves the row to tensor memory as the A operand of every G_i c product.
+            float* dst = scr + cc * 32 * SCR_ROW + j * SCR_ROW + 8 * t;
+            *reinterpret_cast<float4*>(dst) = make_float4(c8[0], c8[1], c8[2], c8[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(c8[4], c8[5], c8[6], c8[7]);
+        };
+        uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
+        int tile = ticket[4 * grp];
+        float p[3];
+        bool active = load_point(tile, p);
+        if (tile < ntiles) {   // the first tile's gather runs under the image's TMA copy; later tiles are gathered during the previous tile's layer phase
+#pragma unroll
+            for (int cc = 0; cc < C / 32; ++cc)
+#pragma unroll 1
+                for (int r = 0; r < 4; ++r) gather_pass(p, active, cc, r);
+        }
+        mbar_wait(bar_img, 0);
+        for (int round = 0; tile < ntiles; ++round) {
+            if (row == 0) ticket[4 * grp + (round + 2) % 3] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // read after the group barrier of this round
+            const int s = tile * TM + row;
+            const int tile_next = ticket[4 * grp + (round + 1) % 3];
+            // ---- grid features: the owner lane reads its row of the scratch, adds the grid-feature part of the output layer and
+            // moves the row to tensor memory as the A operand of every G_i c product
             float outc[NO];
 #pragma unroll
+            for (int o = 0; o < NO; ++o) outc[o] = boc[o];
+            __syncwarp();
+#pragma unroll
             for (int cc = 0; cc < C / 32; ++cc) {
-                const GridView& G = P.grid[cc == 0 ? dec : 1];          // fine decoder: cat(fine, middle) (MLP.cpp:79-84)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int j = 8 * r + q;
-                    float pj[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) pj[a] = __shfl_sync(0xffffffffu, p[a], j);
-                    const bool act = __shfl_sync(0xffffffffu, active ? 1 : 0, j) != 0;
-                    float c8[8];
-                    if (act) gather8(G, P.bnd, pj, t, c8);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) c8[i] = 0.0f;
-                    }
-                    *reinterpret_cast<float4*>(scr + j * SCR_ROW + 8 * t) = make_float4(c8[0], c8[1], c8[2], c8[3]);
-                    *reinterpret_cast<float4*>(scr + j * SCR_ROW + 8 * t + 4) = make_float4(c8[4], c8[5], c8[6], c8[7]);
-                }
-                __syncwarp();
                 float c[32];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(scr + lane * SCR_ROW + 4 * i);
+                    const float4 v4 = *reinterpret_cast<const float4*>(scr + cc * 32 * SCR_ROW + lane * SCR_ROW + 4 * i);
                     c[4 * i] = v4.x; c[4 * i + 1] = v4.y; c[4 * i + 2] = v4.z; c[4 * i + 3] = v4.w;
-                }
-                __syncwarp();                                           // the scratch is rewritten by the next chunk / tile
-                if (!image_ready) { mbar_wait(bar_img, 0); image_ready = true; }   // the first gather ran under the image's TMA copy
-                if (cc == 0) {
-#pragma unroll
-                    for (int o = 0; o < NO; ++o) outc[o] = boc[o];
                 }
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -302,6 +314,9 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                 }
                 store_operand(tm + CCOL + 32 * cc, c);                  // the previous tile's last product has been waited for (layer 4)
             }
+            __syncwarp();                                               // the scratch is rewritten by the next tile's gather below
+            float pn[3];
+            const bool active_n = load_point(tile_next, pn);
             // ---- Fourier features, 32 per handshake, this thread's own sample
 #pragma unroll 1
             for (int j = 0; j < 3; ++j) {
@@ -346,6 +361,10 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                     fence_before();
                     mbar_arrive(full);
                     ++step;
+                    if (tile_next < ntiles) {                            // the next tile's gather, pass i, fills the wait for this layer's products
+#pragma unroll
+                        for (int cc = 0; cc < C / 32; ++cc) gather_pass(pn, active_n, cc, i);
+                    }
                 } else {
                     float out[NO];
 #pragma unroll
@@ -365,8 +384,9 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                 }
             }
             fence_before();       // the accumulator reads above are ordered before the next tile's first arrive
-            group_sync(grp);      // row 0's ticket for the next round is visible to the group and its issuer
-            tile = ticket[2 * grp + ((round + 1) & 1)];
+            group_sync(grp);      // row 0's ticket (two rounds ahead) is visible to the group and its issuer
+            tile = tile_next; active = active_n;
+            p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
         }
         }
     } else {
@@ -383,7 +403,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         const uint64_t dbase = make_desc(smem_u32(sm));
         uint32_t step = 0;
         mbar_wait(bar_img, 0);
-        for (int round = 0, tile = ticket[2 * grp]; tile < ntiles; ++round) {
+        for (int round = 0, tile = ticket[4 * grp]; tile < ntiles; ++round) {
             if (lane == 0) {
 #pragma unroll 1
                 for (int j = 0; j < 3; ++j) {           // [acc0 | accS] (+)= e_j [W0 ; W3E]_j^T
@@ -405,7 +425,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
             } else step += 7;
             __syncwarp();
             group_sync(grp);
-            tile = ticket[2 * grp + ((round + 1) & 1)];
+            tile = ticket[4 * grp + (round + 1) % 3];
         }
         }
     }
