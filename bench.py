@@ -43,6 +43,7 @@ FIRST_COLOR_ITER = 37                      # stage_of_iter: it <= 24 middle, it 
 FLOP_FWD_RAY = 51653 * 2 * 48              # 4.96 MFLOP: three decoders forward
 FLOP_BWD_COLOR_RAY = 49367 * 2 * 48        # 4.74 MFLOP: colour-stage backward (grids + colour decoder wgrad)
 FLOP_BWD_GEOM_RAY = 18496 * 2 * 48         # 1.78 MFLOP: geometry-stage backward (middle + fine data grads)
+FLOP_WGRAD_RAY = 15575 * 2 * 48            # 1.50 MFLOP: colour-decoder weight gradient (one MAC per forward MAC of that decoder), part of FLOP_BWD_COLOR_RAY
 GATHER_BYTES_RAY = 3 * 8 * 32 * 4 * 48     # 147 456 B of voxel-corner lines per ray and direction
 
 
@@ -475,15 +476,25 @@ def run_ours(args, rank, world, local_rank):
             e.set_profiling(profile)
             t0 = time.monotonic()
             evs = []
+            kms_stage = {"geometry": {}, "color": {}}          # per-kernel device time split by iteration kind (profile pass only)
+            prev = None
             for it in its:
                 flush.zero_()                                  # L2 flush between timed steps (not timed)
                 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
                 a.record(ext); run_step(it); b.record(ext)
                 evs.append((a, b))
+                if profile:                                    # cumulative since set_profiling(1): difference per step (synchronises; this pass is not `value`)
+                    cum = e.kernel_ms()
+                    st = kms_stage["color" if it >= FIRST_COLOR_ITER else "geometry"]
+                    for k_, v_ in cum.items():
+                        st[k_] = st.get(k_, 0.0) + v_ - (prev[k_] if prev else 0.0)
+                    prev = cum
             barrier()
             t1 = time.monotonic()
             step_ms = [a.elapsed_time(b) for a, b in evs]
             kms = e.kernel_ms() if profile else None
+            if profile:
+                kms = dict(kms, by_stage=kms_stage)
             launches = e.launch_count()
             e.set_profiling(False)
         return step_ms, kms, launches, (t0, t1)
@@ -553,25 +564,31 @@ def run_ours(args, rank, world, local_rank):
         n_geom = K - n_color
         frac_in = float(np.mean(n_inside[n_inside > 0])) / n_global if np.any(n_inside > 0) else 1.0
         rays_rank = RAYS_PER_GPU * frac_in                 # rays that survive the inside filter, per rank and step
-        bwd_flop = (n_color * FLOP_BWD_COLOR_RAY + n_geom * FLOP_BWD_GEOM_RAY) * rays_rank
-        fwd_flop = K * FLOP_FWD_RAY * rays_rank
-        bwd_s = (kms["decode_bwd"] + kms["wgrad"]) * 1e-3
-        fwd_s = kms["decode_fwd"] * 1e-3
         traffic = load_profile_json("traffic.json")        # dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel VARIANT (ncu --set full)
+        by = kms.pop("by_stage")
+        tc = os.environ.get("NSB_TCGEN05", "3")
+        fwd_geo = {"3": "k_decode_fwd_t5", "2": "k_decode_fwd_tc16", "1": "k_decode_fwd_tc"}.get(tc, "k_decode_fwd")
+        stash = os.environ.get("NSB_WGRAD_STASH", "1") != "0"
+        fwd_col = "k_decode_fwd" if stash else fwd_geo      # a colour iteration that stashes activations for k_wgrad runs the warp-MMA forward
 
-        def mix(name):
-            g, c_ = traffic.get(name + "<geometry>"), traffic.get(name + "<color>")
-            if g is None or c_ is None:
+        def entry(name, stage, key, n_it, flop_ray, extra=None):
+            ms = by[stage].get(key, 0.0)
+            if n_it == 0 or ms <= 0:
                 return None
-            return (n_geom * g + n_color * c_) / K
-        fwd_name = "k_decode_fwd_tc" if os.environ.get("NSB_TCGEN05", "0") not in ("", "0") else "k_decode_fwd"
-        kern = {fwd_name: {"achieved": fwd_flop / fwd_s * 1e-12 if fwd_s > 0 else 0.0, "avg_launch_ms": kms["decode_fwd"] / K, "flop_per_launch": fwd_flop / K,
-                           "gather_gbs": K * GATHER_BYTES_RAY * rays_rank / fwd_s * 1e-9 if fwd_s > 0 else 0.0, "traffic": mix(fwd_name)},
-                "k_decode_bwd(+wgrad)": {"achieved": bwd_flop / bwd_s * 1e-12 if bwd_s > 0 else 0.0, "avg_launch_ms": (kms["decode_bwd"] + kms["wgrad"]) / K, "flop_per_launch": bwd_flop / K,
-                                         "scatter_gbs": K * GATHER_BYTES_RAY * rays_rank / (kms["decode_bwd"] * 1e-3) * 1e-9 if kms["decode_bwd"] > 0 else 0.0,
-                                         "traffic": mix("k_decode_bwd")}}
-        dom = fwd_name if fwd_s >= bwd_s else "k_decode_bwd(+wgrad)"       # the dominant kernel of the step
-        ach = kern[dom]["achieved"]
+            d = {"kernel": name, "iterations": stage, "launches": n_it, "avg_launch_ms": ms / n_it, "total_ms": ms,
+                 "flop_per_launch": flop_ray * rays_rank, "achieved": flop_ray * rays_rank * n_it / (ms * 1e-3) * 1e-12,
+                 "traffic": traffic.get("%s<%s>" % (name, stage))}
+            if extra:
+                d[extra] = GATHER_BYTES_RAY * (2.0 / 3.0 if stage == "geometry" and extra == "scatter_gbs" else 1.0) * rays_rank * n_it / (ms * 1e-3) * 1e-9
+            return d
+        ents = [entry(fwd_geo, "geometry", "decode_fwd", n_geom, FLOP_FWD_RAY, "gather_gbs"), entry(fwd_col, "color", "decode_fwd", n_color, FLOP_FWD_RAY, "gather_gbs"),
+                entry("k_decode_bwd", "geometry", "decode_bwd", n_geom, FLOP_BWD_GEOM_RAY, "scatter_gbs"),
+                entry("k_decode_bwd", "color", "decode_bwd", n_color, FLOP_BWD_COLOR_RAY - FLOP_WGRAD_RAY, "scatter_gbs"),
+                entry("k_wgrad", "color", "wgrad", n_color, FLOP_WGRAD_RAY)]
+        ents = [x for x in ents if x]
+        kern = {"%s<%s>" % (x["kernel"], x["iterations"]): x for x in ents}
+        dom = max(ents, key=lambda x: x["total_ms"])         # the single kernel with the largest share of the K timed steps
+        ach = dom["achieved"]
         gat = load_profile_json("gather_ncu.json")        # l1tex / lts / dram bytes of k_gather_only per launch (ncu), measured L2 gather peak
         gs = {"kernel": "k_gather_only", "ms": gather_ms, "rays": int(n_global // world),
               "algorithmic_gbs": GATHER_BYTES_RAY * RAYS_PER_GPU / (gather_ms * 1e-3) * 1e-9 if gather_ms > 0 else 0.0,
@@ -582,13 +599,15 @@ def run_ours(args, rank, world, local_rank):
                        "l2_gbs": gat["lts_t_bytes"] / (gather_ms * 1e-3) * 1e-9, "l2_peak_gbs_measured": gat.get("l2_gather_peak_gbs"),
                        "frac_of_l2_peak": gat["lts_t_bytes"] / (gather_ms * 1e-3) * 1e-9 / gat["l2_gather_peak_gbs"] if gat.get("l2_gather_peak_gbs") else None,
                        "l1_gbs": (gat.get("l1tex_t_bytes") or 0) / (gather_ms * 1e-3) * 1e-9, "source": gat.get("_source")})
-        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": kern[dom]["traffic"], "traffic_by_variant": {k: v for k, v in traffic.items() if not k.startswith("_")},
+        roof = {"bound": "tensor", "kernel": "%s<%s>" % (dom["kernel"], dom["iterations"]), "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": dom["traffic"], "traffic_by_variant": {k: v for k, v in traffic.items() if not k.startswith("_")},
                 "peak_source": pk["source"] + " bf16 dense (sustained, kernel timed inside the step)",
                 "note": "algorithmic FLOPs (SURVEY 8-d: 2 x MACs of the three decoders x 48 samples x rays surviving the inside filter) / CUDA-event time of the kernel "
-                        "(second pass over the same K steps, kernels enqueued one by one); the arithmetic is the fp32-grade fp16 two-way split (3 tensor-core MMAs per "
-                        "product, measured warp-MMA ceiling 556 TFLOP/s), so the design ceiling is 185 TFLOP/s algorithmic",
-                "launches": K, "avg_launch_ms": kern[dom]["avg_launch_ms"], "kernels": kern,
+                        "(second pass over the same K steps, kernels enqueued one by one, split by iteration kind); the arithmetic is the fp32-grade fp16 two-way split "
+                        "(3 tensor-core MMAs per product).  k_decode_fwd_t5 issues them as tcgen05.mma kind::f16 with operands in tensor memory (tensor pipe ~20 % busy: "
+                        "the kernel is bound by the per-value ALU work -- sines, fp16 splits, relu, gather -- not by the tensor pipe); the warp-MMA kernels (backward, "
+                        "stash forward, wgrad) are bound by T(HMMA) + T(ALU), legacy HMMA ceiling 556 TFLOP/s / 3 = 185 TFLOP/s algorithmic",
+                "launches": dom["launches"], "avg_launch_ms": dom["avg_launch_ms"], "kernels": kern,
                 "kernel_ms_total": kms, "ms_per_step_eager": float(np.mean(step_ms_eager)), "grid_sampling": gs}
         cpu = None
         try:
@@ -613,7 +632,7 @@ def run_ours(args, rank, world, local_rank):
                "config": {"workload": "mapper_iteration_5000rays_60iters_keyframe", "rays_per_gpu": RAYS_PER_GPU, "global_rays": n_global,
                           "samples_per_ray": 48, "frames": N_FRAMES, "schedule": "timed step k = iteration floor(k*60/K) (K<60) or k%60 of optimize_map (37 geometry + 23 colour)",
                           "launch": "one cudaGraphLaunch per iteration (device-resident iteration state)",
-                          "mma": "fp16 two-way split (3 products) on mma.sync m16n8k16, fp32 accumulate: fp32-grade", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
+                          "mma": "fp16 two-way split (3 products), fp32 accumulate: fp32-grade; forward on tcgen05.mma kind::f16 (operands in tensor memory), backward / wgrad on mma.sync m16n8k16", "l2": "256 MiB flush write between timed steps", "parallelism": ("rays sharded x%d, " % world) + ("single GPU" if world == 1 else "fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory" if args.comm == "p2p" else "NCCL all-reduce of grads + Adam"),
                           "raydir": "pinhole (library default)", "inside_fraction": frac_in},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "tracking": tracking, "configs": configs,
                "parity": parity, "p2p_exchange": p2p_times,

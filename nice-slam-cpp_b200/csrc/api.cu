@@ -159,7 +159,7 @@ struct nsb_ctx {
                                  // trained changes every iteration but runs on the plain image while its stash is needed)
     unsigned long long* tile_ctr = nullptr;          // [8] ticket counters of the decoder kernels' tile scheduler: [0..3] forward,
                                                      // [4..7] backward; cleared on the device by the kernel preceding each decoder launch
-    int use_tc = 0;              // tcgen05 forward kernel (NSB_TCGEN05 env, 3xTF32 precision only)
+    int use_tc = 3;              // forward decoder kernel (NSB_TCGEN05 env; fp32-grade precision only): 3 = decode_fwd_t5.cu (default), 0 = warp MMA
     unsigned long long* dbg = nullptr;   // 32 cycle counters (NSB_TC_TIMING builds)
     float* scratch_ncdhw = nullptr; size_t scratch_n = 0;
     int last_n = 0, last_S = 0;
@@ -466,7 +466,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
     for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_t5[d], t5_img_bytes(d))); }
-    { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 0; }
+    { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 3; }   // forward decoders: 3 = tcgen05, operands in tensor memory (default); 0 = warp MMA; 1, 2 = earlier tcgen05 generations
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
     CK(dalloc(&ctx->tile_ctr, 8)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -842,7 +842,9 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         float w[4]; stage_decoders(stage, w);
         if (P.stash) { w[1] = 700; w[2] = 972; w[3] = 860; }   // the colour decoder also writes its activations to the wgrad stash (measured split, tools/sweep_split.sh)
         env_weights("NSB_SPLIT_FWD", w);
-        const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && P.stash == nullptr;
+        // the stash-free weight-gradient kernel reads the warp-MMA forward's fragment-packed relu masks
+        const bool fused_wg = train && stash_fwd && stage == NSB_COLOR && !ctx->wg_stash;
+        const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && P.stash == nullptr && !fused_wg;
         if (tc_ok) {
             // tcgen05 path: one 320-thread CTA per SM, per-sample mask words, composed weights refreshed when stale
             int need = 0;
