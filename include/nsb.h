@@ -268,11 +268,12 @@ int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int rank, int wor
  * the reference batch element that ray i of the rendered order is, and its frame.  Rank r renders rays [r*n/world, (r+1)*n/world). */
 int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, int i, int* frame);
 int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world);
-/* Timing of the fused exchange kernel, stamped on the device with %globaltimer: out5 = {last wait-for-peers us, last kernel us,
- * mean wait us, mean kernel us, exchanges averaged}; reset != 0 clears the sums.  wait = barrier 1 (the slowest rank's backward),
+/* Timing of the fused exchange kernel, stamped on the device with %globaltimer: out8 = {last wait-for-peers us, last kernel us,
+ * mean wait us, mean kernel us, exchanges averaged, mean exchanged range in bytes, NVLink bytes per direction and rank under the
+ * (W-1)/W model, GB/s per direction over kernel - wait}; reset != 0 clears the sums.  wait = barrier 1 (the slowest rank's backward),
  * kernel - wait = reduce-scatter + Adam + all-gather + barrier 2.  All ranks must issue the same call sequence: a barrier that
  * waits longer than NSB_P2P_TIMEOUT_MS (default 20000) gives up and the next synchronising mapping call returns an error. */
-int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out5, int reset);
+int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out8, int reset);
 
 /* ---- instrumentation ----------------------------------------------------------------------------------- */
 /* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */

@@ -524,9 +524,11 @@ class Engine:
 
     def p2p_times(self, reset=False):
         """Device-stamped timing of the fused exchange kernel (us): wait for the slowest rank vs the exchange itself."""
-        o = (C.c_double * 5)()
+        o = (C.c_double * 8)()
         self._ck(self.lib.nsb_comm_p2p_stats(self.h, o, int(reset)))
-        return {"last_wait_us": o[0], "last_kernel_us": o[1], "mean_wait_us": o[2], "mean_kernel_us": o[3], "mean_exchange_us": o[3] - o[2], "exchanges": int(o[4])}
+        return {"last_wait_us": o[0], "last_kernel_us": o[1], "mean_wait_us": o[2], "mean_kernel_us": o[3], "mean_exchange_us": o[3] - o[2], "exchanges": int(o[4]),
+                "mean_range_bytes": o[5], "nvlink_bytes_per_direction_model": o[6], "nvlink_gbs_per_direction": o[7],
+                "model": "a rank reads its 1/W slice of the exchanged range from W-1 peers and writes the updated slice to W-1 peers: (W-1)/W of the range per direction"}
 
     def bench_gather(self, reps=20):
         ms = C.c_float(0)

@@ -182,6 +182,8 @@ struct nsb_ctx {
     // comm
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // colour iterations: the stashing colour decoder runs beside the tcgen05 forward
+    int split_color_sms = 65;    // SMs given to the colour decoder's warp-MMA forward in that split (NSB_SPLIT_COLOR_SMS; 0 = one warp-MMA launch)
     bool ar_request = false, ar_overlapped = false;
     // peer-memory optimiser step (nsb_comm_p2p_import): every rank's gradient / parameter arena and flag block, opened through CUDA IPC
     bool p2p = false; uint32_t* p2p_flags = nullptr;
@@ -420,6 +422,9 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_bwd, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    { const char* e = getenv("NSB_SPLIT_COLOR_SMS"); if (e) ctx->split_color_sms = atoi(e); }
     for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
     auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
@@ -510,6 +515,9 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     if (c->ev_bwd) cudaEventDestroy(c->ev_bwd);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -845,7 +853,29 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         // the stash-free weight-gradient kernel reads the warp-MMA forward's fragment-packed relu masks
         const bool fused_wg = train && stash_fwd && stage == NSB_COLOR && !ctx->wg_stash;
         const bool tc_ok = ctx->use_tc && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && P.stash == nullptr && !fused_wg;
-        if (tc_ok) {
+        // Colour iteration with a weight-gradient stash: decoders 1 and 2 run on the tcgen05 kernel while the stashing colour
+        // decoder runs on the warp-MMA kernel, side by side on disjoint SMs (both kernels take a whole SM per CTA), forked
+        // onto a second stream and joined before the composite -- capturable, so it lives inside the iteration's graph.
+        const bool split_fwd = ctx->use_tc == 3 && c.precision == NSB_PREC_FP32_GRADE && stage == NSB_COLOR && P.stash != nullptr && train &&
+                               ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
+        if (split_fwd) {
+            DecodeParams PA = P, PB = P;
+            PA.stash = nullptr;
+            for (int d = 0; d < 4; ++d) PA.comp[d] = ctx->comp[d];
+            PA.mask_layout = 0x6; PA.mask_stride = n * S; PA.tile_ctr = ctx->tile_ctr;
+            float wa[4] = {0, 700.f, 1300.f, 0}; env_weights("NSB_SPLIT_FWD_T5", wa); wa[3] = 0;
+            partition(ctx->n_sm - ctx->split_color_sms, wa, PA.cta_begin);
+            const float wb[4] = {0, 0, 0, 1};
+            partition(ctx->split_color_sms, wb, PB.cta_begin);
+            PB.tile_ctr = ctx->tile_ctr;
+            ctx->mask_layout = 0x6; ctx->mask_stride = n * S;     // decoders 1, 2: per-sample words; decoder 3: fragment-packed
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            CK(launch_decode_fwd(PB, c.precision, PB.cta_begin[4], ctx->aux_stream)); ctx->launches++;
+            CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            CK(launch_decode_fwd_t5(PA, PA.cta_begin[4], ctx->stream)); ctx->launches++;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        } else if (tc_ok) {
             // tcgen05 path: one 320-thread CTA per SM, per-sample mask words, composed weights refreshed when stale
             int need = 0;
             for (int d = 1; d < 4; ++d) if (w[d] > 0 && ((ctx->comp_dirty >> d) & 1)) need |= 1 << d;
@@ -857,8 +887,8 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
             }
             for (int d = 0; d < 4; ++d) P.comp[d] = ctx->comp[d];
             P.dbg = ctx->dbg;
-            P.mask_layout = 1; P.mask_stride = n * S;
-            if (train) { ctx->mask_layout = 1; ctx->mask_stride = n * S; }
+            P.mask_layout = 0xE; P.mask_stride = n * S;     // bit d: decoder d's relu masks are per-sample words
+            if (train) { ctx->mask_layout = 0xE; ctx->mask_stride = n * S; }
             float wt[4] = {0, w[1], w[2], w[3]}; env_weights("NSB_SPLIT_FWD_TC", wt);
             if (ctx->use_tc >= 2) {   // kind::f16 kernels: three 128-sample tiles per CTA (3 = every A operand in tensor memory)
                 partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 384))), wt, P.cta_begin);
@@ -967,7 +997,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
     } else if (wg) {
         // colour-decoder weight gradient without a stash: recomputed per tile, contracted through shared memory (wgrad_fused.cu)
         Timer t(ctx, T_WGRAD);
-        if (ctx->mask_layout != 0) return fail(ctx, "the fused weight-gradient kernel needs the warp-MMA forward's relu-mask layout (NSB_TCGEN05 must be 0)");
+        if ((ctx->mask_layout >> 3) & 1) return fail(ctx, "the fused weight-gradient kernel needs the warp-MMA forward's relu-mask layout (NSB_TCGEN05 must be 0)");
         if (c.precision != NSB_PREC_FP32_GRADE) return fail(ctx, "the fused weight-gradient kernel is fp32-grade only");
         CK(launch_wgrad_fused(Pw, ctx->wg_img, ctx->param + ctx->off_dec[3], ctx->grad + ctx->off_dec[3], ctx->wg_scratch, ctx->n_sm, ctx->stream)); ctx->launches += 2;
     }
@@ -1872,17 +1902,23 @@ extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int ra
 // Instrumentation of the fused exchange (k_reduce_adam stamps %globaltimer): out5 = {last barrier-1 wait us, last kernel total us,
 // mean wait us, mean total us, exchanges averaged}.  The wait is the time this rank spent waiting for the slowest rank's backward;
 // total - wait is the reduce-scatter + Adam + all-gather + barrier 2 itself.  reset != 0 clears the sums.
-extern "C" int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out5, int reset) {
+extern "C" int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out8, int reset) {
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < 5; ++i) out5[i] = 0.0;
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
     if (!ctx->p2p) return 0;
     uint32_t h[32];
     CK(cudaMemcpyAsync(h, ctx->p2p_flags, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    unsigned long long ts[4]; memcpy(ts, h + 20, sizeof ts);
+    unsigned long long ts[4], bytes; memcpy(ts, h + 20, sizeof ts); memcpy(&bytes, h + 30, sizeof bytes);
     const double n = (double)h[28];
-    out5[0] = ts[0] * 1e-3; out5[1] = ts[1] * 1e-3; out5[2] = n > 0 ? ts[2] * 1e-3 / n : 0.0; out5[3] = n > 0 ? ts[3] * 1e-3 / n : 0.0; out5[4] = n;
-    if (reset) { CK(cudaMemsetAsync(ctx->p2p_flags + 24, 0, 5 * 4, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    out8[0] = ts[0] * 1e-3; out8[1] = ts[1] * 1e-3; out8[2] = n > 0 ? ts[2] * 1e-3 / n : 0.0; out8[3] = n > 0 ? ts[3] * 1e-3 / n : 0.0; out8[4] = n;
+    // NVLink traffic model of the fused exchange: a rank reads its 1/W slice of the range from each of the W-1 peers and writes
+    // the updated slice to each of them: (W-1)/W of the range per direction and rank
+    out8[5] = n > 0 ? (double)bytes / n : 0.0;
+    out8[6] = out8[5] * (ctx->world - 1) / std::max(1, ctx->world);
+    const double ex_us = out8[3] - out8[2];
+    out8[7] = ex_us > 0 ? out8[6] / ex_us * 1e-3 : 0.0;     // GB/s per direction over (kernel - barrier-1 wait)
+    if (reset) { CK(cudaMemsetAsync(ctx->p2p_flags + 24, 0, 8 * 4, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
     return 0;
 }
 extern "C" int nsb_comm_rank_world(nsb_ctx* ctx, int* rank, int* world) { *rank = ctx->rank; *world = ctx->world; return 0; }

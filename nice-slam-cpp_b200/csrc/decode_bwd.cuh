@@ -302,7 +302,8 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
     const float4 gr[2] = {*reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[0]), *reinterpret_cast<const float4*>(P.g_raw + 4 * (size_t)sidx[1])};
     // relu masks saved by the training forward (k_decode_fwd<.., TRAIN>): the data gradient needs nothing else
     uint32_t mw[10];
-    if (P.mask_layout == 0) {
+    const bool per_sample = (P.mask_layout >> dec) & 1;   // bit d: decoder d's masks are one word per sample and layer (tcgen05 forward)
+    if (!per_sample) {
         const uint32_t* mb = P.masks + ((size_t)(dec - 1) * (P.P / TILE) + base / TILE) * 96 + lane;
         mw[0] = mb[0]; mw[1] = mb[32]; mw[2] = mb[64];
     } else {   // one word per sample and layer (bit f = relu of feature f)
@@ -328,7 +329,7 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
     if (!WG && !__any_sync(0xffffffffu, any)) return;   // nothing flows into this tile
 
     uint32_t masks[5];
-    if (P.mask_layout == 0) {
+    if (!per_sample) {
         masks[0] = mw[0] & 0xffffu; masks[1] = mw[0] >> 16; masks[2] = mw[1] & 0xffffu; masks[3] = mw[1] >> 16; masks[4] = mw[2];
     } else {   // pick this thread's fragment bits out of the per-sample words
 #pragma unroll

@@ -19,7 +19,8 @@ struct P2PParams {
                                            // [17] this rank's own epoch (number of exchanges done: the kernel reads its epoch from
                                            // here so that a captured graph can be replayed), [18] barrier time-out flag,
                                            // [20..27] globaltimer durations in ns as 64-bit values: last barrier-1 wait, last kernel
-                                           // total, sum of the waits, sum of the totals; [28] number of exchanges summed
+                                           // total, sum of the waits, sum of the totals; [28] number of exchanges summed; [30..31] sum of the exchanged range
+                                           // sizes in bytes (64-bit)
     int rank, world;
     int lo4, hi4;                          // the exchanged range of the arena in float4 units (ownership: see the kernel)
     int loss4;                             // float4 index of the loss slot (summed, written to param arenas, no Adam), or -1
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) k_reduce_adam(P2PParams P) {
             unsigned long long* ts = reinterpret_cast<unsigned long long*>(my_flags + 20);
             const unsigned long long t_total = globaltimer_ns() - t_start;
             ts[0] = t_wait - t_start; ts[1] = t_total; ts[2] += t_wait - t_start; ts[3] += t_total; my_flags[28] += 1u;
+            *reinterpret_cast<unsigned long long*>(my_flags + 30) += 16ull * (unsigned long long)(P.hi4 - P.lo4);
             // every rank's owner has stored the summed loss into this rank's parameter arena before it signalled barrier 2
             if (P.stats_base && P.loss4 >= 0) P.stats_base[4 * slot + 3] = __ldcg(P.A.param + 4 * (size_t)P.loss4);
             if (P.A.it.state) iter_advance(P.A.it, P.stats_base);

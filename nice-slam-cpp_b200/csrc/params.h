@@ -49,7 +49,7 @@ struct DecodeParams {
     uint32_t* masks;               // relu masks written by the training forward, read by the backward:
                                    //   mask_layout 0: [3][P/16][3][32] fragment-packed (mma.sync forward)
                                    //   mask_layout 1: [3][5][mask_stride] one 32-bit word per sample and layer (tcgen05 forward)
-    int mask_layout, mask_stride;
+    int mask_layout, mask_stride;  // mask_layout: bit d set = decoder d uses layout 1 (0 = all fragment-packed, 0xE = all per-sample)
     const float* comp[4];          // composed weights of the tcgen05 forward (k_compose), per decoder
     unsigned long long* dbg;       // optional cycle counters of the tcgen05 forward (NSB_TC_TIMING builds), or nullptr
 };
