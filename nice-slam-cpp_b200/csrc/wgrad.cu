@@ -4,7 +4,10 @@
 //     dW[a][b] = sum_s L[s][a] * R[s][b]
 // with the sample index as the contraction dimension.  Each CTA walks a contiguous range of samples; each warp owns one
 // task = up to four 16-row A tiles x ONE 32-column B block (accumulators in registers), one warp sums the bias columns;
-// the per-CTA partial sums are added to the flat gradient with fp32 reductions at the end.
+// the per-CTA partial sums are added to the flat gradient with fp32 reductions at the end.  The 16 stash rows of a k-step are one
+// contiguous 45.6 KB block: a producer lane moves them with ONE bulk TMA copy per stage (cp.async.bulk -> mbarrier complete_tx) and
+// the consumer warps run decoupled behind full / empty mbarriers -- no CTA-wide barrier per k-step (it cost 2.8 stalled warps per
+// issue slot: the warps' tasks differ by 4x in size), no per-thread copy instructions.
 #include "decode.cuh"
 #include "params.h"
 #include <cstring>
@@ -77,12 +80,15 @@ constexpr int WG_STAGES = 4;                       // cp.async ring depth (k-ste
 constexpr int WG_KROWS = 16;                       // samples per k-step (MMA k = 16)
 constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B block of a row may read past it (values unused)
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+__device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wg_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void wg_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void wg_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 // The CTA streams its sample range through a shared-memory ring (one stage = the 16 stash rows of a k-step, 45.6 KB,
 // fetched once with 16-byte cp.async), so every stash element crosses L2/HBM exactly once and the MMA fragments come from
@@ -93,6 +99,7 @@ template <bool P3>
 __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
                                                          int P, int S, float* __restrict__ dflat) {
     extern __shared__ __align__(128) float ring[];
+    __shared__ __align__(8) unsigned long long bars[2 * WG_STAGES];       // full[stage], empty[stage]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int kind = c_wg.t[warp].kind, nL = c_wg.t[warp].nL;
     float acc[WG_MAXL][4][4];     // bias warp: acc[q][j][e] doubles as 44 column-sum accumulators
@@ -108,25 +115,37 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
     const int per = (nks + gridDim.x - 1) / gridDim.x;
     const int k_lo = blockIdx.x * per, k_hi = min(nks, k_lo + per);
     const int n_my = max(0, k_hi - k_lo);
-    constexpr int CHUNKS = WG_KROWS * stash::W / 4;    // 16-byte chunks per stage
-    auto issue = [&](int i) {                          // fetch k-step k_lo + i into ring slot i % WG_STAGES
-        if (i < n_my) {
-            const float* src = st + (size_t)(k_lo + i) * WG_KROWS * stash::W;
-            float* dst = ring + (i % WG_STAGES) * WG_STAGE_FLOATS;
-            for (int c = threadIdx.x; c < CHUNKS; c += blockDim.x) cp_async16(dst + 4 * c, src + 4 * c);
+    const uint32_t bar0 = wg_smem_u32(bars);
+    if (threadIdx.x == 0) {
+        int consumers = 0;
+        for (int w = 0; w < WG_WARPS; ++w) consumers += c_wg.t[w].kind != 0;
+        for (int s_ = 0; s_ < WG_STAGES; ++s_) { wg_mbar_init(bar0 + 8 * s_, 1); wg_mbar_init(bar0 + 8 * (WG_STAGES + s_), consumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    constexpr uint32_t STAGE_BYTES = WG_KROWS * stash::W * 4;
+    if (kind == 0) {
+        // ---- producer: the first idle warp's lane 0 streams the CTA's sample range, one bulk TMA copy per k-step
+        bool first_idle = true;
+        for (int w = 0; w < warp; ++w) if (c_wg.t[w].kind == 0) first_idle = false;
+        if (first_idle && lane == 0) {
+            for (int i = 0; i < n_my; ++i) {
+                const int slot = i % WG_STAGES;
+                if (i >= WG_STAGES) wg_mbar_wait(bar0 + 8 * (WG_STAGES + slot), ((i / WG_STAGES) - 1) & 1);    // every consumer warp is done with the slot
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * slot), "r"(STAGE_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(wg_smem_u32(ring + slot * WG_STAGE_FLOATS)), "l"(st + (size_t)(k_lo + i) * WG_KROWS * stash::W), "r"(STAGE_BYTES), "r"(bar0 + 8 * slot) : "memory");
+            }
         }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int i = 0; i < WG_STAGES - 1; ++i) issue(i);
+        return;
+    }
     for (int i = 0; i < n_my; ++i) {
-        cp_async_wait<WG_STAGES - 2>();                // stage i has landed (for this thread's copies) ...
-        __syncthreads();                               // ... and for everybody's; also: slot (i-1) % STAGES is free again
-        issue(i + WG_STAGES - 1);
+        const int slot = i % WG_STAGES;
         const int s0 = (k_lo + i) * WG_KROWS;
-        if (valid && !valid[s0 / S]) continue;         // rows of rays dropped by the inside filter were never written
-        const float* r0 = ring + (i % WG_STAGES) * WG_STAGE_FLOATS + t * stash::W;
-        if (kind == 2) {
+        const bool live = !(valid && !valid[s0 / S]);   // rows of rays dropped by the inside filter were never written
+        wg_mbar_wait(bar0 + 8 * slot, (i / WG_STAGES) & 1);   // the k-step's 16 rows have landed
+        const float* r0 = ring + slot * WG_STAGE_FLOATS + t * stash::W;
+        if (live && kind == 2) {
             float4 bv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) bv[u] = *reinterpret_cast<const float4*>(r0 + 4 * u * stash::W + Rc);
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
                     mma_f16(acc[q][j], a.hi, bh[j][0], bh[j][1]);
                 }
             }
-        } else if (kind == 1) {
+        } else if (live && kind == 1) {
             float* sums = &acc[0][0][0];
 #pragma unroll
             for (int b = 0; b < WG_NBIAS; ++b) {
@@ -170,8 +189,9 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
                 }
             }
         }
+        __syncwarp();                                  // every lane's reads of the slot are done
+        if (lane == 0) wg_mbar_arrive(bar0 + 8 * (WG_STAGES + slot));
     }
-    cp_async_wait<0>();
     if (kind == 2) {
         const int nb = c_wg.t[warp].nb;
 #pragma unroll
