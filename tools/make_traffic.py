@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def rows_of(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[0]
     return hdr, rows[2:]
@@ -43,7 +43,9 @@ if len(sys.argv) > 3:
     for r in rows:
         if "k_gather_only" in r[hdr.index("Kernel Name")]:
             g = {"_source": "ncu --set full of nsb_bench_gather (" + os.path.basename(sys.argv[3]) + "), per launch, bytes",
-                 "l1tex_t_bytes": num(r, hdr, "l1tex__t_bytes.sum"), "lts_t_bytes": num(r, hdr, "lts__t_bytes.sum"),
+                 "l1tex_t_bytes": num(r, hdr, "l1tex__t_bytes.sum") or 32.0 * (num(r, hdr, "l1tex__t_sectors.sum") or num(r, hdr, "SM_B.TriageCompute.l1tex__t_sectors.sum") or 0),
+                 "lts_t_bytes": num(r, hdr, "lts__t_bytes.sum") or 32.0 * (num(r, hdr, "lts__t_sectors.sum") or num(r, hdr, "lts__t_sectors_srcunit_tex.sum") or 0),
+                 "l1_hit_rate_pct": num(r, hdr, "l1tex__t_sector_hit_rate.pct"),
                  "dram_bytes": (num(r, hdr, "dram__bytes_read.sum") or 0) + (num(r, hdr, "dram__bytes_write.sum") or 0),
                  "gpu_time_us": (num(r, hdr, "gpu__time_duration.sum") or 0) / 1e3,
                  "l2_gather_peak_gbs": float(sys.argv[4]) if len(sys.argv) > 4 else None}
