@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 BASE = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("decode_fwd_tc.cu", []), ("decode_fwd_tc16.cu", []), ("decode_fwd_t5.cu", []), ("wgrad.cu", []), ("wgrad_fused.cu", [])] + \
+UNITS = [("api.cu", []), ("decode_fwd.cu", []), ("decode_fwd_tc.cu", []), ("decode_fwd_tc16.cu", []), ("decode_fwd_t5.cu", []), ("decode_bwd_t5.cu", []), ("wgrad.cu", []), ("wgrad_fused.cu", [])] + \
         [("decode_bwd_inst.cu", ["-DNSB_BWD_COMBO=%d" % k]) for k in range(6)]
 VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC_TIMING"],
             # occupancy experiments: warps per CTA of the forward / backward decoder kernels

@@ -57,6 +57,9 @@ cudaError_t launch_decode_fwd_tc(const DecodeParams& P, int grid, cudaStream_t s
 cudaError_t launch_decode_fwd_tc16(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_decode_fwd_t5(const DecodeParams& P, int grid, cudaStream_t st);
 size_t t5_img_bytes(int which);
+size_t t5b_img_bytes();
+cudaError_t launch_build_t5bimg(const float* const flat[4], const float* const comp[4], uint8_t* const img[4], int mask, cudaStream_t st);
+cudaError_t launch_decode_bwd_t5(const DecodeParams& P, int grid, cudaStream_t st);
 cudaError_t launch_build_t5img(const float* const flat[4], const float* const comp[4], uint8_t* const img[4], int mask, cudaStream_t st);
 cudaError_t launch_compose(const float* const flat[4], float* const comp[4], int mask, cudaStream_t st);
 int compose_floats(int which);
@@ -149,6 +152,9 @@ struct nsb_ctx {
     uint32_t* masks = nullptr;   // relu masks of the last training forward
     int mask_layout = 0, mask_stride = 0;
     float* comp[4] = {nullptr, nullptr, nullptr, nullptr};   // composed weights for the tcgen05 forward
+    uint8_t* wimg_t5b[4] = {nullptr, nullptr, nullptr, nullptr};  // images of the tcgen05 backward (decoders 1, 2)
+    int bwd_t5 = 0;              // NSB_BWD_T5=1: geometry iterations run the data gradient of decoders 1, 2 on the tcgen05 backward (decode_bwd_t5.cu);
+                                 // measured equal to the warp-MMA kernel (both are dominated by the scatter walk), so the older kernel stays default
     uint8_t* wimg_t5[4] = {nullptr, nullptr, nullptr, nullptr};   // images of the tcgen05 forward (NSB_TCGEN05=3), rebuilt with the composed images
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
     float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
@@ -470,7 +476,8 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(dalloc(&ctx->absdiff, cap)); CK(dalloc(&ctx->valid, cap)); CK(dalloc(&ctx->idx, cap)); CK(dalloc(&ctx->pts, 3 * PS));
     CK(dalloc(&ctx->masks, 3 * (PS / TILE) * 96));
     for (int d = 1; d < 4; ++d) CK(dalloc(&ctx->comp[d], (size_t)compose_floats(d)));
-    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_t5[d], t5_img_bytes(d))); }
+    for (int d = 1; d < 4; ++d) { CK(dalloc(&ctx->wimg_fwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_bwd[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_cmp[d], wimg_floats(d))); CK(dalloc(&ctx->wimg_t5[d], t5_img_bytes(d))); if (d < 3) CK(dalloc(&ctx->wimg_t5b[d], t5b_img_bytes())); }
+    { const char* e = getenv("NSB_BWD_T5"); if (e) ctx->bwd_t5 = atoi(e); }
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 3; }   // forward decoders: 3 = tcgen05, operands in tensor memory (default); 0 = warp MMA; 1, 2 = earlier tcgen05 generations
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
@@ -507,7 +514,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->wg_img, c->wg_scratch, c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -778,6 +785,7 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
     }
     CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
     if (ctx->use_tc == 3 && cmp_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, cmp_need, ctx->stream)); ctx->launches++; }
+    if (ctx->use_tc == 3 && (cmp_need & 0x6)) { CK(launch_build_t5bimg(flat, ctx->comp, ctx->wimg_t5b, cmp_need, ctx->stream)); ctx->launches++; }
     if (plain & 8) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (fused weight gradient)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
@@ -785,7 +793,7 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
 
 static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
     memset(&P, 0, sizeof P);
-    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; P.wimg_t5[d] = ctx->wimg_t5[d]; }
+    for (int d = 0; d < 4; ++d) { P.dec_flat[d] = ctx->param + ctx->off_dec[d]; P.grid[d] = grid_view(ctx, d); P.wimg_fwd[d] = ctx->wimg_fwd[d]; P.wimg_bwd[d] = ctx->wimg_bwd[d]; P.wimg_cmp[d] = ctx->wimg_cmp[d]; P.wimg_t5[d] = ctx->wimg_t5[d]; P.wimg_t5b[d] = ctx->wimg_t5b[d]; }
     P.bnd = ctx->bnd;
     P.rays_o = ctx->rays_o; P.rays_d = ctx->rays_d; P.z = ctx->z; P.valid = valid; P.pts = nullptr;
     P.S = S; P.P = n * S;
@@ -975,11 +983,21 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
             return 0;
         }
         env_weights("NSB_SPLIT_BWD", w);
+        P.tile_ctr = ctx->tile_ctr + 4;
+        // geometry iterations (grid gradients of the two occupancy decoders only) run on the tcgen05 backward when the forward
+        // left its per-sample relu masks for both decoders
+        const bool t5_bwd = ctx->use_tc == 3 && ctx->bwd_t5 && c.precision == NSB_PREC_FP32_GRADE && P.flags == 1 && !wg && w[1] > 0 && w[2] > 0 && w[3] == 0 &&
+                            (ctx->mask_layout & 0x6) == 0x6;
+        if (t5_bwd) {
+            float wb[4] = {0, 1000.f, 1000.f, 0}; env_weights("NSB_SPLIT_BWD_T5", wb);
+            partition(std::min(ctx->n_sm, std::max(2, cdiv(n * S, 512))), wb, P.cta_begin);
+            CK(launch_decode_bwd_t5(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        } else {
         const int grid = decode_grid_size(ctx, n * S);
         partition(grid, w, P.cta_begin);
         P.cta_begin[1] = 0;   // no coarse CTAs: decoder 1 starts at block 0
-        P.tile_ctr = ctx->tile_ctr + 4;
         if (P.flags != 0) { CK(launch_decode_bwd(P, c.precision, P.cta_begin[4], ctx->stream)); ctx->launches++; }
+        }
     }
     ctx->ar_overlapped = false;
     if (wg && ctx->ar_request && ctx->world > 1) {

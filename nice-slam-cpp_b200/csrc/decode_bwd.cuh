@@ -165,12 +165,24 @@ __device__ __forceinline__ void scatter_tile(const GridView& G, const Bound& bnd
 #pragma unroll 1
     for (int s = 0; s <= TILE; ++s) {
         const uint32_t fm = s == TILE ? 0xffu : (uint32_t)scri[SCAT_CELL + TILE + s];
-        if (fm) {                                            // warp-uniform: flush the leaving vertices of the previous sample's cell
+        if (fm) {                                            // warp-uniform: flush the vertices that leave with the previous sample's cell
             const int4 oa = *reinterpret_cast<const int4*>(scri + SCAT_OFF + 8 * (s - 1)), ob = *reinterpret_cast<const int4*>(scri + SCAT_OFF + 8 * (s - 1) + 4);
             const int off[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+#define NSB_FLUSH(j) { red_add_f32(base + off[j], acc[j]); acc[j] = 0.0f; }
+            // a move to a face neighbour (the common case) retires the four vertices of one face: six fixed patterns without per-slot tests
+            switch (fm) {
+                case 0x55u: NSB_FLUSH(0) NSB_FLUSH(2) NSB_FLUSH(4) NSB_FLUSH(6) break;
+                case 0xaau: NSB_FLUSH(1) NSB_FLUSH(3) NSB_FLUSH(5) NSB_FLUSH(7) break;
+                case 0x33u: NSB_FLUSH(0) NSB_FLUSH(1) NSB_FLUSH(4) NSB_FLUSH(5) break;
+                case 0xccu: NSB_FLUSH(2) NSB_FLUSH(3) NSB_FLUSH(6) NSB_FLUSH(7) break;
+                case 0x0fu: NSB_FLUSH(0) NSB_FLUSH(1) NSB_FLUSH(2) NSB_FLUSH(3) break;
+                case 0xf0u: NSB_FLUSH(4) NSB_FLUSH(5) NSB_FLUSH(6) NSB_FLUSH(7) break;
+                default:
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if ((fm >> j) & 1u) { red_add_f32(base + off[j], acc[j]); acc[j] = 0.0f; }
+                    for (int j = 0; j < 8; ++j)
+                        if ((fm >> j) & 1u) { if (acc[j] != 0.0f) red_add_f32(base + off[j], acc[j]); acc[j] = 0.0f; }
+            }
+#undef NSB_FLUSH
         }
         if (s == TILE) break;
         const float4 wa = *reinterpret_cast<const float4*>(scr + SCAT_W + 8 * s), wb = *reinterpret_cast<const float4*>(scr + SCAT_W + 8 * s + 4);

@@ -20,6 +20,7 @@ struct DecodeParams {
     const float* dec_flat[4];      // coarse, middle, fine, color flat parameter vectors (device)
     const float* wimg_fwd[4];      // pre-split shared-memory images of decoders 1..3 (k_build_wimg): forward orientation ...
     const float* wimg_bwd[4];      // ... and transposed for the backward kernel; a CTA copies its decoder's image with 16-byte loads
+    const uint8_t* wimg_t5b[4];    // images of the tcgen05 backward (decode_bwd_t5.cu): transposed weight tiles, decoders 1 and 2
     const uint8_t* wimg_t5[4];     // images of the tcgen05 forward (decode_fwd_t5.cu): weight / bias tiles in the UMMA shared-memory layout
     const float* wimg_cmp[4];      // forward images with the grid-feature terms composed into the next layer (decoder_forward_composed)
     GridView grid[4];
