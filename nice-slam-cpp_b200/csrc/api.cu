@@ -163,6 +163,7 @@ struct nsb_ctx {
     int wimg_dirty = 0xE;        // bit d: decoder d's plain forward / backward images are stale
     int wimg_cmp_dirty = 0xE;    // bit d: decoder d's composed forward image is stale (rebuilt lazily: a colour decoder that is being
                                  // trained changes every iteration but runs on the plain image while its stash is needed)
+    int* ray_list = nullptr; int* ray_count = nullptr;   // valid-ray compaction for the tcgen05 forward (k_zvals fills, the forward consumes and clears)
     unsigned long long* tile_ctr = nullptr;          // [8] ticket counters of the decoder kernels' tile scheduler: [0..3] forward,
                                                      // [4..7] backward; cleared on the device by the kernel preceding each decoder launch
     int use_tc = 3;              // forward decoder kernel (NSB_TCGEN05 env; fp32-grade precision only): 3 = decode_fwd_t5.cu (default), 0 = warp MMA
@@ -189,6 +190,7 @@ struct nsb_ctx {
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
     cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // colour iterations: the stashing colour decoder runs beside the tcgen05 forward
+    int compact_rays = 1;        // tcgen05 forward walks the compacted list of valid rays (NSB_COMPACT_RAYS=0: all rays, filtered rows idle)
     int split_color_sms = 65;    // SMs given to the colour decoder's warp-MMA forward in that split (NSB_SPLIT_COLOR_SMS; 0 = one warp-MMA launch)
     bool ar_request = false, ar_overlapped = false;
     // peer-memory optimiser step (nsb_comm_p2p_import): every rank's gradient / parameter arena and flag block, opened through CUDA IPC
@@ -431,6 +433,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     { const char* e = getenv("NSB_SPLIT_COLOR_SMS"); if (e) ctx->split_color_sms = atoi(e); }
+    { const char* e = getenv("NSB_COMPACT_RAYS"); if (e) ctx->compact_rays = atoi(e); }
     for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
     auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
@@ -481,6 +484,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 3; }   // forward decoders: 3 = tcgen05, operands in tensor memory (default); 0 = warp MMA; 1, 2 = earlier tcgen05 generations
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(dalloc(&ctx->ray_list, cap)); CK(dalloc(&ctx->ray_count, 4)); CK(cudaMemsetAsync(ctx->ray_count, 0, 16, ctx->stream));
     CK(dalloc(&ctx->tile_ctr, 8)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CK(dalloc(&ctx->it_state, 8)); CK(cudaMemsetAsync(ctx->it_state, 0, 8 * sizeof(int), ctx->stream));
     CK(dalloc(&ctx->rstats, 8)); CK(cudaMemsetAsync(ctx->rstats, 0, 8 * 4, ctx->stream));
@@ -514,7 +518,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->wg_img, c->wg_scratch, c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->ray_list, c->ray_count, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -837,10 +841,16 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
     const nsb_config& c = ctx->cfg;
     const int S = have_depth ? c.n_samples + c.n_surface : c.n_samples;
     ctx->last_n = n; ctx->last_S = S;
+    // will the tcgen05 forward run (alone, or beside the stashing colour decoder)?  Then k_zvals also compacts the rays that pass the inside filter.
+    const bool want_stash = train && stash_fwd && stage == NSB_COLOR && ctx->wg_stash;
+    const bool t5_base = ctx->use_tc == 3 && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && !(train && stash_fwd && stage == NSB_COLOR && !ctx->wg_stash);
+    const bool t5_split = t5_base && want_stash && ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
+    const bool compact = valid != nullptr && ctx->compact_rays && (t5_split || (t5_base && !want_stash));
     {
         Timer t(ctx, T_SAMPLE);
         ZParams Z; Z.rays_o = ctx->rays_o + 3 * off; Z.rays_d = ctx->rays_d + 3 * off; Z.gt_depth = have_depth ? ctx->gt_depth + off : nullptr;
         Z.valid = valid ? valid + off : nullptr; Z.stats = stats; Z.it = it; Z.zero_ctr = ctx->tile_ctr; Z.t_samples = ctx->t_samples; Z.t_surface = ctx->t_surface; Z.bnd = ctx->bnd;
+        Z.ray_list = compact ? ctx->ray_list : nullptr; Z.ray_count = ctx->ray_count;
         Z.n = n; Z.n_samples = c.n_samples; Z.n_surface = have_depth ? c.n_surface : 0; Z.z = ctx->z + (size_t)off * S;
         k_zvals<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Z); ctx->launches++;
         CK(cudaGetLastError());
@@ -854,6 +864,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         P.rays_o += 3 * off; P.rays_d += 3 * off; P.z += (size_t)off * S;
         P.out_rgb += 4 * (size_t)off * S; for (int k = 0; k < 3; ++k) P.out_occ[k] += (size_t)off * S;
         if (train) P.masks = ctx->masks;
+        if (compact) { P.ray_list = ctx->ray_list; P.ray_count = ctx->ray_count; }
         if (train && stash_fwd && stage == NSB_COLOR && ctx->wg_stash) { if (ensure_stash(ctx, (size_t)n * S)) return -1; P.stash = ctx->stash; }
         float w[4]; stage_decoders(stage, w);
         if (P.stash) { w[1] = 700; w[2] = 972; w[3] = 860; }   // the colour decoder also writes its activations to the wgrad stash (measured split, tools/sweep_split.sh)
@@ -868,7 +879,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
                                ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
         if (split_fwd) {
             DecodeParams PA = P, PB = P;
-            PA.stash = nullptr;
+            PA.stash = nullptr; PB.ray_list = nullptr; PB.ray_count = nullptr;
             for (int d = 0; d < 4; ++d) PA.comp[d] = ctx->comp[d];
             PA.mask_layout = 0x6; PA.mask_stride = n * S; PA.tile_ctr = ctx->tile_ctr;
             float wa[4] = {0, 700.f, 1300.f, 0}; env_weights("NSB_SPLIT_FWD_T5", wa); wa[3] = 0;

@@ -114,7 +114,9 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
     using L = Smem<C>;
     constexpr int GCOLS = gcols(C), XCOL = xcol(C), NGC = ngroups(C);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = (P.P + TM - 1) / TM;
+    // with a compacted ray list (k_zvals) the tiles walk only the rays that passed the inside filter: no idle rows
+    const int total = P.ray_list ? *reinterpret_cast<volatile const int*>(P.ray_count) * P.S : P.P;
+    const int ntiles = (total + TM - 1) / TM;
     const uint32_t bar0 = smem_u32(sm + L::BAR), bar_img = bar0 + 16 * NG;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::TMEMPTR);
     volatile int* ticket = reinterpret_cast<volatile int*>(sm + L::TICKET);
@@ -158,15 +160,18 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
         float* scr = reinterpret_cast<float*>(sm + L::SCR + warp * L::SCRW);
         // position of this thread's sample in tile `tile` (zero, and inactive, past the end or on a filtered ray)
-        auto load_point = [&](int tile, float (&pp)[3]) -> bool {
-            const int s = tile * TM + row;
+        auto load_point = [&](int tile, float (&pp)[3], int& s_out) -> bool {
+            const int sp = tile * TM + row;
             pp[0] = pp[1] = pp[2] = 0.0f;
-            if (tile >= ntiles || s >= P.P) return false;
-            if (P.pts) { pp[0] = P.pts[3 * (size_t)s]; pp[1] = P.pts[3 * (size_t)s + 1]; pp[2] = P.pts[3 * (size_t)s + 2]; return true; }
-            const int ray = s / P.S;
-            const uint8_t ok = P.valid ? P.valid[ray] : (uint8_t)1;
+            s_out = -1;
+            if (tile >= ntiles || sp >= total) return false;
+            if (P.pts) { s_out = sp; pp[0] = P.pts[3 * (size_t)sp]; pp[1] = P.pts[3 * (size_t)sp + 1]; pp[2] = P.pts[3 * (size_t)sp + 2]; return true; }
+            const int ray = P.ray_list ? P.ray_list[sp / P.S] : sp / P.S;
+            const int s = P.ray_list ? ray * P.S + sp % P.S : sp;
+            const uint8_t ok = (P.valid && !P.ray_list) ? P.valid[ray] : (uint8_t)1;
             const float z = P.z[s];
             if (!ok) return false;                                       // sin(0 . B) = 0: an inactive row contributes exact zeros
+            s_out = s;
 #pragma unroll
             for (int a = 0; a < 3; ++a) pp[a] = __fadd_rn(P.rays_o[3 * ray + a], __fmul_rn(P.rays_d[3 * ray + a], z));   // Renderer.cpp:121
             return true;
@@ -193,7 +198,8 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
         int tile = ticket[4 * grp];
         float p[3];
-        bool active = load_point(tile, p);
+        int s = -1;
+        bool active = load_point(tile, p, s);
         if (tile < ntiles) {   // the first tile's gather runs under the image's TMA copy; later tiles are gathered during the previous tile's layer phase
 #pragma unroll
             for (int cc = 0; cc < C / 32; ++cc)
@@ -203,7 +209,6 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         mbar_wait(bar_img, 0);
         for (int round = 0; tile < ntiles; ++round) {
             if (row == 0) ticket[4 * grp + (round + 2) % 3] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // read after the group barrier of this round
-            const int s = tile * TM + row;
             const int tile_next = ticket[4 * grp + (round + 1) % 3];
             // ---- grid features: the owner lane reads its row of the scratch, adds the grid-feature part of the output layer and
             // moves the row to tensor memory as the A operand of every G_i c product
@@ -233,7 +238,8 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
             }
             __syncwarp();                                               // the scratch is rewritten by the next tile's gather below
             float pn[3];
-            const bool active_n = load_point(tile_next, pn);
+            int s_next = -1;
+            const bool active_n = load_point(tile_next, pn, s_next);
             // ---- Fourier features, 32 per handshake, this thread's own sample
 #pragma unroll 1
             for (int j = 0; j < 3; ++j) {
@@ -302,7 +308,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
             }
             fence_before();       // the accumulator reads above are ordered before the next tile's first arrive
             group_sync(grp);      // row 0's ticket (two rounds ahead) is visible to the group and its issuer
-            tile = tile_next; active = active_n;
+            tile = tile_next; active = active_n; s = s_next;
             p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
         }
         }
@@ -349,6 +355,10 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
     fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    if (tid == 0 && P.ray_list) {      // every CTA has read the list length: the last one to finish clears it for the next k_zvals
+        __threadfence();
+        if (atomicAdd(P.ray_count + 1, 1) == (int)gridDim.x - 1) { P.ray_count[0] = 0; P.ray_count[1] = 0; }
+    }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_decode_fwd_t5(const DecodeParams P) {

@@ -30,6 +30,8 @@ struct DecodeParams {
     const float* rays_d;           // [N][3]
     const float* z;                // [N][S]
     const uint8_t* valid;          // [N] or nullptr: rays dropped by the inside filter are skipped
+    const int* ray_list;           // tcgen05 forward: rays that pass the inside filter, compacted by k_zvals (nullptr: tiles walk all rays)
+    int* ray_count;                // [0] its length, [1] CTAs finished (the last one clears both for the next launch)
     const float* pts;              // [P][3] or nullptr
     int S;                         // samples per ray (multiple of 16)
     int P;                         // total samples

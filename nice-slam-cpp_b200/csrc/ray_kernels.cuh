@@ -170,6 +170,8 @@ struct ZParams {
     Bound bnd;
     int n, n_samples, n_surface;
     float* z;                // [n][S]
+    int* ray_list;           // or nullptr: compacted list of the rays that pass the inside filter (any order), for the tcgen05 forward
+    int* ray_count;          // its length (zeroed by the forward kernel's last CTA)
 };
 
 // Renderer.cpp:46-119: one warp per ray.  32 stratified + 16 near-surface values, then an exact rank sort.
@@ -178,6 +180,7 @@ __global__ void k_zvals(ZParams P) {
     if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
     if (ray >= P.n) return;
     if (P.valid && !P.valid[ray]) return;
+    if (P.ray_list && l == 0) P.ray_list[atomicAdd(P.ray_count, 1)] = ray;
     const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
     const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
     const float far_bb = __fadd_rn(aabb_exit(P.bnd, o, d), 0.01f);                 // :69-73
