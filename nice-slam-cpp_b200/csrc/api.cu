@@ -46,7 +46,7 @@ int wgrad_fused_scratch_floats();
 cudaError_t wgrad_fused_init();
 cudaError_t launch_build_wgimg(const float* flat, uint8_t* img, cudaStream_t st);
 cudaError_t launch_wgrad_fused(const DecodeParams& P, const uint8_t* img, const float* flat, float* dflat, float* scratch, int n_sm, cudaStream_t st);
-cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st);
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
 cudaError_t launch_coarse_bwd(const DecodeParams& P, int precision, int grid, cudaStream_t st);
@@ -163,6 +163,7 @@ struct nsb_ctx {
     int wimg_dirty = 0xE;        // bit d: decoder d's plain forward / backward images are stale
     int wimg_cmp_dirty = 0xE;    // bit d: decoder d's composed forward image is stale (rebuilt lazily: a colour decoder that is being
                                  // trained changes every iteration but runs on the plain image while its stash is needed)
+    float* wg_mscr = nullptr;    // [5][32][32] scratch of k_wgrad (sums of g_u (x) c), consumed and cleared by k_wgrad_finish
     int* ray_list = nullptr; int* ray_count = nullptr;   // valid-ray compaction for the tcgen05 forward (k_zvals fills, the forward consumes and clears)
     unsigned long long* tile_ctr = nullptr;          // [8] ticket counters of the decoder kernels' tile scheduler: [0..3] forward,
                                                      // [4..7] backward; cleared on the device by the kernel preceding each decoder launch
@@ -484,6 +485,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     { const char* e = getenv("NSB_TCGEN05"); ctx->use_tc = e ? atoi(e) : 3; }   // forward decoders: 3 = tcgen05, operands in tensor memory (default); 0 = warp MMA; 1, 2 = earlier tcgen05 generations
     { const char* e = getenv("NSB_AR_MODE"); ctx->ar_mode = e ? atoi(e) : 1; }
     CK(dalloc(&ctx->dbg, 32)); CK(cudaMemsetAsync(ctx->dbg, 0, 32 * 8, ctx->stream));
+    CK(dalloc(&ctx->wg_mscr, 5 * 1024)); CK(cudaMemsetAsync(ctx->wg_mscr, 0, 5 * 1024 * 4, ctx->stream));
     CK(dalloc(&ctx->ray_list, cap)); CK(dalloc(&ctx->ray_count, 4)); CK(cudaMemsetAsync(ctx->ray_count, 0, 16, ctx->stream));
     CK(dalloc(&ctx->tile_ctr, 8)); CK(cudaMemsetAsync(ctx->tile_ctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CK(dalloc(&ctx->it_state, 8)); CK(cudaMemsetAsync(ctx->it_state, 0, 8 * sizeof(int), ctx->stream));
@@ -518,7 +520,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
     void* ptrs[] = {c->wg_img, c->wg_scratch, c->it_state, c->rstats, c->bc1_tab, c->bc2s_tab, c->grad_snap, c->param, c->grad, c->m, c->v, c->t_samples, c->t_surface, c->f_depth, c->f_color, c->f_pose, c->rays_o, c->rays_d, c->gt_depth,
                     c->gt_color, c->z, c->raw_rgb, c->occ[0], c->occ[1], c->occ[2], c->g_raw, c->o_rgb, c->o_depth, c->o_var, c->o_w, c->g_rgb, c->g_depth,
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
-                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->ray_list, c->ray_count, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
+                    c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->ray_list, c->ray_count, c->wg_mscr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
@@ -1022,7 +1024,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
     }
     if (wg_stash) {
         Timer t(ctx, T_WGRAD);
-        CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->grad + ctx->off_dec[3], c.precision, ctx->n_sm, ctx->stream)); ctx->launches++;
+        CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->param + ctx->off_dec[3], ctx->grad + ctx->off_dec[3], ctx->wg_mscr, c.precision, ctx->n_sm, ctx->stream)); ctx->launches += 2;
     } else if (wg) {
         // colour-decoder weight gradient without a stash: recomputed per tile, contracted through shared memory (wgrad_fused.cu)
         Timer t(ctx, T_WGRAD);

@@ -227,7 +227,6 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
     }
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
-        if (STASH) stash_tile(st0, st1, stash::GH + HID * i, gh, t);
         apply_mask(gu, gh, masks[i]);
         if (STASH) stash_tile(st0, st1, stash::GU + HID * i, gu, t);
         if (NEED_E && i == 3) {

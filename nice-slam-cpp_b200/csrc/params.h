@@ -57,17 +57,18 @@ struct DecodeParams {
     unsigned long long* dbg;       // optional cycle counters of the tcgen05 forward (NSB_TC_TIMING builds), or nullptr
 };
 
-// Row layout of the colour-decoder weight-gradient stash (floats per sample).
+// Row layout of the colour-decoder weight-gradient stash (floats per sample).  The gradients at the block outputs (g_h) are NOT
+// stashed: d Fc_i = W_{i+1}^T (sum_s g_u_{i+1} (x) c) and d bc_i = W_{i+1}^T d b_{i+1}, so k_wgrad contracts g_u with c instead and a tiny
+// finishing kernel applies W^T (k_wgrad_finish) -- 552 instead of 712 floats per sample cross HBM three times.
 namespace stash {
 constexpr int E = 0;          // embedding e            96
 constexpr int H = 96;         // h_1..h_5               5 x 32  (inputs of layers 1..4 and of the output layer)
 constexpr int Cc = 256;       // grid feature c         32 (channel order)
 constexpr int GU = 288;       // g_u_0..g_u_4           5 x 32  (gradient at the relu output, masked)
-constexpr int GH = 448;       // g_h_1..g_h_5           5 x 32  (gradient at the block output)
-constexpr int GE = 608;       // g_e * cos(pB)          96
-constexpr int GO = 704;       // g_out                  4
-constexpr int Pp = 708;       // p                      4
-constexpr int W = 712;
+constexpr int GE = 448;       // g_e * cos(pB)          96
+constexpr int GO = 544;       // g_out                  4
+constexpr int Pp = 548;       // p                      4
+constexpr int W = 552;        // = 8 (mod 32): conflict-free fragment loads from the ring in k_wgrad
 }  // namespace stash
 
 }  // namespace nsb

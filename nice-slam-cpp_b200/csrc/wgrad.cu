@@ -17,16 +17,18 @@ namespace nsb {
 
 constexpr int WG_WARPS = 16;
 constexpr int WG_MAXL = 4;          // A tiles (16 stash columns each) a warp multiplies with its one B block (32 stash columns)
-constexpr int WG_NBIAS = 11;        // column-sum blocks of the bias warp
+constexpr int WG_SCRATCH = 1 << 24;  // dst tag of the tasks that accumulate into the M scratch ([5][32][32] floats: M_1..M_4, M_out)
+constexpr int WG_NBIAS = 6;         // column-sum blocks of the bias warp (b_0..b_4, bo)
 
 struct WGroup {
     int L;             // stash column of row 0 of the A tile
-    int dst, ld;       // flat-gradient offset of element (a_lo, 0) and its row stride
+    int dst, ld;       // flat-gradient offset of element (a_lo, 0) and its row stride; dst >= WG_SCRATCH: offset into the M scratch instead
+                       // (M_i = sum_s g_u_i (x) c, finished by k_wgrad_finish)
     int a_lo, a_hi;    // valid rows of the A tile (relative to L)
 };
 // One task per warp: dW[L rows][R cols] += sum_s stash[s][L + a] * stash[s][R + b] for up to four A tiles that share ONE B
 // block, so that the B operand is split into fp16 hi/lo once per k-step and reused (the split, not the MMA, dominates the
-// instruction count).  kind 1 is the bias warp: plain fp32 column sums of eleven blocks (b_i = sum GU_i, bc_i = sum GH_i, bo = sum GO).
+// instruction count).  kind 1 is the bias warp: plain fp32 column sums of six blocks (b_i = sum GU_i, bo = sum GO; bc_i follows in k_wgrad_finish).
 struct WTask {
     int kind;          // 0 idle, 1 bias sums, 2 MMA task
     int nL, R, nb;     // number of A tiles, stash column of the B block, valid B columns (<= 32)
@@ -43,16 +45,15 @@ static WGTable build_table() {
         for (const WGroup& g : gs) t.g[t.nL++] = g;
     };
     auto G = [&](int L, int dst, int ld, int a_hi = 16, int a_lo = 0) { return WGroup{L, dst, ld, a_lo, a_hi}; };
-    const int GU = stash::GU, GH = stash::GH, LD3 = EMB + HID;
+    const int GU = stash::GU, LD3 = EMB + HID, MS = WG_SCRATCH;
     // warps are spread over the four schedulers (warp & 3) so that each gets ~600 instructions per k-step
-    // scheduler 0: bias sums, Cc x GH4, H0 x GU1 (W1), H4 x GO (Wo)
+    // scheduler 0: bias sums, Cc x GO (M_out), H0 x GU1 (W1), H4 x GO (Wo)
     {
         WTask& t = T.t[0]; t.kind = 1;
         for (int i = 0; i < 5; ++i) { t.bias_col[i] = GU + 32 * i; t.bias_dst[i] = f.b[i]; t.bias_n[i] = 32; }
-        for (int i = 0; i < 5; ++i) { t.bias_col[5 + i] = GH + 32 * i; t.bias_dst[5 + i] = f.bc[i]; t.bias_n[5 + i] = 32; }
-        t.bias_col[10] = stash::GO; t.bias_dst[10] = f.bo; t.bias_n[10] = 4;
+        t.bias_col[5] = stash::GO; t.bias_dst[5] = f.bo; t.bias_n[5] = 4;
     }
-    mma(4, stash::Cc, 32, {G(GH + 128, f.Fc[4], 32), G(GH + 144, f.Fc[4] + 16 * 32, 32)});
+    mma(4, stash::Cc, 32, {G(stash::GO, MS + 4 * 1024, 32, 4)});
     mma(8, stash::H + 0, 32, {G(GU + 32, f.W[1], 32), G(GU + 48, f.W[1] + 16 * 32, 32)});
     mma(12, stash::H + 128, 32, {G(stash::GO, f.Wo, 32, 4)});
     // scheduler 1: E0 / E1 x {GU0 (W0), GU3 (W3 embedding columns)}, H1 x GU2 (W2)
@@ -60,14 +61,14 @@ static WGTable build_table() {
         mma(1 + 4 * j, stash::E + 32 * j, 32, {G(GU + 0, f.W[0] + 32 * j, EMB), G(GU + 16, f.W[0] + 16 * EMB + 32 * j, EMB),
                                                G(GU + 96, f.W[3] + 32 * j, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 32 * j, LD3)});
     mma(9, stash::H + 32, 32, {G(GU + 64, f.W[2], 32), G(GU + 80, f.W[2] + 16 * 32, 32)});
-    // scheduler 2: E2 x {GU0, GU3}, Cc x {GH0, GH1}, GE0 / GE1 x p (dB)
+    // scheduler 2: E2 x {GU0, GU3}, Cc x {GU1, GU2} (M_1, M_2), GE0 / GE1 x p (dB)
     mma(2, stash::E + 64, EMB - 64, {G(GU + 0, f.W[0] + 64, EMB), G(GU + 16, f.W[0] + 16 * EMB + 64, EMB),
                                      G(GU + 96, f.W[3] + 64, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 64, LD3)});
-    mma(6, stash::Cc, 32, {G(GH + 0, f.Fc[0], 32), G(GH + 16, f.Fc[0] + 16 * 32, 32), G(GH + 32, f.Fc[1], 32), G(GH + 48, f.Fc[1] + 16 * 32, 32)});
+    mma(6, stash::Cc, 32, {G(GU + 32, MS + 0, 32), G(GU + 48, MS + 16 * 32, 32), G(GU + 64, MS + 1024, 32), G(GU + 80, MS + 1024 + 16 * 32, 32)});
     mma(10, stash::GE + 0, 32, {G(stash::Pp, f.B, EMB, 3)});
     mma(14, stash::GE + 32, 32, {G(stash::Pp, f.B + 32, EMB, 3)});
-    // scheduler 3: Cc x {GH2, GH3}, H2 x GU3 (W3 hidden columns), H3 x GU4 (W4), GE2 x p
-    mma(3, stash::Cc, 32, {G(GH + 64, f.Fc[2], 32), G(GH + 80, f.Fc[2] + 16 * 32, 32), G(GH + 96, f.Fc[3], 32), G(GH + 112, f.Fc[3] + 16 * 32, 32)});
+    // scheduler 3: Cc x {GU3, GU4} (M_3, M_4), H2 x GU3 (W3 hidden columns), H3 x GU4 (W4), GE2 x p
+    mma(3, stash::Cc, 32, {G(GU + 96, MS + 2048, 32), G(GU + 112, MS + 2048 + 16 * 32, 32), G(GU + 128, MS + 3072, 32), G(GU + 144, MS + 3072 + 16 * 32, 32)});
     mma(7, stash::H + 64, 32, {G(GU + 96, f.W[3] + EMB, LD3), G(GU + 112, f.W[3] + 16 * LD3 + EMB, LD3)});
     mma(11, stash::H + 96, 32, {G(GU + 128, f.W[4], 32), G(GU + 144, f.W[4] + 16 * 32, 32)});
     mma(15, stash::GE + 64, EMB - 64, {G(stash::Pp, f.B + 64, EMB, 3)});
@@ -76,7 +77,7 @@ static WGTable build_table() {
 
 __constant__ WGTable c_wg;
 
-constexpr int WG_STAGES = 4;                       // cp.async ring depth (k-steps in flight)
+constexpr int WG_STAGES = 6;                       // ring depth (k-steps in flight): 6 x 35.5 KB
 constexpr int WG_KROWS = 16;                       // samples per k-step (MMA k = 16)
 constexpr int WG_STAGE_FLOATS = WG_KROWS * stash::W + 32;   // +32: the last B block of a row may read past it (values unused)
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void wg_mbar_wait(uint32_t bar, uint32_t parity) {
 // L + 2g + 1; B column g of n-tile j <-> stash column R + 4g + j (one float4 per row serves the four n-tiles).
 template <bool P3>
 __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict__ st, const uint8_t* __restrict__ valid,
-                                                         int P, int S, float* __restrict__ dflat) {
+                                                         int P, int S, float* __restrict__ dflat, float* __restrict__ mscr) {
     extern __shared__ __align__(128) float ring[];
     __shared__ __align__(8) unsigned long long bars[2 * WG_STAGES];       // full[stage], empty[stage]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int a = 2 * g + (e >> 1), b = 4 * (2 * t + (e & 1)) + j;
-                    if (a >= G.a_lo && a < G.a_hi && b < nb) atomicAdd(dflat + G.dst + (a - G.a_lo) * G.ld + b, acc[q][j][e]);
+                    if (a >= G.a_lo && a < G.a_hi && b < nb) atomicAdd((G.dst >= WG_SCRATCH ? mscr + (G.dst - WG_SCRATCH) : dflat + G.dst) + (a - G.a_lo) * G.ld + b, acc[q][j][e]);
                 }
         }
     } else if (kind == 1) {
@@ -217,6 +218,40 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
             }
         }
     }
+}
+
+// d Fc_{i-1} = W_i(hidden columns)^T M_i and d bc_{i-1} = W_i^T d b_i for i = 1..4, d Fc_4 = Wo^T M_out and d bc_4 = Wo^T d bo: the gradients at the
+// block outputs are linear images of the g_u sums k_wgrad has just produced.  One block per Fc matrix; clears the M scratch for the next iteration.
+__global__ void __launch_bounds__(256) k_wgrad_finish(const float* __restrict__ flat, float* __restrict__ dflat, float* __restrict__ mscr) {
+    const DecFlat f = DecFlat::make(32, 4);
+    const int i = blockIdx.x;                       // Fc_i, i = 0..4
+    __shared__ float sW[32][33], sM[32][33], sb[32];
+    const int no = i == 4 ? 3 : 32;                 // contraction length (the colour decoder's 4th output is overwritten: no gradient)
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+        const int o = k / 32, m = k % 32;
+        float w = 0.0f, mm = 0.0f;
+        if (o < no) {
+            w = i == 4 ? flat[f.Wo + o * HID + m] : i == 2 ? flat[f.W[3] + o * (EMB + HID) + EMB + m] : flat[f.W[i + 1] + o * HID + m];
+            mm = mscr[i * 1024 + o * 32 + m];       // here m is the channel index of M
+        }
+        sW[o][m] = w; sM[o][m] = mm;
+    }
+    if (threadIdx.x < 32) sb[threadIdx.x] = threadIdx.x < no ? (i == 4 ? dflat[f.bo + threadIdx.x] : dflat[f.b[i + 1] + threadIdx.x]) : 0.0f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+        const int m = k / 32, ch = k % 32;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int o = 0; o < 32; ++o) acc = fmaf(sW[o][m], sM[o][ch], acc);
+        dflat[f.Fc[i] + m * 32 + ch] += acc;
+    }
+    if (threadIdx.x < 32) {
+        float acc = 0.0f;
+        for (int o = 0; o < 32; ++o) acc = fmaf(sW[o][threadIdx.x], sb[o], acc);
+        dflat[f.bc[i] + threadIdx.x] += acc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) mscr[i * 1024 + k] = 0.0f;
 }
 
 // Per-device one-time setup (task table in constant memory, shared-memory attribute); called from nsb_create so that the launches
@@ -236,11 +271,13 @@ cudaError_t wgrad_init() {
     return cudaSuccess;
 }
 
-cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, float* dflat, int precision, int grid, cudaStream_t st) {
+// flat: the colour decoder's parameters (W^T of the finishing step); mscr: [5][32][32] floats, zero on entry and on exit
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int precision, int grid, cudaStream_t st) {
     const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
     { const cudaError_t e = wgrad_init(); if (e != cudaSuccess) return e; }
-    if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
-    else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat);
+    if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
+    else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
+    k_wgrad_finish<<<5, 256, 0, st>>>(flat, dflat, mscr);
     return cudaGetLastError();
 }
 
