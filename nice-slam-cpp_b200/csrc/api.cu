@@ -779,12 +779,15 @@ static void env_weights(const char* name, float w[4]) {
 // Rebuilds the pre-split shared-memory images of the decoders whose weights changed (set_decoder / an Adam step with a decoder
 // learning rate).  cmp_mask: decoders whose COMPOSED forward image the coming launches read.  force: rebuild these decoders
 // whatever the dirty bits say (the captured colour iteration ends with the rebuild of the colour decoder it has just stepped).
-static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
+static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0, bool lazy_cmp = false) {
+    // lazy_cmp (the stash path's colour iterations): the stepped decoder's composed / tcgen05 images are not read until the next
+    // non-stash forward, so only its plain forward / backward images are rebuilt inside the iteration; the host marks the composed
+    // ones stale per iteration (nsb_mapping_iter_async) and the next API entry that needs them rebuilds them once.
     const int plain = ctx->wimg_dirty | force;
-    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | force;
+    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | (lazy_cmp ? 0 : force);
     if (!plain && !cmp_need) return 0;
     const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
-    const int comp_need = (ctx->comp_dirty & cmp_need) | force;
+    const int comp_need = (ctx->comp_dirty & cmp_need) | (lazy_cmp ? 0 : force);
     if (comp_need) {   // the composed images are built from k_compose's output
         CK(launch_compose(flat, ctx->comp, comp_need, ctx->stream)); ctx->launches++;
         ctx->comp_dirty &= ~comp_need;
@@ -792,10 +795,13 @@ static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0) {
     CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
     if (ctx->use_tc == 3 && cmp_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, cmp_need, ctx->stream)); ctx->launches++; }
     if (ctx->use_tc == 3 && (cmp_need & 0x6)) { CK(launch_build_t5bimg(flat, ctx->comp, ctx->wimg_t5b, cmp_need, ctx->stream)); ctx->launches++; }
-    if (plain & 8) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (fused weight gradient)
+    if ((plain & 8) && !ctx->wg_stash) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (stash-free weight gradient only)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
 }
+
+// Colour iterations of the stash path rebuild the stepped colour decoder's composed images lazily (see refresh_images).
+static bool lazy_color_images(const nsb_ctx* ctx) { return ctx->wg_stash != 0 && !ctx->map_fix_color && !ctx->coarse_map && ctx->use_tc == 3; }
 
 static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
     memset(&P, 0, sizeof P);
@@ -1573,8 +1579,16 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
     }
     // the colour decoder has just been stepped: rebuild its pre-split images right away, so that every iteration starts from
     // fresh images (no host-side dirty tracking inside the loop)
-    if (dec_color && !coarse && !pristine && lr[0] != 0.f) { if (refresh_images(ctx, 0, 1 << 3)) return -1; }
+    if (dec_color && !coarse && !pristine && lr[0] != 0.f) { if (refresh_images(ctx, 0, 1 << 3, lazy_color_images(ctx))) return -1; }
     return 0;
+}
+
+// Host side of the lazy rebuild: an iteration that steps the colour decoder leaves its composed / tcgen05 images stale (this runs per
+// iteration on the host, also when the iteration itself is a graph replay).
+static void mark_color_stale(nsb_ctx* ctx, const IterPlan& pl) {
+    if (!lazy_color_images(ctx) || pl.pristine || pl.stage != NSB_COLOR) return;
+    if (ctx->cfg.stage_lr[NSB_COLOR][0] * ctx->map_lr_factor == 0.f) return;
+    ctx->comp_dirty |= 8; ctx->wimg_cmp_dirty |= 8;
 }
 
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
@@ -1596,10 +1610,12 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
         CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (refresh_images(ctx, 0xE)) return -1;   // no-op unless a decoder was replaced since the last iteration
+    // no-op unless a decoder was replaced since the last iteration; a stash colour iteration does not read the colour decoder's composed
+    // images (left stale by the previous one on purpose)
+    if (refresh_images(ctx, (lazy_color_images(ctx) && pl.stage == NSB_COLOR && !pl.pristine) ? 0x6 : 0xE)) return -1;
     ctx->map_step++;
     const bool graph_ok = ctx->use_graph && !ctx->profiling && (ctx->world == 1 || ctx->p2p);
-    if (!graph_ok) return enqueue_iteration(ctx, pl);
+    if (!graph_ok) { const int rc = enqueue_iteration(ctx, pl); mark_color_stale(ctx, pl); return rc; }
     const uint64_t key = (uint64_t)pl.stage | (pl.use_color ? 8u : 0u) | (pl.pristine ? 16u : 0u) | (pl.use_pool ? 32u : 0u) | (ctx->capture_grads ? 64u : 0u);
     auto g = ctx->graphs.find(key);
     if (g == ctx->graphs.end()) {
@@ -1622,6 +1638,7 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     }
     CK(cudaGraphLaunch(g->second.exec, ctx->stream));
     ctx->launches += g->second.launches;
+    mark_color_stale(ctx, pl);
     return 0;
 }
 

@@ -226,6 +226,53 @@ def test_stash_free_weight_gradient_kernel(nsb, model_inputs, frames, monkeypatc
     assert np.abs(res["0"][2] - decs["color"]).max() > 1e-4                                             # the decoder was stepped
 
 
+def test_kernel_variants_agree(nsb, model_inputs, frames, monkeypatch):
+    """The tcgen05 forward (default), the warp-MMA forward (NSB_TCGEN05=0), the tcgen05 data-gradient kernel (NSB_BWD_T5=1), the
+    forward without ray compaction (NSB_COMPACT_RAYS=0) and the one-launch colour forward (NSB_SPLIT_COLOR_SMS=0) are the same
+    arithmetic up to fp32 rounding: the same render outputs and the same whole-iteration gradients in a geometry and in a colour
+    iteration, which in turn match oracle/_ref's libtorch autograd (golden) on the colour-decoder gradient."""
+    grids, decs, _ = model_inputs
+    depths, colors, poses = frames
+    gm = load_golden("mapping_iters.npz"); gv = load_golden("render_vjp.npz")
+    variants = {"default": {}, "warp_mma_fwd": {"NSB_TCGEN05": "0"}, "t5_bwd": {"NSB_BWD_T5": "1"}, "no_compaction": {"NSB_COMPACT_RAYS": "0"},
+                "one_launch_color_fwd": {"NSB_SPLIT_COLOR_SMS": "0"}}
+    knobs = ("NSB_TCGEN05", "NSB_BWD_T5", "NSB_COMPACT_RAYS", "NSB_SPLIT_COLOR_SMS")
+    res = {}
+    for name, env in variants.items():
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        cfg = nsb.default_config(); cfg.max_rays = 8192; cfg.mapping_pixels = int(gm["pixels"]); cfg.frustum_feature_selection = 0; cfg.raydir = 0
+        e = nsb.Engine(cfg)
+        e.set_model(grids, decs); e.set_ttables(gv["t_samples"], gv["t_surface"])
+        for f in range(int(gm["n_frames"])):
+            e.set_frame(f, depths[f], colors[f], poses[f])
+        rgb, depth, var, w = e.render_batch_ray(gv["rays_d"], gv["rays_o"], "color", gv["gt_depth"])
+        out = {"rgb": rgb, "depth": depth, "var": var}
+        e.mapping_capture_grads(True)
+        for tag, it, seed in (("geom", 0, int(gm["seed"])), ("color", 59, int(gm["c0_seed"]))):
+            e.set_model(grids, decs)
+            e.seed(seed)
+            e.mapping_begin(list(range(int(gm["n_frames"]))), 60, 1.0)
+            out[tag + "_loss"] = np.float64(e.mapping_iter(it))
+            cg = e.captured_grads()
+            for lv in ("middle", "fine") + (("color",) if tag == "color" else ()):
+                out[tag + "_grid_" + lv] = cg["grid_" + lv]
+            if tag == "color":
+                assert relerr(cg["dec_color"], gm["c0_grad_dec_color"]) < GRAD_TOL, name
+                assert np.allclose(out["color_loss"], gm["c0_loss"], rtol=1e-4), name
+                out["color_dec"] = cg["dec_color"]
+        res[name] = out
+        e.close()
+    for k in knobs:
+        monkeypatch.delenv(k, raising=False)
+    ref = res["default"]
+    for name, out in res.items():
+        for k, v in out.items():
+            assert relerr(np.asarray(v, np.float64), np.asarray(ref[k], np.float64)) < 2e-5, (name, k)
+
+
 # --------------------------------------------------------------------------------- mapping / tracking loops
 def test_mapping_iterations_vs_reference(engine_factory, frames, syn, model_inputs):
     """Mapper.cpp:330-465: sampling stream, inside filter, render, loss, backward, fused Adam -- four iterations
