@@ -60,7 +60,7 @@ struct Smem {   // bytes; every UMMA tile starts on a multiple of 1024 B, rows a
     static constexpr int SCR = IMG;                                // gather scratch: C/32 blocks of [32][SCR_ROW] fp32 per active compute warp
     static constexpr int SCRW = (C / 32) * 32 * SCR_ROW * 4;       // bytes per warp
     static constexpr int BAR = SCR + ngroups(C) * 4 * SCRW;        // mbarriers: full[NG], done[NG], image
-    static constexpr int TMEMPTR = BAR + (2 * NG + 1) * 8;
+    static constexpr int TMEMPTR = BAR + (3 * NG + 1) * 8;         // full[NG], done[NG], image, ready[NG]
     static constexpr int TICKET = TMEMPTR + 8;                     // [NG][3] ring of tiles drawn by a group's row 0 (current, next, the one after)
     static constexpr int TOTAL = TICKET + NG * 16;
 };
@@ -125,7 +125,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int s = 0; s < NG; ++s) { mbar_init(bar0 + 8 * s, GTHREADS); mbar_init(bar0 + 8 * NG + 8 * s, 1); }
+        for (int s = 0; s < NG; ++s) { mbar_init(bar0 + 8 * s, GTHREADS); mbar_init(bar0 + 8 * NG + 8 * s, 1); mbar_init(bar0 + 16 * NG + 8 + 8 * s, GTHREADS); }
         mbar_init(bar_img, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
         // the decoder's image: one-dimensional bulk TMA copies, completion counted in bytes on bar_img
@@ -196,6 +196,8 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
             *reinterpret_cast<float4*>(dst + 4) = make_float4(c8[4], c8[5], c8[6], c8[7]);
         };
         uint32_t step = 0;   // handshakes completed by this group: parity of both barriers
+        uint32_t rstep = 0;  // "accumulator read" signals (parity of the ready barrier)
+        const uint32_t rdy = bar0 + 16 * NG + 8 + 8 * grp;
         int tile = ticket[4 * grp];
         float p[3];
         int s = -1;
@@ -271,6 +273,11 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                 float v[32];
                 tmem_ld32(tm + (i == 3 ? ACCS : ACC0), v);
                 tmem_ld_wait();
+                if (i < 4) {          // the accumulator is in registers: the issuer may start the next layer's grid-feature and bias
+                    fence_before();   // products (they do not depend on this layer's result) under the epilogue below
+                    mbar_arrive(rdy);
+                    ++rstep;
+                }
                 uint32_t m = 0;
 #pragma unroll
                 for (int k = 31; k >= 0; --k) {
@@ -324,7 +331,8 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         // every shared-memory descriptor is the image's base descriptor plus a byte offset >> 4 (few live registers: the issuer
         // runs on 32 registers per thread)
         const uint64_t dbase = make_desc(smem_u32(sm));
-        uint32_t step = 0;
+        uint32_t step = 0, rstep = 0;
+        const uint32_t rdy = bar0 + 16 * NG + 8 + 8 * grp;
         mbar_wait(bar_img, 0);
         for (int round = 0, tile = ticket[4 * grp]; tile < ntiles; ++round) {
             if (lane == 0) {
@@ -336,16 +344,17 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                     mma_commit(done); ++step;
                 }
 #pragma unroll 1
-                for (int l = 0; l < 4; ++l) {           // layer l+1: acc = u_l W_{l+1}^T + c G_l^T + b'  (layer 3 accumulates into accS)
-                    mbar_wait(full, step & 1); fence_after();
+                for (int l = 0; l < 4; ++l) {           // layer l+1: acc = c G_l^T + b' (early: under the epilogue of layer l) + u_l W_{l+1}^T (late); layer 3 accumulates into accS
                     const uint32_t d = tm + (l == 2 ? ACCS : ACC0);
-                    issue3(d, tm + XCOL, dbase + (uint64_t)((L::WH + l * 4096) >> 4), I32, l != 2);
-                    if (l != 2) mma_ss(d, dbase + (L::ONE >> 4), dbase + (uint64_t)((L::BT >> 4) + 2 * (l == 3 ? 3 : l + 1)), I32, 1u);   // + b'_{l+1}
+                    mbar_wait(rdy, rstep & 1); fence_after(); ++rstep;      // every thread has the previous accumulator in registers
 #pragma unroll 1
-                    for (int cc = 0; cc < NC; ++cc) issue3(d, tm + CCOL + 32 * cc, dbase + (uint64_t)((L::G + (l * NC + cc) * 4096) >> 4), I32, false);
+                    for (int cc = 0; cc < NC; ++cc) issue3(d, tm + CCOL + 32 * cc, dbase + (uint64_t)((L::G + (l * NC + cc) * 4096) >> 4), I32, l != 2 && cc == 0);
+                    if (l != 2) mma_ss(d, dbase + (L::ONE >> 4), dbase + (uint64_t)((L::BT >> 4) + 2 * (l == 3 ? 3 : l + 1)), I32, 1u);   // + b'_{l+1}
+                    mbar_wait(full, step & 1); fence_after();
+                    issue3(d, tm + XCOL, dbase + (uint64_t)((L::WH + l * 4096) >> 4), I32, false);
                     mma_commit(done); ++step;
                 }
-            } else step += 7;
+            } else { step += 7; rstep += 4; }
             __syncwarp();
             group_sync(grp);
             tile = ticket[4 * grp + (round + 1) % 3];
