@@ -46,31 +46,32 @@ static WGTable build_table() {
     };
     auto G = [&](int L, int dst, int ld, int a_hi = 16, int a_lo = 0) { return WGroup{L, dst, ld, a_lo, a_hi}; };
     const int GU = stash::GU, LD3 = EMB + HID, MS = WG_SCRATCH;
-    // warps are spread over the four schedulers (warp & 3) so that each gets ~600 instructions per k-step
-    // scheduler 0: bias sums, Cc x GO (M_out), H0 x GU1 (W1), H4 x GO (Wo)
+    // Warps are spread over the four schedulers (warp & 3) by their HMMA count per k-step (48 / 24 / 12 per task, 396 in all): 96 + 96 +
+    // 108 + 96 (measured: rebalancing from 48 / 120 / 120 / 108 changed nothing -- the ring is paced by per-warp latency chains, not by
+    // one scheduler's HMMA count).
+    // scheduler 0: E0 x {GU0, GU3} (48), H0 x GU1 (W1, 24), Cc x GO (M_out, 12), H4 x GO (Wo, 12)
+    mma(0, stash::E + 0, 32, {G(GU + 0, f.W[0], EMB), G(GU + 16, f.W[0] + 16 * EMB, EMB), G(GU + 96, f.W[3], LD3), G(GU + 112, f.W[3] + 16 * LD3, LD3)});
+    mma(4, stash::H + 0, 32, {G(GU + 32, f.W[1], 32), G(GU + 48, f.W[1] + 16 * 32, 32)});
+    mma(8, stash::Cc, 32, {G(stash::GO, MS + 4 * 1024, 32, 4)});
+    mma(12, stash::H + 128, 32, {G(stash::GO, f.Wo, 32, 4)});
+    // scheduler 1: E1, E2 x {GU0, GU3} (48 + 48), the bias sums (no MMAs), and the idle warp 13 = the TMA producer
+    mma(1, stash::E + 32, 32, {G(GU + 0, f.W[0] + 32, EMB), G(GU + 16, f.W[0] + 16 * EMB + 32, EMB), G(GU + 96, f.W[3] + 32, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 32, LD3)});
+    mma(5, stash::E + 64, EMB - 64, {G(GU + 0, f.W[0] + 64, EMB), G(GU + 16, f.W[0] + 16 * EMB + 64, EMB),
+                                     G(GU + 96, f.W[3] + 64, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 64, LD3)});
     {
-        WTask& t = T.t[0]; t.kind = 1;
+        WTask& t = T.t[9]; t.kind = 1;
         for (int i = 0; i < 5; ++i) { t.bias_col[i] = GU + 32 * i; t.bias_dst[i] = f.b[i]; t.bias_n[i] = 32; }
         t.bias_col[5] = stash::GO; t.bias_dst[5] = f.bo; t.bias_n[5] = 4;
     }
-    mma(4, stash::Cc, 32, {G(stash::GO, MS + 4 * 1024, 32, 4)});
-    mma(8, stash::H + 0, 32, {G(GU + 32, f.W[1], 32), G(GU + 48, f.W[1] + 16 * 32, 32)});
-    mma(12, stash::H + 128, 32, {G(stash::GO, f.Wo, 32, 4)});
-    // scheduler 1: E0 / E1 x {GU0 (W0), GU3 (W3 embedding columns)}, H1 x GU2 (W2)
-    for (int j = 0; j < 2; ++j)
-        mma(1 + 4 * j, stash::E + 32 * j, 32, {G(GU + 0, f.W[0] + 32 * j, EMB), G(GU + 16, f.W[0] + 16 * EMB + 32 * j, EMB),
-                                               G(GU + 96, f.W[3] + 32 * j, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 32 * j, LD3)});
-    mma(9, stash::H + 32, 32, {G(GU + 64, f.W[2], 32), G(GU + 80, f.W[2] + 16 * 32, 32)});
-    // scheduler 2: E2 x {GU0, GU3}, Cc x {GU1, GU2} (M_1, M_2), GE0 / GE1 x p (dB)
-    mma(2, stash::E + 64, EMB - 64, {G(GU + 0, f.W[0] + 64, EMB), G(GU + 16, f.W[0] + 16 * EMB + 64, EMB),
-                                     G(GU + 96, f.W[3] + 64, LD3), G(GU + 112, f.W[3] + 16 * LD3 + 64, LD3)});
-    mma(6, stash::Cc, 32, {G(GU + 32, MS + 0, 32), G(GU + 48, MS + 16 * 32, 32), G(GU + 64, MS + 1024, 32), G(GU + 80, MS + 1024 + 16 * 32, 32)});
-    mma(10, stash::GE + 0, 32, {G(stash::Pp, f.B, EMB, 3)});
-    mma(14, stash::GE + 32, 32, {G(stash::Pp, f.B + 32, EMB, 3)});
-    // scheduler 3: Cc x {GU3, GU4} (M_3, M_4), H2 x GU3 (W3 hidden columns), H3 x GU4 (W4), GE2 x p
+    // scheduler 2: Cc x {GU1, GU2} (M_1, M_2, 48), H1 x GU2 (W2, 24), H2 x GU3 (W3 hidden columns, 24), GE0 x p (dB, 12)
+    mma(2, stash::Cc, 32, {G(GU + 32, MS + 0, 32), G(GU + 48, MS + 16 * 32, 32), G(GU + 64, MS + 1024, 32), G(GU + 80, MS + 1024 + 16 * 32, 32)});
+    mma(6, stash::H + 32, 32, {G(GU + 64, f.W[2], 32), G(GU + 80, f.W[2] + 16 * 32, 32)});
+    mma(10, stash::H + 64, 32, {G(GU + 96, f.W[3] + EMB, LD3), G(GU + 112, f.W[3] + 16 * LD3 + EMB, LD3)});
+    mma(14, stash::GE + 0, 32, {G(stash::Pp, f.B, EMB, 3)});
+    // scheduler 3: Cc x {GU3, GU4} (M_3, M_4, 48), H3 x GU4 (W4, 24), GE1, GE2 x p (12 + 12)
     mma(3, stash::Cc, 32, {G(GU + 96, MS + 2048, 32), G(GU + 112, MS + 2048 + 16 * 32, 32), G(GU + 128, MS + 3072, 32), G(GU + 144, MS + 3072 + 16 * 32, 32)});
-    mma(7, stash::H + 64, 32, {G(GU + 96, f.W[3] + EMB, LD3), G(GU + 112, f.W[3] + 16 * LD3 + EMB, LD3)});
-    mma(11, stash::H + 96, 32, {G(GU + 128, f.W[4], 32), G(GU + 144, f.W[4] + 16 * 32, 32)});
+    mma(7, stash::H + 96, 32, {G(GU + 128, f.W[4], 32), G(GU + 144, f.W[4] + 16 * 32, 32)});
+    mma(11, stash::GE + 32, 32, {G(stash::Pp, f.B + 32, EMB, 3)});
     mma(15, stash::GE + 64, EMB - 64, {G(stash::Pp, f.B + 64, EMB, 3)});
     return T;
 }
@@ -170,11 +171,16 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
                 for (int u = 0; u < 4; ++u) av[u] = *reinterpret_cast<const float2*>(r0 + 4 * u * stash::W + Lc[q]);
                 AFrag<P3> a;
                 a.set(av[0].x, av[1].x, av[2].x, av[3].x, av[0].y, av[1].y, av[2].y, av[3].y);
+                // product by product over the four n-tiles: consecutive HMMAs hit different accumulators (the three products of one
+                // accumulator are a dependent chain)
+                if (P3) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (P3) { mma_f16(acc[q][j], a.lo, bh[j][0], bh[j][1]); mma_f16(acc[q][j], a.hi, bl[j][0], bl[j][1]); }
-                    mma_f16(acc[q][j], a.hi, bh[j][0], bh[j][1]);
+                    for (int j = 0; j < 4; ++j) mma_f16(acc[q][j], a.lo, bh[j][0], bh[j][1]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_f16(acc[q][j], a.hi, bl[j][0], bl[j][1]);
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_f16(acc[q][j], a.hi, bh[j][0], bh[j][1]);
             }
         } else if (live && kind == 1) {
             float* sums = &acc[0][0][0];
