@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
 
 // d Fc_{i-1} = W_i(hidden columns)^T M_i and d bc_{i-1} = W_i^T d b_i for i = 1..4, d Fc_4 = Wo^T M_out and d bc_4 = Wo^T d bo: the gradients at the
 // block outputs are linear images of the g_u sums k_wgrad has just produced.  One block per Fc matrix; clears the M scratch for the next iteration.
-__global__ void __launch_bounds__(256) k_wgrad_finish(const float* __restrict__ flat, float* __restrict__ dflat, float* __restrict__ mscr) {
+__global__ void __launch_bounds__(1024) k_wgrad_finish(const float* __restrict__ flat, float* __restrict__ dflat, float* __restrict__ mscr) {
     const DecFlat f = DecFlat::make(32, 4);
     const int i = blockIdx.x;                       // Fc_i, i = 0..4
     __shared__ float sW[32][33], sM[32][33], sb[32];
@@ -283,7 +283,7 @@ cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, in
     { const cudaError_t e = wgrad_init(); if (e != cudaSuccess) return e; }
     if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
     else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
-    k_wgrad_finish<<<5, 256, 0, st>>>(flat, dflat, mscr);
+    k_wgrad_finish<<<5, 1024, 0, st>>>(flat, dflat, mscr);
     return cudaGetLastError();
 }
 
