@@ -993,7 +993,11 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
         const float ge = (flags & 4) ? 288.f : 0.f;
         if (stage == NSB_MIDDLE) w[1] = 480 + ge;
         else if (stage == NSB_FINE) { w[1] = 480 + ge; w[2] = 480 + ge; }
-        else if (stage == NSB_COLOR) { w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg_stash ? 288.f + 300.f : ge); if (wg_stash && !ge) { w[1] = 460; w[2] = 500; w[3] = 1250; } }   // measured (tools/sweep_split.sh)
+        else if (stage == NSB_COLOR) {
+            w[1] = 480 + ge; w[2] = 480 + ge; if (color_active) w[3] = 480 + (wg_stash ? 288.f + 300.f : ge);
+            if (!ge && !color_active) { w[1] = 460; w[2] = 500; }               // geometry iterations: the fine grid's scatter touches more vertices (measured)
+            if (wg_stash && !ge) { w[1] = 460; w[2] = 500; w[3] = 1100; }       // measured with the 552-float stash (tools/bench_short.sh sweeps)
+        }
         else {   // coarse stage (the coarse mapper): MLP_no_xyz data gradient -> grid_coarse; no embedding, so no ray gradient path here
             if (flags & 4) return fail(ctx, "ray gradients through the coarse stage are not supported (the coarse mapper runs without bundle adjustment, Mapper.cpp:530)");
             if (ctx->mask_layout != 0) return fail(ctx, "coarse backward needs the warp-MMA forward's mask layout");
