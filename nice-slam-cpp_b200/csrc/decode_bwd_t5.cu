@@ -86,7 +86,7 @@ __device__ __forceinline__ void scatter_stage(const GridView& G, const Bound& bn
             int off;
             const float w = tri_corner(G, s, k, off);
             scr[SC_W + 8 * lane + (k ^ pc)] = live ? w : 0.0f;
-            scri[SC_OFF + 8 * lane + (k ^ pc)] = off;
+            scri[SC_OFF + 8 * lane + (k ^ pc)] = off * 4;       // byte offset (unsigned 32-bit: a grid is far below 4 GB)
         }
         scri[SC_CELL + lane] = s.i0[0] | (s.i0[1] << 10) | (s.i0[2] << 20);
     }
@@ -110,14 +110,15 @@ __device__ __forceinline__ void scatter_walk(const GridView& G, const float* __r
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
-    float* const base = G.grad + lane;
+    const char* const base = reinterpret_cast<const char*>(G.grad + lane);   // + unsigned byte offset: two integer adds per address
 #pragma unroll 1
     for (int s = 0; s <= WROW; ++s) {
         const uint32_t fm = s == WROW ? 0xffu : (uint32_t)scri[SC_CELL + WROW + s];
         if (fm) {                                            // warp-uniform: flush the vertices that leave with the previous sample's cell
             const int4 oa = *reinterpret_cast<const int4*>(scri + SC_OFF + 8 * (s - 1)), ob = *reinterpret_cast<const int4*>(scri + SC_OFF + 8 * (s - 1) + 4);
             const int off[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-#define NSB_FLUSH(j) { red_add_f32(base + off[j], acc[j]); acc[j] = 0.0f; }
+#define NSB_ADDR(j) reinterpret_cast<float*>(const_cast<char*>(base + (size_t)(uint32_t)off[j]))
+#define NSB_FLUSH(j) { red_add_f32(NSB_ADDR(j), acc[j]); acc[j] = 0.0f; }
             // a move to a face neighbour (the common case) retires the four vertices of one face: six fixed patterns without per-slot tests
             switch (fm) {
                 case 0x55u: NSB_FLUSH(0) NSB_FLUSH(2) NSB_FLUSH(4) NSB_FLUSH(6) break;
@@ -129,9 +130,10 @@ __device__ __forceinline__ void scatter_walk(const GridView& G, const float* __r
                 default:
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if ((fm >> j) & 1u) { if (acc[j] != 0.0f) red_add_f32(base + off[j], acc[j]); acc[j] = 0.0f; }
+                        if ((fm >> j) & 1u) { if (acc[j] != 0.0f) red_add_f32(NSB_ADDR(j), acc[j]); acc[j] = 0.0f; }
             }
 #undef NSB_FLUSH
+#undef NSB_ADDR
         }
         if (s == WROW) break;
         const float4 wa = *reinterpret_cast<const float4*>(scr + SC_W + 8 * s), wb = *reinterpret_cast<const float4*>(scr + SC_W + 8 * s + 4);
