@@ -177,6 +177,16 @@ __device__ __forceinline__ float tri_corner(const GridView& G, const Tri& s, int
     return __fmul_rn(__fmul_rn(wx, wy), wz);
 }
 
+// the same with the voxel INDEX (z Y + y) X + x instead of the float offset: the caller forms the address as
+// base + (unsigned) index * 128 bytes, one IMAD.WIDE.U32 instead of shift + sign extension + 64-bit LEA pair
+__device__ __forceinline__ float tri_corner_idx(const GridView& G, const Tri& s, int k, unsigned& idx) {
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+    const int x = dx ? s.i1[0] : s.i0[0], y = dy ? s.i1[1] : s.i0[1], z = dz ? s.i1[2] : s.i0[2];
+    idx = (unsigned)((z * G.Y + y) * G.X + x);
+    const float wx = dx ? s.w1[0] : s.w0[0], wy = dy ? s.w1[1] : s.w0[1], wz = dz ? s.w1[2] : s.w0[2];
+    return __fmul_rn(__fmul_rn(wx, wy), wz);
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // 256-bit read-only load (sm_100): the four lanes of a quad fetch one whole 128-byte voxel line in a single L1 wavefront
 __device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {

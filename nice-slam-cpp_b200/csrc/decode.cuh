@@ -223,12 +223,13 @@ __device__ __forceinline__ void gather8(const GridView& G, const Bound& bnd, con
     tri_setup(G, bnd, p, s);
 #pragma unroll
     for (int i = 0; i < 8; ++i) c[i] = 0.0f;
+    const char* const base = reinterpret_cast<const char*>(G.data + 8 * t);    // + voxel index * 128 bytes (CDIM floats per voxel)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        int off;
-        const float w = tri_corner(G, s, k, off);
+        unsigned idx;
+        const float w = tri_corner_idx(G, s, k, idx);
         float v[8];
-        ldg8(G.data + off + 8 * t, v);
+        ldg8(reinterpret_cast<const float*>(base + (unsigned long long)idx * (CDIM * 4)), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) c[i] = fmaf(v[i], w, c[i]);
     }
