@@ -25,6 +25,7 @@ VARIANTS = {"": [], "precise_sin": ["-DNSB_PRECISE_SIN"], "tctiming": ["-DNSB_TC
             # occupancy experiments: warps per CTA of the forward / backward decoder kernels
             "f20b20": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=20"], "f16b24": ["-DNSB_BWD_WARPS=24"], "f20b24": ["-DNSB_FWD_WARPS=20", "-DNSB_BWD_WARPS=24"],
             "f24b24": ["-DNSB_FWD_WARPS=24", "-DNSB_BWD_WARPS=24"], "f16b20": ["-DNSB_BWD_WARPS=20"],
+            "nohint": ["-DNSB_MBAR_HINT_NS=0"],   # mbarrier waits without the suspend-time hint (A/B)
             "scat0": ["-DNSB_SCATTER_AGG=0"],   # per-sample quad reductions instead of the warp-aggregated scatter (A/B)
             "emb1": ["-DNSB_EMB_UNROLL=1"], "emb3": ["-DNSB_EMB_UNROLL=3"], "emb6": ["-DNSB_EMB_UNROLL=6"]}
 

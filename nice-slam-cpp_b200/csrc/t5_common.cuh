@@ -3,6 +3,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef NSB_MBAR_HINT_NS
+#define NSB_MBAR_HINT_NS 4000   // suspend-time hint of mbarrier.try_wait in ns (0: the loop spins; measured neutral in time, fewer issued instructions)
+#endif
+
 namespace nsb {
 namespace t5 {
 
@@ -20,8 +24,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // try_wait sleeps in hardware until the phase flips or a time limit
     asm volatile(
         "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"      // suspend-time hint: sleep in hardware instead of spinning
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((unsigned)NSB_MBAR_HINT_NS) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major SWIZZLE_128B, SBO 1024 B, version 1
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);

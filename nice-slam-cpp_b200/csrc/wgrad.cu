@@ -13,6 +13,10 @@
 #include <cstring>
 #include <initializer_list>
 
+#ifndef NSB_MBAR_HINT_NS
+#define NSB_MBAR_HINT_NS 4000   // suspend-time hint of mbarrier.try_wait in ns (0: the loop spins; measured neutral in time, fewer issued instructions)
+#endif
+
 namespace nsb {
 
 constexpr int WG_WARPS = 16;
@@ -88,8 +92,8 @@ __device__ __forceinline__ void wg_mbar_arrive(uint32_t bar) { asm volatile("mba
 __device__ __forceinline__ void wg_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"      // suspend-time hint: sleep in hardware instead of spinning
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((unsigned)NSB_MBAR_HINT_NS) : "memory");
 }
 
 // The CTA streams its sample range through a shared-memory ring (one stage = the 16 stash rows of a k-step, 45.6 KB,
