@@ -1951,8 +1951,9 @@ extern "C" int nsb_comm_p2p_import(nsb_ctx* ctx, const char* all_handles, int ra
     ctx->rank = rank; ctx->world = world; ctx->p2p = true;
     return 0;
 }
-// Instrumentation of the fused exchange (k_reduce_adam stamps %globaltimer): out5 = {last barrier-1 wait us, last kernel total us,
-// mean wait us, mean total us, exchanges averaged}.  The wait is the time this rank spent waiting for the slowest rank's backward;
+// Instrumentation of the fused exchange (k_reduce_adam stamps %globaltimer): out8 = {last barrier-1 wait us, last kernel total us,
+// mean wait us, mean total us, exchanges averaged, mean exchanged range bytes, NVLink bytes per direction ((W-1)/W model), GB/s per
+// direction}.  The wait is the time this rank spent waiting for the slowest rank's backward;
 // total - wait is the reduce-scatter + Adam + all-gather + barrier 2 itself.  reset != 0 clears the sums.
 extern "C" int nsb_comm_p2p_stats(nsb_ctx* ctx, double* out8, int reset) {
     cudaSetDevice(ctx->device);
