@@ -569,7 +569,10 @@ def run_ours(args, rank, world, local_rank):
         tc = os.environ.get("NSB_TCGEN05", "3")
         fwd_geo = {"3": "k_decode_fwd_t5", "2": "k_decode_fwd_tc16", "1": "k_decode_fwd_tc"}.get(tc, "k_decode_fwd")
         stash = os.environ.get("NSB_WGRAD_STASH", "1") != "0"
-        fwd_col = "k_decode_fwd" if stash else fwd_geo      # a colour iteration that stashes activations for k_wgrad runs the warp-MMA forward
+        t5_stash = tc == "3" and os.environ.get("NSB_T5_STASH", "1") != "0"
+        # a colour iteration that stashes activations for k_wgrad: the tcgen05 forward writes the stash itself (default) or the colour decoder
+        # runs on the warp-MMA forward beside it (NSB_T5_STASH=0)
+        fwd_col = fwd_geo if (not stash or t5_stash) else "k_decode_fwd"
 
         def entry(name, stage, key, n_it, flop_ray, extra=None):
             ms = by[stage].get(key, 0.0)

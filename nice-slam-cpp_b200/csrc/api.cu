@@ -46,7 +46,7 @@ int wgrad_fused_scratch_floats();
 cudaError_t wgrad_fused_init();
 cudaError_t launch_build_wgimg(const float* flat, uint8_t* img, cudaStream_t st);
 cudaError_t launch_wgrad_fused(const DecodeParams& P, const uint8_t* img, const float* flat, float* dflat, float* scratch, int n_sm, cudaStream_t st);
-cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int precision, int grid, cudaStream_t st);
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int h_is_u, int precision, int grid, cudaStream_t st);
 int decode_fwd_occupancy(int precision);
 cudaError_t launch_gather_only(const DecodeParams& P, float* out, int grid, cudaStream_t st);
 cudaError_t launch_coarse_bwd(const DecodeParams& P, int precision, int grid, cudaStream_t st);
@@ -191,6 +191,8 @@ struct nsb_ctx {
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     cudaStream_t comm_stream = nullptr; cudaEvent_t ev_bwd = nullptr, ev_comm = nullptr;   // grid all-reduce overlapped with the wgrad kernel
     cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // colour iterations: the stashing colour decoder runs beside the tcgen05 forward
+    int t5_stash = 1;            // colour iterations with a stash: ONE tcgen05 forward launch writes it (NSB_T5_STASH=0: warp-MMA colour decoder beside the tcgen05 one)
+    bool stash_is_u = false;     // the stash's H slots hold relu outputs (written by the tcgen05 forward): k_wgrad_finish adds the Fc c + bc part
     int compact_rays = 1;        // tcgen05 forward walks the compacted list of valid rays (NSB_COMPACT_RAYS=0: all rays, filtered rows idle)
     int split_color_sms = 65;    // SMs given to the colour decoder's warp-MMA forward in that split (NSB_SPLIT_COLOR_SMS; 0 = one warp-MMA launch)
     bool ar_request = false, ar_overlapped = false;
@@ -435,6 +437,7 @@ extern "C" int nsb_create(const nsb_config* cfg, int device, nsb_ctx** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     { const char* e = getenv("NSB_SPLIT_COLOR_SMS"); if (e) ctx->split_color_sms = atoi(e); }
     { const char* e = getenv("NSB_COMPACT_RAYS"); if (e) ctx->compact_rays = atoi(e); }
+    { const char* e = getenv("NSB_T5_STASH"); if (e) ctx->t5_stash = atoi(e); }
     for (int a = 0; a < 3; ++a) { ctx->bnd.lo[a] = cfg->bound[a][0]; ctx->bnd.hi[a] = cfg->bound[a][1]; ctx->bnd.len[a] = cfg->bound[a][1] - cfg->bound[a][0]; ctx->bnd.inv_len[a] = 1.0f / ctx->bnd.len[a]; }
     size_t off = 0;
     auto seg = [&](size_t n) { size_t o = off; off += pad32(n); return o; };
@@ -779,29 +782,35 @@ static void env_weights(const char* name, float w[4]) {
 // Rebuilds the pre-split shared-memory images of the decoders whose weights changed (set_decoder / an Adam step with a decoder
 // learning rate).  cmp_mask: decoders whose COMPOSED forward image the coming launches read.  force: rebuild these decoders
 // whatever the dirty bits say (the captured colour iteration ends with the rebuild of the colour decoder it has just stepped).
-static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0, bool lazy_cmp = false) {
-    // lazy_cmp (the stash path's colour iterations): the stepped decoder's composed / tcgen05 images are not read until the next
-    // non-stash forward, so only its plain forward / backward images are rebuilt inside the iteration; the host marks the composed
-    // ones stale per iteration (nsb_mapping_iter_async) and the next API entry that needs them rebuilds them once.
+static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0, int lazy = 0) {
+    // lazy (the stash path's colour iterations, `force` = the decoder the iteration has just stepped): images nobody reads before the
+    // next non-stash forward are not rebuilt inside the iteration; the host marks them stale per iteration (mark_color_stale) and the
+    // next API entry that needs them rebuilds them once.
+    //   lazy 1 (warp-MMA stash forward): only the plain forward / backward images now; composed weights, composed image, tcgen05 image later
+    //   lazy 2 (tcgen05 stash forward):  plain images + composed weights + tcgen05 image now; the warp-MMA composed image later
     const int plain = ctx->wimg_dirty | force;
-    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | (lazy_cmp ? 0 : force);
-    if (!plain && !cmp_need) return 0;
+    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | (lazy ? 0 : force);
+    const int t5_need = cmp_need | (lazy == 2 ? force : 0);
+    if (!plain && !cmp_need && !t5_need) return 0;
     const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
-    const int comp_need = (ctx->comp_dirty & cmp_need) | (lazy_cmp ? 0 : force);
+    const int comp_need = (ctx->comp_dirty & (cmp_need | t5_need)) | (lazy == 1 ? 0 : force);
     if (comp_need) {   // the composed images are built from k_compose's output
         CK(launch_compose(flat, ctx->comp, comp_need, ctx->stream)); ctx->launches++;
         ctx->comp_dirty &= ~comp_need;
     }
-    CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++;
-    if (ctx->use_tc == 3 && cmp_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, cmp_need, ctx->stream)); ctx->launches++; }
+    if (plain || cmp_need) { CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++; }
+    if (ctx->use_tc == 3 && t5_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, t5_need, ctx->stream)); ctx->launches++; }
     if (ctx->use_tc == 3 && (cmp_need & 0x6)) { CK(launch_build_t5bimg(flat, ctx->comp, ctx->wimg_t5b, cmp_need, ctx->stream)); ctx->launches++; }
     if ((plain & 8) && !ctx->wg_stash) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (stash-free weight gradient only)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
 }
 
-// Colour iterations of the stash path rebuild the stepped colour decoder's composed images lazily (see refresh_images).
-static bool lazy_color_images(const nsb_ctx* ctx) { return ctx->wg_stash != 0 && !ctx->map_fix_color && !ctx->coarse_map && ctx->use_tc == 3; }
+// Colour iterations of the stash path rebuild the stepped colour decoder's images lazily (see refresh_images): 0 = no, 1 / 2 = which set.
+static int lazy_color_images(const nsb_ctx* ctx) {
+    if (!ctx->wg_stash || ctx->map_fix_color || ctx->coarse_map || ctx->use_tc != 3) return 0;
+    return ctx->t5_stash ? 2 : 1;
+}
 
 static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, const uint8_t* valid) {
     memset(&P, 0, sizeof P);
@@ -852,8 +861,9 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
     // will the tcgen05 forward run (alone, or beside the stashing colour decoder)?  Then k_zvals also compacts the rays that pass the inside filter.
     const bool want_stash = train && stash_fwd && stage == NSB_COLOR && ctx->wg_stash;
     const bool t5_base = ctx->use_tc == 3 && c.precision == NSB_PREC_FP32_GRADE && stage != NSB_COARSE && !(train && stash_fwd && stage == NSB_COLOR && !ctx->wg_stash);
-    const bool t5_split = t5_base && want_stash && ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
-    const bool compact = valid != nullptr && ctx->compact_rays && (t5_split || (t5_base && !want_stash));
+    const bool t5_all_stash = t5_base && want_stash && ctx->t5_stash && !((ctx->comp_dirty >> 1) & 7);     // one tcgen05 launch also writes the stash
+    const bool t5_split = t5_base && want_stash && !t5_all_stash && ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
+    const bool compact = valid != nullptr && ctx->compact_rays && (t5_split || t5_all_stash || (t5_base && !want_stash));
     {
         Timer t(ctx, T_SAMPLE);
         ZParams Z; Z.rays_o = ctx->rays_o + 3 * off; Z.rays_d = ctx->rays_d + 3 * off; Z.gt_depth = have_depth ? ctx->gt_depth + off : nullptr;
@@ -883,9 +893,18 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         // Colour iteration with a weight-gradient stash: decoders 1 and 2 run on the tcgen05 kernel while the stashing colour
         // decoder runs on the warp-MMA kernel, side by side on disjoint SMs (both kernels take a whole SM per CTA), forked
         // onto a second stream and joined before the composite -- capturable, so it lives inside the iteration's graph.
-        const bool split_fwd = ctx->use_tc == 3 && c.precision == NSB_PREC_FP32_GRADE && stage == NSB_COLOR && P.stash != nullptr && train &&
-                               ctx->split_color_sms > 0 && ctx->split_color_sms < ctx->n_sm - 8 && !((ctx->comp_dirty >> 1) & 3);
-        if (split_fwd) {
+        const bool split_fwd = t5_split && P.stash != nullptr;
+        if (P.stash) ctx->stash_is_u = false;
+        if (t5_all_stash && P.stash) {
+            // all three decoders on the tcgen05 kernel; the colour decoder's threads write the stash rows of their samples
+            for (int d = 0; d < 4; ++d) P.comp[d] = ctx->comp[d];
+            P.mask_layout = 0xE; P.mask_stride = n * S;
+            ctx->mask_layout = 0xE; ctx->mask_stride = n * S; ctx->stash_is_u = true;
+            float w5[4] = {0, 700.f, 1300.f, 1300.f}; env_weights("NSB_SPLIT_FWD_T5S", w5);     // measured (the colour decoder also writes 288 floats per sample)
+            partition(std::min(ctx->n_sm, std::max(1, cdiv(n * S, 512))), w5, P.cta_begin);
+            P.tile_ctr = ctx->tile_ctr;
+            CK(launch_decode_fwd_t5(P, P.cta_begin[4], ctx->stream)); ctx->launches++;
+        } else if (split_fwd) {
             DecodeParams PA = P, PB = P;
             PA.stash = nullptr; PB.ray_list = nullptr; PB.ray_count = nullptr;
             for (int d = 0; d < 4; ++d) PA.comp[d] = ctx->comp[d];
@@ -1034,7 +1053,7 @@ static int run_backward(nsb_ctx* ctx, int stage, int off, int n, const uint8_t* 
     }
     if (wg_stash) {
         Timer t(ctx, T_WGRAD);
-        CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->param + ctx->off_dec[3], ctx->grad + ctx->off_dec[3], ctx->wg_mscr, c.precision, ctx->n_sm, ctx->stream)); ctx->launches += 2;
+        CK(launch_wgrad(ctx->stash, valid ? valid + off : nullptr, n * S, S, ctx->param + ctx->off_dec[3], ctx->grad + ctx->off_dec[3], ctx->wg_mscr, ctx->stash_is_u ? 1 : 0, c.precision, ctx->n_sm, ctx->stream)); ctx->launches += 2;
     } else if (wg) {
         // colour-decoder weight gradient without a stash: recomputed per tile, contracted through shared memory (wgrad_fused.cu)
         Timer t(ctx, T_WGRAD);
@@ -1592,7 +1611,8 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
 static void mark_color_stale(nsb_ctx* ctx, const IterPlan& pl) {
     if (!lazy_color_images(ctx) || pl.pristine || pl.stage != NSB_COLOR) return;
     if (ctx->cfg.stage_lr[NSB_COLOR][0] * ctx->map_lr_factor == 0.f) return;
-    ctx->comp_dirty |= 8; ctx->wimg_cmp_dirty |= 8;
+    if (lazy_color_images(ctx) == 1) ctx->comp_dirty |= 8;
+    ctx->wimg_cmp_dirty |= 8;
 }
 
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
@@ -1616,7 +1636,12 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
     }
     // no-op unless a decoder was replaced since the last iteration; a stash colour iteration does not read the colour decoder's composed
     // images (left stale by the previous one on purpose)
-    if (refresh_images(ctx, (lazy_color_images(ctx) && pl.stage == NSB_COLOR && !pl.pristine) ? 0x6 : 0xE)) return -1;
+    {
+        const int lz = (pl.stage == NSB_COLOR && !pl.pristine) ? lazy_color_images(ctx) : 0;
+        if (refresh_images(ctx, lz ? 0x6 : 0xE)) return -1;
+        // the tcgen05 stash forward reads the colour decoder's composed weights: fresh before the first colour iteration (later ones rebuild them themselves)
+        if (lz == 2 && (ctx->comp_dirty & 8)) { if (refresh_images(ctx, 0, 8, 2)) return -1; }
+    }
     ctx->map_step++;
     const bool graph_ok = ctx->use_graph && !ctx->profiling && (ctx->world == 1 || ctx->p2p);
     if (!graph_ok) { const int rc = enqueue_iteration(ctx, pl); mark_color_stale(ctx, pl); return rc; }

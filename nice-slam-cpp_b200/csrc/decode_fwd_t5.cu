@@ -59,7 +59,9 @@ struct Smem {   // bytes; every UMMA tile starts on a multiple of 1024 B, rows a
     static constexpr int IMG = BOC + 16;                           // everything above is the decoder's image, prebuilt in global memory (k_build_t5img)
     static constexpr int SCR = IMG;                                // gather scratch: C/32 blocks of [32][SCR_ROW] fp32 per active compute warp
     static constexpr int SCRW = (C / 32) * 32 * SCR_ROW * 4;       // bytes per warp
-    static constexpr int BAR = SCR + ngroups(C) * 4 * SCRW;        // mbarriers: full[NG], done[NG], image
+    static constexpr int STX = SCR + ngroups(C) * 4 * SCRW;        // stash transposition block [32][SCR_ROW] per compute warp (32-channel decoders only: the colour decoder)
+    static constexpr int STXW = C == 32 ? 32 * SCR_ROW * 4 : 0;
+    static constexpr int BAR = STX + ngroups(C) * 4 * STXW;        // mbarriers: full[NG], done[NG], image
     static constexpr int TMEMPTR = BAR + (3 * NG + 1) * 8;         // full[NG], done[NG], image, ready[NG]
     static constexpr int TICKET = TMEMPTR + 8;                     // [NG][3] ring of tiles drawn by a group's row 0 (current, next, the one after)
     static constexpr int TOTAL = TICKET + NG * 16;
@@ -107,6 +109,23 @@ __device__ void stage(uint8_t* sm, const float* __restrict__ flat, const float* 
     for (int i = tid; i < 4 * C; i += nthr) woc[i] = comp[comp_woc(C) + i];
     float* boc = reinterpret_cast<float*>(sm + L::BOC);
     if (tid < 4) boc[tid] = comp[comp_boc(C) + tid];
+}
+
+// 32 values per thread (its own sample's row) -> columns [col, col + 32) of the samples' stash rows, transposed through a per-warp block so
+// that every store instruction writes whole 128-byte pieces of four rows (row-per-thread stores touch 32 lines with 16 bytes each and
+// cost 0.1 ms per launch).  srow: the thread's sample index or -1.
+__device__ __forceinline__ void stash_block(float* __restrict__ stx, float* __restrict__ stash_base, int srow, int col, const float (&v)[32], int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stx + lane * SCR_ROW + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3), c4 = 4 * (lane & 7);
+        const int sr = __shfl_sync(0xffffffffu, srow, r);
+        const float4 x = *reinterpret_cast<const float4*>(stx + r * SCR_ROW + c4);
+        if (sr >= 0) *reinterpret_cast<float4*>(stash_base + (size_t)sr * stash::W + col + c4) = x;
+    }
 }
 
 template <int C, int O>
@@ -159,6 +178,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         const float* woc = reinterpret_cast<const float*>(sm + L::WOC);
         const float* boc = reinterpret_cast<const float*>(sm + L::BOC);
         float* scr = reinterpret_cast<float*>(sm + L::SCR + warp * L::SCRW);
+        float* stx = reinterpret_cast<float*>(sm + L::STX + warp * L::STXW);
         // position of this thread's sample in tile `tile` (zero, and inactive, past the end or on a filtered ray)
         auto load_point = [&](int tile, float (&pp)[3], int& s_out) -> bool {
             const int sp = tile * TM + row;
@@ -212,6 +232,10 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
         for (int round = 0; tile < ntiles; ++round) {
             if (row == 0) ticket[4 * grp + (round + 2) % 3] = (int)atomicAdd(P.tile_ctr + dec, 1ull);   // read after the group barrier of this round
             const int tile_next = ticket[4 * grp + (round + 1) % 3];
+            // colour decoder of a training iteration whose weights are optimised: the thread leaves e, c and the relu outputs u_i of its
+            // sample in the weight-gradient stash (E | H slots | Cc of params.h; the H slots hold u_i, k_wgrad_finish adds the Fc c + bc part)
+            const bool do_stash = O == 4 && P.stash != nullptr;
+            const int srow = active ? s : -1;
             // ---- grid features: the owner lane reads its row of the scratch, adds the grid-feature part of the output layer and
             // moves the row to tensor memory as the A operand of every G_i c product
             float outc[NO];
@@ -236,6 +260,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                     }
                     outc[o] = acc;
                 }
+                if (O == 4 && do_stash) stash_block(stx, P.stash, srow, stash::Cc, c, lane);
                 store_operand(tm + CCOL + 32 * cc, c);                  // the previous tile's last product has been waited for (layer 4)
             }
             __syncwarp();                                               // the scratch is rewritten by the next tile's gather below
@@ -255,6 +280,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                     e[4 * k4 + 2] = ff_sin(fmaf(p[2], b2.z, fmaf(p[1], b1.z, p[0] * b0.z)));
                     e[4 * k4 + 3] = ff_sin(fmaf(p[2], b2.w, fmaf(p[1], b1.w, p[0] * b0.w)));   // padded columns of B are 0 -> sin(0) = 0
                 }
+                if (O == 4 && do_stash) stash_block(stx, P.stash, srow, stash::E + 32 * j, e, lane);
                 uint32_t w[32];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split_f16(e[2 * i], e[2 * i + 1], w[i], w[16 + i]);
@@ -285,6 +311,7 @@ __device__ void run_decoder(const DecodeParams& P, uint8_t* sm, int dec) {
                     v[k] = fmaxf(v[k], 0.0f);
                 }
                 if (P.masks && active) P.masks[((size_t)(dec - 1) * 5 + i) * P.mask_stride + s] = ~m;
+                if (O == 4 && do_stash) stash_block(stx, P.stash, srow, stash::H + HID * i, v, lane);
                 if (i < 4) {
                     store_operand(tm + XCOL, v);
                     tmem_st_wait();
@@ -404,7 +431,7 @@ cudaError_t launch_build_t5img(const float* const flat[4], const float* const co
 }
 
 cudaError_t launch_decode_fwd_t5(const DecodeParams& P, int grid, cudaStream_t st) {
-    const size_t smem = (size_t)t5::Smem<64>::TOTAL;
+    const size_t smem = (size_t)(t5::Smem<64>::TOTAL > t5::Smem<32>::TOTAL ? t5::Smem<64>::TOTAL : t5::Smem<32>::TOTAL);
     static unsigned attr_done = 0;      // per device: function attributes are per-device state
     int dev = 0; cudaGetDevice(&dev);
     if (!((attr_done >> (dev & 31)) & 1u)) {

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
 
 // d Fc_{i-1} = W_i(hidden columns)^T M_i and d bc_{i-1} = W_i^T d b_i for i = 1..4, d Fc_4 = Wo^T M_out and d bc_4 = Wo^T d bo: the gradients at the
 // block outputs are linear images of the g_u sums k_wgrad has just produced.  One block per Fc matrix; clears the M scratch for the next iteration.
-__global__ void __launch_bounds__(1024) k_wgrad_finish(const float* __restrict__ flat, float* __restrict__ dflat, float* __restrict__ mscr) {
+__global__ void __launch_bounds__(1024) k_wgrad_finish(const float* __restrict__ flat, float* __restrict__ dflat, float* __restrict__ mscr, int h_is_u) {
     const DecFlat f = DecFlat::make(32, 4);
     const int i = blockIdx.x;                       // Fc_i, i = 0..4
     __shared__ float sW[32][33], sM[32][33], sb[32];
@@ -260,6 +260,23 @@ __global__ void __launch_bounds__(1024) k_wgrad_finish(const float* __restrict__
         for (int o = 0; o < 32; ++o) acc = fmaf(sW[o][threadIdx.x], sb[o], acc);
         dflat[f.bc[i] + threadIdx.x] += acc;
     }
+    if (h_is_u) {
+        // The tcgen05 forward stashes the relu outputs u_i in the H slots, not the block outputs h_{i+1} = u_i + Fc_i c + bc_i, so k_wgrad's
+        // H x g_u products miss  (sum_s g_u (x) c) Fc_i^T + (sum_s g_u) bc_i^T = M Fc_i^T + db bc_i^T  -- added here, same M and db as above.
+        __shared__ float sF[32][33], sbc[32];
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) sF[k / 32][k % 32] = flat[f.Fc[i] + k];        // Fc_i[m][ch]
+        if (threadIdx.x < 32) sbc[threadIdx.x] = flat[f.bc[i] + threadIdx.x];
+        __syncthreads();
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+            const int o = k / 32, m = k % 32;
+            if (o >= no) continue;
+            float acc = sb[o] * sbc[m];
+#pragma unroll 8
+            for (int ch = 0; ch < 32; ++ch) acc = fmaf(sM[o][ch], sF[m][ch], acc);
+            float* dst = i == 4 ? dflat + f.Wo + o * HID + m : i == 2 ? dflat + f.W[3] + o * (EMB + HID) + EMB + m : dflat + f.W[i + 1] + o * HID + m;
+            *dst += acc;
+        }
+    }
     __syncthreads();
     for (int k = threadIdx.x; k < 1024; k += blockDim.x) mscr[i * 1024 + k] = 0.0f;
 }
@@ -281,13 +298,14 @@ cudaError_t wgrad_init() {
     return cudaSuccess;
 }
 
-// flat: the colour decoder's parameters (W^T of the finishing step); mscr: [5][32][32] floats, zero on entry and on exit
-cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int precision, int grid, cudaStream_t st) {
+// flat: the colour decoder's parameters (W^T of the finishing step); mscr: [5][32][32] floats, zero on entry and on exit; h_is_u: the stash's
+// H slots hold the relu outputs (tcgen05 forward) instead of the block outputs (warp-MMA forward)
+cudaError_t launch_wgrad(const float* stash_buf, const uint8_t* valid, int P, int S, const float* flat, float* dflat, float* mscr, int h_is_u, int precision, int grid, cudaStream_t st) {
     const size_t smem = sizeof(float) * WG_STAGES * WG_STAGE_FLOATS;
     { const cudaError_t e = wgrad_init(); if (e != cudaSuccess) return e; }
     if (precision == 0) k_wgrad<true><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
     else k_wgrad<false><<<grid, WG_WARPS * 32, smem, st>>>(stash_buf, valid, P, S, dflat, mscr);
-    k_wgrad_finish<<<5, 1024, 0, st>>>(flat, dflat, mscr);
+    k_wgrad_finish<<<5, 1024, 0, st>>>(flat, dflat, mscr, h_is_u);
     return cudaGetLastError();
 }
 

@@ -228,15 +228,16 @@ def test_stash_free_weight_gradient_kernel(nsb, model_inputs, frames, monkeypatc
 
 def test_kernel_variants_agree(nsb, model_inputs, frames, monkeypatch):
     """The tcgen05 forward (default), the warp-MMA forward (NSB_TCGEN05=0), the tcgen05 data-gradient kernel (NSB_BWD_T5=1), the
-    forward without ray compaction (NSB_COMPACT_RAYS=0) and the one-launch colour forward (NSB_SPLIT_COLOR_SMS=0) are the same
+    forward without ray compaction (NSB_COMPACT_RAYS=0) and the two warp-MMA stash forwards of the colour iteration (NSB_T5_STASH=0, with
+    and without the SM split) are the same
     arithmetic up to fp32 rounding: the same render outputs and the same whole-iteration gradients in a geometry and in a colour
     iteration, which in turn match oracle/_ref's libtorch autograd (golden) on the colour-decoder gradient."""
     grids, decs, _ = model_inputs
     depths, colors, poses = frames
     gm = load_golden("mapping_iters.npz"); gv = load_golden("render_vjp.npz")
     variants = {"default": {}, "warp_mma_fwd": {"NSB_TCGEN05": "0"}, "t5_bwd": {"NSB_BWD_T5": "1"}, "no_compaction": {"NSB_COMPACT_RAYS": "0"},
-                "one_launch_color_fwd": {"NSB_SPLIT_COLOR_SMS": "0"}}
-    knobs = ("NSB_TCGEN05", "NSB_BWD_T5", "NSB_COMPACT_RAYS", "NSB_SPLIT_COLOR_SMS")
+                "split_color_fwd": {"NSB_T5_STASH": "0"}, "one_launch_warp_mma_color_fwd": {"NSB_T5_STASH": "0", "NSB_SPLIT_COLOR_SMS": "0"}}
+    knobs = ("NSB_TCGEN05", "NSB_BWD_T5", "NSB_COMPACT_RAYS", "NSB_SPLIT_COLOR_SMS", "NSB_T5_STASH")
     res = {}
     for name, env in variants.items():
         for k in knobs:
