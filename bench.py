@@ -390,8 +390,11 @@ def parity_selfcheck(nsb, e, torch, dist, rank, world, local_rank, grids, decs, 
         res = {"iterations": its, "rays": int(n_global), "ranks_bit_identical": bool(identical),
                "loss_rel_vs_1gpu": float(np.max(np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(ref_losses))),
                "grid_rms_vs_1gpu": rms, "dec_color_rel_vs_1gpu": float(np.abs(got["dec"] - dref).max() / max(np.abs(dref - decs["color"]).max(), 1e-30)),
+               "dec_color_rms_vs_1gpu": float(np.sqrt(((got["dec"] - dref) ** 2).mean()) / max(np.sqrt(((dref - decs["color"]) ** 2).mean()), 1e-30)),
                "note": "grid_rms = RMS(param_N - param_1) / RMS(update): Adam turns gradients at the fp32 noise level into +-lr steps of random sign in any "
-                       "implementation, and the sharded sum only re-associates the fp32 additions"}
+                       "implementation, and the sharded sum only re-associates the fp32 additions; the second colour step's gradient is taken at those parameters and the "
+                       "loss is piecewise linear (L1, relu), so dec_color_rel (a max) also moves by a few % of a step between two ONE-GPU runs "
+                       "(profiles/r4t_determinism_seed_sweep.log) -- dec_color_rms is the stable figure"}
         e1.close()
     return res
 

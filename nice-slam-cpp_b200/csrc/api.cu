@@ -387,7 +387,12 @@ extern "C" void nsb_get_tensor_from_camera(const float* c2w, float* cam7) {
 }
 
 // ---- create / destroy ------------------------------------------------------------------------------------------
-template <typename T> static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+template <typename T> static cudaError_t dalloc(T** p, size_t n) {
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e == cudaSuccess && getenv("NSB_DEBUG_FILL")) e = cudaMemset(*p, atoi(getenv("NSB_DEBUG_FILL")), bytes);   // debug: every buffer starts from a known byte pattern
+    return e;
+}
 
 static void drop_graphs(nsb_ctx* ctx) {
     for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

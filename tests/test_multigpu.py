@@ -71,7 +71,13 @@ def test_two_gpu_mapping_equals_one_gpu(nsb, ba, p2p):
         for lv in ("middle", "fine", "color"):
             move = np.sqrt(((ref[lv] - grids0[lv]) ** 2).mean())
             assert move > 0 and np.sqrt(((o[lv] - ref[lv]) ** 2).mean()) < 2e-2 * move, lv     # Adam sign noise on ~zero gradients
-        assert np.abs(o["dec"] - ref["dec"]).max() < 2e-2 * np.abs(ref["dec"] - nsb.synthetic.make_decoders(0, bias_scale=0.05)["color"]).max()
+        # The decoder after two colour steps: the second step's gradient is taken at parameters that carry the sign noise above, and the
+        # loss is piecewise linear (L1 terms, relu), so ONE ray sitting on a kink changes that gradient by ~1/n_rays of its norm -- in the
+        # one-GPU run against itself as well (tools/diag_determinism.py, profiles/r4t_determinism_seed_sweep.log).  RMS bounds the bulk,
+        # the max bound leaves room for a few such elements; a shard lost or counted twice moves both by O(1).
+        dmove = ref["dec"] - nsb.synthetic.make_decoders(0, bias_scale=0.05)["color"]
+        assert np.sqrt(((o["dec"] - ref["dec"]) ** 2).mean()) < 1e-2 * np.sqrt((dmove ** 2).mean())
+        assert np.abs(o["dec"] - ref["dec"]).max() < 0.1 * np.abs(dmove).max()
         assert np.abs(o["cams"] - ref["cams"]).max() < 1e-4
     assert np.array_equal(got[0]["middle"], got[1]["middle"]) and np.array_equal(got[0]["dec"], got[1]["dec"])   # replicas stay bit-identical
 
