@@ -64,6 +64,15 @@ __device__ __forceinline__ void iter_advance(const IterRef& it, float* stats_bas
 // arithmetic, so that the 90 MB pass is bandwidth- rather than latency-bound:
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g g;  p -= (lr / bc1) * m / (sqrt(v)/sqrt(bc2) + eps);  g = 0
 constexpr int ADAM_VEC = 2;
+// +-0 in all four lanes.  A slot whose gradient, m and v are all zero is left alone: m and v stay 0 and the update is
+// p + (-step * 0) / (0 / sqrt(bc2) + eps) = p exactly.  Most of a grid is like that (voxels no ray has reached yet), and those are the
+// slow operands of the IEEE divide / sqrt sequences (zero numerators take their out-of-line paths).
+__device__ __forceinline__ bool all_zero4(const float4& a) {
+    return ((__float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z) | __float_as_uint(a.w)) << 1) == 0u;
+}
+__device__ __forceinline__ bool all_pos_zero4(const float4& a) {
+    return (__float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z) | __float_as_uint(a.w)) == 0u;
+}
 __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
     const int total = P.cum4[P.n_seg];
     const int t0 = blockIdx.x * (blockDim.x * ADAM_VEC) + threadIdx.x;
@@ -95,8 +104,9 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
     for (int u = 0; u < ADAM_VEC; ++u) {
         if (!live[u]) continue;
         if (loss_dst && idx[u] == P.loss_idx4) *loss_dst = g[u].x;
-        reinterpret_cast<float4*>(P.grad)[idx[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!all_pos_zero4(g[u])) reinterpret_cast<float4*>(P.grad)[idx[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!upd[u]) continue;
+        if (all_zero4(g[u]) && all_zero4(m[u]) && all_zero4(v[u])) continue;
         float* gg = reinterpret_cast<float*>(&g[u]); float* mm = reinterpret_cast<float*>(&m[u]);
         float* vv = reinterpret_cast<float*>(&v[u]); float* pp = reinterpret_cast<float*>(&p[u]);
 #pragma unroll

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256) k_reduce_adam(P2PParams P) {
         if (i4 == P.loss4) { p = g; write = true; }
         else if (in_seg && sg.active && !(sg.mask && !sg.mask[(i4 * 4 - sg.begin) / CDIM])) {
             float4 m = reinterpret_cast<const float4*>(P.A.m)[i4], v = reinterpret_cast<const float4*>(P.A.v)[i4];
+            // gradient sum, m and v all zero: the update is the identity on every replica (see all_zero4) -- nothing to compute or send
+            if (all_zero4(g) && all_zero4(m) && all_zero4(v)) continue;
             p = reinterpret_cast<const float4*>(P.A.param)[i4];
             float* gg = reinterpret_cast<float*>(&g); float* mm = reinterpret_cast<float*>(&m);
             float* vv = reinterpret_cast<float*>(&v); float* pp = reinterpret_cast<float*>(&p);

@@ -178,12 +178,33 @@ struct ZParams {
 __global__ void k_zvals(ZParams P) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
-    if (ray >= P.n) return;
-    if (P.valid && !P.valid[ray]) return;
-    if (P.ray_list && l == 0) P.ray_list[atomicAdd(P.ray_count, 1)] = ray;
+    const bool live = ray < P.n && !(P.valid && !P.valid[ray]);
+    if (P.ray_list) {   // one global atomic per block: the block's surviving rays take consecutive slots of the list
+        __shared__ int s_cnt, s_base;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int pos = 0;
+        if (live && l == 0) pos = atomicAdd(&s_cnt, 1);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_cnt > 0) s_base = atomicAdd(P.ray_count, s_cnt);
+        __syncthreads();
+        if (live && l == 0) P.ray_list[s_base + pos] = ray;
+    }
+    if (!live) return;
     const float o[3] = {P.rays_o[3 * ray], P.rays_o[3 * ray + 1], P.rays_o[3 * ray + 2]};
     const float d[3] = {P.rays_d[3 * ray], P.rays_d[3 * ray + 1], P.rays_d[3 * ray + 2]};
-    const float far_bb = __fadd_rn(aabb_exit(P.bnd, o, d), 0.01f);                 // :69-73
+    // :69-73, aabb_exit with one IEEE divide per lane instead of six per lane: lane a < 6 forms (bound - o) / d of axis a % 3 (lo: a < 3, hi: a >= 3)
+    float far_bb;
+    {
+        const int ax = l % 3;
+        const float bv = (l % 6) < 3 ? (ax == 0 ? P.bnd.lo[0] : ax == 1 ? P.bnd.lo[1] : P.bnd.lo[2]) : (ax == 0 ? P.bnd.hi[0] : ax == 1 ? P.bnd.hi[1] : P.bnd.hi[2]);
+        const float oa = ax == 0 ? o[0] : ax == 1 ? o[1] : o[2], da = ax == 0 ? d[0] : ax == 1 ? d[1] : d[2];
+        const float tq = __fdiv_rn(__fsub_rn(bv, oa), da);
+        float te = INFINITY;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) te = fminf(te, fmaxf(__shfl_sync(0xffffffffu, tq, a), __shfl_sync(0xffffffffu, tq, a + 3)));
+        far_bb = __fadd_rn(te, 0.01f);
+    }
     const float t = P.t_samples[l], u = __fsub_rn(1.0f, t);
     if (!P.gt_depth) {                                                               // :54-58,78,106
         P.z[ray * P.n_samples + l] = __fadd_rn(__fmul_rn(0.01f, u), __fmul_rn(far_bb, t));
@@ -201,11 +222,31 @@ __global__ void k_zvals(ZParams P) {
         else v1 = __fadd_rn(__fmul_rn(0.001f, us), __fmul_rn(gmax, ts));             // :94
     }
     if (P.n_surface == 0) { P.z[ray * S + l] = v0; return; }
-    int r0 = 0, r1 = 0;                                                              // :119 sort == rank placement
-    for (int k = 0; k < S; ++k) {
-        const float uk = k < 32 ? __shfl_sync(0xffffffffu, v0, k) : __shfl_sync(0xffffffffu, v1, k - 32);
-        r0 += (uk < v0) || (uk == v0 && k < l);
-        r1 += (uk < v1) || (uk == v1 && k < 32 + l);
+    // :119 sort == rank placement (stable: ties keep the concatenation order [stratified | surface]).  Both runs ascend by construction
+    // (t ascending, near <= far), so a value's rank is its own index plus the number of values of the OTHER run that go before it -- a
+    // binary search over the other run's lanes.  If a run does not ascend (or holds a NaN) the plain O(S) count below decides.
+    int r0, r1;
+    {
+        const float p0 = __shfl_up_sync(0xffffffffu, v0, 1), p1 = __shfl_up_sync(0xffffffffu, v1, 1);
+        const bool asc = (l == 0 || p0 <= v0) && (l == 0 || l >= P.n_surface || p1 <= v1) && P.n_samples == 32;
+        if (__all_sync(0xffffffffu, asc)) {
+            int c0 = 0, c1 = 0;          // c0 = #{j < n_surface : v1[j] < v0},  c1 = #{k < 32 : v0[k] <= v1}
+#pragma unroll
+            for (int step = 32; step > 0; step >>= 1) {
+                const float e1 = __shfl_sync(0xffffffffu, v1, (c0 + step - 1) & 31);
+                const float e0 = __shfl_sync(0xffffffffu, v0, (c1 + step - 1) & 31);
+                if (c0 + step <= P.n_surface && e1 < v0) c0 += step;
+                if (c1 + step <= 32 && e0 <= v1) c1 += step;
+            }
+            r0 = l + c0; r1 = l + c1;
+        } else {
+            r0 = 0; r1 = 0;
+            for (int k = 0; k < S; ++k) {
+                const float uk = k < 32 ? __shfl_sync(0xffffffffu, v0, k) : __shfl_sync(0xffffffffu, v1, k - 32);
+                r0 += (uk < v0) || (uk == v0 && k < l);
+                r1 += (uk < v1) || (uk == v1 && k < 32 + l);
+            }
+        }
     }
     P.z[ray * S + r0] = v0;
     if (l < P.n_surface) P.z[ray * S + r1] = v1;
@@ -394,29 +435,33 @@ __global__ void k_composite_map(CompositeParams P, const float* __restrict__ gt_
                                 int use_color, float w_color, float* loss_out) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
-    if (ray >= P.n) return;
-    if (P.valid && !P.valid[ray]) {
+    __shared__ float s_loss[32];              // per-warp loss terms: one global atomic per block instead of one per ray
+    float loss = 0.0f;
+    if (ray < P.n && P.valid && !P.valid[ray]) {
         if (l == 0) { P.rgb[3 * ray] = P.rgb[3 * ray + 1] = P.rgb[3 * ray + 2] = 0.0f; P.depth[ray] = 0.0f; P.var[ray] = 0.0f; }
-        return;
-    }
-    RaySamples s; float rgb[3], depth, var;
-    composite_forward(P, ray, l, s, rgb, depth, var);
-    float loss = 0.0f, gD = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
-    const float g = gt_depth[ray];
-    if (g > 0.0f) { const float df = g - depth; loss += fabsf(df); gD = df > 0.0f ? -1.0f : (df < 0.0f ? 1.0f : 0.0f); }
-    if (use_color) {
+    } else if (ray < P.n) {
+        RaySamples s; float rgb[3], depth, var;
+        composite_forward(P, ray, l, s, rgb, depth, var);
+        float gD = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
+        const float g = gt_depth[ray];
+        if (g > 0.0f) { const float df = g - depth; loss += fabsf(df); gD = df > 0.0f ? -1.0f : (df < 0.0f ? 1.0f : 0.0f); }
+        if (use_color) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float df = gt_color[3 * ray + c] - rgb[c];
-            loss += w_color * fabsf(df);
-            gC[c] = df > 0.0f ? -w_color : (df < 0.0f ? w_color : 0.0f);
+            for (int c = 0; c < 3; ++c) {
+                const float df = gt_color[3 * ray + c] - rgb[c];
+                loss += w_color * fabsf(df);
+                gC[c] = df > 0.0f ? -w_color : (df < 0.0f ? w_color : 0.0f);
+            }
         }
+        if (l == 0) { P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var; }
+        composite_backward(P, ray, l, s, depth, gC, gD, 0.0f);
     }
-    if (l == 0) {
-        P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var;
-        if (loss != 0.0f) atomicAdd(loss_out, loss);
+    if (l == 0) s_loss[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const float v = warp_sum(threadIdx.x < (blockDim.x >> 5) ? s_loss[threadIdx.x] : 0.0f);
+        if (threadIdx.x == 0 && v != 0.0f) atomicAdd(loss_out, v);
     }
-    composite_backward(P, ray, l, s, depth, gC, gD, 0.0f);
 }
 
 // Tracking iteration: loss of Tracker.cpp:67-82 (median mask, uncertainty-weighted depth term, colour term) + composite backward
