@@ -156,6 +156,7 @@ struct nsb_ctx {
     int bwd_t5 = 0;              // NSB_BWD_T5=1: geometry iterations run the data gradient of decoders 1, 2 on the tcgen05 backward (decode_bwd_t5.cu);
                                  // measured equal to the warp-MMA kernel (both are dominated by the scatter walk), so the older kernel stays default
     uint8_t* wimg_t5[4] = {nullptr, nullptr, nullptr, nullptr};   // images of the tcgen05 forward (NSB_TCGEN05=3), rebuilt with the composed images
+    bool pending_join = false;   // a rebuild of the colour decoder's images is in flight on aux_stream (fork_rebuild / join_rebuild)
     int comp_dirty = 0xE;        // bit d: decoder d's composed weights are stale
     float* wimg_fwd[4] = {nullptr, nullptr, nullptr, nullptr};   // pre-split shared-memory images of the decoders (k_build_wimg)
     float* wimg_bwd[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -787,26 +788,30 @@ static void env_weights(const char* name, float w[4]) {
 // Rebuilds the pre-split shared-memory images of the decoders whose weights changed (set_decoder / an Adam step with a decoder
 // learning rate).  cmp_mask: decoders whose COMPOSED forward image the coming launches read.  force: rebuild these decoders
 // whatever the dirty bits say (the captured colour iteration ends with the rebuild of the colour decoder it has just stepped).
-static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0, int lazy = 0) {
-    // lazy (the stash path's colour iterations, `force` = the decoder the iteration has just stepped): images nobody reads before the
-    // next non-stash forward are not rebuilt inside the iteration; the host marks them stale per iteration (mark_color_stale) and the
-    // next API entry that needs them rebuilds them once.
+static int refresh_images(nsb_ctx* ctx, int cmp_mask, int force = 0, int lazy = 0, int skip = 0, cudaStream_t on = nullptr) {
+    // lazy (the stash path's colour iterations, `force` = the colour decoder, stepped by the previous iteration): only the images the
+    // iteration itself reads are rebuilt -- at its START, on the auxiliary stream beside k_sample / k_zvals (enqueue_iteration); the host
+    // marks all of the decoder's images stale after every such iteration (mark_color_stale) and the next API entry that needs them
+    // rebuilds them once.
     //   lazy 1 (warp-MMA stash forward): only the plain forward / backward images now; composed weights, composed image, tcgen05 image later
     //   lazy 2 (tcgen05 stash forward):  plain images + composed weights + tcgen05 image now; the warp-MMA composed image later
-    const int plain = ctx->wimg_dirty | force;
-    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask) | (lazy ? 0 : force);
+    // skip: decoders left alone whatever their dirty bits say (a stash colour iteration rebuilds the colour decoder's images itself).
+    // on: the stream the launches go to (default: the context's main stream).
+    cudaStream_t st = on ? on : ctx->stream;
+    const int plain = (ctx->wimg_dirty & ~skip) | force;
+    const int cmp_need = (ctx->wimg_cmp_dirty & cmp_mask & ~skip) | (lazy ? 0 : force);
     const int t5_need = cmp_need | (lazy == 2 ? force : 0);
     if (!plain && !cmp_need && !t5_need) return 0;
     const float* flat[4]; for (int d = 0; d < 4; ++d) flat[d] = ctx->param + ctx->off_dec[d];
     const int comp_need = (ctx->comp_dirty & (cmp_need | t5_need)) | (lazy == 1 ? 0 : force);
     if (comp_need) {   // the composed images are built from k_compose's output
-        CK(launch_compose(flat, ctx->comp, comp_need, ctx->stream)); ctx->launches++;
+        CK(launch_compose(flat, ctx->comp, comp_need, st)); ctx->launches++;
         ctx->comp_dirty &= ~comp_need;
     }
-    if (plain || cmp_need) { CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, ctx->stream)); ctx->launches++; }
-    if (ctx->use_tc == 3 && t5_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, t5_need, ctx->stream)); ctx->launches++; }
-    if (ctx->use_tc == 3 && (cmp_need & 0x6)) { CK(launch_build_t5bimg(flat, ctx->comp, ctx->wimg_t5b, cmp_need, ctx->stream)); ctx->launches++; }
-    if ((plain & 8) && !ctx->wg_stash) { CK(launch_build_wgimg(flat[3], ctx->wg_img, ctx->stream)); ctx->launches++; }   // plane image of the colour decoder (stash-free weight gradient only)
+    if (plain || cmp_need) { CK(launch_build_wimg(flat, ctx->comp, ctx->wimg_fwd, ctx->wimg_bwd, ctx->wimg_cmp, plain, cmp_need, st)); ctx->launches++; }
+    if (ctx->use_tc == 3 && t5_need) { CK(launch_build_t5img(flat, ctx->comp, ctx->wimg_t5, t5_need, st)); ctx->launches++; }
+    if (ctx->use_tc == 3 && (cmp_need & 0x6)) { CK(launch_build_t5bimg(flat, ctx->comp, ctx->wimg_t5b, cmp_need, st)); ctx->launches++; }
+    if ((plain & 8) && !ctx->wg_stash) { CK(launch_build_wgimg(flat[3], ctx->wg_img, st)); ctx->launches++; }   // plane image of the colour decoder (stash-free weight gradient only)
     ctx->wimg_dirty &= ~plain; ctx->wimg_cmp_dirty &= ~cmp_need;
     return 0;
 }
@@ -828,6 +833,22 @@ static void fill_decode_params(nsb_ctx* ctx, DecodeParams& P, int n, int S, cons
 }
 
 static const IterRef NO_ITER = {nullptr, 1};
+
+// Stash colour iterations rebuild the colour decoder's images on the auxiliary stream at their start (see refresh_images): fork / join.
+static int fork_rebuild(nsb_ctx* ctx, int lazy) {
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    if (refresh_images(ctx, 0, 1 << 3, lazy, 0, ctx->aux_stream)) return -1;
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    ctx->pending_join = true;
+    return 0;
+}
+static int join_rebuild(nsb_ctx* ctx) {
+    if (!ctx->pending_join) return 0;
+    ctx->pending_join = false;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return 0;
+}
 
 static int decode_grid_size(nsb_ctx* ctx, int P) {
     const int occ = std::max(1, ctx->occ_blocks[ctx->cfg.precision ? 1 : 0]);
@@ -878,6 +899,7 @@ static int run_forward(nsb_ctx* ctx, int stage, int off, int n, bool have_depth,
         k_zvals<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(Z); ctx->launches++;
         CK(cudaGetLastError());
     }
+    if (join_rebuild(ctx)) return -1;   // the colour decoder's images, rebuilt beside the two kernels above
     {
         Timer t(ctx, T_FWD);
         // the forward runs on the composed images, except for a colour decoder whose activations are stashed for the weight gradient
@@ -1505,6 +1527,13 @@ extern "C" int nsb_ray_order_source(int world, int n_rays, int pix_per_frame, in
 // device iteration state, so the same sequence is either enqueued kernel by kernel or captured once and replayed as a graph.
 struct IterPlan { int stage; bool use_color, pristine, use_pool; };
 
+// Which lazy set (refresh_images) this iteration rebuilds at its start: colour iterations of the stash path that step the colour decoder.
+static int iter_lazy(const nsb_ctx* ctx, const IterPlan& pl) {
+    if (pl.stage != NSB_COLOR || pl.pristine) return 0;
+    if (ctx->cfg.stage_lr[NSB_COLOR][0] * ctx->map_lr_factor == 0.f) return 0;
+    return lazy_color_images(ctx);
+}
+
 static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
     const nsb_config& c = ctx->cfg;
     const int pix = c.mapping_pixels / ctx->map_frames, n = pix * ctx->map_frames;
@@ -1514,6 +1543,9 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
     IterRef it; it.state = ctx->it_state; it.ring = ctx->ring;
     float* stats = ctx->stats;
     const bool pool = pl.use_pool;
+    // the previous colour iteration stepped the colour decoder: its images are rebuilt now, beside the sampling kernels (joined in run_forward)
+    const int lz = iter_lazy(ctx, pl);
+    if (lz && fork_rebuild(ctx, lz)) return -1;
     {
         Timer t(ctx, T_SAMPLE);
         SampleParams P; fill_sample_params(ctx, P, n, 0, c.H, 0, c.W, stats, 1);
@@ -1572,6 +1604,7 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
             CK(cudaGetLastError());
         }
     }
+    if (join_rebuild(ctx)) return -1;   // a rank without rays has not joined in run_forward
     float lr[6];
     for (int g = 0; g < 5; ++g) lr[g] = c.stage_lr[stage][g] * ctx->map_lr_factor;   // Mapper.cpp:360-364
     lr[5] = (ctx->map_ba_mask && stage == NSB_COLOR) ? c.BA_cam_lr : 0.f;   // Mapper.cpp:366-368 (not scaled by lr_factor)
@@ -1605,19 +1638,18 @@ static int enqueue_iteration(nsb_ctx* ctx, const IterPlan& pl) {
         // the Adam kernel also moves the (all-reduced) loss out of the gradient arena into the step's statistics slot
         if (run_adam(ctx, lr, !c.fix_fine, dec_color, n_cam, pristine)) return -1;
     }
-    // the colour decoder has just been stepped: rebuild its pre-split images right away, so that every iteration starts from
-    // fresh images (no host-side dirty tracking inside the loop)
-    if (dec_color && !coarse && !pristine && lr[0] != 0.f) { if (refresh_images(ctx, 0, 1 << 3, lazy_color_images(ctx))) return -1; }
+    // the colour decoder has just been stepped.  Stash colour iterations (lz) leave its images stale: the next one rebuilds what it reads at
+    // its start and the host marks the rest (mark_color_stale).  Any other iteration that moves it (a geometry stage configured with a
+    // decoder learning rate, the stash-free path) rebuilds all of its images right away.
+    if (!lz && dec_color && !coarse && !pristine && lr[0] != 0.f) { if (refresh_images(ctx, 0, 1 << 3)) return -1; }
     return 0;
 }
 
 // Host side of the lazy rebuild: an iteration that steps the colour decoder leaves its composed / tcgen05 images stale (this runs per
 // iteration on the host, also when the iteration itself is a graph replay).
 static void mark_color_stale(nsb_ctx* ctx, const IterPlan& pl) {
-    if (!lazy_color_images(ctx) || pl.pristine || pl.stage != NSB_COLOR) return;
-    if (ctx->cfg.stage_lr[NSB_COLOR][0] * ctx->map_lr_factor == 0.f) return;
-    if (lazy_color_images(ctx) == 1) ctx->comp_dirty |= 8;
-    ctx->wimg_cmp_dirty |= 8;
+    if (!iter_lazy(ctx, pl)) return;
+    ctx->wimg_dirty |= 8; ctx->wimg_cmp_dirty |= 8; ctx->comp_dirty |= 8;
 }
 
 extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx) {
@@ -1639,13 +1671,11 @@ extern "C" int nsb_mapping_iter_async(nsb_ctx* ctx, int iter, const int64_t* idx
         for (int f = 0; f < ctx->map_frames; ++f) draw_indices(ctx, pix, (int64_t)c.H * c.W, ctx->h_idx.data() + (size_t)f * pix);   // one randint per frame (Mapper.cpp:404)
         CK(cudaMemcpyAsync(ctx->idx, ctx->h_idx.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    // no-op unless a decoder was replaced since the last iteration; a stash colour iteration does not read the colour decoder's composed
-    // images (left stale by the previous one on purpose)
+    // no-op unless a decoder was replaced since the last iteration; a stash colour iteration rebuilds the colour decoder's images itself
+    // (the previous one left them stale on purpose), so they are skipped here
     {
-        const int lz = (pl.stage == NSB_COLOR && !pl.pristine) ? lazy_color_images(ctx) : 0;
-        if (refresh_images(ctx, lz ? 0x6 : 0xE)) return -1;
-        // the tcgen05 stash forward reads the colour decoder's composed weights: fresh before the first colour iteration (later ones rebuild them themselves)
-        if (lz == 2 && (ctx->comp_dirty & 8)) { if (refresh_images(ctx, 0, 8, 2)) return -1; }
+        const int lz = iter_lazy(ctx, pl);
+        if (refresh_images(ctx, lz ? 0x6 : 0xE, 0, 0, lz ? 8 : 0)) return -1;
     }
     ctx->map_step++;
     const bool graph_ok = ctx->use_graph && !ctx->profiling && (ctx->world == 1 || ctx->p2p);
