@@ -133,6 +133,7 @@ struct nsb_ctx {
     int64_t* idx = nullptr;
     int64_t* idx_pool = nullptr; int pool_iters = 0, pool_n = 0, pool_cursor = 0;   // optional device-resident pixel indices for many iterations
     float* pts = nullptr;
+    float* h_stats = nullptr;     // pinned host landing zone of nsb_mapping_losses (H_STATS_STEPS slots): no staged pageable copy on the per-step path
     float* stats = nullptr;       // mapping loop: [ring][4]: max gt depth, n inside, sum 1/|d|, loss -- one slot per step
     int ring = 0;                 // slots of `stats` (>= the n_iters of the current optimize_map: no loss is lost to a wrap)
     float* rstats = nullptr;      // [2][4] scratch of the render / sampling / keyframe entry points (never the mapping ring)
@@ -531,6 +532,7 @@ extern "C" void nsb_destroy(nsb_ctx* c) {
                     c->g_var, c->d_rays, c->absdiff, c->valid, c->idx, c->idx_pool, c->pts, c->stats, c->median, c->count, c->stash, c->masks, c->comp[1], c->comp[2], c->comp[3], c->dbg, c->scratch_ncdhw,
                     c->cam_grad_last, c->trk_scratch, c->tile_ctr, c->ray_list, c->ray_count, c->wg_mscr, c->wimg_fwd[1], c->wimg_fwd[2], c->wimg_fwd[3], c->wimg_bwd[1], c->wimg_bwd[2], c->wimg_bwd[3], c->wimg_cmp[1], c->wimg_cmp[2], c->wimg_cmp[3], c->wimg_t5[1], c->wimg_t5[2], c->wimg_t5[3], c->wimg_t5b[1], c->wimg_t5b[2], c->vmask[0], c->vmask[1], c->vmask[2], c->vmask[3], c->vmask_tmp[0], c->vmask_tmp[1], c->vmask_tmp[2], c->vmask_tmp[3]};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
     for (auto& r : c->ev_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
@@ -1764,10 +1766,16 @@ extern "C" int nsb_mapping_losses(nsb_ctx* ctx, int first, int n, float* losses,
     cudaSetDevice(ctx->device);   // one context = one GPU; the caller's current device may differ
     if (n <= 0) return 0;
     if (n > ctx->ring) return fail(ctx, "the loss ring keeps the last %d steps, asked for %d", ctx->ring, n);
-    std::vector<float> h(4 * (size_t)n);
+    constexpr int H_STATS_STEPS = 256;
+    std::vector<float> big;
+    float* h;
+    if (n <= H_STATS_STEPS) {
+        if (!ctx->h_stats) CK(cudaHostAlloc((void**)&ctx->h_stats, 16 * H_STATS_STEPS, cudaHostAllocDefault));
+        h = ctx->h_stats;
+    } else { big.resize(4 * (size_t)n); h = big.data(); }
     const int s0 = ((first % ctx->ring) + ctx->ring) % ctx->ring, n0 = std::min(n, ctx->ring - s0);
-    CK(cudaMemcpyAsync(h.data(), ctx->stats + 4 * (size_t)s0, 16 * (size_t)n0, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n0 < n) CK(cudaMemcpyAsync(h.data() + 4 * (size_t)n0, ctx->stats, 16 * (size_t)(n - n0), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h, ctx->stats + 4 * (size_t)s0, 16 * (size_t)n0, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n0 < n) CK(cudaMemcpyAsync(h + 4 * (size_t)n0, ctx->stats, 16 * (size_t)(n - n0), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n; ++i) {
         if (losses) losses[i] = h[4 * i + 3];

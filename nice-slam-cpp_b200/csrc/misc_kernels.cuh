@@ -76,24 +76,42 @@ __device__ __forceinline__ bool all_pos_zero4(const float4& a) {
 __global__ void __launch_bounds__(256) k_adam(AdamParams P) {
     const int total = P.cum4[P.n_seg];
     const int t0 = blockIdx.x * (blockDim.x * ADAM_VEC) + threadIdx.x;
-    double bc1; float bc2s;
-    adam_bias(P, bc1, bc2s);
-    float* loss_dst = P.loss_dst ? (P.it.state ? P.loss_dst + 4 * iter_slot(P.it) + 3 : P.loss_dst) : nullptr;
+    // Per-block table of the segments (first float4, mask, active flag, -lr / bc1): thread k < ADAM_MAX_SEG prepares segment k, so that the
+    // double-precision divide, the bias-correction lookup and the statistics-slot modulo run once per block, not once per thread.
+    __shared__ int s_begin4[ADAM_MAX_SEG], s_begin[ADAM_MAX_SEG], s_cum[ADAM_MAX_SEG], s_active[ADAM_MAX_SEG];
+    __shared__ const uint8_t* s_mask[ADAM_MAX_SEG];
+    __shared__ float s_nstep[ADAM_MAX_SEG], s_bc2s;
+    __shared__ float* s_loss_dst;
+    if (threadIdx.x < ADAM_MAX_SEG) {
+        AdamSegment sg = P.seg[0]; int cum = P.cum4[0];
+#pragma unroll
+        for (int k = 1; k < ADAM_MAX_SEG; ++k)      // compile-time indices only: a runtime index into the by-value parameter struct would go through local memory
+            if ((int)threadIdx.x == k) { sg = P.seg[k]; cum = P.cum4[k]; }
+        double bc1; float bc2s;
+        adam_bias(P, bc1, bc2s);
+        s_begin4[threadIdx.x] = sg.begin / 4; s_begin[threadIdx.x] = sg.begin; s_cum[threadIdx.x] = cum; s_active[threadIdx.x] = sg.active; s_mask[threadIdx.x] = sg.mask;
+        s_nstep[threadIdx.x] = -(float)((double)sg.lr / bc1);
+        if (threadIdx.x == 0) {
+            s_bc2s = bc2s;
+            s_loss_dst = P.loss_dst ? (P.it.state ? P.loss_dst + 4 * iter_slot(P.it) + 3 : P.loss_dst) : nullptr;
+        }
+    }
+    __syncthreads();
+    const float bc2s = s_bc2s;
+    float* loss_dst = s_loss_dst;
     int idx[ADAM_VEC]; bool live[ADAM_VEC], upd[ADAM_VEC]; float nstep[ADAM_VEC];
     float4 g[ADAM_VEC], m[ADAM_VEC], v[ADAM_VEC], p[ADAM_VEC];
 #pragma unroll
     for (int u = 0; u < ADAM_VEC; ++u) {
         const int tid = t0 + u * blockDim.x;
         live[u] = tid < total;
-        // compile-time indices only: a runtime index into the by-value parameter struct would go through local memory
-        AdamSegment sg = P.seg[0];
-        int base = 0;
+        int si = 0;
 #pragma unroll
-        for (int k = 1; k < ADAM_MAX_SEG; ++k)
-            if (k < P.n_seg && tid >= P.cum4[k]) { sg = P.seg[k]; base = P.cum4[k]; }
-        idx[u] = live[u] ? sg.begin / 4 + (tid - base) : 0;
-        nstep[u] = -(float)((double)sg.lr / bc1);
-        upd[u] = live[u] && sg.active && !(sg.mask && !sg.mask[(idx[u] * 4 - sg.begin) / CDIM]);
+        for (int k = 1; k < ADAM_MAX_SEG; ++k) si += (k < P.n_seg && tid >= P.cum4[k]) ? 1 : 0;     // cum4 ascends: the number of segment starts <= tid
+        idx[u] = live[u] ? s_begin4[si] + (tid - s_cum[si]) : 0;
+        nstep[u] = s_nstep[si];
+        const uint8_t* mask = s_mask[si];
+        upd[u] = live[u] && s_active[si] && !(mask && !mask[(idx[u] * 4 - s_begin[si]) / CDIM]);
     }
 #pragma unroll
     for (int u = 0; u < ADAM_VEC; ++u) {

@@ -1,7 +1,7 @@
-"""Two-GPU mapping: rays sharded over the ranks, gradients summed with NCCL (grids under the wgrad kernel in
+"""Two- and eight-GPU mapping: rays sharded over the ranks, gradients summed with NCCL (grids under the wgrad kernel in
 colour iterations, the [loss | middle | fine] prefix in geometry iterations), identical Adam on every rank -- or, in
 peer-memory mode, one reduce-scatter + Adam + all-gather kernel over NVLink (p2p_kernels.cuh).  The result
-must equal the one-GPU run on the same global batch up to the association of the fp32 sums.  Needs 2 GPUs (skipped else)."""
+must equal the one-GPU run on the same global batch up to the association of the fp32 sums.  Needs 2 (8) GPUs (skipped else)."""
 import importlib
 import os
 import sys
@@ -49,23 +49,23 @@ def _run(rank, world, uid, q, ba, p2p=False, port=0):
     return out
 
 
-@pytest.mark.parametrize("ba,p2p", [(False, False), (True, False), (False, True), (True, True)])
-def test_two_gpu_mapping_equals_one_gpu(nsb, ba, p2p):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world,ba,p2p", [(2, False, False), (2, True, False), (2, False, True), (2, True, True), (8, True, True), (8, False, False)])
+def test_sharded_mapping_equals_one_gpu(nsb, world, ba, p2p):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ref = _run(0, 1, None, None, ba)
     uid = nsb.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + 2 * int(ba) + int(p2p)
-    procs = [ctx.Process(target=_run, args=(r, 2, uid, q, ba, p2p, port)) for r in range(2)]
+    port = 29600 + 2 * int(ba) + int(p2p) + 4 * int(world > 2)
+    procs = [ctx.Process(target=_run, args=(r, world, uid, q, ba, p2p, port)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=300) for _ in range(2))
+    got = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
     grids0 = nsb.synthetic.make_grids(0)
-    for r in range(2):
+    for r in range(world):
         o = got[r]
         assert np.allclose(o["losses"], ref["losses"], rtol=5e-4), (o["losses"], ref["losses"])
         for lv in ("middle", "fine", "color"):
@@ -79,7 +79,8 @@ def test_two_gpu_mapping_equals_one_gpu(nsb, ba, p2p):
         assert np.sqrt(((o["dec"] - ref["dec"]) ** 2).mean()) < 1e-2 * np.sqrt((dmove ** 2).mean())
         assert np.abs(o["dec"] - ref["dec"]).max() < 0.1 * np.abs(dmove).max()
         assert np.abs(o["cams"] - ref["cams"]).max() < 1e-4
-    assert np.array_equal(got[0]["middle"], got[1]["middle"]) and np.array_equal(got[0]["dec"], got[1]["dec"])   # replicas stay bit-identical
+    for r in range(1, world):   # replicas stay bit-identical
+        assert np.array_equal(got[0]["middle"], got[r]["middle"]) and np.array_equal(got[0]["dec"], got[r]["dec"]) and np.array_equal(got[0]["color"], got[r]["color"])
 
 
 def test_two_contexts_in_one_process(nsb):
