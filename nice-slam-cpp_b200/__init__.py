@@ -528,7 +528,8 @@ class Engine:
         self._ck(self.lib.nsb_comm_p2p_stats(self.h, o, int(reset)))
         return {"last_wait_us": o[0], "last_kernel_us": o[1], "mean_wait_us": o[2], "mean_kernel_us": o[3], "mean_exchange_us": o[3] - o[2], "exchanges": int(o[4]),
                 "mean_range_bytes": o[5], "nvlink_bytes_per_direction_model": o[6], "nvlink_gbs_per_direction": o[7],
-                "model": "a rank reads its 1/W slice of the exchanged range from W-1 peers and writes the updated slice to W-1 peers: (W-1)/W of the range per direction"}
+                "model": "a rank reads its 1/W slice of the exchanged range from W-1 peers and writes the updated slice to W-1 peers: (W-1)/W of the range per direction "
+                         "(an upper bound for the write direction: slots whose gradient sum, m and v are all zero are not rewritten)"}
 
     def bench_gather(self, reps=20):
         ms = C.c_float(0)
