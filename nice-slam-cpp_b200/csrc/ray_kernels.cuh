@@ -352,21 +352,31 @@ __device__ __forceinline__ void composite_forward(const CompositeParams& P, int 
 
 __global__ void k_composite_fwd(CompositeParams P) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
-    if (ray >= P.n) return;
-    if (P.valid && !P.valid[ray]) {
+    const bool live = ray < P.n && !(P.valid && !P.valid[ray]);
+    float absd = 0.0f;
+    if (ray < P.n && !live) {
         if (l == 0) { P.rgb[3 * ray] = P.rgb[3 * ray + 1] = P.rgb[3 * ray + 2] = 0.0f; P.depth[ray] = 0.0f; P.var[ray] = 0.0f; }
         if (P.weights) for (int k = l; k < P.S; k += 32) P.weights[ray * P.S + k] = 0.0f;
-        return;
+    } else if (live) {
+        RaySamples s; float rgb[3], depth, var;
+        composite_forward(P, ray, l, s, rgb, depth, var);
+        if (l == 0) { P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var; }
+        if (P.trk_absdiff && l == 0) absd = fabsf(P.trk_gt_depth[ray] - depth);
+        if (P.weights) {
+            P.weights[ray * P.S + l] = s.w[0];
+            if (s.has[1]) P.weights[ray * P.S + 32 + l] = s.w[1];
+        }
     }
-    RaySamples s; float rgb[3], depth, var;
-    composite_forward(P, ray, l, s, rgb, depth, var);
-    if (l == 0) {
-        P.rgb[3 * ray] = rgb[0]; P.rgb[3 * ray + 1] = rgb[1]; P.rgb[3 * ray + 2] = rgb[2]; P.depth[ray] = depth; P.var[ray] = var;
-        if (P.trk_absdiff) P.trk_absdiff[atomicAdd(P.trk_count, 1)] = fabsf(P.trk_gt_depth[ray] - depth);
-    }
-    if (P.weights) {
-        P.weights[ray * P.S + l] = s.w[0];
-        if (s.has[1]) P.weights[ray * P.S + 32 + l] = s.w[1];
+    if (P.trk_absdiff) {   // tracking: |gt_depth - depth| of the surviving rays, compacted for the median (any order); one global atomic per block
+        __shared__ int s_cnt, s_base;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int pos = 0;
+        if (live && l == 0) pos = atomicAdd(&s_cnt, 1);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_cnt > 0) s_base = atomicAdd(P.trk_count, s_cnt);
+        __syncthreads();
+        if (live && l == 0) P.trk_absdiff[s_base + pos] = absd;
     }
 }
 
@@ -470,30 +480,37 @@ __global__ void k_composite_track(CompositeParams P, const float* __restrict__ g
                                   const float* __restrict__ median, int handle_dynamic, int use_color, float w_color, float* loss_out) {
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) zero_tile_counters(P.zero_ctr);
-    if (ray >= P.n) return;
-    if (P.valid && !P.valid[ray]) return;
-    RaySamples s; float rgb[3], depth, var;
-    composite_forward(P, ray, l, s, rgb, depth, var);
-    float loss = 0.0f, gD = 0.0f, gV = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
-    const float g = gt_depth[ray], df = g - depth;
-    bool m = g > 0.0f;
-    if (handle_dynamic) m = m && (fabsf(df) < 10.0f * median[0]);
-    if (m) {
-        const float vv = var + 1e-10f, r = 1.0f / sqrtf(vv);
-        loss += fabsf(df) * r;
-        gD = -(df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) * r;
-        gV = -0.5f * fabsf(df) * r / vv;
-        if (use_color) {
+    __shared__ float s_loss[32];              // per-warp loss terms: one global atomic per block
+    float loss = 0.0f;
+    if (ray < P.n && !(P.valid && !P.valid[ray])) {
+        RaySamples s; float rgb[3], depth, var;
+        composite_forward(P, ray, l, s, rgb, depth, var);
+        float gD = 0.0f, gV = 0.0f, gC[3] = {0.0f, 0.0f, 0.0f};
+        const float g = gt_depth[ray], df = g - depth;
+        bool m = g > 0.0f;
+        if (handle_dynamic) m = m && (fabsf(df) < 10.0f * median[0]);
+        if (m) {
+            const float vv = var + 1e-10f, r = 1.0f / sqrtf(vv);
+            loss += fabsf(df) * r;
+            gD = -(df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f)) * r;
+            gV = -0.5f * fabsf(df) * r / vv;
+            if (use_color) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float dc = gt_color[3 * ray + c] - rgb[c];
-                loss += w_color * fabsf(dc);
-                gC[c] = dc > 0.0f ? -w_color : (dc < 0.0f ? w_color : 0.0f);
+                for (int c = 0; c < 3; ++c) {
+                    const float dc = gt_color[3 * ray + c] - rgb[c];
+                    loss += w_color * fabsf(dc);
+                    gC[c] = dc > 0.0f ? -w_color : (dc < 0.0f ? w_color : 0.0f);
+                }
             }
         }
+        composite_backward(P, ray, l, s, depth, gC, gD, gV);
     }
-    if (l == 0 && loss != 0.0f) atomicAdd(loss_out, loss);
-    composite_backward(P, ray, l, s, depth, gC, gD, gV);
+    if (l == 0) s_loss[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const float v = warp_sum(threadIdx.x < (blockDim.x >> 5) ? s_loss[threadIdx.x] : 0.0f);
+        if (threadIdx.x == 0 && v != 0.0f) atomicAdd(loss_out, v);
+    }
 }
 
 // ---- lower median of the tracking residuals (Tracker.cpp:70) ------------------------------------------
@@ -516,10 +533,24 @@ __global__ void k_median(const float* __restrict__ v, const int* __restrict__ co
             if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned want = want_s, b = 0;
-            while (b < 255 && hist[b] <= want) { want -= hist[b]; ++b; }
-            want_s = want; prefix_s = prefix | (b << shift);
+        if (threadIdx.x < 32) {   // first bin whose cumulative count exceeds `want` (bin 255 at the latest): lane = 8 bins, warp scan over the lanes
+            const int lane = threadIdx.x;
+            const unsigned want = want_s;
+            unsigned h[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+            unsigned inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += nb; }
+            const unsigned exc = inc - sum;
+            const unsigned hit = __ballot_sync(0xffffffffu, exc <= want && want < inc);
+            const int sel = hit ? __ffs(hit) - 1 : 31;
+            if (lane == sel) {
+                unsigned w = want - exc; int j = 0; bool done = false;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) if (!done) { if (h[k] <= w) { w -= h[k]; j = k + 1; } else done = true; }
+                want_s = w; prefix_s = prefix | ((unsigned)(8 * lane + j) << shift);
+            }
         }
         __syncthreads();
     }
