@@ -311,8 +311,8 @@ __device__ __forceinline__ uint32_t relu_mask(float (&h)[4][4], const float (&ac
 __device__ __forceinline__ void stash_tile(float* st0, float* st1, int off, const float (&h)[4][4], int t) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<float2*>(st0 + off + 8 * j + 2 * t) = make_float2(h[j][0], h[j][1]);
-        *reinterpret_cast<float2*>(st1 + off + 8 * j + 2 * t) = make_float2(h[j][2], h[j][3]);
+        __stcs(reinterpret_cast<float2*>(st0 + off + 8 * j + 2 * t), make_float2(h[j][0], h[j][1]));   // streaming: the stash is written once, read once
+        __stcs(reinterpret_cast<float2*>(st1 + off + 8 * j + 2 * t), make_float2(h[j][2], h[j][3]));
     }
 }
 

@@ -290,8 +290,8 @@ __device__ __forceinline__ void decoder_backward(const float* __restrict__ sm, c
                 ff_sincos(fmaf(p[1][2], B2.y, fmaf(p[1][1], B1.y, p[1][0] * B0.y)), sn, c11);
                 const float q00 = ge[jj][0] * c00, q01 = ge[jj][1] * c01, q10 = ge[jj][2] * c10, q11 = ge[jj][3] * c11;
                 if (STASH) {
-                    *reinterpret_cast<float2*>(st0 + stash::GE + f0) = make_float2(q00, q01);
-                    *reinterpret_cast<float2*>(st1 + stash::GE + f0) = make_float2(q10, q11);
+                    __stcs(reinterpret_cast<float2*>(st0 + stash::GE + f0), make_float2(q00, q01));
+                    __stcs(reinterpret_cast<float2*>(st1 + stash::GE + f0), make_float2(q10, q11));
                 }
                 gp[0][0] += q00 * B0.x + q01 * B0.y; gp[0][1] += q00 * B1.x + q01 * B1.y; gp[0][2] += q00 * B2.x + q01 * B2.y;
                 gp[1][0] += q10 * B0.x + q11 * B0.y; gp[1][1] += q10 * B1.x + q11 * B1.y; gp[1][2] += q10 * B2.x + q11 * B2.y;
@@ -358,10 +358,10 @@ __device__ __forceinline__ void backward_tile(const DecodeParams& P, const float
     if (WG) {   // E / H / Cc columns of the stash rows were written by the forward; add the gradient side
         st0 = P.stash + (size_t)sidx[0] * stash::W; st1 = P.stash + (size_t)sidx[1] * stash::W;
         if (t == 0) {
-            *reinterpret_cast<float4*>(st0 + stash::GO) = make_float4(gout[0][0], gout[0][1], gout[0][2], 0.0f);
-            *reinterpret_cast<float4*>(st1 + stash::GO) = make_float4(gout[1][0], gout[1][1], gout[1][2], 0.0f);
-            *reinterpret_cast<float4*>(st0 + stash::Pp) = make_float4(p[0][0], p[0][1], p[0][2], 1.0f);
-            *reinterpret_cast<float4*>(st1 + stash::Pp) = make_float4(p[1][0], p[1][1], p[1][2], 1.0f);
+            __stcs(reinterpret_cast<float4*>(st0 + stash::GO), make_float4(gout[0][0], gout[0][1], gout[0][2], 0.0f));
+            __stcs(reinterpret_cast<float4*>(st1 + stash::GO), make_float4(gout[1][0], gout[1][1], gout[1][2], 0.0f));
+            __stcs(reinterpret_cast<float4*>(st0 + stash::Pp), make_float4(p[0][0], p[0][1], p[0][2], 1.0f));
+            __stcs(reinterpret_cast<float4*>(st1 + stash::Pp), make_float4(p[1][0], p[1][1], p[1][2], 1.0f));
         }
     }
     float gcf[2][8], gp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};

@@ -124,7 +124,7 @@ __device__ __forceinline__ void stash_block(float* __restrict__ stx, float* __re
         const int r = 4 * i + (lane >> 3), c4 = 4 * (lane & 7);
         const int sr = __shfl_sync(0xffffffffu, srow, r);
         const float4 x = *reinterpret_cast<const float4*>(stx + r * SCR_ROW + c4);
-        if (sr >= 0) *reinterpret_cast<float4*>(stash_base + (size_t)sr * stash::W + col + c4) = x;
+        if (sr >= 0) __stcs(reinterpret_cast<float4*>(stash_base + (size_t)sr * stash::W + col + c4), x);   // streaming: written once, read once by k_wgrad
     }
 }
 

@@ -135,12 +135,15 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const float* __restrict
         bool first_idle = true;
         for (int w = 0; w < warp; ++w) if (c_wg.t[w].kind == 0) first_idle = false;
         if (first_idle && lane == 0) {
+            // the stash is read exactly once: evict-first in L2, so that the grids and the arenas of the optimiser step stay resident
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
             for (int i = 0; i < n_my; ++i) {
                 const int slot = i % WG_STAGES;
                 if (i >= WG_STAGES) wg_mbar_wait(bar0 + 8 * (WG_STAGES + slot), ((i / WG_STAGES) - 1) & 1);    // every consumer warp is done with the slot
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * slot), "r"(STAGE_BYTES) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(wg_smem_u32(ring + slot * WG_STAGE_FLOATS)), "l"(st + (size_t)(k_lo + i) * WG_KROWS * stash::W), "r"(STAGE_BYTES), "r"(bar0 + 8 * slot) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(wg_smem_u32(ring + slot * WG_STAGE_FLOATS)), "l"(st + (size_t)(k_lo + i) * WG_KROWS * stash::W), "r"(STAGE_BYTES), "r"(bar0 + 8 * slot), "l"(pol) : "memory");
             }
         }
         return;
